@@ -1,0 +1,195 @@
+"""ctypes bindings for the test-side native helpers (generator + CPU oracle).
+
+Nothing in here is imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import sgd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "build")
+
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def _newer(target, *srcs):
+    return os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        raise RuntimeError("build failed: " + " ".join(cmd) + "\n" + r.stdout)
+
+
+# ------------------------------------------------------------------ generator
+_gen = None
+
+
+def cnfgen_lib():
+    global _gen
+    if _gen is None:
+        os.makedirs(BUILD, exist_ok=True)
+        src = os.path.join(ROOT, "tools", "cnfgen.cpp")
+        so = os.path.join(BUILD, "libcnfgen.so")
+        if not _newer(so, src):
+            _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+        lib = C.CDLL(so)
+        lib.cnfgen_create.argtypes = [C.c_char_p, _u64p, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]
+        lib.cnfgen_create.restype = C.c_int
+        lib.cnfgen_nvars.argtypes = [C.c_void_p]; lib.cnfgen_nvars.restype = C.c_uint32
+        lib.cnfgen_nclauses.argtypes = [C.c_void_p]; lib.cnfgen_nclauses.restype = C.c_uint64
+        lib.cnfgen_nlits.argtypes = [C.c_void_p]; lib.cnfgen_nlits.restype = C.c_uint64
+        lib.cnfgen_copy.argtypes = [C.c_void_p, _u32p, _u64p]
+        lib.cnfgen_write_dimacs.argtypes = [C.c_void_p, C.c_char_p]; lib.cnfgen_write_dimacs.restype = C.c_int
+        lib.cnfgen_destroy.argtypes = [C.c_void_p]
+        _gen = lib
+    return _gen
+
+
+def gen_cnf(family: str, seed: int, args, dimacs_path: str | None = None):
+    """-> (max_var, lits uint32[L], offs uint64[C+1])"""
+    lib = cnfgen_lib()
+    h = C.c_void_p()
+    a = np.asarray(list(args), np.uint64)
+    rc = lib.cnfgen_create(family.encode(), a, len(a), seed, C.byref(h))
+    assert rc == 0, f"unknown family {family}"
+    try:
+        nv, nc, nl = lib.cnfgen_nvars(h), lib.cnfgen_nclauses(h), lib.cnfgen_nlits(h)
+        lits = np.empty(nl, np.uint32)
+        offs = np.empty(nc + 1, np.uint64)
+        lib.cnfgen_copy(h, lits, offs)
+        if dimacs_path:
+            assert lib.cnfgen_write_dimacs(h, dimacs_path.encode()) == 0
+    finally:
+        lib.cnfgen_destroy(h)
+    return nv, lits, offs
+
+
+# ------------------------------------------------------------------ oracle
+class OracleOpts(C.Structure):
+    _fields_ = [
+        ("phases", C.c_int32), ("ve_en", C.c_int32), ("ve_plus_en", C.c_int32), ("sub_en", C.c_int32),
+        ("bce_en", C.c_int32), ("ere_en", C.c_int32), ("all_en", C.c_int32),
+        ("mu_pos", C.c_uint32), ("mu_neg", C.c_uint32), ("lcve_min_vars", C.c_uint32),
+        ("lcve_max_occurs", C.c_uint32), ("lcve_clause_max", C.c_int32), ("phase_lits_min", C.c_int32),
+        ("shrink_rate", C.c_int32), ("lits_mul", C.c_double),
+        ("ve_fun_en", C.c_int32), ("ve_lbound_en", C.c_int32), ("ve_clause_max", C.c_uint32),
+        ("xor_max_arity", C.c_uint32), ("ere_clause_max", C.c_int32), ("ere_max_occurs", C.c_uint32),
+        ("sub_max_occurs", C.c_uint32), ("bce_max_occurs", C.c_uint32), ("sh_max_bve_out1", C.c_uint32),
+        ("sigma_calls", C.c_int32), ("final_gc", C.c_int32),
+    ]
+
+
+_orc = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        src = os.path.join(ROOT, "oracle", "sigma_oracle.cpp")
+        hdr = os.path.join(ROOT, "oracle", "sigma_oracle.h")
+        so = os.path.join(ROOT, "oracle", "libsigma_oracle.so")
+        if not _newer(so, src, hdr):
+            _run(["make", "-s", "-f", os.path.join(ROOT, "oracle", "Makefile"), so])
+        lib = C.CDLL(so)
+        P = C.c_void_p
+        lib.oracle_default_opts.argtypes = [C.POINTER(OracleOpts)]
+        lib.oracle_normalize_opts.argtypes = [C.POINTER(OracleOpts)]
+        lib.oracle_create.argtypes = [C.POINTER(OracleOpts), C.c_uint32, C.c_uint64, _u32p, _u64p, P, P, P, C.POINTER(P)]
+        lib.oracle_create.restype = C.c_int
+        lib.oracle_run.argtypes = [P]; lib.oracle_run.restype = C.c_int
+        lib.oracle_rounds.argtypes = [P]; lib.oracle_rounds.restype = C.c_int
+        lib.oracle_round_stats.argtypes = [P, _u64p]
+        for f in ("oracle_num_clauses", "oracle_num_literals", "oracle_num_resolved", "oracle_num_trail"):
+            getattr(lib, f).argtypes = [P]; getattr(lib, f).restype = C.c_uint64
+        lib.oracle_copy_result.argtypes = [P, _u32p, _u32p, _u64p, _u32p, _u8p, _u32p, _u32p]
+        lib.oracle_keep_snapshots.argtypes = [P, C.c_int]
+        lib.oracle_snapshot_clauses.argtypes = [P, C.c_int]; lib.oracle_snapshot_clauses.restype = C.c_uint64
+        lib.oracle_snapshot_literals.argtypes = [P, C.c_int]; lib.oracle_snapshot_literals.restype = C.c_uint64
+        lib.oracle_copy_snapshot.argtypes = [P, C.c_int, _u32p, _u32p, _u64p, _u32p]
+        lib.oracle_destroy.argtypes = [P]
+        lib.oracle_prep.argtypes = [C.c_uint64, _u32p, _u64p, _u32p]
+        lib.oracle_histogram.argtypes = [C.c_uint64, _u32p, C.c_uint32, _u32p]
+        lib.oracle_extend_model.argtypes = [_u8p, C.c_uint32, _u32p, C.c_uint64]; lib.oracle_extend_model.restype = C.c_uint64
+        lib.oracle_check_model.argtypes = [_u8p, C.c_uint64, _u32p, _u64p]; lib.oracle_check_model.restype = C.c_uint64
+        _orc = lib
+    return _orc
+
+
+FLAG_MAP = {  # reference CLI flag -> option override
+    "-no-ere": {"ere_en": 0}, "-no-vefunction": {"ve_fun_en": 0}, "-bce": {"bce_en": 1}, "-all": {"all_en": 1},
+    "-no-sub": {"sub_en": 0}, "-no-veextend": {"ve_plus_en": 0}, "-no-ve": {"ve_en": 0},
+    "-no-lcvefast": {}, "-quiet": {},
+}
+
+
+def opts_from_flags(flags) -> dict:
+    o = {}
+    for f in flags:
+        if f.startswith("--phases="):
+            o["phases"] = int(f.split("=")[1])
+        elif f.startswith("--mapperc="):
+            pass
+        else:
+            o.update(FLAG_MAP[f])
+    return o
+
+
+def make_oracle_opts(**over) -> OracleOpts:
+    lib = oracle_lib()
+    o = OracleOpts()
+    lib.oracle_default_opts(C.byref(o))
+    for k, v in over.items():
+        setattr(o, k, v)
+    lib.oracle_normalize_opts(C.byref(o))
+    return o
+
+
+def run_oracle(max_var, lits, offs, meta=None, snapshots=False, **over):
+    """Run the CPU oracle -> (Dump, round_stats uint64[R,5], [snapshot Dumps])."""
+    lib = oracle_lib()
+    o = make_oracle_opts(**over)
+    h = C.c_void_p()
+    lits = np.ascontiguousarray(lits, np.uint32)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    meta_p = None
+    if meta is not None:
+        meta = np.ascontiguousarray(meta, np.uint32)
+        meta_p = meta.ctypes.data_as(C.c_void_p)
+    lib.oracle_create(C.byref(o), max_var, len(offs) - 1, lits, offs, meta_p, None, None, C.byref(h))
+    try:
+        lib.oracle_keep_snapshots(h, int(snapshots))
+        state = lib.oracle_run(h)
+        nc, nl = lib.oracle_num_clauses(h), lib.oracle_num_literals(h)
+        nr, nt = lib.oracle_num_resolved(h), lib.oracle_num_trail(h)
+        bits = np.empty(nc, np.uint32); sig = np.empty(nc, np.uint32)
+        o_offs = np.empty(nc + 1, np.uint64); o_lits = np.empty(nl, np.uint32)
+        elim = np.empty(max_var + 1, np.uint8)
+        res = np.empty(nr, np.uint32); trail = np.empty(nt, np.uint32)
+        lib.oracle_copy_result(h, bits, sig, o_offs, o_lits, elim, res, trail)
+        d = sgd.Dump.from_arrays(max_var, state, bits, sig, o_offs, o_lits, elim, res, trail)
+        R = lib.oracle_rounds(h)
+        rs = np.zeros((R, 5), np.uint64)
+        if R:
+            lib.oracle_round_stats(h, rs.reshape(-1))
+        snaps = []
+        if snapshots:
+            for r in range(R):
+                c, l = lib.oracle_snapshot_clauses(h, r), lib.oracle_snapshot_literals(h, r)
+                b = np.empty(c, np.uint32); sg = np.empty(c, np.uint32)
+                of = np.empty(c + 1, np.uint64); li = np.empty(l, np.uint32)
+                lib.oracle_copy_snapshot(h, r, b, sg, of, li)
+                snaps.append(sgd.Dump.from_arrays(max_var, 2, b, sg, of, li, np.zeros(max_var + 1, np.uint8),
+                                                  np.empty(0, np.uint32), np.empty(0, np.uint32)))
+    finally:
+        lib.oracle_destroy(h)
+    return d, rs, snaps

@@ -1,0 +1,46 @@
+"""Pins the CPU oracle (oracle/sigma_oracle.cpp) against dumps of the UNMODIFIED reference GPU
+solver (tests/golden/, produced on a B200 by tests/golden/make_golden.py through
+oracle/ref/ref_driver.cpp).  Bit-exact: same clause list in the same order with the same
+flags and signatures, same eliminated set, same witness groups, same units."""
+import json
+import os
+
+import pytest
+
+import helpers
+import sgd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SUMMARY = json.load(open(os.path.join(HERE, "golden", "summary.json")))
+KEYS = ["cnfstate", "clauses", "literals", "eliminated", "forced", "resolved_words", "resolved_groups", "trail",
+        "h_lits_multiset", "h_full_multiset", "h_lits_ordered", "h_full_ordered", "h_eliminated", "h_forced",
+        "h_resolved_groups", "h_trail_multiset"]
+
+
+def valid(entry):
+    """Reference runs whose dump is trustworthy: the ERE kernel of the reference leaves a sticky
+    CUDA error on sm_100 ('ERE and the reference'), so only -no-ere runs pin."""
+    return "fingerprint" in entry and "-no-ere" in entry["flags"]
+
+
+CASES = sorted(k for k, e in SUMMARY.items() if valid(e))
+BIG = {"cfg1_k3_100k", "miter_50k", "mult48", "k5_20k"}
+
+
+@pytest.mark.parametrize("key", CASES)
+def test_oracle_matches_reference(key):
+    e = SUMMARY[key]
+    V, lits, offs = helpers.gen_cnf(e["family"], e["seed"], e["args"])
+    d, _, _ = helpers.run_oracle(V, lits, offs, **helpers.opts_from_flags(e["flags"]))
+    fp, g = d.fingerprint(), e["fingerprint"]
+    diff = {k: (fp[k], g[k]) for k in KEYS if fp[k] != g[k]}
+    assert not diff, diff
+    name = key.split("__")[0]
+    path = os.path.join(HERE, "golden", key + ".sgd.gz")
+    if name not in BIG and os.path.exists(path):
+        ref = sgd.Dump.load(path)
+        assert ref.ordered_clauses() == d.ordered_clauses()
+        assert ref.eliminated_vars() == d.eliminated_vars()
+        assert ref.resolved_groups() == d.resolved_groups()
+        assert sorted(ref.trail.tolist()) == sorted(d.trail.tolist())
+        assert (ref.bits == d.bits).all() and (ref.sig == d.sig).all()
