@@ -1,0 +1,168 @@
+/* include/sigma.h -- C ABI of the B200-native SIGmA inprocessing engine (libsigma_b200.so).
+ *
+ * Drop-in boundary for ParaFROST's GPU simplifier.  The reference has no plugin API: the
+ * simplifier is a set of `Solver` members compiled into libparafrost.a
+ * (src/gpu/solver.hpp:674-789).  A shim translation unit re-defines the 7 symbols the host
+ * objects import from the reference's CUDA objects (INTEGRATION.md shows it)
+ * and forwards to the entry points below, each of which replaces the reference interface
+ * named beside it.  Plain pointers and sizes only; no exceptions, no exit(): every call
+ * returns 0 on success, a positive reference `simpstate` code
+ * (src/gpu/constants.cuh:28-31) or a negative CUDA error (-cudaError_t).
+ *
+ * Re-entrant and context based (the reference is process-global): one context = one CNF on
+ * one device; contexts on different devices/threads are independent (instance-parallel
+ * batches, no collective).
+ *
+ * Literal encoding is the reference's: lit = 2*var + sign, var >= 1 (constants.hpp:72-80).
+ */
+#ifndef SIGMA_B200_H
+#define SIGMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIGMA_OK             0
+#define SIGMA_AWAKEN_FAIL    1   /* AWAKEN_FAIL    constants.cuh:29 */
+#define SIGMA_CNFALLOC_FAIL  2   /* CNFALLOC_FAIL  constants.cuh:30 */
+#define SIGMA_OTALLOC_FAIL   3   /* OTALLOC_FAIL   constants.cuh:31 */
+#define SIGMA_BAD_ARGUMENT   16
+#define SIGMA_NOT_LOADED     17
+#define SIGMA_OVERFLOW       18  /* a device vector (units / resolved) would overflow; the reference only asserts (vector.cu:77-98) */
+
+#define SIGMA_UNSAT    0         /* CNFState, constants.hpp:27 */
+#define SIGMA_SAT      1
+#define SIGMA_UNSOLVED 2
+
+/* Simplifier options: the reference's flags with their defaults
+ * (src/gpu/options.cpp:24-43, src/gpu/options.cu:36-60); replaces OPTION/GOPTION/kOpts. */
+typedef struct sigma_opts {
+    int32_t  phases;            /* --phases=5 */
+    int32_t  ve_en;             /* -ve */
+    int32_t  ve_plus_en;        /* -veextend */
+    int32_t  sub_en;            /* -sub */
+    int32_t  bce_en;            /* -bce (off) */
+    int32_t  ere_en;            /* -ere */
+    int32_t  all_en;            /* -all */
+    uint32_t mu_pos, mu_neg;    /* --mupos/--muneg = 32 */
+    uint32_t lcve_min_vars;     /* --electionsmin = 2 */
+    uint32_t lcve_max_occurs;   /* --electionsmax = 3000 */
+    int32_t  lcve_clause_max;   /* --lcveclausemax = 30000 */
+    int32_t  phase_lits_min;    /* --eliminatedlitsmin = 500 */
+    int32_t  shrink_rate;       /* --collectfreq = 2 */
+    double   lits_mul;          /* --literalsmul = 1.0 */
+    int32_t  ve_fun_en;         /* -vefunction */
+    int32_t  ve_lbound_en;      /* -velitsbound (off) */
+    uint32_t ve_clause_max;     /* --resolventmax = 100 */
+    uint32_t xor_max_arity;     /* --xormaxarity = 10 */
+    int32_t  ere_clause_max;    /* min(--ereclausemax = 250, 250) */
+    uint32_t ere_max_occurs;    /* --eremaxoccurs = 3000 */
+    uint32_t sub_max_occurs;    /* --submaxoccurs = 3000 */
+    uint32_t bce_max_occurs;    /* --bcemaxoccurs = 3000 */
+    uint32_t sh_max_bve_out1;   /* SH_MAX_BVE_OUT1 of the replaced build: 250 (EXTSHMEM) / 190 */
+    int32_t  sigma_calls;       /* stats.sigma.calls of this call: 1 = preprocessing */
+    int32_t  final_gc;          /* compact before store (simplify(skip_transfer_to_host)) */
+    int32_t  profile;           /* -profilegpu: per-stage CUDA-event times */
+} sigma_opts;
+
+/* Per-round report; replaces the LOG2 lines + inf.* updates of simplify.cu:163-186. */
+typedef struct sigma_round_report {
+    uint32_t round;             /* phase index of this iteration */
+    uint32_t kind;              /* 0 = SUB/BVE/BCE round, 1 = ERE-and-stop, 2 = loop left before eliminations */
+    uint32_t elected;           /* vars->numElected after LCVE */
+    uint32_t eliminated;        /* inf.currDeletedVars */
+    uint32_t resolvents;        /* clauses appended by BVE */
+    uint32_t units;             /* vars->nUnits produced this round */
+    uint32_t propagated;        /* units propagated by prop() at the top of this round */
+    uint32_t gc;                /* 1 if the CNF was compacted this round */
+    uint64_t clauses;           /* inf.numClauses after the round */
+    uint64_t literals;          /* inf.numLiterals after the round */
+    uint64_t literals_in;       /* live literals when the round started */
+    float    ms;                /* wall ms of the round (host clock, stream synchronised) */
+    float    pad;
+} sigma_round_report;
+
+/* Whole-call report; replaces stats.sigma.* (statistics.hpp:33-35). */
+typedef struct sigma_report {
+    int32_t  cnfstate;          /* SIGMA_UNSAT / SAT / UNSOLVED */
+    int32_t  simpstate;
+    uint32_t rounds;
+    uint32_t eliminated_vars;   /* vars->currMelted */
+    uint64_t clauses, literals; /* live after the call */
+    uint64_t clauses_in, literals_in;
+    uint64_t resolved_words;
+    uint64_t trail_units;
+    double   ms_total;          /* awaken .. end of loop, host clock */
+    /* -profilegpu stage totals in ms (statistics.cpp:37-49): vo sig io gc cot sot rot ve sub bce ere + prop lcve */
+    float    stage_ms[16];
+    uint64_t kernel_launches;   /* kernels launched by this call */
+} sigma_report;
+
+typedef struct sigma_ctx sigma_ctx;
+
+/* options.cpp:168-300 / options.cu:66-89 */
+void sigma_default_opts(sigma_opts* o);
+void sigma_normalize_opts(sigma_opts* o);          /* derivations of options.cpp:291-296 */
+
+/* Solver::optSimp + createStreams (simplify.cu:243, solver.hpp:728): bind a device, create the
+ * stream; no device memory yet. */
+int  sigma_create(int device, const sigma_opts* o, sigma_ctx** out);
+/* Solver::freeSimp (simplify.cu:254) */
+int  sigma_destroy(sigma_ctx* c);
+int  sigma_set_opts(sigma_ctx* c, const sigma_opts* o);
+
+/* Solver::awaken's host half: extractCNF + reflectCNF (cnf.cu:166-184) and cuMM::init*/
+/* (memory.cu:99-387).  HOST buffers in CSR form; sizes the arena (ONE cudaMalloc, reused
+ * while it fits) and copies the formula to the device.
+ *   lits[offs[C]]  literals, offs[C+1]
+ *   meta[C]        NULL or per clause: bit0 learnt, bits 4..5 usage, bits 6.. lbd (SCLAUSE word 0)
+ *   vorg[V+1]      NULL (identity) or current->original variable map   (solver.hpp:84)
+ *   vstate[V+1]    NULL or sp->vstate[].state: non-zero = inactive      (vstate.hpp:26-29)
+ *   assumed[V+1]   NULL or the incremental assumption mask               (lcve.cu:88,163) */
+int  sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses,
+                const uint32_t* lits, const uint64_t* offs, const uint32_t* meta,
+                const uint32_t* vorg, const uint8_t* vstate, const uint8_t* assumed);
+
+/* Solver::simplifying (simplify.cu:136-241): awaken's device half (prep_cnf_k) + the round
+ * loop.  Can be called repeatedly on the loaded formula (each call restarts from it). */
+int  sigma_run(sigma_ctx* c, sigma_report* rep);
+/* The same, one loop iteration at a time: sigma_begin, then sigma_round until *done. */
+int  sigma_begin(sigma_ctx* c);
+int  sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done);
+int  sigma_finish(sigma_ctx* c, sigma_report* rep);
+uint32_t sigma_num_rounds(const sigma_ctx* c);
+int  sigma_round_reports(const sigma_ctx* c, sigma_round_report* out, uint32_t max_rounds);
+
+/* Solver::cacheCNF / cacheResolved / cacheEliminated / cacheUnits (cnf.cu:200-237,
+ * transfer.cu:62-97): sizes first, then the device->host copy into HOST buffers.
+ * The clause stream is the reference's: clauses in ref order, bits = SCLAUSE word 0. */
+int  sigma_result_sizes(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals,
+                        uint64_t* num_resolved, uint64_t* num_trail);
+int  sigma_store(sigma_ctx* c, uint32_t* bits, uint32_t* sig, uint64_t* offs, uint32_t* lits,
+                 uint8_t* eliminated, uint32_t* resolved, uint32_t* trail);
+/* the reference's own record stream {bits, sig, size, lits...} + uint64 refs, for newClause(SCLAUSE&) */
+int  sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t* refs);
+
+/* parity / debugging */
+int  sigma_snapshot(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals);   /* sizes of the live CNF now */
+int  sigma_debug_elected(sigma_ctx* c, uint32_t* out, uint32_t* n);                 /* elected vars of the last round */
+int  sigma_debug_hist(sigma_ctx* c, uint32_t* out);                                 /* [2V+2] of the last OT build */
+
+/* arena statistics (replaces cuArena's gpu_peak_used, simplify.cu:219-220) */
+int  sigma_memory(const sigma_ctx* c, uint64_t* arena_bytes, uint64_t* peak_used, uint64_t* cuda_mallocs);
+const char* sigma_last_error(const sigma_ctx* c);
+const char* sigma_version(void);
+
+/* Stage entry points (single kernels behind the C ABI, for parity tests and the roofline bench). */
+/* prep_cnf_k (cnf.cu:45): sort literals of every clause, compute signatures; host in/out */
+int  sigma_stage_prep(int device, uint64_t num_clauses, uint32_t* lits, const uint64_t* offs, uint32_t* sig);
+/* flattenCNF + histSimp (cnf.cu:152, histogram.cu:54): literal histogram; host in/out */
+int  sigma_stage_histogram(int device, uint64_t num_lits, const uint32_t* lits, uint32_t nbins, uint32_t* hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -27,6 +27,8 @@
 #include "options.cuh"
 #include <cstdio>
 #include <vector>
+#include <algorithm>
+#include <cstdlib>
 #include <chrono>
 
 using namespace ParaFROST;
@@ -42,15 +44,40 @@ struct RefDriver : public Solver {
 	int run(const char* out_path)
 	{
 		initLimits();
+		const bool hostMode = getenv("REF_DRIVER_HOST") != NULL;
 		const auto t0 = std::chrono::steady_clock::now();
-		if (canPreSimplify()) simplify(true);
-		cudaDeviceSynchronize();
+		if (canPreSimplify()) simplify(!hostMode);
+		const cudaError_t syncErr = cudaDeviceSynchronize();
+		const cudaError_t lastErr = cudaGetLastError();
 		const auto t1 = std::chrono::steady_clock::now();
 		const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+		if (syncErr != cudaSuccess || lastErr != cudaSuccess)
+			printf("c ref_driver: CUDA ERROR after simplify: sync=%d (%s) last=%d (%s)\n",
+				int(syncErr), cudaGetErrorString(syncErr), int(lastErr), cudaGetErrorString(lastErr));
 
 		std::vector<uint32> words;
 		uint32 nClauses = 0;
-		if (hcnf && IS_UNSOLVED(cnfstate)) {
+		if (hostMode && IS_UNSOLVED(cnfstate)) {
+			// simplify(false) rebuilt the host clause database (newBeginning -> writeBackCNF ->
+			// newClause, src/gpu/cnf.cu:186-198): dump orgs then learnts, literals re-sorted
+			// because watch handling may have permuted them. sig/added are not kept by the host.
+			BCNF* sets[2] = { &orgs, &learnts };
+			for (int k = 0; k < 2; k++) {
+				BCNF& set = *sets[k];
+				for (uint32 i = 0; i < set.size(); i++) {
+					CLAUSE& c = cm[set[i]];
+					if (c.deleted()) continue;
+					std::vector<uint32> l(c.data(), c.data() + c.size());
+					std::sort(l.begin(), l.end());
+					uint32 bits = c.learnt() ? 1u : 0u;
+					if (c.learnt()) bits |= (uint32(c.usage()) << 4) | (uint32(c.lbd()) << 6);
+					words.push_back(bits); words.push_back(0); words.push_back(uint32(c.size()));
+					words.insert(words.end(), l.begin(), l.end());
+					nClauses++;
+				}
+			}
+		}
+		else if (hcnf && IS_UNSOLVED(cnfstate)) {
 			for (uint32 i = 0; i < hcnf->size(); i++) {
 				SCLAUSE& c = hcnf->clause(i);
 				if (c.deleted()) continue;
@@ -61,7 +88,7 @@ struct RefDriver : public Solver {
 			}
 		}
 		// witnesses: simplify(true) does not cache them unless the CNF got emptied
-		if (vars && IS_UNSOLVED(cnfstate)) { cacheResolved(streams[2]); cudaDeviceSynchronize(); }
+		if (vars && IS_UNSOLVED(cnfstate) && !hostMode) { cacheResolved(streams[2]); cudaDeviceSynchronize(); }
 		const uint32 nElim = inf.maxVar + 1;
 		std::vector<Byte> elim(nElim, 0);
 		if (vars) {
@@ -78,7 +105,7 @@ struct RefDriver : public Solver {
 		const uint32 hdr[12] = {
 			0x31444753u /* 'SGD1' */, inf.maxVar, uint32(cnfstate), nClauses, uint32(words.size()),
 			nElim, model.resolved.size(), trail.size(), inf.numClauses, inf.numLiterals,
-			uint32(simpstate), 0u };
+			uint32(simpstate), uint32(lastErr != cudaSuccess ? lastErr : syncErr) };
 		fwrite(hdr, sizeof(uint32), 12, f);
 		if (!words.empty()) fwrite(words.data(), sizeof(uint32), words.size(), f);
 		fwrite(elim.data(), 1, elim.size(), f);

@@ -95,6 +95,7 @@ struct oracle_ctx {
     std::vector<RoundStat> rstats;
     bool keep_snaps = false;
     std::vector<Snapshot> snaps;
+    std::vector<std::vector<u32>> electedLog;  // elected variables of every LCVE call, in order
     // BVE phase arrays (elimination.cu:146-149)
     std::vector<u32> ve_type, ve_ucnt, ve_rpos;
     std::vector<u64> ve_rref;
@@ -317,6 +318,7 @@ bool LCVE(S& s) {
         if (depFreeze(s, s.ot[p], cand) && depFreeze(s, s.ot[n], cand)) s.elected.push_back(cand);
     }
     s.numElected = u32(s.elected.size());
+    if (s.keep_snaps) s.electedLog.push_back(s.elected);
     // mapFrozen :400-419 ; varcore aliases eligible (simplify.cu:118)
     if (s.o.ve_fun_en && !s.varcore_dead) {
         if (s.frozenList.empty()) { s.varcore = nullptr; s.varcore_dead = true; }
@@ -1427,6 +1429,12 @@ void oracle_copy_snapshot(const oracle_ctx* s, int r, uint32_t* bits, uint32_t* 
     if (!sn.bits.empty()) { memcpy(bits, sn.bits.data(), sn.bits.size() * 4); memcpy(sig, sn.sig.data(), sn.sig.size() * 4); }
     memcpy(offs, sn.offs.data(), sn.offs.size() * 8);
     if (!sn.lits.empty()) memcpy(lits, sn.lits.data(), sn.lits.size() * 4);
+}
+
+int oracle_num_elections(const oracle_ctx* s) { return int(s->electedLog.size()); }
+uint64_t oracle_election_size(const oracle_ctx* s, int i) { return s->electedLog[i].size(); }
+void oracle_copy_election(const oracle_ctx* s, int i, uint32_t* out) {
+    if (!s->electedLog[i].empty()) memcpy(out, s->electedLog[i].data(), s->electedLog[i].size() * 4);
 }
 
 int oracle_write_dump(const oracle_ctx* s, const char* path) {

@@ -78,6 +78,10 @@ uint64_t oracle_snapshot_clauses(const oracle_ctx* c, int round);
 uint64_t oracle_snapshot_literals(const oracle_ctx* c, int round);
 void oracle_copy_snapshot(const oracle_ctx* c, int round, uint32_t* bits, uint32_t* sig,
                           uint64_t* offs, uint32_t* lits);
+/* elected variables of the i-th election (kept with keep_snapshots), in election order */
+int  oracle_num_elections(const oracle_ctx* c);
+uint64_t oracle_election_size(const oracle_ctx* c, int i);
+void oracle_copy_election(const oracle_ctx* c, int i, uint32_t* out);
 int  oracle_write_dump(const oracle_ctx* c, const char* path);
 void oracle_destroy(oracle_ctx* c);
 

@@ -1,0 +1,573 @@
+// parafrost_b200/csrc/api.cu -- C ABI (include/sigma.h), device arena and the round loop.
+//
+// Host driver = Solver::simplifying (src/gpu/simplify.cu:136-241) restated over the kernels of
+// this directory.  Memory = one cudaMalloc per context, carved by a bump allocator when a
+// formula is loaded (replaces cuMM + cuArena, src/gpu/memory.cu:99-387): no allocation, free or
+// resize happens inside the round loop, and the arena is reused by later loads that fit.
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+struct sigma_ctx : Ctx {};
+
+static double nowMs() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------ options
+extern "C" void sigma_default_opts(sigma_opts* o) {
+    memset(o, 0, sizeof *o);
+    o->phases = 5; o->ve_en = 1; o->ve_plus_en = 1; o->sub_en = 1; o->bce_en = 0; o->ere_en = 1; o->all_en = 0;
+    o->mu_pos = 32; o->mu_neg = 32; o->lcve_min_vars = 2; o->lcve_max_occurs = 3000; o->lcve_clause_max = 30000;
+    o->phase_lits_min = 500; o->shrink_rate = 2; o->lits_mul = 1.0;
+    o->ve_fun_en = 1; o->ve_lbound_en = 0; o->ve_clause_max = 100; o->xor_max_arity = 10;
+    o->ere_clause_max = 250; o->ere_max_occurs = 3000; o->sub_max_occurs = 3000; o->bce_max_occurs = 3000;
+    o->sh_max_bve_out1 = 250; o->sigma_calls = 1; o->final_gc = 1; o->profile = 0;
+}
+extern "C" void sigma_normalize_opts(sigma_opts* o) {  // options.cpp:291-296
+    o->ve_en = o->ve_en || o->ve_plus_en;
+    if (o->all_en) o->ve_en = 1, o->ve_plus_en = 1, o->bce_en = 1, o->ere_en = 1;
+    if (!o->phases && (o->ve_en || o->sub_en || o->bce_en)) o->phases = 1;
+    if (o->phases && !(o->ve_en || o->sub_en || o->bce_en)) o->phases = 0;
+    if (o->phases > 1 && !o->ve_en) o->phases = 1;
+    if (o->ere_clause_max > 250) o->ere_clause_max = 250;
+    if (o->sh_max_bve_out1 > 250) o->sh_max_bve_out1 = 250;
+}
+extern "C" const char* sigma_version(void) { return "sigma-b200 0.1 (sm_100a)"; }
+extern "C" const char* sigma_last_error(const sigma_ctx* c) { return c ? c->err : "null context"; }
+
+// ------------------------------------------------------------------ context
+extern "C" int sigma_create(int device, const sigma_opts* o, sigma_ctx** out) {
+    if (!out) return SIGMA_BAD_ARGUMENT;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) return e != cudaSuccess ? -(int)e : SIGMA_BAD_ARGUMENT;
+    sigma_ctx* c = new (std::nothrow) sigma_ctx();
+    if (!c) return SIGMA_AWAKEN_FAIL;
+    memset(static_cast<Ctx*>(c), 0, sizeof(Ctx));
+    c->device = device;
+    if (o) c->o = *o; else sigma_default_opts(&c->o);
+    sigma_normalize_opts(&c->o);
+    c->cnfstate = SIGMA_UNSOLVED;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMallocHost(&c->hdc, sizeof(DevCounters))) != cudaSuccess || (e = cudaEventCreate(&c->ev0)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        delete c;
+        return -(int)e;
+    }
+    memset(c->hdc, 0, sizeof(DevCounters));
+    *out = c;
+    return SIGMA_OK;
+}
+
+extern "C" int sigma_set_opts(sigma_ctx* c, const sigma_opts* o) {
+    if (!c || !o) return SIGMA_BAD_ARGUMENT;
+    c->o = *o;
+    sigma_normalize_opts(&c->o);
+    return SIGMA_OK;
+}
+
+extern "C" int sigma_destroy(sigma_ctx* c) {
+    if (!c) return SIGMA_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->arena) cudaFree(c->arena);
+    if (c->hdc) cudaFreeHost(c->hdc);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    free(c->rounds);
+    delete c;
+    return SIGMA_OK;
+}
+
+int syncCounters(Ctx* c) {
+    CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ arena
+struct Carver {
+    char* base; size_t off;
+    template <typename T> T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+// lays every buffer out; with base == nullptr it only measures
+static size_t carve(Ctx* c, char* base) {
+    Carver a{base, 0};
+    const size_t V1 = (size_t)c->V + 1, ND = c->ND, capC = c->capC, capW = c->capW;
+    const size_t nflag = (capC > V1 ? capC : V1) + 2;
+    c->inLits = a.take<u32>(c->L0 + 1);
+    c->inOffs = a.take<u64>(c->C0 + 1);
+    c->inMeta = a.take<u32>(c->C0 + 1);
+    for (int b = 0; b < 2; b++) { c->hdr[b] = a.take<uint4>(capC + 1); c->pool[b] = a.take<u32>(capW + 4); }
+    c->key = a.take<uint4>(capC + 1);
+    c->hist = a.take<u32>(ND + 2); c->otStart = a.take<u32>(ND + 2); c->otSize = a.take<u32>(ND + 2);
+    c->occurs = a.take<u32>(capW + 4);
+    c->scores = a.take<u32>(V1); c->eligible = a.take<u32>(V1); c->rank = a.take<u32>(V1);
+    c->sortK = a.take<u32>(V1); c->sortV = a.take<u32>(V1); c->elected = a.take<u32>(V1);
+    c->units = a.take<u32>(2 * V1); c->trail = a.take<u32>(3 * V1);
+    c->resolved = a.take<u32>((size_t)c->resolvedCap + 2);
+    c->vorg = a.take<u32>(V1); c->varcore = a.take<u32>(V1);
+    c->mis = a.take<unsigned char>(V1); c->cstat = a.take<unsigned char>(V1);
+    c->vstate = a.take<unsigned char>(V1); c->vstate0 = a.take<unsigned char>(V1);
+    c->assumed = a.take<unsigned char>(V1); c->eliminated = a.take<unsigned char>(V1);
+    c->wlA = a.take<u32>(V1); c->wlB = a.take<u32>(V1);
+    c->veType = a.take<u32>(V1); c->veUcnt = a.take<u32>(V1); c->veRpos = a.take<u32>(V1); c->veRref = a.take<u64>(V1);
+    const size_t maxScan = (nflag > ND + 2 ? nflag : ND + 2);
+    const size_t radixBlocks = V1 / 4096 + 2;
+    const size_t scanTiles = (maxScan > 256 * radixBlocks ? maxScan : 256 * radixBlocks) / 2048 + 4;
+    c->scanTmp = a.take<u32>(scanTiles); c->scanTmp64 = a.take<u64>(scanTiles);
+    c->flagA = a.take<u32>(nflag); c->flagB = a.take<u32>(nflag); c->flag64 = a.take<u64>(capC + 2);
+    c->radixHist = a.take<u32>(256 * radixBlocks);
+    c->qMed = a.take<u32>(ND); c->qBig = a.take<u32>(ND / 512 + 64); c->qHuge = a.take<u32>(ND / 8192 + 64);
+    c->dc = a.take<DevCounters>(1);
+    return a.off + 256;
+}
+
+// ------------------------------------------------------------------ load
+extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, const uint32_t* lits,
+                          const uint64_t* offs, const uint32_t* meta, const uint32_t* vorg, const uint8_t* vstate,
+                          const uint8_t* assumed) {
+    if (!c || !lits || !offs || !max_var) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const u64 L0 = offs[num_clauses];
+    if (max_var >= 0x7FFFFFFEu || num_clauses >= 0xFFFFFFF0ull) return SIGMA_BAD_ARGUMENT;
+    // stats.clauses.original / stats.literals.original (solver.hpp:164-165)
+    u64 orgC = num_clauses, orgL = L0;
+    if (meta) {
+        orgC = 0; orgL = 0;
+        for (u64 i = 0; i < num_clauses; i++) if (!(meta[i] & CB_LEARNT)) { orgC++; orgL += offs[i + 1] - offs[i]; }
+    }
+    c->V = max_var; c->ND = 2 * (max_var + 1);
+    c->C0 = num_clauses; c->L0 = L0;
+    c->orgClauses = orgC; c->orgLiterals = orgL;
+    // logical capacities of awaken (simplify.cu:84-98); the physical buffers are sized for them
+    u64 numCls = num_clauses, numLits = L0;
+    if (c->o.phases) {
+        numCls += c->o.ve_en ? orgC : 0;
+        numLits += c->o.ve_en ? (u64)((double)orgL * c->o.lits_mul) : 0;
+    }
+    if (numCls >= 0xFFFFFFF0ull || numCls * NBUCKETS + numLits >= 0xFFFFFFF0ull) return SIGMA_CNFALLOC_FAIL;
+    c->capC = (u32)numCls;
+    c->capW = numCls * NBUCKETS + numLits;      // data cap in words: a pool this big can never overflow
+    const u64 rc = num_clauses + L0;            // savedLits (simplify.cu:85)
+    c->resolvedCap = (u32)(rc > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : rc);
+    const size_t need = carve(c, nullptr);
+    if (need > c->arenaBytes) {
+        if (c->arena) { CUDA_TRY(cudaFree(c->arena)); c->arena = nullptr; c->arenaBytes = 0; }
+        cudaError_t e = cudaMalloc(&c->arena, need);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(c->err, sizeof c->err, "arena of %zu bytes: %s", need, cudaGetErrorString(e));
+            return SIGMA_CNFALLOC_FAIL;
+        }
+        c->arenaBytes = need;
+        c->cudaMallocs++;
+    }
+    c->arenaUsed = carve(c, c->arena);
+    if (c->arenaUsed > c->arenaPeak) c->arenaPeak = c->arenaUsed;
+    // host -> device (extractCNF + reflectCNF, cnf.cu:166-184)
+    CUDA_TRY(cudaMemcpyAsync(c->inLits, lits, L0 * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->inOffs, offs, (num_clauses + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (meta) CUDA_TRY(cudaMemcpyAsync(c->inMeta, meta, num_clauses * 4, cudaMemcpyHostToDevice, c->stream));
+    else c->inMeta = nullptr;
+    const size_t V1 = (size_t)max_var + 1;
+    if (vorg) CUDA_TRY(cudaMemcpyAsync(c->vorg, vorg, V1 * 4, cudaMemcpyHostToDevice, c->stream));
+    else {
+        u32* id = (u32*)malloc(V1 * 4);
+        if (!id) return SIGMA_AWAKEN_FAIL;
+        for (size_t v = 0; v < V1; v++) id[v] = (u32)v;
+        cudaError_t e = cudaMemcpyAsync(c->vorg, id, V1 * 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        free(id);
+        CUDA_TRY(e);
+    }
+    if (vstate) CUDA_TRY(cudaMemcpyAsync(c->vstate0, vstate, V1, cudaMemcpyHostToDevice, c->stream));
+    else CUDA_TRY(cudaMemsetAsync(c->vstate0, 0, V1, c->stream));
+    if (assumed) CUDA_TRY(cudaMemcpyAsync(c->assumed, assumed, V1, cudaMemcpyHostToDevice, c->stream));
+    else c->assumed = nullptr;
+    i64 un = max_var;
+    if (vstate) for (size_t v = 1; v < V1; v++) if (vstate[v]) un--;
+    c->unassigned0 = un;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->loaded = true; c->begun = false;
+    return SIGMA_OK;
+}
+
+// ------------------------------------------------------------------ round loop
+static KOpts makeK(Ctx* c) {
+    KOpts k;
+    k.ve_clause_max = c->o.ve_clause_max; k.xor_max_arity = c->o.xor_max_arity;
+    k.sub_max_occurs = c->o.sub_max_occurs; k.ere_max_occurs = c->o.ere_max_occurs; k.bce_max_occurs = c->o.bce_max_occurs;
+    k.sh_max_bve_out1 = c->o.sh_max_bve_out1; k.ere_clause_max = c->o.ere_clause_max;
+    k.ve_fun_en = c->o.ve_fun_en && !c->varcoreDead; k.ve_lbound_en = c->o.ve_lbound_en; k.in_mode = c->o.sigma_calls > 1;
+    k.refsCap = (u32)c->refsCap; k.dataCap = c->dataCap;
+    return k;
+}
+
+struct StageTimer {
+    Ctx* c; int st; bool on;
+    StageTimer(Ctx* c_, int st_) : c(c_), st(st_), on(c_->o.profile != 0) { if (on) cudaEventRecord(c->ev0, c->stream); }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->stageMs[st] += ms;
+    }
+};
+
+extern "C" int sigma_begin(sigma_ctx* c) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    if (!c->loaded) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t V1 = (size_t)c->V + 1;
+    c->cur = 0;
+    c->phase = c->multiplier = 0; c->simpstate = SIGMA_OK; c->cnfstate = SIGMA_UNSOLVED; c->compacted = false;
+    c->nUnits = 0; c->numElected = 0; c->currMelted = 0; c->varcoreDead = false;
+    c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0;
+    memset(c->stageMs, 0, sizeof c->stageMs);
+    c->unassigned = c->unassigned0;
+    memset(c->hdc, 0, sizeof(DevCounters));
+    c->hdc->numCls = (u32)c->C0; c->hdc->poolUsed = (u32)c->L0; c->hdc->dataSize = c->C0 * NBUCKETS + c->L0;
+    c->hdc->lastElimID = -1; c->hdc->misStopRank = NOVAR;
+    for (int i = 0; i < 12; i++) c->hdc->froz12[i] = NOVAR;
+    CUDA_TRY(cudaMemcpyAsync(c->dc, c->hdc, sizeof(DevCounters), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->vstate, c->vstate0, V1, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->eliminated, 0, V1, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->varcore, 0xFF, V1 * 4, c->stream));
+    // logical capacities (simplify.cu:84-98)
+    c->refsCap = c->capC; c->dataCap = c->capW;
+    c->numClauses = c->C0; c->numLiterals = c->L0;
+    c->cdiff = INT64_MAX; c->ldiff = INT64_MAX;
+    c->clsbefore = (i64)c->numClauses; c->litsbefore = (i64)c->numLiterals;
+    { StageTimer t(c, ST_SIG); launchAwaken(c); }
+    c->begun = true;
+    if (!c->C0) c->loopDone = true;
+    // alldisabled (solver.hpp:722)
+    if (!c->o.phases && !(c->o.all_en | c->o.ere_en)) c->loopDone = true;
+    return SIGMA_OK;
+}
+
+static void pushRound(Ctx* c, const sigma_round_report& r) {
+    if (c->nRounds == c->capRounds) {
+        c->capRounds = c->capRounds ? c->capRounds * 2 : 16;
+        c->rounds = (sigma_round_report*)realloc(c->rounds, c->capRounds * sizeof(sigma_round_report));
+    }
+    c->rounds[c->nRounds++] = r;
+}
+
+// histogram -> scan -> (GC) -> scatter : reallocOT + reallocCNF + createOTAsync (simplify.cu:164-167)
+static void buildOT(Ctx* c, bool withGC, bool* didGC) {
+    { StageTimer t(c, ST_VO); launchHistKey(c); }
+    { StageTimer t(c, ST_VO); scanExclusiveU32(c, c->hist, c->otStart, c->ND, 0, c->otStart + c->ND); }
+    if (withGC) {
+        StageTimer t(c, ST_GC);
+        // reallocCNF(true), cnf.cu:129-144: new logical capacities, then compact
+        const u64 maxAddedCls = c->o.ve_en ? c->numClauses : 0;
+        const u64 maxAddedLits = c->o.ve_en ? (u64)((double)c->orgLiterals * c->o.lits_mul) : 0;
+        c->refsCap = c->numClauses + maxAddedCls;
+        c->dataCap = c->refsCap * NBUCKETS + (c->numLiterals + maxAddedLits);
+        launchGC(c);
+        c->hdc->numCls = (u32)c->numClauses; c->hdc->poolUsed = (u32)c->numLiterals;
+        c->hdc->dataSize = c->numClauses * NBUCKETS + c->numLiterals;
+        c->compacted = true;
+        // clause indices changed: the keys gathered by the list sort must follow
+        launchHistKey(c);
+        if (didGC) *didGC = true;
+    }
+    { StageTimer t(c, ST_COT); launchScatter(c); }
+}
+
+extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
+    if (!c || !done) return SIGMA_BAD_ARGUMENT;
+    if (!c->begun) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    sigma_round_report r;
+    memset(&r, 0, sizeof r);
+    r.round = (u32)c->phase;
+    r.kind = 2;
+    r.literals_in = c->numLiterals;
+    *done = 1;
+    if (c->loopDone || !(c->numClauses && c->numLiterals && !c->simpstate)) { c->loopDone = true; if (rep) *rep = r; return SIGMA_OK; }
+    const double t0 = nowMs();
+    int rc;
+    bool didGC = false;
+    // cnf.cu:146-150
+    const int times = c->phase + 1;
+    const bool gc = times > 1 && times != c->o.phases && c->o.shrink_rate > 0 && (times % c->o.shrink_rate) == 0;
+    if (!gc) c->compacted = false;
+    buildOT(c, gc, &didGC);
+    r.gc = didGC;
+    // prop (elimbcp.cu:144-215)
+    if (c->nUnits) {
+        StageTimer t(c, ST_PROP);
+        bool conflict = false;
+        r.propagated = c->nUnits;
+        if ((rc = runProp(c, &conflict))) return rc;
+        if (conflict) {
+            c->cnfstate = SIGMA_UNSAT; c->loopDone = true;
+            r.ms = (float)(nowMs() - t0); pushRound(c, r); if (rep) *rep = r;
+            return SIGMA_OK;
+        }
+        launchCount(c);
+        if ((rc = syncCounters(c))) return rc;
+        c->numClauses = c->hdc->liveCls; c->numLiterals = c->hdc->liveLits;
+        c->unassigned -= (i64)c->hdc->unassignedDec;
+        CUDA_TRY(cudaMemsetAsync(&c->dc->unassignedDec, 0, 4, c->stream));
+        c->nUnits = 0;
+        if (c->numLiterals) buildOT(c, false, nullptr);
+        else launchScatter(c);
+    }
+    if (!c->numClauses) { c->loopDone = true; r.ms = (float)(nowMs() - t0); r.clauses = 0; r.literals = 0; pushRound(c, r); if (rep) *rep = r; return SIGMA_OK; }
+    // LCVE (lcve.cu:302-398)
+    {
+        StageTimer t(c, ST_LCVE);
+        if ((rc = runLCVE(c))) return rc;
+    }
+    c->numElected = c->hdc->numElected;
+    r.elected = c->numElected;
+    c->lastElectedCount = c->numElected;
+    if (c->o.ve_fun_en && !c->varcoreDead && c->hdc->nFrozen == 0) c->varcoreDead = true;  // mapFrozen, lcve.cu:405
+    if (c->numElected < c->o.lcve_min_vars) {
+        c->loopDone = true; r.ms = (float)(nowMs() - t0); r.clauses = c->numClauses; r.literals = c->numLiterals;
+        pushRound(c, r); if (rep) *rep = r;
+        return SIGMA_OK;
+    }
+    { StageTimer t(c, ST_SOT); launchSortOT(c); }
+    const KOpts k = makeK(c);
+    // stop() solver.hpp:748-753
+    const bool stop = (c->phase == c->o.phases) || (c->simpstate == SIGMA_CNFALLOC_FAIL) || (!c->cdiff && !c->ldiff) ||
+                      (c->phase > 2 && c->ldiff <= c->o.phase_lits_min);
+    if (stop) {
+        r.kind = 1;
+        if (c->o.ere_en && c->numElected) { StageTimer t(c, ST_ERE); launchERE(c, k); }
+        c->loopDone = true;
+        launchCount(c);
+        if ((rc = syncCounters(c))) return rc;
+        r.clauses = c->hdc->liveCls; r.literals = c->hdc->liveLits;
+        r.ms = (float)(nowMs() - t0);
+        pushRound(c, r); if (rep) *rep = r;
+        return SIGMA_OK;
+    }
+    r.kind = 0;
+    if (c->o.sub_en || c->o.ve_plus_en) { StageTimer t(c, ST_SUB); launchSUB(c, k); }
+    if (c->o.ve_en) { StageTimer t(c, ST_VE); launchVE(c, k); }
+    if (c->o.bce_en) {
+        // BCE runs over the surviving elected variables (elimination.cu:280-291)
+        if (c->o.ve_en) { if ((rc = syncCounters(c))) return rc; c->numElected = c->hdc->numElected; }
+        if (c->numElected) { StageTimer t(c, ST_BCE); launchBCE(c, k); }
+    }
+    { StageTimer t(c, ST_CNT); launchCount(c); }
+    if ((rc = syncCounters(c))) return rc;
+    if (c->hdc->flags & 3u) { snprintf(c->err, sizeof c->err, "device vector overflow (flags %u)", c->hdc->flags); return SIGMA_OVERFLOW; }
+    // updateNumPVs (simplify.cu:35-41)
+    const u32 remained = c->o.ve_en ? c->hdc->numElected : c->numElected;
+    r.eliminated = c->lastElectedCount - remained;
+    c->currMelted += r.eliminated;
+    c->numElected = remained;
+    r.resolvents = c->o.ve_en ? c->hdc->addedCls : 0;
+    c->numClauses = c->hdc->liveCls; c->numLiterals = c->hdc->liveLits;
+    c->cdiff = c->clsbefore - (i64)c->numClauses; c->clsbefore = (i64)c->numClauses;
+    c->ldiff = c->litsbefore - (i64)c->numLiterals; c->litsbefore = (i64)c->numLiterals;
+    c->nUnits = c->hdc->numUnits;
+    r.units = c->nUnits;
+    c->phase++; c->multiplier++;
+    c->multiplier += (c->phase == c->o.phases);
+    r.clauses = c->numClauses; r.literals = c->numLiterals;
+    r.ms = (float)(nowMs() - t0);
+    pushRound(c, r);
+    if (rep) *rep = r;
+    *done = 0;
+    return SIGMA_OK;
+}
+
+extern "C" int sigma_finish(sigma_ctx* c, sigma_report* rep) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    if (!c->begun) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    launchCount(c);
+    if ((rc = syncCounters(c))) return rc;
+    c->numClauses = c->hdc->liveCls; c->numLiterals = c->hdc->liveLits;
+    // simplify.cu:198-209
+    if (c->cnfstate == SIGMA_UNSOLVED && (c->unassigned <= 0 || !c->numClauses)) c->cnfstate = SIGMA_SAT;
+    if (rep) {
+        memset(rep, 0, sizeof *rep);
+        rep->cnfstate = c->cnfstate; rep->simpstate = c->simpstate; rep->rounds = c->nRounds;
+        rep->eliminated_vars = c->currMelted;
+        rep->clauses = c->numClauses; rep->literals = c->numLiterals;
+        rep->clauses_in = c->C0; rep->literals_in = c->L0;
+        rep->resolved_words = c->hdc->resolvedSize; rep->trail_units = c->hdc->trailSize;
+        rep->ms_total = c->msTotal;
+        for (int i = 0; i < 16; i++) rep->stage_ms[i] = c->stageMs[i];
+        rep->kernel_launches = c->launches;
+    }
+    return SIGMA_OK;
+}
+
+extern "C" int sigma_run(sigma_ctx* c, sigma_report* rep) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    const double t0 = nowMs();
+    int rc = sigma_begin(c);
+    if (rc) return rc;
+    int done = 0;
+    while (!done) { if ((rc = sigma_round(c, nullptr, &done))) return rc; }
+    rc = cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : -1;
+    c->msTotal = nowMs() - t0;
+    if (rc) return rc;
+    return sigma_finish(c, rep);
+}
+
+extern "C" uint32_t sigma_num_rounds(const sigma_ctx* c) { return c ? c->nRounds : 0; }
+extern "C" int sigma_round_reports(const sigma_ctx* c, sigma_round_report* out, uint32_t max_rounds) {
+    if (!c || !out) return SIGMA_BAD_ARGUMENT;
+    const u32 n = c->nRounds < max_rounds ? c->nRounds : max_rounds;
+    memcpy(out, c->rounds, n * sizeof(sigma_round_report));
+    return SIGMA_OK;
+}
+
+// ------------------------------------------------------------------ store
+extern "C" int sigma_snapshot(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals) {
+    if (!c || !c->begun) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = syncCounters(c);
+    if (rc) return rc;
+    u64 nc, nl;
+    if ((rc = launchStore(c, &nc, &nl, false))) return rc;
+    if (num_clauses) *num_clauses = nc;
+    if (num_literals) *num_literals = nl;
+    return SIGMA_OK;
+}
+
+extern "C" int sigma_result_sizes(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals, uint64_t* num_resolved,
+                                  uint64_t* num_trail) {
+    if (!c || !c->begun) return SIGMA_NOT_LOADED;
+    int rc = sigma_snapshot(c, num_clauses, num_literals);
+    if (rc) return rc;
+    if (c->cnfstate != SIGMA_UNSOLVED) { if (num_clauses) *num_clauses = 0; if (num_literals) *num_literals = 0; }
+    if (num_resolved) *num_resolved = c->hdc->resolvedSize;
+    if (num_trail) *num_trail = c->hdc->trailSize;
+    return SIGMA_OK;
+}
+
+extern "C" int sigma_store(sigma_ctx* c, uint32_t* bits, uint32_t* sig, uint64_t* offs, uint32_t* lits, uint8_t* eliminated,
+                           uint32_t* resolved, uint32_t* trail) {
+    if (!c || !c->begun) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = syncCounters(c);
+    if (rc) return rc;
+    u64 nc = 0, nl = 0;
+    if ((rc = launchStore(c, &nc, &nl, false))) return rc;
+    const int dst = 1 - c->cur;
+    const bool live = c->cnfstate == SIGMA_UNSOLVED;
+    if (offs) {
+        if (live) CUDA_TRY(cudaMemcpyAsync(offs, c->flag64, (nc + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        else offs[0] = 0;
+    }
+    if (live && nc) {
+        const u32* oBits = (const u32*)c->hdr[dst];
+        if (bits) CUDA_TRY(cudaMemcpyAsync(bits, oBits, nc * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (sig) CUDA_TRY(cudaMemcpyAsync(sig, oBits + c->capC, nc * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (lits && nl) CUDA_TRY(cudaMemcpyAsync(lits, c->pool[dst], nl * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (eliminated) CUDA_TRY(cudaMemcpyAsync(eliminated, c->eliminated, (size_t)c->V + 1, cudaMemcpyDeviceToHost, c->stream));
+    if (resolved && c->hdc->resolvedSize)
+        CUDA_TRY(cudaMemcpyAsync(resolved, c->resolved, (size_t)c->hdc->resolvedSize * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (trail && c->hdc->trailSize)
+        CUDA_TRY(cudaMemcpyAsync(trail, c->trail, (size_t)c->hdc->trailSize * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SIGMA_OK;
+}
+
+extern "C" int sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t* refs) {
+    if (!c || !c->begun) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = syncCounters(c);
+    if (rc) return rc;
+    u64 nc = 0, nl = 0;
+    if ((rc = launchStore(c, &nc, &nl, true))) return rc;
+    if (c->cnfstate != SIGMA_UNSOLVED || !nc) return SIGMA_OK;
+    const int dst = 1 - c->cur;
+    if (data_words) CUDA_TRY(cudaMemcpyAsync(data_words, c->pool[dst], (nc * NBUCKETS + nl) * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (refs) CUDA_TRY(cudaMemcpyAsync(refs, c->flag64, nc * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SIGMA_OK;
+}
+
+// ------------------------------------------------------------------ debugging / stats
+extern "C" int sigma_debug_elected(sigma_ctx* c, uint32_t* out, uint32_t* n) {
+    if (!c || !c->begun || !n) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    *n = c->lastElectedCount;
+    // note: after BVE the array holds the survivors in its first numElected entries
+    if (out && c->numElected) CUDA_TRY(cudaMemcpy(out, c->elected, (size_t)c->numElected * 4, cudaMemcpyDeviceToHost));
+    *n = c->numElected;
+    return SIGMA_OK;
+}
+extern "C" int sigma_debug_hist(sigma_ctx* c, uint32_t* out) {
+    if (!c || !c->begun || !out) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpy(out, c->hist, (size_t)c->ND * 4, cudaMemcpyDeviceToHost));
+    return SIGMA_OK;
+}
+extern "C" int sigma_memory(const sigma_ctx* c, uint64_t* arena_bytes, uint64_t* peak_used, uint64_t* cuda_mallocs) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    if (arena_bytes) *arena_bytes = c->arenaBytes;
+    if (peak_used) *peak_used = c->arenaPeak;
+    if (cuda_mallocs) *cuda_mallocs = c->cudaMallocs;
+    return SIGMA_OK;
+}
+
+// ------------------------------------------------------------------ stage entry points
+extern "C" int sigma_stage_prep(int device, uint64_t num_clauses, uint32_t* lits, const uint64_t* offs, uint32_t* sig) {
+    if (!lits || !offs) return SIGMA_BAD_ARGUMENT;
+    sigma_ctx* c = nullptr;
+    int rc = sigma_create(device, nullptr, &c);
+    if (rc) return rc;
+    u32 maxv = 1;
+    const u64 L = offs[num_clauses];
+    for (u64 i = 0; i < L; i++) if ((lits[i] >> 1) > maxv) maxv = lits[i] >> 1;
+    rc = sigma_load(c, maxv, num_clauses, lits, offs, nullptr, nullptr, nullptr, nullptr);
+    if (!rc) rc = sigma_begin(c);
+    if (!rc && num_clauses) {
+        // headers carry the signatures; literals stay at their input offsets
+        uint4* h = (uint4*)malloc(num_clauses * sizeof(uint4));
+        cudaError_t e = cudaMemcpyAsync(h, c->hdr[c->cur], num_clauses * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(lits, c->pool[c->cur], L * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = -(int)e;
+        else if (sig) for (u64 i = 0; i < num_clauses; i++) sig[i] = h[i].z;
+        free(h);
+    }
+    sigma_destroy(c);
+    return rc;
+}
+
+__global__ void k_stage_hist(const u32* __restrict__ lits, u64 n, u32* __restrict__ hist) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) atomicAdd(&hist[lits[i]], 1u);
+}
+extern "C" int sigma_stage_histogram(int device, uint64_t num_lits, const uint32_t* lits, uint32_t nbins, uint32_t* hist) {
+    if (!lits || !hist) return SIGMA_BAD_ARGUMENT;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return -(int)e;
+    u32 *dl = nullptr, *dh = nullptr;
+    if ((e = cudaMalloc(&dl, num_lits * 4 + 4)) != cudaSuccess) return -(int)e;
+    if ((e = cudaMalloc(&dh, (size_t)nbins * 4 + 4)) != cudaSuccess) { cudaFree(dl); return -(int)e; }
+    cudaMemcpy(dl, lits, num_lits * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dh, 0, (size_t)nbins * 4);
+    if (num_lits) k_stage_hist<<<gridFor(num_lits, 256), 256>>>(dl, num_lits, dh);
+    e = cudaMemcpy(hist, dh, (size_t)nbins * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dl); cudaFree(dh);
+    return e == cudaSuccess ? SIGMA_OK : -(int)e;
+}

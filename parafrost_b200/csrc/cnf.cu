@@ -1,0 +1,242 @@
+// parafrost_b200/csrc/cnf.cu -- clause store kernels: awaken/prep, literal histogram + sort keys,
+// occurrence scatter, live counts, garbage-collecting compaction, result store.
+//
+// Reference behaviour being replaced (results must be identical):
+//   prep_cnf_k            src/gpu/cnf.cu:45-53        sort literals, 32-bit signature
+//   copy_if_k + histSimp  src/gpu/cnf.cu:33-43, histogram.cu:54-72  (thrust sort only to count!)
+//   create_ot_k           src/gpu/occurrence.cu:50-62
+//   cnt_cls_lits          src/gpu/count.cu:83-106
+//   scatter_k/compact_k   src/gpu/recycle.cu:34-105
+//   cacheCNF              src/gpu/cnf.cu:200-237
+// All of them stream the clause store once: they are HBM-bound, one coalesced pass each.
+#include "common.cuh"
+
+// ------------------------------------------------------------------ awaken + prep
+// algorithmic bytes: read 8(C+1) offsets + 4L literals [+4C meta], write 16C headers + 4L literals
+__global__ void k_awaken(const u32* __restrict__ inLits, const u64* __restrict__ inOffs, const u32* __restrict__ inMeta,
+                         u64 C, uint4* __restrict__ hdr, u32* __restrict__ pool) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (u64)gridDim.x * blockDim.x) {
+        const u64 b = inOffs[i], e = inOffs[i + 1];
+        const int sz = (int)(e - b);
+        u32* dst = pool + b;
+        u32 sig = 0;
+        if (sz <= 8) {
+            u32 r[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) r[k] = (k < sz) ? inLits[b + k] : 0xFFFFFFFFu;
+            // odd-even transposition network on 8 registers (padding sorts to the end)
+#pragma unroll
+            for (int pass = 0; pass < 8; pass++) {
+#pragma unroll
+                for (int k = (pass & 1); k + 1 < 8; k += 2) {
+                    const u32 a = r[k], bb = r[k + 1];
+                    r[k] = min(a, bb); r[k + 1] = max(a, bb);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < sz) { dst[k] = r[k]; sig |= MAPHASH(r[k]); }
+        } else {
+            for (int k = 0; k < sz; k++) {
+                const u32 t = inLits[b + k];
+                int j = k;
+                for (; j > 0 && t < dst[j - 1]; j--) dst[j] = dst[j - 1];
+                dst[j] = t;
+                sig |= MAPHASH(t);
+            }
+        }
+        if (sz <= 1) sig = 0;  // calcSig leaves the signature untouched for size <= 1 (primitives.cuh:177-185)
+        u32 bits = 0;
+        if (inMeta) {
+            const u32 m = inMeta[i];
+            if (m & CB_LEARNT) bits = m & ~(CB_DELETED | CB_MOLTEN | CB_ADDED);
+        }
+        hdr[i] = make_uint4((u32)b, (u32)sz, sig, bits);
+    }
+}
+
+void launchAwaken(Ctx* c) {
+    if (!c->C0) return;
+    LAUNCH(c, k_awaken, gridFor(c->C0, 256), 256, 0, c->inLits, c->inOffs, c->inMeta, c->C0, c->hdr[c->cur], c->pool[c->cur]);
+}
+
+// ------------------------------------------------------------------ histogram + sort keys
+// algorithmic bytes: read 16C + 4L, 4 per literal of atomic traffic on hist (L2 resident), write 16C keys
+__global__ void k_hist_key(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                           u32* __restrict__ hist, uint4* __restrict__ key) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w)) continue;
+        const u32* l = pool + h.x;
+        const int sz = (int)h.y;
+        u32 first = 0, last = 0;
+        for (int k = 0; k < sz; k++) {
+            const u32 lit = l[k];
+            if (k == 0) first = lit;
+            last = lit;
+            atomicAdd(&hist[lit], 1u);
+        }
+        key[i] = make_uint4(h.y, first, last, h.z);
+    }
+}
+
+void launchHistKey(Ctx* c) {
+    cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
+    const u32 n = c->hdc->numCls;
+    if (n) LAUNCH(c, k_hist_key, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->hist, c->key);
+}
+
+// ------------------------------------------------------------------ scatter (occurrence lists)
+// algorithmic bytes: read 16C + 4L, write 4L list entries (random), one atomic per literal
+__global__ void k_scatter(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                          const u32* __restrict__ otStart, u32* __restrict__ otSize, u32* __restrict__ occurs) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w)) continue;
+        const u32* l = pool + h.x;
+        const int sz = (int)h.y;
+        for (int k = 0; k < sz; k++) {
+            const u32 lit = l[k];
+            const u32 pos = atomicAdd(&otSize[lit], 1u);
+            occurs[otStart[lit] + pos] = i;
+        }
+    }
+}
+
+void launchScatter(Ctx* c) {
+    cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream);
+    const u32 n = c->hdc->numCls;
+    if (n) LAUNCH(c, k_scatter, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->otSize, c->occurs);
+}
+
+// ------------------------------------------------------------------ live counts
+// algorithmic bytes: read 16C (headers only)
+__global__ void k_count_reset(DevCounters* dc) { dc->liveCls = 0; dc->liveLits = 0; }
+
+__global__ void k_count(const uint4* __restrict__ hdr, DevCounters* dc) {
+    const u32 n = dc->numCls;
+    u32 nc = 0, nl = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (!C_DELETED(h.w)) nc++, nl += h.y;
+    }
+    nc = warpSum(nc); nl = warpSum(nl);
+    __shared__ u32 sc[32], sl[32];
+    const u32 w = threadIdx.x >> 5, l = threadIdx.x & 31u;
+    if (l == 0) sc[w] = nc, sl[w] = nl;
+    __syncthreads();
+    if (w == 0) {
+        nc = (l < (blockDim.x >> 5)) ? sc[l] : 0;
+        nl = (l < (blockDim.x >> 5)) ? sl[l] : 0;
+        nc = warpSum(nc); nl = warpSum(nl);
+        if (l == 0 && (nc | nl)) { atomicAdd(&dc->liveCls, nc); atomicAdd((unsigned long long*)&dc->liveLits, (unsigned long long)nl); }
+    }
+}
+
+void launchCount(Ctx* c) {
+    LAUNCH(c, k_count_reset, 1, 1, 0, c->dc);
+    LAUNCH(c, k_count, 148 * 4, 256, 0, c->hdr[c->cur], c->dc);
+}
+
+// ------------------------------------------------------------------ GC compaction
+// algorithmic bytes: read 16C_all + 4L_live, write 16C' + 4L' (+ two scans over C_all)
+__global__ void k_gc_flags(const uint4* __restrict__ hdr, u32 n, u32* __restrict__ fCls, u32* __restrict__ fLits) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        const bool live = !C_DELETED(h.w);
+        fCls[i] = live ? 1u : 0u;
+        fLits[i] = live ? h.y : 0u;
+    }
+}
+
+__global__ void k_gc_copy(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                          const u32* __restrict__ pCls, const u32* __restrict__ pLits,
+                          uint4* __restrict__ nhdr, u32* __restrict__ npool) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w)) continue;
+        const u32 j = pCls[i], off = pLits[i];
+        const u32* s = pool + h.x;
+        u32* d = npool + off;
+        for (u32 k = 0; k < h.y; k++) d[k] = s[k];
+        nhdr[j] = make_uint4(off, h.y, h.z, h.w);
+    }
+}
+
+__global__ void k_gc_finish(DevCounters* dc, const u32* totCls, const u32* totLits) {
+    dc->numCls = *totCls;
+    dc->poolUsed = *totLits;
+    dc->dataSize = (u64)NBUCKETS * (*totCls) + (*totLits);
+}
+
+// cuMM::compactCNF (recycle.cu:60-105): order preserving, storage shrunk to the current sizes
+void launchGC(Ctx* c) {
+    const u32 n = c->hdc->numCls;
+    if (!n) return;
+    const int src = c->cur, dst = 1 - c->cur;
+    LAUNCH(c, k_gc_flags, gridFor(n, 256), 256, 0, c->hdr[src], n, c->flagA, c->flagB);
+    u32* tot = c->dc->scratch;
+    scanExclusiveU32(c, c->flagA, c->flagA, n, 0, tot);
+    scanExclusiveU32(c, c->flagB, c->flagB, n, 0, tot + 1);
+    LAUNCH(c, k_gc_copy, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, c->hdr[dst], c->pool[dst]);
+    LAUNCH(c, k_gc_finish, 1, 1, 0, c->dc, tot, tot + 1);
+    c->cur = dst;
+}
+
+// ------------------------------------------------------------------ store
+__global__ void k_store_arrays(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                               const u32* __restrict__ pCls, const u32* __restrict__ pLits,
+                               u32* __restrict__ oBits, u32* __restrict__ oSig, u64* __restrict__ oOffs, u32* __restrict__ oLits,
+                               const u32* totCls, const u32* totLits) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w)) continue;
+        const u32 j = pCls[i], off = pLits[i];
+        const u32* s = pool + h.x;
+        for (u32 k = 0; k < h.y; k++) oLits[off + k] = s[k];
+        oBits[j] = h.w; oSig[j] = h.z; oOffs[j] = off;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) oOffs[*totCls] = *totLits;
+}
+
+// the reference's record stream: {bits, sig, size, lits...} at refs[j] (cnf.cuh:82-97)
+__global__ void k_store_sclause(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                                const u32* __restrict__ pCls, const u32* __restrict__ pLits,
+                                u32* __restrict__ data, u64* __restrict__ refs) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w)) continue;
+        const u32 j = pCls[i];
+        const u64 r = (u64)pLits[i] + (u64)NBUCKETS * j;
+        u32* d = data + r;
+        d[0] = h.w; d[1] = h.z; d[2] = h.y;
+        const u32* s = pool + h.x;
+        for (u32 k = 0; k < h.y; k++) d[3 + k] = s[k];
+        refs[j] = r;
+    }
+}
+
+// Selects the live clauses into the staging buffers (the inactive CNF buffer); returns sizes.
+int launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm) {
+    const u32 n = c->hdc->numCls;
+    const int src = c->cur, dst = 1 - c->cur;
+    u32* tot = c->dc->scratch;
+    *nCls = *nLits = 0;
+    if (!n) return 0;
+    LAUNCH(c, k_gc_flags, gridFor(n, 256), 256, 0, c->hdr[src], n, c->flagA, c->flagB);
+    scanExclusiveU32(c, c->flagA, c->flagA, n, 0, tot);
+    scanExclusiveU32(c, c->flagB, c->flagB, n, 0, tot + 1);
+    if (sclauseForm)
+        LAUNCH(c, k_store_sclause, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, c->pool[dst], c->flag64);
+    else {
+        u32* oBits = (u32*)c->hdr[dst];
+        u32* oSig = oBits + c->capC;
+        LAUNCH(c, k_store_arrays, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, oBits, oSig,
+               c->flag64, c->pool[dst], tot, tot + 1);
+    }
+    u32 t[2];
+    cudaError_t e = cudaMemcpyAsync(t, tot, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { snprintf(c->err, sizeof c->err, "store: %s", cudaGetErrorString(e)); return -(int)e; }
+    *nCls = t[0]; *nLits = t[1];
+    return 0;
+}

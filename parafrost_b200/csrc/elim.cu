@@ -1,0 +1,1014 @@
+// parafrost_b200/csrc/elim.cu -- the elimination kernels: SUB (self-subsuming strengthening +
+// backward subsumption), BVE (gate detection, bounded resolvent counting, compacted resolvent
+// emission), BCE and ERE.
+//
+// Reference semantics reproduced bit for bit (one THREAD per elected variable there):
+//   sub_k       src/gpu/subsume.cuh:402-484
+//   ve_k_1/2    src/gpu/bounded.cuh:282-544, resolve.cuh, and.cuh, equivalence.cuh, ifthenelse.cuh,
+//               xor.cuh, function.cuh, elimination.cuh, model.cuh
+//   bce_k       src/gpu/blocked.cuh:26-97
+//   ere_k       src/gpu/redundancy.cuh:99-174
+//
+// B200 mapping: one WARP per elected variable.  The elected variables are independent (no
+// clause contains two of them), so a warp owns every clause it writes.  Regular work - the
+// |pos| x |neg| resolvent merges, list scans, subsumption candidates - is strided over the 32
+// lanes and combined with ballots / shuffles; the irregular gate searches are executed
+// redundantly by all lanes (uniform control flow, broadcast loads) with lane 0 doing the
+// writes, each followed by __syncwarp().  Results do not depend on the lane mapping: counts
+// are sums, "first match in list order" is taken with ballot + ffs.
+#include "common.cuh"
+
+struct G {
+    uint4* hdr; u32* pool;
+    const u32* otStart; u32* otSize; u32* occurs;
+    const u32* elected; unsigned char* eliminated; const u32* vorg; const u32* varcore;
+    u32* units; u32 unitsCap; u32* resolved; u32 resolvedCap;
+    u32 *veType, *veUcnt, *veRpos; u64* veRref;
+    DevCounters* dc;
+    KOpts k;
+    u32 numElected;
+};
+
+#define LANE (threadIdx.x & 31u)
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ void setBits(G& g, u32 ci, u32 set, u32 clr) {
+    if (LANE == 0) { const u32 w = g.hdr[ci].w; g.hdr[ci].w = (w & ~clr) | set; }
+    __syncwarp();
+}
+__device__ __forceinline__ void melt(G& g, u32 ci) { setBits(g, ci, CB_MOLTEN, 0); }
+__device__ __forceinline__ void freeze(G& g, u32 ci) { setBits(g, ci, 0, CB_MOLTEN); }
+__device__ __forceinline__ void markDeleted(G& g, u32 ci) { setBits(g, ci, CB_DELETED, CB_ST_MASK); }
+
+// resolvent length on x, 0 if tautology (elimination.cuh:180-205)
+__device__ __forceinline__ int mergeLen(const u32* __restrict__ a, int n1, const u32* __restrict__ b, int n2, u32 x) {
+    int it1 = 0, it2 = 0, len = n1 + n2 - 2;
+    while (it1 < n1 && it2 < n2) {
+        const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
+        if (v1 == x) it1++;
+        else if (v2 == x) it2++;
+        else if (IS_TAUT(lit1, lit2)) return 0;
+        else if (v1 < v2) it1++;
+        else if (v2 < v1) it2++;
+        else { it1++; it2++; len--; }
+    }
+    return len;
+}
+// resolvent into out (elimination.cuh:277-310); returns length, 0 if tautology; sig accumulated
+__device__ __forceinline__ int mergeOut(const u32* a, int n1, const u32* b, int n2, u32 x, u32* out, u32& sig) {
+    int it1 = 0, it2 = 0, len = 0;
+    sig = 0;
+    while (it1 < n1 && it2 < n2) {
+        const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
+        if (v1 == x) it1++;
+        else if (v2 == x) it2++;
+        else if (IS_TAUT(lit1, lit2)) return 0;
+        else if (v1 < v2) { it1++; out[len++] = lit1; sig |= MAPHASH(lit1); }
+        else if (v2 < v1) { it2++; out[len++] = lit2; sig |= MAPHASH(lit2); }
+        else { it1++; it2++; out[len++] = lit1; sig |= MAPHASH(lit1); }
+    }
+    while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != x) { out[len++] = l; sig |= MAPHASH(l); } }
+    while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != x) { out[len++] = l; sig |= MAPHASH(l); } }
+    return len;
+}
+__device__ __forceinline__ bool isTautology(const u32* a, int n1, const u32* b, int n2, u32 x) {
+    int it1 = 0, it2 = 0;
+    while (it1 < n1 && it2 < n2) {
+        const u32 v1 = LABS(a[it1]), v2 = LABS(b[it2]);
+        if (v1 == x) it1++;
+        else if (v2 == x) it2++;
+        else if (IS_TAUT(a[it1], b[it2])) return true;
+        else if (v1 < v2) it1++;
+        else if (v2 < v1) it2++;
+        else { it1++; it2++; }
+    }
+    return false;
+}
+__device__ __forceinline__ u32 sigOf(const u32* l, int n) {
+    u32 s = 0;
+    for (int k = 0; k < n; k++) s |= MAPHASH(l[k]);
+    return s;
+}
+
+// ------------------------------------------------------------------ witness stack (model.cuh:29-53)
+// lane 0 writes; callers reserve with atomicAdd on dc->resolvedSize
+__device__ __forceinline__ void saveWitness(G& g, u32*& saved, u32 witness) {
+    *saved++ = V2L(g.vorg[LABS(witness)]) | LSIGN(witness);
+    *saved++ = 1;
+}
+__device__ __forceinline__ void saveClause(G& g, u32*& saved, const uint4 h, u32 witlit) {
+    u32* first = saved; u32* wit = saved;
+    const u32* l = g.pool + h.x;
+    for (u32 k = 0; k < h.y; k++) {
+        const u32 lit = l[k];
+        if (lit == witlit) wit = saved;
+        *saved++ = V2L(g.vorg[LABS(lit)]) | LSIGN(lit);
+    }
+    const u32 t = *first; *first = *wit; *wit = t;
+    *saved++ = h.y;
+}
+// reserve n words of the witness stack; returns NULL on overflow (flagged; the reference only asserts)
+__device__ __forceinline__ u32* jumpResolved(G& g, u32 n) {
+    u32 base = 0;
+    if (LANE == 0) base = atomicAdd(&g.dc->resolvedSize, n);
+    base = __shfl_sync(FULL, base, 0);
+    if ((u64)base + n > g.resolvedCap) { if (LANE == 0) atomicOr(&g.dc->flags, 1u); return nullptr; }
+    return g.resolved + base;
+}
+// count originals / their literals of a list (all lanes redundantly; lists are short)
+__device__ __forceinline__ void countOrgsLits(G& g, const u32* list, u32 n, u32& cls, u32& lits) {
+    u32 c = 0, l = 0;
+    for (u32 j = LANE; j < n; j += 32) { const uint4 h = g.hdr[list[j]]; if (C_ORIGINAL(h.w)) c++, l += h.y; }
+    cls = warpSum(c); lits = warpSum(l);
+}
+// save the originals of `list` (witness literal first) followed by the witness unit of `wit`
+// `reserveCls`: clause count used for the reservation (the reference reserves pOrgs/nOrgs words
+//  in phase 1, elimination.cuh:455-476, which equals the number of originals except when learnt
+//  clauses sit in the list of a first-call run; reserve what the reference reserves)
+__device__ __forceinline__ void saveSide(G& g, const u32* list, u32 n, u32 witlit, u32 wit, u32 reserveCls) {
+    u32 cls, lits;
+    countOrgsLits(g, list, n, cls, lits);
+    u32* saved = jumpResolved(g, reserveCls + lits + 2);
+    if (saved && LANE == 0) {
+        u32* end = saved + reserveCls + lits + 2;
+        for (u32 j = 0; j < n; j++) { const uint4 h = g.hdr[list[j]]; if (C_ORIGINAL(h.w)) saveClause(g, saved, h, witlit); }
+        saveWitness(g, saved, wit);
+        while (saved < end) *saved++ = 0;  // unreachable unless reserveCls > #originals
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void deleteAll(G& g, const u32* list, u32 n) {
+    for (u32 j = LANE; j < n; j += 32) { const u32 ci = list[j]; const u32 w = g.hdr[ci].w; g.hdr[ci].w = (w & ~CB_ST_MASK) | CB_DELETED; }
+    __syncwarp();
+}
+// toblivion with witness saving (elimination.cuh:443-492)
+__device__ void toblivionSave(G& g, u32 p, u32 n, u32 pOrgs, u32 nOrgs, const u32* P, u32 np, const u32* N, u32 nn) {
+    if (pOrgs > nOrgs) saveSide(g, N, nn, n, p, nOrgs);
+    else saveSide(g, P, np, p, n, pOrgs);
+    deleteAll(g, P, np);
+    deleteAll(g, N, nn);
+    if (LANE == 0) { g.otSize[p] = 0; g.otSize[n] = 0; }
+    __syncwarp();
+}
+__device__ __forceinline__ void freezeBinaries(G& g, const u32* list, u32 n) {
+    for (u32 j = LANE; j < n; j += 32) { const u32 ci = list[j]; const uint4 h = g.hdr[ci]; if (C_ORIGINAL(h.w) && h.y == 2) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
+    __syncwarp();
+}
+__device__ __forceinline__ void freezeClauses(G& g, const u32* P, u32 np, const u32* N, u32 nn) {
+    for (u32 j = LANE; j < np; j += 32) { const u32 ci = P[j]; const u32 w = g.hdr[ci].w; if (C_ORIGINAL(w) && C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN; }
+    for (u32 j = LANE; j < nn; j += 32) { const u32 ci = N[j]; const u32 w = g.hdr[ci].w; if (C_ORIGINAL(w) && C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN; }
+    __syncwarp();
+}
+__device__ __forceinline__ void freezeArities(G& g, const u32* P, u32 np, const u32* N, u32 nn) {
+    for (u32 j = LANE; j < np; j += 32) { const u32 ci = P[j]; const uint4 h = g.hdr[ci]; if (h.y > 2 && C_MOLTEN(h.w)) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
+    for (u32 j = LANE; j < nn; j += 32) { const u32 ci = N[j]; const uint4 h = g.hdr[ci]; if (h.y > 2 && C_MOLTEN(h.w)) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
+    __syncwarp();
+}
+// append the unit clauses of a list to the units vector, list order (elimination.cuh:95-105)
+__device__ void appendUnits(G& g, const u32* list, u32 n, u32& cursor) {
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + LANE;
+        u32 lit = 0; bool is = false;
+        if (j < n) { const uint4 h = g.hdr[list[j]]; if (h.y == 1) { is = true; lit = g.pool[h.x]; } }
+        const u32 m = __ballot_sync(FULL, is);
+        if (is) { const u32 slot = cursor + __popc(m & lanemaskLt()); if (slot < g.unitsCap) g.units[slot] = lit; else atomicOr(&g.dc->flags, 2u); }
+        cursor += __popc(m);
+    }
+}
+__device__ __forceinline__ u32 reserveUnits(G& g, u32 n) {
+    u32 base = 0;
+    if (LANE == 0) base = atomicAdd(&g.dc->numUnits, n);
+    return __shfl_sync(FULL, base, 0);
+}
+
+// ------------------------------------------------------------------ pair counting
+// mode 0: countResolvents without the clause bound (resolve.cuh:28-109)
+// mode 1: countResolvents bounded (resolve.cuh:111-199)
+// mode 2: countSubstituted (elimination.cuh:365-441)     pairs with different molten flags
+// mode 3: countCoreSubstituted (function.cuh:181-257)    pairs not both molten
+// returns true when the elimination is NOT possible (bound / size / packing limits exceeded)
+__device__ bool countPairs(G& g, int mode, u32 x, const u32* M, u32 nm, const u32* O, u32 no, u32 nClsBefore,
+                           u32& nElements, u32& nAddedCls, u32& nAddedLits) {
+    const u32 rlimit = g.k.ve_clause_max;
+    u32 units = 0, cls = 0, lits = 0;
+    bool big = false;
+    const u64 total = (u64)nm * no;
+    u32 iter = 0;
+    bool fail = false;
+    for (u64 t0 = 0; t0 < total; t0 += 32, iter++) {
+        const u64 t = t0 + LANE;
+        if (t < total) {
+            const u32 i = (u32)(t / no), j = (u32)(t - (u64)i * no);
+            const uint4 hi = g.hdr[M[i]];
+            if (!C_LEARNT(hi.w)) {
+                const uint4 hj = g.hdr[O[j]];
+                bool take;
+                if (mode <= 1) take = !C_LEARNT(hj.w);
+                else if (mode == 2) take = C_ORIGINAL(hj.w) && ((C_MOLTEN(hi.w) != 0) != (C_MOLTEN(hj.w) != 0));
+                else take = C_ORIGINAL(hj.w) && (!C_MOLTEN(hi.w) || !C_MOLTEN(hj.w));
+                if (take) {
+                    const int rsize = mergeLen(g.pool + hi.x, (int)hi.y, g.pool + hj.x, (int)hj.y, x);
+                    if (rsize == 1) units++;
+                    else if (rsize) { cls++; lits += (u32)rsize; if (rlimit && (u32)rsize > rlimit) big = true; }
+                }
+            }
+        }
+        if ((iter & 7u) == 7u) {  // early exit like the serial loop's `return`
+            if (__any_sync(FULL, big)) { fail = true; break; }
+            if (mode && warpSum(cls) > nClsBefore) { fail = true; break; }
+        }
+    }
+    nElements = warpSum(units); nAddedCls = warpSum(cls); nAddedLits = warpSum(lits);
+    if (__any_sync(FULL, big)) fail = true;
+    if (mode && nAddedCls > nClsBefore) fail = true;
+    if (fail) { if (!nAddedCls) nAddedCls = 1; return true; }
+    if (nAddedCls > ADDEDCLS_MAX || nAddedLits > ADDEDLITS_MAX) return true;
+    if (mode && g.k.ve_lbound_en) {
+        u32 c1, l1, c2, l2;
+        countOrgsLits(g, M, nm, c1, l1);
+        countOrgsLits(g, O, no, c2, l2);
+        if (nAddedLits > l1 + l2) return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ gates (executed redundantly by all lanes)
+// equivalence.cuh:111-171
+__device__ u32 findEquGate(G& g, u32 p, u32 n, const u32* P, u32 np, const u32* N, u32 nn) {
+    if (g.hdr[P[0]].y > 2 || g.hdr[N[0]].y > 2) return 0;
+    // find_sfanin
+    u32 imp = 0; int nImps = 0; bool multi = false;
+    for (u32 j = 0; j < np; j++) {
+        const u32 ci = P[j]; const uint4 h = g.hdr[ci];
+        if (C_ORIGINAL(h.w) && h.y == 2) {
+            imp = LFLIP(g.pool[h.x] ^ g.pool[h.x + 1] ^ p);
+            melt(g, ci);
+            nImps++;
+        }
+        if (nImps > 1) { multi = true; break; }
+    }
+    u32 first = multi ? 0 : imp;
+    if (first) {
+        u32 second = n; const u32 def = first;
+        if (second < first) { first = second; second = def; }
+        for (u32 j = 0; j < nn; j++) {
+            const u32 ci = N[j]; const uint4 h = g.hdr[ci];
+            if (C_ORIGINAL(h.w) && h.y == 2 && g.pool[h.x] == first && g.pool[h.x + 1] == second) { melt(g, ci); return def; }
+        }
+    }
+    freezeBinaries(g, P, np);
+    return 0;
+}
+
+__device__ __forceinline__ bool clauseHas(G& g, const uint4 h, u32 lit) {
+    const u32* l = g.pool + h.x;
+    for (u32 k = 0; k < h.y; k++) if (l[k] == lit) return true;
+    return false;
+}
+// substitute_single on one clause (equivalence.cuh:28-57); lane 0 only
+__device__ void substituteClause(G& g, u32 ci, u32 dx, u32 def, u32& nUnits) {
+    uint4 h = g.hdr[ci];
+    u32* l = g.pool + h.x;
+    if (LANE == 0) {
+        u32 n = 0;
+        for (u32 k = 0; k < h.y; k++) { const u32 lit = l[k]; if (lit == dx) l[n++] = def; else if (lit != def) l[n++] = lit; }
+        h.y = n;
+        if (n > 1) {
+            for (u32 a = 1; a < n; a++) { const u32 t = l[a]; int b = (int)a; for (; b > 0 && t < l[b - 1]; b--) l[b] = l[b - 1]; l[b] = t; }
+            h.z = sigOf(l, (int)n);
+        }
+        g.hdr[ci] = h;
+    }
+    __syncwarp();
+    if (g.hdr[ci].y == 1) nUnits++;
+}
+// equivalence.cuh:59-109
+__device__ void substituteSingle(G& g, u32 p, u32 n, u32 def, const u32* P, u32 np, const u32* N, u32 nn) {
+    const u32 def_f = LFLIP(def);
+    u32 nNegUnits = 0, nPosUnits = 0;
+    for (u32 j = 0; j < nn; j++) {
+        const u32 ci = N[j]; const uint4 h = g.hdr[ci];
+        if (C_LEARNT(h.w) || C_MOLTEN(h.w) || clauseHas(g, h, def)) markDeleted(g, ci);
+        else substituteClause(g, ci, n, def_f, nNegUnits);
+    }
+    for (u32 j = 0; j < np; j++) {
+        const u32 ci = P[j]; const uint4 h = g.hdr[ci];
+        if (C_LEARNT(h.w) || C_MOLTEN(h.w) || clauseHas(g, h, def_f)) markDeleted(g, ci);
+        else substituteClause(g, ci, p, def, nPosUnits);
+    }
+    if (nPosUnits || nNegUnits) {
+        // appendUnits appends every size-1 clause of the list (elimination.cuh:95-105)
+        u32 cn = 0, cp = 0;
+        if (nNegUnits) for (u32 j = 0; j < nn; j++) cn += g.hdr[N[j]].y == 1;
+        if (nPosUnits) for (u32 j = 0; j < np; j++) cp += g.hdr[P[j]].y == 1;
+        u32 cursor = reserveUnits(g, cn + cp);
+        if (nNegUnits) appendUnits(g, N, nn, cursor);
+        if (nPosUnits) appendUnits(g, P, np, cursor);
+    }
+}
+
+// and.cuh:28-113 ; out_c lives in this warp's shared slice
+__device__ bool findAOGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
+                           u32& nElements, u32& nAddedCls, u32& nAddedLits) {
+    if (g.hdr[D[0]].y > 2 || g.hdr[F[nf - 1]].y < 3) return false;
+    u32 sig = 0; u32 nImps = 0;
+    for (u32 j = 0; j < nd; j++) {
+        const u32 ci = D[j]; const uint4 h = g.hdr[ci];
+        if (C_ORIGINAL(h.w) && h.y == 2) {
+            const u32 imp = LFLIP(g.pool[h.x] ^ g.pool[h.x + 1] ^ dx);
+            if (LANE == 0) out_c[nImps] = imp;
+            nImps++;
+            sig |= MAPHASH(imp);
+            melt(g, ci);
+        }
+    }
+    if (nImps > 1) {
+        const u32 x = LABS(dx);
+        if (LANE == 0) {
+            out_c[nImps] = fx;
+            for (u32 a = 1; a <= nImps; a++) { const u32 t = out_c[a]; int b = (int)a; for (; b > 0 && t < out_c[b - 1]; b--) out_c[b] = out_c[b - 1]; out_c[b] = t; }
+        }
+        nImps++;
+        sig |= MAPHASH(fx);
+        __syncwarp();
+        for (u32 j = 0; j < nf; j++) {
+            const u32 ci = F[j]; const uint4 h = g.hdr[ci];
+            if (C_ORIGINAL(h.w) && h.y == nImps && SUBSIG(h.z, sig)) {
+                bool eq = true;
+                for (u32 k = 0; k < nImps; k++) if (g.pool[h.x + k] != out_c[k]) { eq = false; break; }
+                if (!eq) continue;
+                melt(g, ci);
+                nElements = 0; nAddedCls = 0; nAddedLits = 0;
+                if (countPairs(g, 2, x, D, nd, F, nf, nOrgCls, nElements, nAddedCls, nAddedLits)) { freeze(g, ci); break; }
+                return true;
+            }
+        }
+    }
+    freezeBinaries(g, D, nd);
+    return false;
+}
+
+// ifthenelse.cuh:28-50 ; returns clause index or NOVAR
+__device__ u32 fastEqualityCheck(G& g, u32 x, u32 y, u32 z) {
+    u32 t;
+    if (g.otSize[y] > g.otSize[z]) { t = y; y = z; z = t; }
+    if (g.otSize[x] > g.otSize[y]) { t = x; x = y; y = t; }
+    const u32 n = g.otSize[x];
+    const u32* list = g.occurs + g.otStart[x];
+    // sort3
+    if (y > z) { t = y; y = z; z = t; }
+    if (x > z) { t = x; x = z; z = t; }
+    if (x > y) { t = x; x = y; y = t; }
+    // first match in list order; lanes scan 32 entries at a time
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + LANE;
+        bool ok = false;
+        if (j < n) {
+            const uint4 h = g.hdr[list[j]];
+            if (!C_MOLTEN(h.w) && C_ORIGINAL(h.w) && h.y == 3) {
+                const u32* l = g.pool + h.x;
+                ok = l[0] == x && l[1] == y && l[2] == z;
+            }
+        }
+        const u32 m = __ballot_sync(FULL, ok);
+        if (m) return list[base + __ffs(m) - 1];
+    }
+    return NOVAR;
+}
+// ifthenelse.cuh:52-125
+__device__ bool findITEGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls,
+                            u32& nElements, u32& nAddedCls, u32& nAddedLits) {
+    if (g.hdr[D[nd - 1]].y == 2) return false;
+    const u32 v = LABS(dx);
+    for (u32 i = 0; i < nd; i++) {
+        const u32 cii = D[i]; const uint4 hi = g.hdr[cii];
+        if (!(C_ORIGINAL(hi.w) && hi.y == 3)) continue;
+        u32 xi = g.pool[hi.x], yi = g.pool[hi.x + 1], zi = g.pool[hi.x + 2], t;
+        if (yi == dx) { t = xi; xi = yi; yi = t; }
+        if (zi == dx) { t = xi; xi = zi; zi = t; }
+        for (u32 j = i + 1; j < nd; j++) {
+            const u32 cjj = D[j]; const uint4 hj = g.hdr[cjj];
+            if (!(C_ORIGINAL(hj.w) && hj.y == 3)) continue;
+            u32 xj = g.pool[hj.x], yj = g.pool[hj.x + 1], zj = g.pool[hj.x + 2];
+            if (yj == dx) { t = xj; xj = yj; yj = t; }
+            if (zj == dx) { t = xj; xj = zj; zj = t; }
+            if (LABS(yi) == LABS(zj)) { t = yj; yj = zj; zj = t; }
+            if (LABS(zi) == LABS(zj)) continue;
+            if (yi != LFLIP(yj)) continue;
+            const u32 r1 = fastEqualityCheck(g, fx, yi, LFLIP(zi));
+            if (r1 == NOVAR) continue;
+            const u32 r2 = fastEqualityCheck(g, fx, yj, LFLIP(zj));
+            if (r2 == NOVAR) continue;
+            melt(g, cii); melt(g, cjj); melt(g, r1); melt(g, r2);
+            nElements = 0; nAddedCls = 0; nAddedLits = 0;
+            if (countPairs(g, 2, v, D, nd, F, nf, nOrgCls, nElements, nAddedCls, nAddedLits)) {
+                freeze(g, cii); freeze(g, cjj); freeze(g, r1); freeze(g, r2);
+                return false;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+// xor.cuh:58-109 ; literals[] in this warp's shared slice (lane 0 writes)
+__device__ bool makeArity(G& g, u32& parity, u32* literals, int size) {
+    const u32 oldparity = parity;
+    while (__popc(++parity) & 1) {}
+    if (LANE == 0)
+        for (int k = 0; k < size; k++) { const u32 bit = 1u << k; if ((parity & bit) != (oldparity & bit)) literals[k] = LFLIP(literals[k]); }
+    __syncwarp();
+    u32 best = literals[0];
+    u32 minsize = g.otSize[best];
+    for (int k = 1; k < size; k++) { const u32 lit = literals[k]; const u32 ls = g.otSize[lit]; if (ls < minsize) { minsize = ls; best = lit; } }
+    const u32* list = g.occurs + g.otStart[best];
+    for (u32 base = 0; base < minsize; base += 32) {
+        const u32 j = base + LANE;
+        bool ok = false;
+        if (j < minsize) {
+            const uint4 h = g.hdr[list[j]];
+            if (C_ORIGINAL(h.w) && (int)h.y == size) {
+                ok = true;
+                const u32* l = g.pool + h.x;
+                for (int a = 0; a < size && ok; a++) {  // checkArity
+                    bool f = false;
+                    for (int b = 0; b < size; b++) if (l[a] == literals[b]) { f = true; break; }
+                    ok = f;
+                }
+            }
+        }
+        const u32 m = __ballot_sync(FULL, ok);
+        if (m) { melt(g, list[base + __ffs(m) - 1]); return true; }
+    }
+    return false;
+}
+// xor.cuh:111-185
+__device__ bool findXORGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
+                            u32& nElements, u32& nAddedCls, u32& nAddedLits) {
+    if (g.hdr[D[nd - 1]].y == 2 || g.hdr[F[nf - 1]].y == 2) return false;
+    const int maxarity = (int)g.k.xor_max_arity;
+    if ((int)g.hdr[D[0]].y - 1 > maxarity) return false;
+    const u32 v = LABS(dx);
+    for (u32 i = 0; i < nd; i++) {
+        const u32 ci = D[i]; const uint4 h = g.hdr[ci];
+        if (!C_ORIGINAL(h.w)) continue;
+        const int size = (int)h.y, arity = size - 1;
+        if (size < 3 || arity > maxarity) continue;
+        __syncwarp();
+        if (LANE == 0) for (int k = 0; k < size; k++) out_c[k] = g.pool[h.x + k];
+        __syncwarp();
+        u32 parity = 0;
+        int itargets = 1 << arity;
+        while (--itargets && makeArity(g, parity, out_c, size)) {}
+        if (itargets) freezeArities(g, D, nd, F, nf);
+        else {
+            melt(g, ci);
+            nElements = 0; nAddedCls = 0; nAddedLits = 0;
+            if (countPairs(g, 2, v, D, nd, F, nf, nOrgCls, nElements, nAddedCls, nAddedLits)) { freezeArities(g, D, nd, F, nf); break; }
+            return true;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ function tables (function.cuh)
+// One 64x64-bit table = 4096 bits; lane l owns words l and l+32.
+__constant__ u64 MAGICCONSTS[6] = {0xaaaaaaaaaaaaaaaaULL, 0xccccccccccccccccULL, 0xf0f0f0f0f0f0f0f0ULL,
+                                   0xff00ff00ff00ff00ULL, 0xffff0000ffff0000ULL, 0xffffffff00000000ULL};
+struct Fun2 { u64 a, b; };  // words LANE and LANE+32
+__device__ __forceinline__ u64 funWord(int v, bool sign, u32 i) {  // clause2fun contribution to word i (function.cuh:86-112)
+    if (v < 6) { u64 val = MAGICCONSTS[v]; return sign ? ~val : val; }
+    const u32 sv = 1u << (v - 6);
+    const bool flip = (i / sv) & 1u;    // val starts as (sign ? ones : 0) and toggles every sv words
+    const bool ones = sign != flip;
+    return ones ? ~0ULL : 0ULL;
+}
+// OR of the literals of clause h other than lit, as a table; false if a variable index >= 12
+__device__ __forceinline__ bool clauseFun(G& g, const uint4 h, u32 lit, Fun2& cls) {
+    cls.a = cls.b = 0;
+    const u32* l = g.pool + h.x;
+    for (u32 k = 0; k < h.y; k++) {
+        const u32 other = l[k];
+        if (other == lit) continue;
+        const u32 mvar = g.varcore[LABS(other)];
+        if (mvar >= MAXFUNVAR) return false;
+        cls.a |= funWord((int)mvar, LSIGN(other), LANE);
+        cls.b |= funWord((int)mvar, LSIGN(other), LANE + 32);
+    }
+    return true;
+}
+__device__ bool buildFunAll(G& g, u32 lit, Fun2& f) {  // function.cuh:114-148
+    f.a = f.b = ~0ULL;
+    const u32 n = g.otSize[lit];
+    const u32* list = g.occurs + g.otStart[lit];
+    for (u32 j = 0; j < n; j++) {
+        const uint4 h = g.hdr[list[j]];
+        if (C_LEARNT(h.w)) continue;
+        Fun2 cls;
+        if (!clauseFun(g, h, lit, cls)) return false;
+        f.a &= cls.a; f.b &= cls.b;
+    }
+    return true;
+}
+__device__ void buildFunTail(G& g, u32 lit, u32 tail, const u32* list, Fun2& fun, bool& core) {  // function.cuh:150-179
+    for (u32 j = 0; j < tail; j++) {
+        const uint4 h = g.hdr[list[j]];
+        if (C_LEARNT(h.w)) continue;
+        Fun2 cls;
+        clauseFun(g, h, lit, cls);
+        fun.a &= cls.a; fun.b &= cls.b;
+    }
+    if (!__any_sync(FULL, (fun.a | fun.b) != 0)) { melt(g, list[tail]); core = true; }
+}
+__device__ bool findFunGate(G& g, u32 p, u32 n, u32 nOrgCls, const u32* P, u32 np, const u32* N, u32 nn,
+                            u32& nElements, u32& nAddedCls, u32& nAddedLits) {  // function.cuh:275-327
+    Fun2 pos, neg;
+    if (buildFunAll(g, p, pos) && buildFunAll(g, n, neg)) {
+        if (!__any_sync(FULL, ((pos.a & neg.a) | (pos.b & neg.b)) != 0)) {
+            bool core = false;
+            Fun2 fun;
+            for (int i = (int)np - 1; i >= 0; i--) {
+                fun = neg;
+                if (C_ORIGINAL(g.hdr[P[i]].w)) buildFunTail(g, p, (u32)i, P, fun, core);
+            }
+            for (int i = (int)nn - 1; i >= 0; i--) {
+                fun.a = fun.b = ~0ULL;
+                if (C_ORIGINAL(g.hdr[N[i]].w)) buildFunTail(g, n, (u32)i, N, fun, core);
+            }
+            nElements = 0; nAddedCls = 0; nAddedLits = 0;
+            if (countPairs(g, 3, LABS(p), P, np, N, nn, nOrgCls, nElements, nAddedCls, nAddedLits)) {
+                if (core) freezeClauses(g, P, np, N, nn);
+                return false;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ BVE phase 1 (bounded.cuh:282-394)
+#define VE_SLICE 256  // words of shared memory per warp (out_c of the gate searches, >= SH_MAX_BVE_OUT1)
+
+__global__ void __launch_bounds__(128) k_ve_phase1(G g) {
+    __shared__ u32 sh[4][VE_SLICE];
+    u32* out_c = sh[threadIdx.x >> 5];
+    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
+        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
+        const u32 np = g.otSize[p], nn = g.otSize[n];
+        const u32* P = g.occurs + g.otStart[p];
+        const u32* N = g.occurs + g.otStart[n];
+        u32 pOrgs, nOrgs;
+        if (g.k.in_mode) { u32 d; countOrgsLits(g, P, np, pOrgs, d); countOrgsLits(g, N, nn, nOrgs, d); }
+        else { pOrgs = np; nOrgs = nn; }
+        u32 elimType = 0, nElements = 0, nAddedCls = 0, nAddedLits = 0;
+        bool eliminatedNow = false, record = false;
+        if (!pOrgs || !nOrgs) { toblivionSave(g, p, n, pOrgs, nOrgs, P, np, N, nn); eliminatedNow = true; }
+        else {
+            const u32 def = findEquGate(g, p, n, P, np, N, nn);
+            if (def) {
+                // saveResolved(p, n, pOrgs, nOrgs, ...) elimination.cuh:552-594
+                if (pOrgs > nOrgs) saveSide(g, N, nn, n, p, nOrgs); else saveSide(g, P, np, p, n, pOrgs);
+                substituteSingle(g, p, n, def, P, np, N, nn);
+                eliminatedNow = true;
+            }
+            else if ((pOrgs == 1 || nOrgs == 1) && !countPairs(g, 0, x, P, np, N, nn, 0, nElements, nAddedCls, nAddedLits)) {
+                if (nAddedCls) { elimType = RES_MASK; record = true; }
+                else { toblivionSave(g, p, n, pOrgs, nOrgs, P, np, N, nn); eliminatedNow = true; }
+            }
+            else {
+                const u32 nClsBefore = pOrgs + nOrgs;
+                elimType = 0; nElements = 0; nAddedCls = 0; nAddedLits = 0;
+                if (nClsBefore > 2) {
+                    if (nOrgs < g.k.sh_max_bve_out1 && findAOGate(g, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits))
+                        elimType = AOIX_MASK;
+                    else if (!nAddedCls && pOrgs < g.k.sh_max_bve_out1 && findAOGate(g, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits))
+                        elimType = AOIX_MASK;
+                }
+                if (!elimType && nClsBefore > 3) {
+                    if (findITEGate(g, p, P, np, n, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    else if (!nAddedCls && findITEGate(g, n, N, nn, p, P, np, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    else if (findXORGate(g, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    else if (!nAddedCls && findXORGate(g, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                }
+                if (g.k.ve_fun_en && !elimType && nClsBefore > 2 &&
+                    findFunGate(g, p, n, nClsBefore, P, np, N, nn, nElements, nAddedCls, nAddedLits))
+                    elimType = CORE_MASK;
+                else if (!elimType && !nAddedCls && !countPairs(g, 1, x, P, np, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits))
+                    elimType = RES_MASK;
+                if (!nAddedCls) { toblivionSave(g, p, n, pOrgs, nOrgs, P, np, N, nn); eliminatedNow = true; }
+                else if (elimType) record = true;
+            }
+        }
+        if (LANE == 0) {
+            if (record) {
+                g.veType[tid] = ENCODEVARINFO(elimType, nAddedCls, nAddedLits);
+                g.veUcnt[tid] = nElements; g.veRpos[tid] = nAddedCls; g.veRref[tid] = (u64)nAddedLits + (u64)NBUCKETS * nAddedCls;
+            } else { g.veType[tid] = 0; g.veUcnt[tid] = 0; g.veRpos[tid] = 0; g.veRref[tid] = 0; }
+            if (eliminatedNow) g.eliminated[x] |= MELTING_MASK;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ BVE phase 3 (bounded.cuh:488-544, 171-280)
+// start values of the scans: CNF sizes before this BVE (elimination.cu:82-92)
+struct VEBase { u32 numCls0, poolUsed0; u64 dataSize0; };
+
+__global__ void __launch_bounds__(128) k_ve_phase3(G g, VEBase vb, u32* __restrict__ survivorFlag) {
+    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
+        const u32 x = g.elected[tid];
+        const u32 xinfo = g.veType[tid], elimType = RECOVERTYPE(xinfo);
+        if (elimType) {
+            const u32 p = V2L(x), n = p | 1u;
+            const u32 nAddedCls = RECOVERADDEDCLS(xinfo), nAddedLits = RECOVERADDEDLITS(xinfo);
+            const u32 addedPos = g.veRpos[tid];
+            const u64 addedRef = g.veRref[tid];
+            const u32 np = g.otSize[p], nn = g.otSize[n];
+            const u32* P = g.occurs + g.otStart[p];
+            const u32* N = g.occurs + g.otStart[n];
+            const bool safe = ((u64)addedPos + nAddedCls <= g.k.refsCap) &&
+                              (addedRef + nAddedLits + (u64)NBUCKETS * nAddedCls <= g.k.dataCap);
+            if (safe) {
+                // saveResolved(p, n, cnf, poss, negs) elimination.cuh:505-550 : side chosen by list sizes
+                u32 c1, l1;
+                if (np > nn) { countOrgsLits(g, N, nn, c1, l1); saveSide(g, N, nn, n, p, c1); }
+                else { countOrgsLits(g, P, np, c1, l1); saveSide(g, P, np, p, n, c1); }
+                // emission: pairs in pos-major / neg-minor order, 32 at a time
+                u32 clsOut = addedPos;
+                u32 poolOut = vb.poolUsed0 + (u32)((addedRef - vb.dataSize0) - (u64)NBUCKETS * (addedPos - vb.numCls0));
+                const u32 checksum = addedPos + nAddedCls;
+                const u32 nUnitsExp = g.veUcnt[tid];
+                u32 ucursor = nUnitsExp ? reserveUnits(g, nUnitsExp) : 0;
+                const u64 total = (u64)np * nn;
+                for (u64 t0 = 0; t0 < total && clsOut < checksum; t0 += 32) {
+                    const u64 t = t0 + LANE;
+                    int rsize = 0;
+                    uint4 hi = make_uint4(0, 0, 0, 0), hj = hi;
+                    if (t < total) {
+                        const u32 i = (u32)(t / nn), j = (u32)(t - (u64)i * nn);
+                        hi = g.hdr[P[i]];
+                        if (!C_LEARNT(hi.w)) {
+                            hj = g.hdr[N[j]];
+                            bool take = !C_LEARNT(hj.w);
+                            if (elimType == AOIX_MASK) take = take && ((C_MOLTEN(hi.w) != 0) != (C_MOLTEN(hj.w) != 0));
+                            else if (elimType == CORE_MASK) take = take && !(C_MOLTEN(hi.w) && C_MOLTEN(hj.w));
+                            if (take) rsize = mergeLen(g.pool + hi.x, (int)hi.y, g.pool + hj.x, (int)hj.y, x);
+                        }
+                    }
+                    const bool isCls = rsize > 1, isUnit = rsize == 1;
+                    const u32 mc = __ballot_sync(FULL, isCls), mu = __ballot_sync(FULL, isUnit);
+                    const u32 myCls = __popc(mc & lanemaskLt());
+                    const u32 wordsIncl = warpIncl(isCls ? (u32)rsize : 0u);
+                    const u32 myWords = wordsIncl - (isCls ? (u32)rsize : 0u);
+                    const u32 totWords = __shfl_sync(FULL, wordsIncl, 31);
+                    if (isCls && clsOut + myCls < checksum) {
+                        u32 sig;
+                        u32* out = g.pool + poolOut + myWords;
+                        mergeOut(g.pool + hi.x, (int)hi.y, g.pool + hj.x, (int)hj.y, x, out, sig);
+                        // new SCLAUSE: ORIGINAL, added (bounded.cuh:86-120)
+                        g.hdr[clsOut + myCls] = make_uint4(poolOut + myWords, (u32)rsize, sig, CB_ADDED);
+                    }
+                    if (isUnit) {
+                        u32 sig, lit;
+                        mergeOut(g.pool + hi.x, (int)hi.y, g.pool + hj.x, (int)hj.y, x, &lit, sig);
+                        const u32 slot = ucursor + __popc(mu & lanemaskLt());
+                        if (slot < g.unitsCap) g.units[slot] = lit; else atomicOr(&g.dc->flags, 2u);
+                    }
+                    clsOut += __popc(mc); poolOut += totWords; ucursor += __popc(mu);
+                }
+                __syncwarp();
+                deleteAll(g, P, np);
+                deleteAll(g, N, nn);
+                if (LANE == 0) {
+                    g.otSize[p] = 0; g.otSize[n] = 0;
+                    g.eliminated[x] |= (MELTING_MASK | ADDING_MASK);
+                    atomicMax(&g.dc->lastElimID, (int)tid);
+                }
+                __syncwarp();
+            }
+            else {
+                if (LANE == 0) atomicOr(&g.dc->flags, 4u);
+                if (elimType != RES_MASK) freezeClauses(g, P, np, N, nn);
+            }
+        }
+        if (LANE == 0) survivorFlag[tid] = g.eliminated[x] ? 0u : 1u;
+        __syncwarp();
+    }
+}
+
+// resizeCNF_k (cnf.cu:55-79)
+__global__ void k_ve_resize(G g, VEBase vb) {
+    const int last = g.dc->lastElimID;
+    if (last >= 0) {
+        const u32 info = g.veType[last];
+        const u32 cl = RECOVERADDEDCLS(info), li = RECOVERADDEDLITS(info);
+        const u32 pos = g.veRpos[last];
+        const u64 ref = g.veRref[last];
+        g.dc->numCls = pos + cl;
+        g.dc->dataSize = ref + li + (u64)NBUCKETS * cl;
+        g.dc->poolUsed = vb.poolUsed0 + (u32)((ref - vb.dataSize0) - (u64)NBUCKETS * (pos - vb.numCls0)) + li;
+        g.dc->addedCls = pos + cl - vb.numCls0;
+    } else g.dc->addedCls = 0;
+}
+__global__ void k_ve_reset(DevCounters* dc) { dc->lastElimID = -1; dc->addedCls = 0; }
+__global__ void k_select_scatter(const u32* __restrict__ src, const u32* __restrict__ flag, const u32* __restrict__ pos, u32 n,
+                                 u32* __restrict__ dst) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i]) dst[pos[i]] = src[i];
+}
+__global__ void k_copy_u32(const u32* __restrict__ src, u32* __restrict__ dst, const u32* n) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < *n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ SUB (subsume.cuh)
+// selfsub signature test (elimination.cuh:67-71)
+__device__ __forceinline__ bool selfsubSig(u32 A, u32 B) {
+    const u32 Bt = B | ((B & 0xAAAAAAAAu) >> 1) | ((B & 0x55555555u) << 1);
+    return !(A & ~Bt);
+}
+// subsume.cuh:132-176
+__device__ __forceinline__ bool selfsubMerge(const u32* d1, int n1, const u32* d2, int n2, u32 x, u32 fx) {
+    int i1 = 0, i2 = 0, sub = 0; bool self = false;
+    while (i1 < n1 && i2 < n2) {
+        const u32 lit1 = d1[i1], lit2 = d2[i2];
+        if (lit1 == fx) i1++;
+        else if (lit2 == x) { self = true; i2++; }
+        else if (lit1 < lit2) i1++;
+        else if (lit2 < lit1) i2++;
+        else { sub++; i1++; i2++; }
+    }
+    if (sub + 1 == n1) {
+        if (self) return true;
+        while (i2 < n2) { if (d2[i2] == x) return true; i2++; }
+    }
+    return false;
+}
+// subsume.cuh:50-75
+__device__ __forceinline__ bool subMerge(const u32* d1, int n1, const u32* d2, int n2) {
+    int i1 = 0, i2 = 0, sub = 0;
+    while (i1 < n1 && i2 < n2) {
+        const u32 lit1 = d1[i1], lit2 = d2[i2];
+        if (lit1 < lit2) i1++;
+        else if (lit2 < lit1) i2++;
+        else { sub++; i1++; i2++; }
+    }
+    return sub == n1;
+}
+
+// one side of sub_k: every clause of M against the other list O, then against its predecessors in M
+__device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, u32 fx) {
+    u32 nUnits = 0;
+    for (u32 i = 0; i < nm; i++) {
+        const u32 ci = M[i];
+        uint4 h = g.hdr[ci];
+        if ((int)h.y > SUB_MAX_CL_SIZE) break;
+        if (C_DELETED(h.w)) continue;
+        // selfsubsume (subsume.cuh:344-400): first neg clause, in list order, that strengthens cand
+        bool hit = false;
+        for (u32 base = 0; base < no; base += 32) {
+            const u32 j = base + LANE;
+            bool brk = false, ok = false;
+            if (j < no) {
+                const uint4 hj = g.hdr[O[j]];
+                if (hj.y > h.y) brk = true;
+                else if (!C_DELETED(hj.w) && !C_MOLTEN(hj.w) && hj.y > 1 && selfsubSig(hj.z, h.z) &&
+                         selfsubMerge(g.pool + hj.x, (int)hj.y, g.pool + h.x, (int)h.y, x, fx)) ok = true;
+            }
+            const u32 bm = __ballot_sync(FULL, brk), om = __ballot_sync(FULL, ok);
+            const u32 fb = bm ? (u32)__ffs(bm) - 1 : 32u, fo = om ? (u32)__ffs(om) - 1 : 32u;
+            if (fo < fb) { hit = true; break; }
+            if (bm) break;
+        }
+        if (hit) {  // strengthen (subsume.cuh:269-291) + melt
+            if (LANE == 0) {
+                u32* l = g.pool + h.x;
+                u32 n = 0;
+                for (u32 k = 0; k < h.y; k++) if (l[k] != x) l[n++] = l[k];
+                h.y = h.y - 1;
+                if (h.y > 1) {
+                    h.z = sigOf(l, (int)h.y);
+                    if (C_LEARNT(h.w)) {  // bumpShrunken (subsume.cuh:226-238)
+                        const int old_lbd = (int)(h.w >> CB_LBD_SHIFT);
+                        if (old_lbd > LBD_TIER1) {
+                            const int new_lbd = min((int)h.y - 1, old_lbd);
+                            if (new_lbd < old_lbd) h.w = (h.w & ((1u << CB_LBD_SHIFT) - 1) & ~CB_USAGE_MASK) | ((u32)new_lbd << CB_LBD_SHIFT) | (USAGET3 << CB_USAGE_SHIFT);
+                        }
+                    }
+                }
+                h.w |= CB_MOLTEN;
+                g.hdr[ci] = h;
+            }
+            __syncwarp();
+            h = g.hdr[ci];
+            if (h.y == 1) nUnits++;
+        }
+        // subsume (subsume.cuh:305-342): first earlier clause of the same list that subsumes cand
+        const bool candMolten = C_MOLTEN(h.w) != 0;
+        for (u32 base = 0; base < i; base += 32) {
+            const u32 j = base + LANE;
+            bool ok = false;
+            if (j < i) {
+                const uint4 hj = g.hdr[M[j]];
+                if (!C_DELETED(hj.w) && !(candMolten && hj.y > h.y) && hj.y > 1 && SUBSIG(hj.z, h.z) &&
+                    subMerge(g.pool + hj.x, (int)hj.y, g.pool + h.x, (int)h.y)) ok = true;
+            }
+            const u32 om = __ballot_sync(FULL, ok);
+            if (om) {
+                const u32 cj = M[base + __ffs(om) - 1];
+                if (LANE == 0) {
+                    const u32 wj = g.hdr[cj].w;
+                    if (C_LEARNT(wj) && C_ORIGINAL(h.w)) g.hdr[cj].w = wj & ~CB_ST_MASK;
+                    g.hdr[ci].w = (h.w & ~CB_ST_MASK) | CB_DELETED;
+                }
+                __syncwarp();
+                break;
+            }
+        }
+    }
+    return nUnits;
+}
+// updateOL (subsume.cuh:293-303): drop molten (un-melting them) and deleted clauses, keep order
+__device__ void updateOL(G& g, u32 lit) {
+    const u32 n = g.otSize[lit];
+    if (!n) return;
+    u32* list = g.occurs + g.otStart[lit];
+    u32 out = 0;
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + LANE;
+        u32 ci = 0; bool keep = false;
+        if (j < n) {
+            ci = list[j];
+            const u32 w = g.hdr[ci].w;
+            if (C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN;
+            else if (!C_DELETED(w)) keep = true;
+        }
+        const u32 m = __ballot_sync(FULL, keep);
+        __syncwarp();
+        if (keep) list[out + __popc(m & lanemaskLt())] = ci;
+        out += __popc(m);
+        __syncwarp();
+    }
+    if (LANE == 0) g.otSize[lit] = out;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) k_sub(G g) {
+    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
+        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
+        const u32 np = g.otSize[p], nn = g.otSize[n];
+        if (np > g.k.sub_max_occurs || nn > g.k.sub_max_occurs) continue;
+        const u32* P = g.occurs + g.otStart[p];
+        const u32* N = g.occurs + g.otStart[n];
+        const u32 nPosUnits = subSide(g, P, np, N, nn, p, n);
+        const u32 nNegUnits = subSide(g, N, nn, P, np, n, p);
+        if (nPosUnits || nNegUnits) {
+            u32 cursor = reserveUnits(g, nPosUnits + nNegUnits);
+            if (nPosUnits) appendUnits(g, P, np, cursor);
+            if (nNegUnits) appendUnits(g, N, nn, cursor);
+        }
+        updateOL(g, p);
+        updateOL(g, n);
+    }
+}
+
+// ------------------------------------------------------------------ BCE (blocked.cuh:26-97)
+__global__ void __launch_bounds__(128) k_bce(G g) {
+    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
+        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
+        const u32 np = g.otSize[p], nn = g.otSize[n];
+        if (np > g.k.bce_max_occurs || nn > g.k.bce_max_occurs) continue;
+        const u32* P = g.occurs + g.otStart[p];
+        const u32* N = g.occurs + g.otStart[n];
+        for (u32 i = 0; i < nn; i++) {
+            const u32 ci = N[i]; const uint4 hi = g.hdr[ci];
+            if (C_DELETED(hi.w) || C_LEARNT(hi.w)) continue;
+            bool nonTaut = false;
+            for (u32 base = 0; base < np && !nonTaut; base += 32) {
+                const u32 j = base + LANE;
+                bool nt = false;
+                if (j < np) {
+                    const uint4 hj = g.hdr[P[j]];
+                    if (!C_DELETED(hj.w) && !C_LEARNT(hj.w))
+                        nt = !isTautology(g.pool + hj.x, (int)hj.y, g.pool + hi.x, (int)hi.y, x);
+                }
+                nonTaut = __any_sync(FULL, nt);
+            }
+            if (!nonTaut) {
+                u32* saved = jumpResolved(g, hi.y + 1);
+                if (saved && LANE == 0) saveClause(g, saved, hi, n);
+                markDeleted(g, ci);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ERE (redundancy.cuh:99-174)
+#define ERE_SLICE 256
+__global__ void __launch_bounds__(128) k_ere(G g) {
+    __shared__ u32 sh[4][ERE_SLICE];
+    u32* m_c = sh[threadIdx.x >> 5];
+    const int clause_max = g.k.ere_clause_max;
+    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (u32 gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gid < g.numElected; gid += warpsPerGrid) {
+        const u32 v = g.elected[gid], p = V2L(v), n = p | 1u;
+        const u32 ds = g.otSize[p], fs = g.otSize[n];
+        if (!(ds && fs && ds <= g.k.ere_max_occurs && fs <= g.k.ere_max_occurs)) continue;
+        const u32* P = g.occurs + g.otStart[p];
+        const u32* N = g.occurs + g.otStart[n];
+        if ((int)g.hdr[P[0]].y > clause_max || (int)g.hdr[N[0]].y > clause_max) continue;
+        for (u32 i = 0; i < ds; i++) {
+            const uint4 hp = g.hdr[P[i]];
+            if (C_DELETED(hp.w)) continue;
+            for (u32 j = 0; j < fs; j++) {
+                const uint4 hn = g.hdr[N[j]];
+                if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
+                __syncwarp();
+                u32 m_sig = 0; int m_len = 0;
+                if (LANE == 0) m_len = mergeOut(g.pool + hp.x, (int)hp.y, g.pool + hn.x, (int)hn.y, v, m_c, m_sig);
+                m_len = __shfl_sync(FULL, m_len, 0);
+                m_sig = __shfl_sync(FULL, m_sig, 0);
+                __syncwarp();
+                if (m_len <= 1) continue;
+                const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
+                // forward_equ: smallest list among the resolvent's literals
+                u32 best = m_c[0];
+                u32 minsize = g.otSize[best];
+                for (int k = 1; k < m_len; k++) { const u32 lit = m_c[k]; const u32 ls = g.otSize[lit]; if (ls < minsize) { minsize = ls; best = lit; } }
+                const u32* minList = g.occurs + g.otStart[best];
+                for (u32 e = LANE; e < minsize; e += 32) {
+                    const u32 ci = minList[e];
+                    const uint4 h = g.hdr[ci];
+                    if ((int)h.y == m_len && (C_LEARNT(h.w) || (h.w & CB_ST_MASK) == type) && SUBSIG(m_sig, h.z) && !C_DELETED(h.w)) {
+                        const u32* l = g.pool + h.x;
+                        bool eq = true;
+                        for (int k = 0; k < m_len; k++) if (l[k] != m_c[k]) { eq = false; break; }
+                        if (eq) { g.hdr[ci].w = (h.w & ~CB_ST_MASK) | CB_DELETED; break; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host launchers
+static G makeG(Ctx* c, const KOpts& k) {
+    G g;
+    g.hdr = c->hdr[c->cur]; g.pool = c->pool[c->cur];
+    g.otStart = c->otStart; g.otSize = c->otSize; g.occurs = c->occurs;
+    g.elected = c->elected; g.eliminated = c->eliminated; g.vorg = c->vorg; g.varcore = c->varcore;
+    g.units = c->units; g.unitsCap = 2 * (c->V + 1); g.resolved = c->resolved; g.resolvedCap = c->resolvedCap;
+    g.veType = c->veType; g.veUcnt = c->veUcnt; g.veRpos = c->veRpos; g.veRref = c->veRref;
+    g.dc = c->dc; g.k = k; g.numElected = c->numElected;
+    return g;
+}
+static u32 warpGrid(u32 nWarps, u32 warpsPerBlock) {
+    u32 b = divup(nWarps, warpsPerBlock);
+    const u32 cap = 148u * 16;
+    return b > cap ? cap : (b ? b : 1);
+}
+
+void launchSUB(Ctx* c, const KOpts& k) {
+    if (!c->numElected) return;
+    G g = makeG(c, k);
+    LAUNCH(c, k_sub, warpGrid(c->numElected, 4), 128, 0, g);
+}
+
+// veAsync + postVE (elimination.cu:131-154, 235-266)
+void launchVE(Ctx* c, const KOpts& k) {
+    if (!c->numElected) return;
+    G g = makeG(c, k);
+    const u32 E = c->numElected;
+    LAUNCH(c, k_ve_reset, 1, 1, 0, c->dc);
+    LAUNCH(c, k_ve_phase1, warpGrid(E, 4), 128, 0, g);
+    // phase 2: exclusive scans seeded with the current CNF sizes
+    VEBase vb;
+    vb.numCls0 = c->hdc->numCls; vb.poolUsed0 = c->hdc->poolUsed; vb.dataSize0 = c->hdc->dataSize;
+    scanExclusiveU32(c, c->veRpos, c->veRpos, E, vb.numCls0, nullptr);
+    scanExclusiveU64(c, c->veRref, c->veRref, E, vb.dataSize0);
+    LAUNCH(c, k_ve_phase3, warpGrid(E, 4), 128, 0, g, vb, c->flagA);
+    LAUNCH(c, k_ve_resize, 1, 1, 0, g, vb);
+    // elected := survivors, order kept (cub::DeviceSelect::If in postVE)
+    scanExclusiveU32(c, c->flagA, c->flagB, E, 0, &c->dc->numElected);
+    {
+        // flagA still holds the flags, flagB the positions; compact through sortV then copy back
+        LAUNCH(c, k_select_scatter, gridFor(E, 256), 256, 0, c->elected, c->flagA, c->flagB, E, c->sortV);
+        LAUNCH(c, k_copy_u32, gridFor(E, 256), 256, 0, c->sortV, c->elected, &c->dc->numElected);
+    }
+}
+
+void launchBCE(Ctx* c, const KOpts& k) {
+    if (!c->numElected) return;
+    G g = makeG(c, k);
+    LAUNCH(c, k_bce, warpGrid(c->numElected, 4), 128, 0, g);
+}
+
+void launchERE(Ctx* c, const KOpts& k) {
+    if (!c->numElected) return;
+    G g = makeG(c, k);
+    LAUNCH(c, k_ere, warpGrid(c->numElected, 4), 128, 0, g);
+}

@@ -1,0 +1,286 @@
+// parafrost_b200/csrc/lcve.cu -- the elected-variable schedule ("melting" an independent set).
+//
+// Replaces Solver::varReorder + Solver::LCVE (src/gpu/lcve.cu:280-398) in the reference's
+// fixed-order mode (-no-lcvefast), where ONE GPU thread walks every candidate
+// (lcve_k<<<1,1>>>, lcve.cu:64-101).  The serial walk elects, in ascending (score, var)
+// order, every candidate that no earlier elected variable froze, and stops at the first
+// unfrozen candidate that violates the occurrence bounds.  That is the lexicographically
+// first maximal independent set of the prefix before the stop, so it is computed here in
+// parallel and deterministically:
+//   1. scores ps*ns (uint32 wrap) and candidate class            k_scores
+//   2. stable LSD radix sort by score (ties keep ascending var)   k_radix_* (replaces thrust::sort + GPU_LCV_CMP, key.cuh:33-42)
+//   3. rank-priority MIS rounds over a shrinking worklist, a candidate decides once no
+//      lower-ranked undecided candidate shares a clause with it; "stoppers" (bound
+//      violators) never block or freeze others, the first one that stays unfrozen cuts the
+//      schedule                                                   k_mis_round
+//   4. elected = decided-elected candidates below the cut, in rank order   k_elect_*
+//   5. the first 12 frozen variables in the serial walk's order get their function-table
+//      index (mapfrozen_k, lcve.cu:253-260; only indices < 12 are observable,
+//      function.cuh:35,143)                                        k_frozen12
+#include "common.cuh"
+
+// ------------------------------------------------------------------ scores
+__global__ void k_scores(const u32* __restrict__ hist, const unsigned char* __restrict__ vstate,
+                         const unsigned char* __restrict__ assumed, u32 V, u32 pmax, u32 nmax, u32 maxoccurs,
+                         u32* __restrict__ keys, u32* __restrict__ vals, unsigned char* __restrict__ cstat,
+                         unsigned char* __restrict__ mis, DevCounters* dc) {
+    for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < V; t += gridDim.x * blockDim.x) {
+        const u32 v = t + 1;
+        const u32 ps = hist[V2L(v)], ns = hist[V2L(v) | 1u];
+        keys[t] = ps * ns;
+        vals[t] = v;
+        unsigned char cs = CS_NONE;
+        if (!vstate[v] && !(assumed && assumed[v]) && (ps || ns))
+            cs = (ps > maxoccurs || ns > maxoccurs || (ps >= pmax && ns >= nmax)) ? CS_STOP : CS_CAND;
+        cstat[v] = cs;
+        mis[v] = cs ? MIS_UNDECIDED : MIS_NONE;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { dc->misStopRank = NOVAR; dc->numElected = 0; dc->wlNext = 0; }
+}
+
+// ------------------------------------------------------------------ LSD radix sort (8-bit digits)
+#define RS_THREADS 256
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const u32* __restrict__ keys, u32 n, u32 shift,
+                                                            u32* __restrict__ ghist, u32 nblocks) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; k++) {
+        const u32 i = base + k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    ghist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
+                                                               u32* __restrict__ keysOut, u32* __restrict__ valsOut, u32 n,
+                                                               u32 shift, const u32* __restrict__ ghist, u32 nblocks) {
+    __shared__ u32 base[256];
+    __shared__ u32 wc[RS_THREADS / 32][256];
+    const u32 w = threadIdx.x >> 5, l = threadIdx.x & 31u;
+    base[threadIdx.x] = ghist[threadIdx.x * nblocks + blockIdx.x];
+    const u32 tile = blockIdx.x * RS_TILE;
+    for (int k = 0; k < RS_ITEMS; k++) {
+        for (u32 z = threadIdx.x; z < (RS_THREADS / 32) * 256; z += RS_THREADS) (&wc[0][0])[z] = 0;
+        __syncthreads();
+        const u32 i = tile + k * RS_THREADS + threadIdx.x;
+        const bool valid = i < n;
+        u32 key = 0, val = 0;
+        if (valid) { key = keysIn[i]; val = valsIn[i]; }
+        const u32 d = valid ? ((key >> shift) & 255u) : (256u + l);
+        const u32 peers = __match_any_sync(0xffffffffu, d);
+        const u32 rankInWarp = __popc(peers & lanemaskLt());
+        if (valid && rankInWarp == 0) wc[w][d] = __popc(peers);
+        __syncthreads();
+        {   // digit threadIdx.x: exclusive prefix over warps, advance the running base
+            u32 run = base[threadIdx.x];
+#pragma unroll
+            for (int ww = 0; ww < RS_THREADS / 32; ww++) { const u32 t = wc[ww][threadIdx.x]; wc[ww][threadIdx.x] = run; run += t; }
+            base[threadIdx.x] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const u32 pos = wc[w][d] + rankInWarp;
+            keysOut[pos] = key; valsOut[pos] = val;
+        }
+        __syncthreads();
+    }
+}
+
+// sorts (keys, vals) ascending by key, stable; result ends in (keys, vals) after 4 passes
+static void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, u32 n) {
+    const u32 nblocks = divup(n, RS_TILE);
+    u32 *ki = keys, *vi = vals, *ko = keys2, *vo = vals2;
+    for (u32 shift = 0; shift < 32; shift += 8) {
+        LAUNCH(c, k_radix_hist, nblocks, RS_THREADS, 0, ki, n, shift, c->radixHist, nblocks);
+        scanExclusiveU32(c, c->radixHist, c->radixHist, (u64)256 * nblocks, 0, nullptr);
+        LAUNCH(c, k_radix_scatter, nblocks, RS_THREADS, 0, ki, vi, ko, vo, n, shift, c->radixHist, nblocks);
+        u32* t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+}
+
+__global__ void k_rank(const u32* __restrict__ eligible, u32 V, u32* __restrict__ rank) {
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < V; r += gridDim.x * blockDim.x) rank[eligible[r]] = r;
+}
+
+// ------------------------------------------------------------------ MIS
+__global__ void k_mis_fill(const u32* __restrict__ eligible, const unsigned char* __restrict__ cstat, u32 rBegin, u32 rEnd,
+                           u32* __restrict__ wl, DevCounters* dc) {
+    for (u32 r = rBegin + blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x) {
+        const u32 v = eligible[r];
+        if (cstat[v] != CS_NONE) wl[warpAggInc(&dc->wlNext)] = v;
+    }
+}
+
+// one warp per undecided candidate; lanes stride over the clauses of its two lists
+__global__ void __launch_bounds__(256) k_mis_round(const u32* __restrict__ wlIn, u32 nIn, u32* __restrict__ wlOut, DevCounters* dc,
+                                                   const uint4* __restrict__ hdr, const u32* __restrict__ pool,
+                                                   const u32* __restrict__ otStart, const u32* __restrict__ otSize,
+                                                   const u32* __restrict__ occurs, const u32* __restrict__ rank,
+                                                   const unsigned char* __restrict__ cstat, volatile unsigned char* mis,
+                                                   int maxcsize) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < nIn; it += warpsPerGrid) {
+        const u32 v = wlIn[it];
+        const u32 r = rank[v];
+        if (r > dc->misStopRank) continue;  // beyond the cut: never looked at by the serial walk
+        bool frozen = false, blocked = false, oversize = false;
+        for (u32 side = 0; side < 2; side++) {
+            const u32 lit = V2L(v) | side;
+            const u32 n = otSize[lit];
+            const u32* list = occurs + otStart[lit];
+            for (u32 j = lane; j < n; j += 32) {
+                const uint4 h = hdr[list[j]];
+                if (C_DELETED(h.w)) continue;
+                if ((int)h.y > maxcsize) oversize = true;
+                const u32* l = pool + h.x;
+                for (u32 k = 0; k < h.y; k++) {
+                    const u32 u = LABS(l[k]);
+                    if (u == v) continue;
+                    const unsigned char m = mis[u];
+                    if (m == MIS_ELECTED) { if (rank[u] < r) frozen = true; }
+                    else if (m == MIS_UNDECIDED && cstat[u] == CS_CAND && rank[u] < r) blocked = true;
+                }
+            }
+        }
+        frozen = __any_sync(0xffffffffu, frozen);
+        blocked = __any_sync(0xffffffffu, blocked);
+        oversize = __any_sync(0xffffffffu, oversize);
+        if (lane == 0) {
+            if (frozen) mis[v] = MIS_FROZEN;
+            else if (!blocked) {
+                if (cstat[v] == CS_STOP) { mis[v] = MIS_LIVESTOP; atomicMin(&dc->misStopRank, r); }
+                // a clause longer than lcveclausemax makes depFreeze_d fail (lcve.cu:46-51): not elected, freezes nothing
+                else mis[v] = oversize ? MIS_FROZEN : MIS_ELECTED;
+            }
+            else wlOut[atomicAdd(&dc->wlNext, 1u)] = v;
+        }
+    }
+}
+
+__global__ void k_elect_flags(const u32* __restrict__ eligible, const unsigned char* __restrict__ mis, u32 rEnd, u32* __restrict__ flags) {
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x)
+        flags[r] = mis[eligible[r]] == MIS_ELECTED ? 1u : 0u;
+}
+__global__ void k_elect_scatter(const u32* __restrict__ eligible, const unsigned char* __restrict__ mis, u32 rEnd,
+                                const u32* __restrict__ pos, u32* __restrict__ elected) {
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x) {
+        const u32 v = eligible[r];
+        if (mis[v] == MIS_ELECTED) elected[pos[r]] = v;
+    }
+}
+
+// ------------------------------------------------------------------ function-table indices
+// Walks the elected variables like depFreeze_d (lcve.cu:33-62) - positive list then negative
+// list, clauses in clause-index order (the unsorted-list policy), literals in
+// clause order - until 12 distinct frozen variables are known.  One CTA; tiny.
+__global__ void __launch_bounds__(128) k_frozen12(const u32* __restrict__ elected, DevCounters* dc, const uint4* __restrict__ hdr,
+                                                  const u32* __restrict__ pool, const u32* __restrict__ otStart,
+                                                  const u32* __restrict__ otSize, const u32* __restrict__ occurs,
+                                                  u32* __restrict__ varcore, u32* __restrict__ prev12) {
+    __shared__ u32 fv[MAXFUNVAR];
+    __shared__ u32 nf, sMin[4], cur;
+    const u32 nE = dc->numElected;
+    if (threadIdx.x < MAXFUNVAR) { const u32 old = prev12[threadIdx.x]; if (old != NOVAR) varcore[old] = NOVAR; }
+    if (threadIdx.x == 0) nf = 0;
+    __syncthreads();
+    for (u32 ei = 0; ei < nE && nf < MAXFUNVAR; ei++) {
+        const u32 x = elected[ei];
+        for (u32 side = 0; side < 2 && nf < MAXFUNVAR; side++) {
+            const u32 lit = V2L(x) | side;
+            const u32 n = otSize[lit];
+            const u32* list = occurs + otStart[lit];
+            u64 last = 0;  // clause index + 1 of the last processed clause
+            while (nf < MAXFUNVAR) {
+                u32 m = NOVAR;
+                for (u32 j = threadIdx.x; j < n; j += blockDim.x) { const u32 ci = list[j]; if ((u64)ci + 1 > last && ci < m) m = ci; }
+                for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if ((threadIdx.x & 31u) == 0) sMin[threadIdx.x >> 5] = m;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    u32 mm = min(min(sMin[0], sMin[1]), min(sMin[2], sMin[3]));
+                    cur = mm;
+                    if (mm != NOVAR) {
+                        const uint4 h = hdr[mm];
+                        if (!C_DELETED(h.w)) {
+                            const u32* l = pool + h.x;
+                            for (u32 k = 0; k < h.y && nf < MAXFUNVAR; k++) {
+                                const u32 v = LABS(l[k]);
+                                if (v == x) continue;
+                                bool seen = false;
+                                for (u32 q = 0; q < nf; q++) seen |= fv[q] == v;
+                                if (!seen) fv[nf++] = v;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (cur == NOVAR) break;
+                last = (u64)cur + 1;
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < MAXFUNVAR) {
+        const bool on = threadIdx.x < nf;
+        prev12[threadIdx.x] = on ? fv[threadIdx.x] : NOVAR;
+        if (on) varcore[fv[threadIdx.x]] = threadIdx.x;
+    }
+    if (threadIdx.x == 0) dc->nFrozen = nf;
+}
+
+// ------------------------------------------------------------------ host driver
+int runLCVE(Ctx* c) {
+    const u32 V = c->V;
+    const u32 pmax = c->o.mu_pos << c->multiplier, nmax = c->o.mu_neg << c->multiplier;
+    LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
+           c->scores, c->eligible, c->cstat, c->mis, c->dc);
+    radixSortPairs(c, c->scores, c->eligible, c->sortK, c->sortV, V);
+    LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, V, c->rank);
+
+    u32 hPrev = 0, stopRank = NOVAR, hEnd = 0;
+    u32* wlIn = c->wlA; u32* wlOut = c->wlB;
+    while (hPrev < V && stopRank == NOVAR) {
+        u64 h64 = hPrev ? (u64)hPrev * 8 : 8192;
+        const u32 H = (u32)(h64 > V ? V : h64);
+        LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, c->cstat, hPrev, H, wlIn, c->dc);
+        CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        u32 n = c->hdc->wlNext;
+        u32 guard = 0;
+        while (n) {
+            if (++guard > 100000u) { snprintf(c->err, sizeof c->err, "MIS did not converge"); return SIGMA_AWAKEN_FAIL; }
+            CUDA_TRY(cudaMemsetAsync(&c->dc->wlNext, 0, 4, c->stream));
+            const u32 warps = n, blocks = divup((u64)warps * 32, 256);
+            LAUNCH(c, k_mis_round, blocks > 148u * 32 ? 148u * 32 : blocks, 256, 0, wlIn, n, wlOut, c->dc, c->hdr[c->cur], c->pool[c->cur],
+                   c->otStart, c->otSize, c->occurs, c->rank, c->cstat, c->mis, c->o.lcve_clause_max);
+            CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            n = c->hdc->wlNext;
+            u32* t = wlIn; wlIn = wlOut; wlOut = t;
+        }
+        CUDA_TRY(cudaMemsetAsync(&c->dc->wlNext, 0, 4, c->stream));
+        stopRank = c->hdc->misStopRank;
+        hPrev = H;
+        hEnd = H;
+    }
+    const u32 rEnd = stopRank < hEnd ? stopRank : hEnd;
+    if (rEnd) {
+        LAUNCH(c, k_elect_flags, gridFor(rEnd, 256), 256, 0, c->eligible, c->mis, rEnd, c->flagA);
+        scanExclusiveU32(c, c->flagA, c->flagA, rEnd, 0, &c->dc->numElected);
+        LAUNCH(c, k_elect_scatter, gridFor(rEnd, 256), 256, 0, c->eligible, c->mis, rEnd, c->flagA, c->elected);
+    }
+    if (c->o.ve_fun_en)
+        LAUNCH(c, k_frozen12, 1, 128, 0, c->elected, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart, c->otSize, c->occurs,
+               c->varcore, c->dc->froz12);
+    return syncCounters(c);
+}

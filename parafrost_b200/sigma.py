@@ -1,0 +1,298 @@
+"""ctypes binding of libsigma_b200.so (include/sigma.h).
+
+Mirrors the simplifier surface of the reference's ``class Solver`` (src/gpu/solver.hpp:674-789):
+``optSimp`` (options), ``awaken`` (load), ``simplify`` (the round loop), ``cacheCNF`` /
+``cacheResolved`` / ``cacheEliminated`` (store), ``freeSimp``.  Flags carry the reference's CLI
+names (``-no-ere``, ``--phases=K`` ...).  There is no fallback path: if the CUDA library cannot
+be loaded this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import lib_path
+
+UNSAT, SAT, UNSOLVED = 0, 1, 2
+
+
+class SigmaOpts(C.Structure):
+    _fields_ = [
+        ("phases", C.c_int32), ("ve_en", C.c_int32), ("ve_plus_en", C.c_int32), ("sub_en", C.c_int32),
+        ("bce_en", C.c_int32), ("ere_en", C.c_int32), ("all_en", C.c_int32),
+        ("mu_pos", C.c_uint32), ("mu_neg", C.c_uint32), ("lcve_min_vars", C.c_uint32),
+        ("lcve_max_occurs", C.c_uint32), ("lcve_clause_max", C.c_int32), ("phase_lits_min", C.c_int32),
+        ("shrink_rate", C.c_int32), ("lits_mul", C.c_double),
+        ("ve_fun_en", C.c_int32), ("ve_lbound_en", C.c_int32), ("ve_clause_max", C.c_uint32),
+        ("xor_max_arity", C.c_uint32), ("ere_clause_max", C.c_int32), ("ere_max_occurs", C.c_uint32),
+        ("sub_max_occurs", C.c_uint32), ("bce_max_occurs", C.c_uint32), ("sh_max_bve_out1", C.c_uint32),
+        ("sigma_calls", C.c_int32), ("final_gc", C.c_int32), ("profile", C.c_int32),
+    ]
+
+
+class RoundReport(C.Structure):
+    _fields_ = [
+        ("round", C.c_uint32), ("kind", C.c_uint32), ("elected", C.c_uint32), ("eliminated", C.c_uint32),
+        ("resolvents", C.c_uint32), ("units", C.c_uint32), ("propagated", C.c_uint32), ("gc", C.c_uint32),
+        ("clauses", C.c_uint64), ("literals", C.c_uint64), ("literals_in", C.c_uint64),
+        ("ms", C.c_float), ("pad", C.c_float),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}
+
+
+class Report(C.Structure):
+    _fields_ = [
+        ("cnfstate", C.c_int32), ("simpstate", C.c_int32), ("rounds", C.c_uint32), ("eliminated_vars", C.c_uint32),
+        ("clauses", C.c_uint64), ("literals", C.c_uint64), ("clauses_in", C.c_uint64), ("literals_in", C.c_uint64),
+        ("resolved_words", C.c_uint64), ("trail_units", C.c_uint64), ("ms_total", C.c_double),
+        ("stage_ms", C.c_float * 16), ("kernel_launches", C.c_uint64),
+    ]
+
+    STAGES = ["vo", "sig", "io", "gc", "cot", "sot", "rot", "ve", "sub", "bce", "ere", "prop", "lcve", "cnt"]
+
+    def asdict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "stage_ms"}
+        d["stage_ms"] = {s: float(self.stage_ms[i]) for i, s in enumerate(self.STAGES)}
+        return d
+
+
+class SigmaError(RuntimeError):
+    pass
+
+
+_lib = None
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+# every symbol include/sigma.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "sigma_default_opts", "sigma_normalize_opts", "sigma_create", "sigma_destroy", "sigma_set_opts", "sigma_load",
+    "sigma_run", "sigma_begin", "sigma_round", "sigma_finish", "sigma_num_rounds", "sigma_round_reports",
+    "sigma_result_sizes", "sigma_store", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
+    "sigma_debug_hist", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
+]
+
+
+def lib():
+    """Loads the CUDA library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise SigmaError(f"{path} is missing: run `python -m parafrost_b200.build` (nvcc, sm_100a); there is no CPU fallback")
+        L = C.CDLL(path)
+        P = C.c_void_p
+        L.sigma_default_opts.argtypes = [C.POINTER(SigmaOpts)]
+        L.sigma_normalize_opts.argtypes = [C.POINTER(SigmaOpts)]
+        L.sigma_create.argtypes = [C.c_int, C.POINTER(SigmaOpts), C.POINTER(P)]
+        L.sigma_destroy.argtypes = [P]
+        L.sigma_set_opts.argtypes = [P, C.POINTER(SigmaOpts)]
+        L.sigma_load.argtypes = [P, C.c_uint32, C.c_uint64, P, P, P, P, P, P]
+        L.sigma_run.argtypes = [P, C.POINTER(Report)]
+        L.sigma_begin.argtypes = [P]
+        L.sigma_round.argtypes = [P, C.POINTER(RoundReport), C.POINTER(C.c_int)]
+        L.sigma_finish.argtypes = [P, C.POINTER(Report)]
+        L.sigma_num_rounds.argtypes = [P]; L.sigma_num_rounds.restype = C.c_uint32
+        L.sigma_round_reports.argtypes = [P, C.POINTER(RoundReport), C.c_uint32]
+        L.sigma_result_sizes.argtypes = [P] + [C.POINTER(C.c_uint64)] * 4
+        L.sigma_store.argtypes = [P, P, P, P, P, P, P, P]
+        L.sigma_store_sclauses.argtypes = [P, P, P]
+        L.sigma_snapshot.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.sigma_debug_elected.argtypes = [P, P, C.POINTER(C.c_uint32)]
+        L.sigma_debug_hist.argtypes = [P, P]
+        L.sigma_memory.argtypes = [P] + [C.POINTER(C.c_uint64)] * 3
+        L.sigma_last_error.argtypes = [P]; L.sigma_last_error.restype = C.c_char_p
+        L.sigma_version.restype = C.c_char_p
+        L.sigma_stage_prep.argtypes = [C.c_int, C.c_uint64, _u32p, _u64p, _u32p]
+        L.sigma_stage_histogram.argtypes = [C.c_int, C.c_uint64, _u32p, C.c_uint32, _u32p]
+        _lib = L
+    return _lib
+
+
+FLAG_MAP = {  # the reference's CLI flags (src/gpu/options.cpp:24-43, options.cu:36-60)
+    "-no-ere": {"ere_en": 0}, "-ere": {"ere_en": 1}, "-no-vefunction": {"ve_fun_en": 0}, "-bce": {"bce_en": 1},
+    "-all": {"all_en": 1}, "-no-sub": {"sub_en": 0}, "-no-veextend": {"ve_plus_en": 0}, "-no-ve": {"ve_en": 0},
+    "-velitsbound": {"ve_lbound_en": 1}, "-profilegpu": {"profile": 1}, "-no-lcvefast": {}, "-quiet": {},
+}
+VALUE_FLAGS = {
+    "--phases": "phases", "--mupos": "mu_pos", "--muneg": "mu_neg", "--electionsmin": "lcve_min_vars",
+    "--electionsmax": "lcve_max_occurs", "--lcveclausemax": "lcve_clause_max", "--eliminatedlitsmin": "phase_lits_min",
+    "--collectfreq": "shrink_rate", "--literalsmul": "lits_mul", "--resolventmax": "ve_clause_max",
+    "--xormaxarity": "xor_max_arity", "--ereclausemax": "ere_clause_max", "--eremaxoccurs": "ere_max_occurs",
+    "--submaxoccurs": "sub_max_occurs", "--bcemaxoccurs": "bce_max_occurs",
+}
+
+
+def opts_from_flags(flags) -> dict:
+    o = {}
+    for f in flags:
+        if "=" in f:
+            k, v = f.split("=", 1)
+            if k in VALUE_FLAGS:
+                o[VALUE_FLAGS[k]] = float(v) if k == "--literalsmul" else int(v)
+            elif k != "--mapperc":
+                raise ValueError(f"unknown flag {f}")
+        else:
+            o.update(FLAG_MAP[f])
+    return o
+
+
+def make_opts(**over) -> SigmaOpts:
+    o = SigmaOpts()
+    lib().sigma_default_opts(C.byref(o))
+    for k, v in over.items():
+        setattr(o, k, v)
+    lib().sigma_normalize_opts(C.byref(o))
+    return o
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Simplifier:
+    """One SIGmA context on one device (the simplifier half of the reference's ``Solver``)."""
+
+    def __init__(self, device: int = 0, flags=(), **opts):
+        self._h = C.c_void_p()
+        self._lib = lib()
+        o = dict(opts_from_flags(flags))
+        o.update(opts)
+        self.opts = make_opts(**o)
+        rc = self._lib.sigma_create(device, C.byref(self.opts), C.byref(self._h))
+        if rc:
+            raise SigmaError(f"sigma_create failed ({rc}): no usable CUDA device {device}?")
+        self.max_var = 0
+
+    # Solver::optSimp
+    def optSimp(self, flags=(), **opts):
+        o = dict(opts_from_flags(flags))
+        o.update(opts)
+        self.opts = make_opts(**o)
+        self._check(self._lib.sigma_set_opts(self._h, C.byref(self.opts)))
+
+    def _check(self, rc):
+        if rc:
+            raise SigmaError(f"sigma error {rc}: {self._lib.sigma_last_error(self._h).decode()}")
+
+    # Solver::awaken (host half)
+    def load(self, max_var, lits, offs, meta=None, vorg=None, vstate=None, assumed=None):
+        self._keep = [np.ascontiguousarray(lits, np.uint32), np.ascontiguousarray(offs, np.uint64),
+                      None if meta is None else np.ascontiguousarray(meta, np.uint32),
+                      None if vorg is None else np.ascontiguousarray(vorg, np.uint32),
+                      None if vstate is None else np.ascontiguousarray(vstate, np.uint8),
+                      None if assumed is None else np.ascontiguousarray(assumed, np.uint8)]
+        k = self._keep
+        self.max_var = int(max_var)
+        self._check(self._lib.sigma_load(self._h, self.max_var, len(k[1]) - 1, *[_ptr(a) for a in k]))
+
+    def load_pointers(self, max_var, num_clauses, lits_ptr, offs_ptr):
+        """Raw host pointers (e.g. pinned torch tensors) - used by bench.py's e2e leg."""
+        self.max_var = int(max_var)
+        self._check(self._lib.sigma_load(self._h, self.max_var, num_clauses, lits_ptr, offs_ptr, None, None, None, None))
+
+    # Solver::simplify
+    def simplify(self) -> dict:
+        rep = Report()
+        self._check(self._lib.sigma_run(self._h, C.byref(rep)))
+        return rep.asdict()
+
+    def begin(self):
+        self._check(self._lib.sigma_begin(self._h))
+
+    def round(self):
+        r = RoundReport()
+        done = C.c_int(0)
+        self._check(self._lib.sigma_round(self._h, C.byref(r), C.byref(done)))
+        return r.asdict(), bool(done.value)
+
+    def finish(self) -> dict:
+        rep = Report()
+        self._check(self._lib.sigma_finish(self._h, C.byref(rep)))
+        return rep.asdict()
+
+    def rounds(self):
+        n = self._lib.sigma_num_rounds(self._h)
+        arr = (RoundReport * max(n, 1))()
+        self._check(self._lib.sigma_round_reports(self._h, arr, n))
+        return [arr[i].asdict() for i in range(n)]
+
+    # Solver::cacheCNF / cacheResolved / cacheEliminated
+    def store(self) -> dict:
+        nc, nl, nr, nt = (C.c_uint64() for _ in range(4))
+        self._check(self._lib.sigma_result_sizes(self._h, C.byref(nc), C.byref(nl), C.byref(nr), C.byref(nt)))
+        out = {
+            "bits": np.empty(nc.value, np.uint32), "sig": np.empty(nc.value, np.uint32),
+            "offs": np.zeros(nc.value + 1, np.uint64), "lits": np.empty(nl.value, np.uint32),
+            "eliminated": np.zeros(self.max_var + 1, np.uint8), "resolved": np.empty(nr.value, np.uint32),
+            "trail": np.empty(nt.value, np.uint32),
+        }
+        self._check(self._lib.sigma_store(self._h, *[_ptr(out[k]) for k in ("bits", "sig", "offs", "lits", "eliminated", "resolved", "trail")]))
+        return out
+
+    def store_sclauses(self):
+        nc, nl, nr, nt = (C.c_uint64() for _ in range(4))
+        self._check(self._lib.sigma_result_sizes(self._h, C.byref(nc), C.byref(nl), C.byref(nr), C.byref(nt)))
+        data = np.empty(3 * nc.value + nl.value, np.uint32)
+        refs = np.empty(nc.value, np.uint64)
+        self._check(self._lib.sigma_store_sclauses(self._h, _ptr(data), _ptr(refs)))
+        return data, refs
+
+    def snapshot(self) -> dict:
+        """Live clause list right now (per-round parity checks)."""
+        return self.store()
+
+    def debug_elected(self):
+        n = C.c_uint32(0)
+        buf = np.zeros(self.max_var + 1, np.uint32)
+        self._check(self._lib.sigma_debug_elected(self._h, _ptr(buf), C.byref(n)))
+        return buf[: n.value].copy()
+
+    def debug_hist(self):
+        buf = np.zeros(2 * (self.max_var + 1), np.uint32)
+        self._check(self._lib.sigma_debug_hist(self._h, _ptr(buf)))
+        return buf
+
+    def memory(self) -> dict:
+        a, p, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._lib.sigma_memory(self._h, C.byref(a), C.byref(p), C.byref(m))
+        return {"arena_bytes": a.value, "peak_used": p.value, "cuda_mallocs": m.value}
+
+    # Solver::freeSimp
+    def freeSimp(self):
+        if self._h:
+            self._lib.sigma_destroy(self._h)
+            self._h = C.c_void_p()
+
+    close = freeSimp
+
+    def __del__(self):
+        try:
+            self.freeSimp()
+        except Exception:
+            pass
+
+
+def stage_prep(lits, offs, device: int = 0):
+    """prep_cnf_k through the C ABI: returns (sorted lits, sig)."""
+    lits = np.ascontiguousarray(lits, np.uint32).copy()
+    offs = np.ascontiguousarray(offs, np.uint64)
+    sig = np.zeros(len(offs) - 1, np.uint32)
+    rc = lib().sigma_stage_prep(device, len(offs) - 1, lits, offs, sig)
+    if rc:
+        raise SigmaError(f"sigma_stage_prep failed ({rc})")
+    return lits, sig
+
+
+def stage_histogram(lits, nbins, device: int = 0):
+    lits = np.ascontiguousarray(lits, np.uint32)
+    hist = np.zeros(nbins, np.uint32)
+    rc = lib().sigma_stage_histogram(device, len(lits), lits, nbins, hist)
+    if rc:
+        raise SigmaError(f"sigma_stage_histogram failed ({rc})")
+    return hist

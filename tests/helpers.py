@@ -117,6 +117,9 @@ def oracle_lib():
         lib.oracle_snapshot_literals.argtypes = [P, C.c_int]; lib.oracle_snapshot_literals.restype = C.c_uint64
         lib.oracle_copy_snapshot.argtypes = [P, C.c_int, _u32p, _u32p, _u64p, _u32p]
         lib.oracle_destroy.argtypes = [P]
+        lib.oracle_num_elections.argtypes = [P]; lib.oracle_num_elections.restype = C.c_int
+        lib.oracle_election_size.argtypes = [P, C.c_int]; lib.oracle_election_size.restype = C.c_uint64
+        lib.oracle_copy_election.argtypes = [P, C.c_int, _u32p]
         lib.oracle_prep.argtypes = [C.c_uint64, _u32p, _u64p, _u32p]
         lib.oracle_histogram.argtypes = [C.c_uint64, _u32p, C.c_uint32, _u32p]
         lib.oracle_extend_model.argtypes = [_u8p, C.c_uint32, _u32p, C.c_uint64]; lib.oracle_extend_model.restype = C.c_uint64
@@ -190,6 +193,12 @@ def run_oracle(max_var, lits, offs, meta=None, snapshots=False, **over):
                 lib.oracle_copy_snapshot(h, r, b, sg, of, li)
                 snaps.append(sgd.Dump.from_arrays(max_var, 2, b, sg, of, li, np.zeros(max_var + 1, np.uint8),
                                                   np.empty(0, np.uint32), np.empty(0, np.uint32)))
+            elections = []
+            for i in range(lib.oracle_num_elections(h)):
+                e = np.empty(lib.oracle_election_size(h, i), np.uint32)
+                lib.oracle_copy_election(h, i, e)
+                elections.append(e)
+            d.extra["elections"] = elections
     finally:
         lib.oracle_destroy(h)
     return d, rs, snaps
