@@ -99,6 +99,7 @@ typedef struct sigma_report {
     /* -profilegpu stage totals in ms (statistics.cpp:37-49): vo sig io gc cot sot rot ve sub bce ere + prop lcve */
     float    stage_ms[16];
     uint64_t kernel_launches;   /* kernels launched by this call */
+    double   ms_device;         /* sigma_run only: CUDA-event time begin..end on the launch stream */
 } sigma_report;
 
 typedef struct sigma_ctx sigma_ctx;
@@ -113,6 +114,9 @@ int  sigma_create(int device, const sigma_opts* o, sigma_ctx** out);
 /* Solver::freeSimp (simplify.cu:254) */
 int  sigma_destroy(sigma_ctx* c);
 int  sigma_set_opts(sigma_ctx* c, const sigma_opts* o);
+/* streams[] of the reference (solver.hpp:728): run every launch and copy of this context on the
+ * caller's CUDA stream (a cudaStream_t passed as void*), so the caller can order and time it. */
+int  sigma_set_stream(sigma_ctx* c, void* cuda_stream);
 
 /* Solver::awaken's host half: extractCNF + reflectCNF (cnf.cu:166-184) and cuMM::init*/
 /* (memory.cu:99-387).  HOST buffers in CSR form; sizes the arena (ONE cudaMalloc, reused
@@ -150,6 +154,13 @@ int  sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t* refs);
 int  sigma_snapshot(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals);   /* sizes of the live CNF now */
 int  sigma_debug_elected(sigma_ctx* c, uint32_t* out, uint32_t* n);                 /* elected vars of the last round */
 int  sigma_debug_hist(sigma_ctx* c, uint32_t* out);                                 /* [2V+2] of the last OT build */
+
+/* Per-kernel device times (replaces -profilegpu's cuTIMER pairs, src/gpu/timer.cuh:27-59, at kernel
+ * granularity): CUDA-event pairs recorded on the context's launch stream around every kernel.
+ * enable: 0 = off, 1 = on and reset the totals, 2 = on and keep the totals.
+ * sigma_kernel_times: names is n*64 chars, *n = capacity in, entries out. */
+int  sigma_kernel_profile(sigma_ctx* c, int enable);
+int  sigma_kernel_times(sigma_ctx* c, char* names, float* ms, uint32_t* counts, uint32_t* n);
 
 /* arena statistics (replaces cuArena's gpu_peak_used, simplify.cu:219-220) */
 int  sigma_memory(const sigma_ctx* c, uint64_t* arena_bytes, uint64_t* peak_used, uint64_t* cuda_mallocs);

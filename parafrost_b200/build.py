@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     so = lib_path()
     objs = [os.path.join(OBJ, u + ".o") for u in UNITS]
     if force or jobs or _stale(so, objs):
-        run([NVCC, "-shared", "-o", so] + objs)  # static cudart (nvcc default)
+        run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs)  # static cudart (nvcc default)
     return so
 
 

@@ -17,6 +17,66 @@ static double nowMs() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ------------------------------------------------------------------ per-kernel event timing
+#include <mutex>
+static std::mutex gKtMutex;
+static char gKtNames[KT_MAX_KERNELS][64];
+static int gKtN = 0;
+int ktRegister(const char* name) {
+    std::lock_guard<std::mutex> lk(gKtMutex);
+    for (int i = 0; i < gKtN; i++) if (!strncmp(gKtNames[i], name, 63)) return i;
+    if (gKtN == KT_MAX_KERNELS - 1) return KT_MAX_KERNELS - 1;   // overflow bucket
+    strncpy(gKtNames[gKtN], name, 63);
+    return gKtN++;
+}
+static void ktFlush(Ctx* c) {
+    if (!c->ktUsed) return;
+    cudaEventSynchronize(c->ktEv[2 * (c->ktUsed - 1) + 1]);
+    for (u32 i = 0; i < c->ktUsed; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ktEv[2 * i], c->ktEv[2 * i + 1]) == cudaSuccess) { c->ktMs[c->ktId[i]] += ms; c->ktCount[c->ktId[i]]++; }
+    }
+    c->ktUsed = 0;
+}
+void ktBegin(Ctx* c, int id) {
+    if (c->ktUsed == KT_POOL) ktFlush(c);
+    c->ktId[c->ktUsed] = id;
+    cudaEventRecord(c->ktEv[2 * c->ktUsed], c->stream);
+}
+void ktEnd(Ctx* c) { cudaEventRecord(c->ktEv[2 * c->ktUsed + 1], c->stream); c->ktUsed++; }
+
+extern "C" int sigma_kernel_profile(sigma_ctx* c, int enable) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (enable && !c->ktEv) {
+        c->ktEv = (cudaEvent_t*)calloc(2 * KT_POOL, sizeof(cudaEvent_t));
+        c->ktId = (int*)calloc(KT_POOL, sizeof(int));
+        if (!c->ktEv || !c->ktId) return SIGMA_AWAKEN_FAIL;
+        for (int i = 0; i < 2 * KT_POOL; i++) CUDA_TRY(cudaEventCreate(&c->ktEv[i]));
+    }
+    if (c->ktOn) ktFlush(c);
+    if (enable == 2 || !enable) { /* keep totals */ } else { memset(c->ktMs, 0, sizeof c->ktMs); memset(c->ktCount, 0, sizeof c->ktCount); }
+    c->ktOn = enable != 0;
+    return SIGMA_OK;
+}
+extern "C" int sigma_kernel_times(sigma_ctx* c, char* names, float* ms, uint32_t* counts, uint32_t* n) {
+    if (!c || !n) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->ktOn) ktFlush(c);
+    u32 out = 0;
+    const u32 cap = *n;
+    std::lock_guard<std::mutex> lk(gKtMutex);
+    for (int i = 0; i < KT_MAX_KERNELS && out < cap; i++) {
+        if (!c->ktCount[i]) continue;
+        if (names) { strncpy(names + 64 * out, i < gKtN ? gKtNames[i] : "(other)", 63); names[64 * out + 63] = 0; }
+        if (ms) ms[out] = c->ktMs[i];
+        if (counts) counts[out] = c->ktCount[i];
+        out++;
+    }
+    *n = out;
+    return SIGMA_OK;
+}
+
 // ------------------------------------------------------------------ options
 extern "C" void sigma_default_opts(sigma_opts* o) {
     memset(o, 0, sizeof *o);
@@ -54,11 +114,13 @@ extern "C" int sigma_create(int device, const sigma_opts* o, sigma_ctx** out) {
     c->cnfstate = SIGMA_UNSOLVED;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMallocHost(&c->hdc, sizeof(DevCounters))) != cudaSuccess || (e = cudaEventCreate(&c->ev0)) != cudaSuccess ||
-        (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->evRun0)) != cudaSuccess || (e = cudaEventCreate(&c->evRun1)) != cudaSuccess) {
         delete c;
         return -(int)e;
     }
     memset(c->hdc, 0, sizeof(DevCounters));
+    c->ownStream = true;
     *out = c;
     return SIGMA_OK;
 }
@@ -70,6 +132,15 @@ extern "C" int sigma_set_opts(sigma_ctx* c, const sigma_opts* o) {
     return SIGMA_OK;
 }
 
+extern "C" int sigma_set_stream(sigma_ctx* c, void* cuda_stream) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->ownStream) { cudaStreamDestroy(c->stream); c->ownStream = false; }
+    c->stream = (cudaStream_t)cuda_stream;
+    return SIGMA_OK;
+}
+
 extern "C" int sigma_destroy(sigma_ctx* c) {
     if (!c) return SIGMA_OK;
     cudaSetDevice(c->device);
@@ -78,7 +149,10 @@ extern "C" int sigma_destroy(sigma_ctx* c) {
     if (c->hdc) cudaFreeHost(c->hdc);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->evRun0) cudaEventDestroy(c->evRun0);
+    if (c->evRun1) cudaEventDestroy(c->evRun1);
+    if (c->stream && c->ownStream) cudaStreamDestroy(c->stream);
+    if (c->ktEv) { for (int i = 0; i < 2 * KT_POOL; i++) if (c->ktEv[i]) cudaEventDestroy(c->ktEv[i]); free(c->ktEv); free(c->ktId); }
     free(c->rounds);
     delete c;
     return SIGMA_OK;
@@ -134,6 +208,10 @@ static size_t carve(Ctx* c, char* base) {
     return a.off + 256;
 }
 
+__global__ void k_iota(u32* __restrict__ a, u32 n) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = i;
+}
+
 // ------------------------------------------------------------------ load
 extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, const uint32_t* lits,
                           const uint64_t* offs, const uint32_t* meta, const uint32_t* vorg, const uint8_t* vstate,
@@ -183,15 +261,7 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
     else c->inMeta = nullptr;
     const size_t V1 = (size_t)max_var + 1;
     if (vorg) CUDA_TRY(cudaMemcpyAsync(c->vorg, vorg, V1 * 4, cudaMemcpyHostToDevice, c->stream));
-    else {
-        u32* id = (u32*)malloc(V1 * 4);
-        if (!id) return SIGMA_AWAKEN_FAIL;
-        for (size_t v = 0; v < V1; v++) id[v] = (u32)v;
-        cudaError_t e = cudaMemcpyAsync(c->vorg, id, V1 * 4, cudaMemcpyHostToDevice, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        free(id);
-        CUDA_TRY(e);
-    }
+    else LAUNCH(c, k_iota, gridFor(V1, 256), 256, 0, c->vorg, (u32)V1);
     if (vstate) CUDA_TRY(cudaMemcpyAsync(c->vstate0, vstate, V1, cudaMemcpyHostToDevice, c->stream));
     else CUDA_TRY(cudaMemsetAsync(c->vstate0, 0, V1, c->stream));
     if (assumed) CUDA_TRY(cudaMemcpyAsync(c->assumed, assumed, V1, cudaMemcpyHostToDevice, c->stream));
@@ -419,14 +489,21 @@ extern "C" int sigma_finish(sigma_ctx* c, sigma_report* rep) {
 extern "C" int sigma_run(sigma_ctx* c, sigma_report* rep) {
     if (!c) return SIGMA_BAD_ARGUMENT;
     const double t0 = nowMs();
+    cudaSetDevice(c->device);
+    cudaEventRecord(c->evRun0, c->stream);
     int rc = sigma_begin(c);
     if (rc) return rc;
     int done = 0;
     while (!done) { if ((rc = sigma_round(c, nullptr, &done))) return rc; }
-    rc = cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : -1;
+    if ((rc = sigma_finish(c, rep))) return rc;
+    cudaEventRecord(c->evRun1, c->stream);
+    rc = cudaEventSynchronize(c->evRun1) == cudaSuccess ? 0 : -1;
     c->msTotal = nowMs() - t0;
     if (rc) return rc;
-    return sigma_finish(c, rep);
+    float dms = 0;
+    cudaEventElapsedTime(&dms, c->evRun0, c->evRun1);
+    if (rep) { rep->ms_total = c->msTotal; rep->ms_device = dms; }
+    return SIGMA_OK;
 }
 
 extern "C" uint32_t sigma_num_rounds(const sigma_ctx* c) { return c ? c->nRounds : 0; }

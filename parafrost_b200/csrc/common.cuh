@@ -114,6 +114,13 @@ struct KOpts {   // kernel-side options (replaces __constant__ kOpts, options.cu
     u64 dataCap;       // logical data capacity (words)
 };
 
+#define KT_MAX_KERNELS 96
+#define KT_POOL 2048
+struct Ctx;
+int  ktRegister(const char* name);       // api.cu: kernel name -> stable index
+void ktBegin(Ctx* c, int id);
+void ktEnd(Ctx* c);
+
 // ---------------------------------------------------------------- context
 struct Ctx {
     int device;
@@ -153,11 +160,14 @@ struct Ctx {
     sigma_round_report* rounds; u32 nRounds, capRounds;
     u64 launches;
     float stageMs[16];
-    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev0, ev1, evRun0, evRun1; bool ownStream;
     double msTotal;
     u32 lastElectedCount;
     bool varcoreDead, attrSort, attrElim;
     i64 unassigned0;   // unassigned variables of the loaded formula (inf.unassigned)
+    // per-kernel CUDA-event timing (sigma_kernel_profile): event pairs recorded on the launch stream
+    bool ktOn; cudaEvent_t* ktEv; int* ktId; u32 ktUsed;
+    float ktMs[KT_MAX_KERNELS]; u32 ktCount[KT_MAX_KERNELS];
 };
 
 enum Stage { ST_VO = 0, ST_SIG, ST_IO, ST_GC, ST_COT, ST_SOT, ST_ROT, ST_VE, ST_SUB, ST_BCE, ST_ERE, ST_PROP, ST_LCVE, ST_CNT };
@@ -173,7 +183,10 @@ enum Stage { ST_VO = 0, ST_SIG, ST_IO, ST_GC, ST_COT, ST_SOT, ST_ROT, ST_VE, ST_
 
 #define LAUNCH(c, kern, grid, block, smem, ...)                     \
     do {                                                            \
+        static int _kid = -1;                                       \
+        if ((c)->ktOn) { if (_kid < 0) _kid = ktRegister(#kern); ktBegin((c), _kid); } \
         kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__); \
+        if ((c)->ktOn) ktEnd(c);                                    \
         (c)->launches++;                                            \
     } while (0)
 

@@ -49,7 +49,7 @@ class Report(C.Structure):
         ("cnfstate", C.c_int32), ("simpstate", C.c_int32), ("rounds", C.c_uint32), ("eliminated_vars", C.c_uint32),
         ("clauses", C.c_uint64), ("literals", C.c_uint64), ("clauses_in", C.c_uint64), ("literals_in", C.c_uint64),
         ("resolved_words", C.c_uint64), ("trail_units", C.c_uint64), ("ms_total", C.c_double),
-        ("stage_ms", C.c_float * 16), ("kernel_launches", C.c_uint64),
+        ("stage_ms", C.c_float * 16), ("kernel_launches", C.c_uint64), ("ms_device", C.c_double),
     ]
 
     STAGES = ["vo", "sig", "io", "gc", "cot", "sot", "rot", "ve", "sub", "bce", "ere", "prop", "lcve", "cnt"]
@@ -71,10 +71,10 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 # every symbol include/sigma.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "sigma_default_opts", "sigma_normalize_opts", "sigma_create", "sigma_destroy", "sigma_set_opts", "sigma_load",
+    "sigma_default_opts", "sigma_normalize_opts", "sigma_create", "sigma_destroy", "sigma_set_opts", "sigma_set_stream", "sigma_load",
     "sigma_run", "sigma_begin", "sigma_round", "sigma_finish", "sigma_num_rounds", "sigma_round_reports",
     "sigma_result_sizes", "sigma_store", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
-    "sigma_debug_hist", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
+    "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
         L.sigma_create.argtypes = [C.c_int, C.POINTER(SigmaOpts), C.POINTER(P)]
         L.sigma_destroy.argtypes = [P]
         L.sigma_set_opts.argtypes = [P, C.POINTER(SigmaOpts)]
+        L.sigma_set_stream.argtypes = [P, P]
         L.sigma_load.argtypes = [P, C.c_uint32, C.c_uint64, P, P, P, P, P, P]
         L.sigma_run.argtypes = [P, C.POINTER(Report)]
         L.sigma_begin.argtypes = [P]
@@ -105,6 +106,8 @@ def lib():
         L.sigma_snapshot.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.sigma_debug_elected.argtypes = [P, P, C.POINTER(C.c_uint32)]
         L.sigma_debug_hist.argtypes = [P, P]
+        L.sigma_kernel_profile.argtypes = [P, C.c_int]
+        L.sigma_kernel_times.argtypes = [P, P, P, P, C.POINTER(C.c_uint32)]
         L.sigma_memory.argtypes = [P] + [C.POINTER(C.c_uint64)] * 3
         L.sigma_last_error.argtypes = [P]; L.sigma_last_error.restype = C.c_char_p
         L.sigma_version.restype = C.c_char_p
@@ -176,6 +179,10 @@ class Simplifier:
         self.opts = make_opts(**o)
         self._check(self._lib.sigma_set_opts(self._h, C.byref(self.opts)))
 
+    def set_stream(self, cuda_stream: int):
+        """Run this context on the caller's CUDA stream (e.g. ``torch.cuda.Stream().cuda_stream``)."""
+        self._check(self._lib.sigma_set_stream(self._h, C.c_void_p(cuda_stream)))
+
     def _check(self, rc):
         if rc:
             raise SigmaError(f"sigma error {rc}: {self._lib.sigma_last_error(self._h).decode()}")
@@ -223,9 +230,19 @@ class Simplifier:
         return [arr[i].asdict() for i in range(n)]
 
     # Solver::cacheCNF / cacheResolved / cacheEliminated
-    def store(self) -> dict:
+    def store(self, into: dict | None = None) -> dict:
+        """cacheCNF + cacheResolved + cacheEliminated.  `into` may hold preallocated (e.g. pinned)
+        arrays under the keys below, each at least as large as the result; views are returned."""
         nc, nl, nr, nt = (C.c_uint64() for _ in range(4))
         self._check(self._lib.sigma_result_sizes(self._h, C.byref(nc), C.byref(nl), C.byref(nr), C.byref(nt)))
+        if into is not None:
+            need = {"bits": nc.value, "sig": nc.value, "offs": nc.value + 1, "lits": nl.value,
+                    "eliminated": self.max_var + 1, "resolved": nr.value, "trail": nt.value}
+            for k, n in need.items():
+                if len(into[k]) < n:
+                    raise SigmaError(f"store: buffer {k} holds {len(into[k])} < {n}")
+            self._check(self._lib.sigma_store(self._h, *[_ptr(into[k]) for k in ("bits", "sig", "offs", "lits", "eliminated", "resolved", "trail")]))
+            return {k: into[k][:n] for k, n in need.items()}
         out = {
             "bits": np.empty(nc.value, np.uint32), "sig": np.empty(nc.value, np.uint32),
             "offs": np.zeros(nc.value + 1, np.uint64), "lits": np.empty(nl.value, np.uint32),
@@ -257,6 +274,20 @@ class Simplifier:
         buf = np.zeros(2 * (self.max_var + 1), np.uint32)
         self._check(self._lib.sigma_debug_hist(self._h, _ptr(buf)))
         return buf
+
+    def kernel_profile(self, enable: int = 1):
+        """CUDA-event pair around every kernel launch, on the engine's own stream."""
+        self._check(self._lib.sigma_kernel_profile(self._h, int(enable)))
+
+    def kernel_times(self) -> dict:
+        """-> {kernel name: (total ms, launches)} since kernel_profile(1)."""
+        cap = 128
+        names = C.create_string_buffer(64 * cap)
+        ms = (C.c_float * cap)()
+        cnt = (C.c_uint32 * cap)()
+        n = C.c_uint32(cap)
+        self._check(self._lib.sigma_kernel_times(self._h, names, ms, cnt, C.byref(n)))
+        return {names.raw[64 * i:64 * (i + 1)].split(b"\0", 1)[0].decode(): (float(ms[i]), int(cnt[i])) for i in range(n.value)}
 
     def memory(self) -> dict:
         a, p, m = C.c_uint64(), C.c_uint64(), C.c_uint64()

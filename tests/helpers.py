@@ -30,48 +30,10 @@ def _run(cmd):
         raise RuntimeError("build failed: " + " ".join(cmd) + "\n" + r.stdout)
 
 
-# ------------------------------------------------------------------ generator
-_gen = None
-
-
-def cnfgen_lib():
-    global _gen
-    if _gen is None:
-        os.makedirs(BUILD, exist_ok=True)
-        src = os.path.join(ROOT, "tools", "cnfgen.cpp")
-        so = os.path.join(BUILD, "libcnfgen.so")
-        if not _newer(so, src):
-            _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
-        lib = C.CDLL(so)
-        lib.cnfgen_create.argtypes = [C.c_char_p, _u64p, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]
-        lib.cnfgen_create.restype = C.c_int
-        lib.cnfgen_nvars.argtypes = [C.c_void_p]; lib.cnfgen_nvars.restype = C.c_uint32
-        lib.cnfgen_nclauses.argtypes = [C.c_void_p]; lib.cnfgen_nclauses.restype = C.c_uint64
-        lib.cnfgen_nlits.argtypes = [C.c_void_p]; lib.cnfgen_nlits.restype = C.c_uint64
-        lib.cnfgen_copy.argtypes = [C.c_void_p, _u32p, _u64p]
-        lib.cnfgen_write_dimacs.argtypes = [C.c_void_p, C.c_char_p]; lib.cnfgen_write_dimacs.restype = C.c_int
-        lib.cnfgen_destroy.argtypes = [C.c_void_p]
-        _gen = lib
-    return _gen
-
-
-def gen_cnf(family: str, seed: int, args, dimacs_path: str | None = None):
-    """-> (max_var, lits uint32[L], offs uint64[C+1])"""
-    lib = cnfgen_lib()
-    h = C.c_void_p()
-    a = np.asarray(list(args), np.uint64)
-    rc = lib.cnfgen_create(family.encode(), a, len(a), seed, C.byref(h))
-    assert rc == 0, f"unknown family {family}"
-    try:
-        nv, nc, nl = lib.cnfgen_nvars(h), lib.cnfgen_nclauses(h), lib.cnfgen_nlits(h)
-        lits = np.empty(nl, np.uint32)
-        offs = np.empty(nc + 1, np.uint64)
-        lib.cnfgen_copy(h, lits, offs)
-        if dimacs_path:
-            assert lib.cnfgen_write_dimacs(h, dimacs_path.encode()) == 0
-    finally:
-        lib.cnfgen_destroy(h)
-    return nv, lits, offs
+# ------------------------------------------------------------------ generator (tools/cnfgen.py)
+import sys
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from cnfgen import CONFIGS, cnfgen_lib, gen_cnf  # noqa: E402,F401
 
 
 # ------------------------------------------------------------------ oracle

@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA engine (through the C ABI, include/sigma.h) against the CPU oracle
+on the same seeded inputs, against the committed golden dumps of the unmodified reference, and
+- at BASELINE.json's full sizes - through size-independent properties.
+
+Bit-exact bar (integer work): same elected counts, same eliminated set, same resolvent counts,
+same clause list *in the same order with the same flag and signature words* after every round,
+same witness groups, same units; every model extended from the witness stack satisfies the
+original CNF."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import sgd
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SUMMARY = json.load(open(os.path.join(HERE, "golden", "summary.json")))
+
+SMALL = {
+    "k3_r30": ("ksat", 12, [800, 2400, 3]),
+    "k3_r42": ("ksat", 11, [600, 2520, 3]),
+    "k5_r10": ("ksat", 13, [400, 4000, 5]),
+    "k4_r7": ("ksat", 14, [500, 3500, 4]),
+    "miter_x": ("miter", 21, [30, 600, 900, 100, 8]),
+    "miter_a": ("miter", 22, [40, 700, 300, 200, 8]),
+    "mult6": ("mult", 31, [6]),
+    "mult10": ("mult", 32, [10]),
+    "parity": ("parity", 41, [300]),
+    "multpar": ("multpar", 51, [5, 120]),
+}
+MEDIUM = {
+    "cfg1_k3_100k": ("ksat", 1, [100000, 426000, 3]),      # BASELINE config 1, full size
+    "miter_50k": ("miter", 3, [2000, 50000, 900, 100, 32]),
+    "mult48": ("mult", 4, [48]),
+    "k5_20k": ("ksat", 2, [20000, 200000, 5]),
+}
+VARIANTS = {
+    "p5": ["--phases=5", "-no-ere"],
+    "def": [],
+    "nofun": ["-no-vefunction"],
+    "all": ["-all"],
+    "bce": ["-bce"],
+    "nosub_p2": ["-no-sub", "-no-veextend", "--phases=2", "-no-ere"],
+}
+
+
+def sigma():
+    from parafrost_b200 import sigma as s
+    return s
+
+
+def to_dump(V, st, state=2):
+    return sgd.Dump.from_arrays(V, state, st["bits"], st["sig"], st["offs"], st["lits"], st["eliminated"], st["resolved"], st["trail"])
+
+
+def run_engine_rounds(V, lits, offs, flags, oracle_stats=None, oracle_snaps=None, elections=None, meta=None):
+    """Drives sigma_begin/round/finish and checks every round against the oracle's."""
+    s = sigma().Simplifier(0, flags=flags)
+    try:
+        s.load(V, lits, offs, meta=meta)
+        s.begin()
+        r = 0
+        while True:
+            rep, done = s.round()
+            if rep["kind"] == 0:
+                if oracle_stats is not None:
+                    assert r < len(oracle_stats), f"engine ran an extra round {rep}"
+                    got = (rep["elected"], rep["eliminated"], rep["resolvents"], rep["clauses"], rep["literals"])
+                    assert got == tuple(int(x) for x in oracle_stats[r]), f"round {r}"
+                if oracle_snaps is not None:
+                    snap = to_dump(V, s.snapshot())
+                    d = [x for x in sgd.compare(snap, oracle_snaps[r]) if x.split(":")[0] in
+                         ("clauses", "literals", "h_lits_multiset", "h_full_multiset", "h_lits_ordered", "h_full_ordered")]
+                    assert not d, f"round {r}: {d}"
+                r += 1
+            if done:
+                break
+        if oracle_stats is not None:
+            assert r == len(oracle_stats)
+        fin = s.finish()
+        return to_dump(V, s.store(), fin["cnfstate"]), fin, s.rounds(), s.memory()
+    finally:
+        s.close()
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("var", list(VARIANTS))
+@pytest.mark.parametrize("name", list(SMALL))
+def test_rounds_match_oracle_small(name, var):
+    fam, seed, args = SMALL[name]
+    flags = VARIANTS[var]
+    V, lits, offs = helpers.gen_cnf(fam, seed, args)
+    od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True, **helpers.opts_from_flags(flags))
+    ed, fin, _, mem = run_engine_rounds(V, lits, offs, flags, ors, osnaps)
+    assert not sgd.compare(ed, od)
+    assert (ed.bits == od.bits).all() and (ed.sig == od.sig).all()
+    assert mem["cuda_mallocs"] == 1   # one arena allocation per context, none in the round loop
+
+
+@pytest.mark.parametrize("var", ["p5", "def"])
+@pytest.mark.parametrize("name", list(MEDIUM))
+def test_rounds_match_oracle_medium(name, var):
+    fam, seed, args = MEDIUM[name]
+    flags = VARIANTS[var]
+    V, lits, offs = helpers.gen_cnf(fam, seed, args)
+    od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True, **helpers.opts_from_flags(flags))
+    ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags, ors, osnaps)
+    assert not sgd.compare(ed, od)
+
+
+GOLD = sorted(k for k, e in SUMMARY.items() if "fingerprint" in e and "-no-ere" in e["flags"])
+FP_KEYS = ["cnfstate", "clauses", "literals", "eliminated", "forced", "resolved_words", "resolved_groups", "trail",
+           "h_lits_multiset", "h_full_multiset", "h_lits_ordered", "h_full_ordered", "h_eliminated", "h_forced",
+           "h_resolved_groups", "h_trail_multiset"]
+
+
+@pytest.mark.parametrize("key", GOLD)
+def test_engine_matches_reference_golden(key):
+    """The CUDA engine against dumps of the UNMODIFIED reference GPU solver (tests/golden)."""
+    e = SUMMARY[key]
+    V, lits, offs = helpers.gen_cnf(e["family"], e["seed"], e["args"])
+    flags = [f for f in e["flags"] if f not in ("-no-lcvefast", "-quiet")]
+    ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags)
+    fp, g = ed.fingerprint(), e["fingerprint"]
+    diff = {k: (fp[k], g[k]) for k in FP_KEYS if fp[k] != g[k]}
+    assert not diff, diff
+    path = os.path.join(HERE, "golden", key + ".sgd.gz")
+    if os.path.exists(path):
+        ref = sgd.Dump.load(path)
+        assert ref.ordered_clauses() == ed.ordered_clauses()
+        assert ref.eliminated_vars() == ed.eliminated_vars()
+        assert ref.resolved_groups() == ed.resolved_groups()
+        assert (ref.bits == ed.bits).all() and (ref.sig == ed.sig).all()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_stage_prep_and_histogram():
+    rng = np.random.default_rng(5)
+    sizes = np.concatenate([rng.integers(1, 9, 5000), rng.integers(9, 60, 300), [1, 2, 8, 9, 250]]).astype(np.uint64)
+    offs = np.zeros(len(sizes) + 1, np.uint64)
+    np.cumsum(sizes, out=offs[1:])
+    lits = np.empty(int(offs[-1]), np.uint32)
+    for i, sz in enumerate(sizes.tolist()):  # distinct variables inside a clause
+        v = rng.choice(4000, size=sz, replace=False) + 1
+        lits[int(offs[i]):int(offs[i + 1])] = 2 * v + rng.integers(0, 2, sz)
+    gl, gs = sigma().stage_prep(lits, offs)
+    ol = lits.copy()
+    os_ = np.zeros(len(sizes), np.uint32)
+    helpers.oracle_lib().oracle_prep(len(sizes), ol, offs, os_)
+    assert (gl == ol).all() and (gs == os_).all()
+    nb = 2 * 4002
+    gh = sigma().stage_histogram(lits, nb)
+    oh = np.zeros(nb, np.uint32)
+    helpers.oracle_lib().oracle_histogram(len(lits), lits, nb, oh)
+    assert (gh == oh).all()
+    assert (gh == np.bincount(lits, minlength=nb).astype(np.uint32)).all()
+
+
+def test_edge_cases():
+    S = sigma()
+    # single clause, unit clauses, duplicate clauses, a pure literal, an immediately empty formula
+    cases = [
+        (3, [[2, 4, 6]]),
+        (3, [[2, 4], [3, 4], [2, 5], [3, 5]]),                   # UNSAT core on x1,x2 through BVE
+        (4, [[2, 4, 6], [2, 4, 6], [3, 8], [5, 8], [7, 9]]),     # duplicates + pure literals
+        (2, [[2], [3, 4]]),                                      # unit in the input
+        (5, [[2, 4, 6, 8, 10]] * 3),
+    ]
+    for V, cls in cases:
+        lits = np.array([l for c in cls for l in c], np.uint32)
+        offs = np.zeros(len(cls) + 1, np.uint64)
+        np.cumsum([len(c) for c in cls], out=offs[1:])
+        for flags in ([], ["-all"], ["--phases=1", "-no-ere"]):
+            od, ors, osn = helpers.run_oracle(V, lits, offs, snapshots=True, **helpers.opts_from_flags(flags))
+            ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags, ors, osn)
+            assert not sgd.compare(ed, od), (V, cls, flags)
+    # long clauses (insertion-sort path of prep, > 8 literals) and learnt clauses in the input
+    rng = np.random.default_rng(9)
+    V = 300
+    cls = [sorted(set((2 * (rng.choice(V, size=int(rng.integers(2, 40)), replace=False) + 1) + rng.integers(0, 2)).tolist()))
+           for _ in range(900)]
+    lits = np.array([l for c in cls for l in c], np.uint32)
+    offs = np.zeros(len(cls) + 1, np.uint64)
+    np.cumsum([len(c) for c in cls], out=offs[1:])
+    meta = np.zeros(len(cls), np.uint32)
+    lrn = rng.random(len(cls)) < 0.2
+    meta[lrn] = 1 | (2 << 4) | (rng.integers(2, 9, int(lrn.sum())).astype(np.uint32) << 6)
+    for flags, calls in (([], 1), (["-all"], 2)):
+        over = helpers.opts_from_flags(flags)
+        over["sigma_calls"] = calls
+        od, ors, osn = helpers.run_oracle(V, lits, offs, meta=meta, snapshots=True, **over)
+        s = S.Simplifier(0, flags=flags, sigma_calls=calls)
+        s.load(V, lits, offs, meta=meta)
+        fin = s.simplify()
+        ed = to_dump(V, s.store(), fin["cnfstate"])
+        s.close()
+        assert not sgd.compare(ed, od), flags
+    # bad arguments are reported, not crashed on
+    s = S.Simplifier(0)
+    with pytest.raises(S.SigmaError):
+        s.simplify()          # nothing loaded
+    s.close()
+
+
+def test_reload_reuses_arena_and_is_idempotent():
+    """A context can be re-run and re-loaded; the arena is allocated once while the formula fits,
+    and running the simplifier twice on the same formula gives the same result."""
+    S = sigma()
+    V, lits, offs = helpers.gen_cnf("ksat", 12, [800, 2400, 3])
+    s = S.Simplifier(0)
+    s.load(V, lits, offs)
+    a = s.simplify(); da = to_dump(V, s.store(), a["cnfstate"])
+    b = s.simplify(); db = to_dump(V, s.store(), b["cnfstate"])
+    assert not sgd.compare(da, db)
+    V2, l2, o2 = helpers.gen_cnf("ksat", 11, [600, 2520, 3])
+    s.load(V2, l2, o2)
+    s.simplify()
+    assert s.memory()["cuda_mallocs"] == 1
+    s.close()
+
+
+def check_model_roundtrip(V, lits, offs, store, cnfstate):
+    """Every model of the simplified formula, extended over the witness stack, satisfies the
+    original CNF (MODEL::extend, src/gpu/model.cpp:101-162).  The simplified formula is solved
+    here by a tiny CPU routine only when it is empty (SAT by simplification) or by reusing the
+    oracle's result otherwise."""
+    lib = helpers.oracle_lib()
+    value = np.zeros(V + 1, np.uint8)
+    for u in store["trail"].tolist():
+        value[u >> 1] = 0 if (u & 1) else 1
+    flips = lib.oracle_extend_model(value, V, store["resolved"], len(store["resolved"]))
+    return lib.oracle_check_model(value, len(offs) - 1, lits, offs), flips
+
+
+def test_model_reconstruction_when_solved_by_simplification():
+    # parity chains and pure-literal formulas are emptied by BVE: the witness stack alone must
+    # rebuild a model of the ORIGINAL formula
+    S = sigma()
+    for fam, seed, args in (("parity", 41, [300]), ("parity", 43, [5000]), ("ksat", 77, [5000, 5000, 3])):
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        s = S.Simplifier(0, flags=["--phases=8"])
+        s.load(V, lits, offs)
+        fin = s.simplify()
+        st = s.store()
+        s.close()
+        if fin["cnfstate"] == S.SAT:
+            bad, _ = check_model_roundtrip(V, lits, offs, st, fin["cnfstate"])
+            assert bad == 0, (fam, bad)
+        od, _, _ = helpers.run_oracle(V, lits, offs, phases=8)
+        assert od.cnfstate == fin["cnfstate"]
+        assert not sgd.compare(to_dump(V, st, fin["cnfstate"]), od)
+
+
+def test_full_size_properties_cfg1():
+    """BASELINE config 1 at full size: parity with the oracle (it finishes in seconds) plus the
+    size-independent properties - literal sortedness, signature consistency, eliminated variables
+    absent from the result, idempotent histogram."""
+    S = sigma()
+    V, lits, offs = helpers.gen_cnf("ksat", 1, [100000, 426000, 3])
+    s = S.Simplifier(0)
+    s.load(V, lits, offs)
+    fin = s.simplify()
+    st = s.store()
+    s.close()
+    o = st["offs"].astype(np.int64)
+    L = st["lits"]
+    sz = np.diff(o)
+    # sorted strictly ascending inside every clause
+    inner = np.ones(len(L), bool)
+    inner[o[:-1]] = False
+    assert (L[1:][inner[1:]] > L[:-1][inner[1:]]).all()
+    # signatures
+    h = (np.uint32(1) << (L & np.uint32(31))).astype(np.uint32)
+    sig = np.bitwise_or.reduceat(h, o[:-1])
+    assert (sig[sz > 1] == st["sig"][sz > 1]).all()
+    # eliminated variables do not occur any more
+    elim = st["eliminated"]
+    assert not (elim[L >> 1] & 1).any()
+    assert fin["clauses"] == len(sz) and fin["literals"] == len(L)
+    od, _, _ = helpers.run_oracle(V, lits, offs)
+    assert not sgd.compare(to_dump(V, st, fin["cnfstate"]), od)
+
+
+def test_full_size_properties_cfg2_shape():
+    """BASELINE config 2 (random 5-SAT, n=1M, m=21M) at FULL size through the C ABI: properties
+    only (the oracle needs minutes here) - histogram == bincount, sortedness, counters."""
+    S = sigma()
+    V, lits, offs = helpers.gen_cnf("ksat", 2, [1000000, 21000000, 5])
+    s = S.Simplifier(0)
+    s.load(V, lits, offs)
+    s.begin()
+    rep, done = s.round()
+    hist = s.debug_hist()
+    assert (hist == np.bincount(lits, minlength=len(hist)).astype(np.uint32)).all()
+    while not done:
+        rep, done = s.round()
+    fin = s.finish()
+    st = s.store()
+    s.close()
+    o = st["offs"].astype(np.int64)
+    L = st["lits"]
+    inner = np.ones(len(L), bool)
+    inner[o[:-1]] = False
+    assert (L[1:][inner[1:]] > L[:-1][inner[1:]]).all()
+    assert fin["clauses"] == len(o) - 1 and fin["literals"] == len(L)
+    assert not (st["eliminated"][L >> 1] & 1).any()
+    # the eliminated variables' clauses went to the witness stack: extending any assignment that
+    # satisfies the remaining clauses must satisfy the original ones.  Check the cheap direction:
+    # every original clause is either still present, or contains an eliminated/forced variable.
+    gone = (st["eliminated"] != 0)
+    touched = np.bitwise_or.reduceat(gone[lits >> 1].astype(np.uint8), offs[:-1].astype(np.int64))
+    assert int((touched == 0).sum()) <= fin["clauses"]
