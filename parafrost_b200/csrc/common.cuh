@@ -102,6 +102,7 @@ struct DevCounters {
     u32 unassignedDec; // variables assigned by prop()
     u32 qMed, qBig, qHuge; // list-sort work queues
     u32 addedCls;      // resolvents appended by the last BVE
+    u32 bin[4];        // group-size class sizes of the elected variables (elim.cu) + redo queue
     u32 scratch[8];
     u32 froz12[12];    // variables currently holding a function-table index in varcore
 };

@@ -16,11 +16,14 @@
 // redundantly by all lanes (uniform control flow, broadcast loads) with lane 0 doing the
 // writes, each followed by __syncwarp().  Results do not depend on the lane mapping: counts
 // are sums, "first match in list order" is taken with ballot + ffs.
+#include <cstdlib>
+
 #include "common.cuh"
 
 struct G {
     uint4* hdr; u32* pool;
     const u32* otStart; u32* otSize; u32* occurs;
+    const uint4* key;   // OLIST_CMP keys of this round (k_hist_key); lists are sorted by (key, index)
     const u32* elected; unsigned char* eliminated; const u32* vorg; const u32* varcore;
     u32* units; u32 unitsCap; u32* resolved; u32 resolvedCap;
     u32 *veType, *veUcnt, *veRpos; u64* veRref;
@@ -29,17 +32,35 @@ struct G {
     u32 numElected;
 };
 
-#define LANE (threadIdx.x & 31u)
-#define FULL 0xffffffffu
+// Cooperative group of GS lanes (4, 8 or 32) inside a warp: one group per elected variable.
+// Small variables (Tseitin / adder gates: a handful of short clauses per side) run 8 or 4 to a
+// warp instead of wasting 28 lanes; the classes are built by k_bin_elected.
+template <int GS> struct GT : G {};
+#define LANE (threadIdx.x & (u32)(GS - 1))
+#define GBASE ((threadIdx.x & 31u) & ~(u32)(GS - 1))
+#define FULL (GS == 32 ? 0xffffffffu : (((1u << (GS & 31)) - 1u) << GBASE))
+#define BALLOT(p) (__ballot_sync(FULL, (p)) >> GBASE)
+#define LTMASK ((1u << LANE) - 1u)
+#define GSYNC() __syncwarp(FULL)
+template <int GS> __device__ __forceinline__ u32 gSum(u32 v) {
+#pragma unroll
+    for (int o = GS / 2; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o, GS);
+    return v;
+}
+template <int GS> __device__ __forceinline__ u32 gIncl(u32 v) {
+#pragma unroll
+    for (int o = 1; o < GS; o <<= 1) { const u32 t = __shfl_up_sync(FULL, v, o, GS); if (LANE >= (u32)o) v += t; }
+    return v;
+}
 
 // ------------------------------------------------------------------ small helpers
-__device__ __forceinline__ void setBits(G& g, u32 ci, u32 set, u32 clr) {
+template <int GS> __device__ __forceinline__ void setBits(GT<GS>& g, u32 ci, u32 set, u32 clr) {
     if (LANE == 0) { const u32 w = g.hdr[ci].w; g.hdr[ci].w = (w & ~clr) | set; }
-    __syncwarp();
+    GSYNC();
 }
-__device__ __forceinline__ void melt(G& g, u32 ci) { setBits(g, ci, CB_MOLTEN, 0); }
-__device__ __forceinline__ void freeze(G& g, u32 ci) { setBits(g, ci, 0, CB_MOLTEN); }
-__device__ __forceinline__ void markDeleted(G& g, u32 ci) { setBits(g, ci, CB_DELETED, CB_ST_MASK); }
+template <int GS> __device__ __forceinline__ void melt(GT<GS>& g, u32 ci) { setBits(g, ci, CB_MOLTEN, 0); }
+template <int GS> __device__ __forceinline__ void freeze(GT<GS>& g, u32 ci) { setBits(g, ci, 0, CB_MOLTEN); }
+template <int GS> __device__ __forceinline__ void markDeleted(GT<GS>& g, u32 ci) { setBits(g, ci, CB_DELETED, CB_ST_MASK); }
 
 // resolvent length on x, 0 if tautology (elimination.cuh:180-205)
 __device__ __forceinline__ int mergeLen(const u32* __restrict__ a, int n1, const u32* __restrict__ b, int n2, u32 x) {
@@ -93,11 +114,11 @@ __device__ __forceinline__ u32 sigOf(const u32* l, int n) {
 
 // ------------------------------------------------------------------ witness stack (model.cuh:29-53)
 // lane 0 writes; callers reserve with atomicAdd on dc->resolvedSize
-__device__ __forceinline__ void saveWitness(G& g, u32*& saved, u32 witness) {
+template <int GS> __device__ __forceinline__ void saveWitness(GT<GS>& g, u32*& saved, u32 witness) {
     *saved++ = V2L(g.vorg[LABS(witness)]) | LSIGN(witness);
     *saved++ = 1;
 }
-__device__ __forceinline__ void saveClause(G& g, u32*& saved, const uint4 h, u32 witlit) {
+template <int GS> __device__ __forceinline__ void saveClause(GT<GS>& g, u32*& saved, const uint4 h, u32 witlit) {
     u32* first = saved; u32* wit = saved;
     const u32* l = g.pool + h.x;
     for (u32 k = 0; k < h.y; k++) {
@@ -109,24 +130,24 @@ __device__ __forceinline__ void saveClause(G& g, u32*& saved, const uint4 h, u32
     *saved++ = h.y;
 }
 // reserve n words of the witness stack; returns NULL on overflow (flagged; the reference only asserts)
-__device__ __forceinline__ u32* jumpResolved(G& g, u32 n) {
+template <int GS> __device__ __forceinline__ u32* jumpResolved(GT<GS>& g, u32 n) {
     u32 base = 0;
     if (LANE == 0) base = atomicAdd(&g.dc->resolvedSize, n);
-    base = __shfl_sync(FULL, base, 0);
+    base = __shfl_sync(FULL, base, 0, GS);
     if ((u64)base + n > g.resolvedCap) { if (LANE == 0) atomicOr(&g.dc->flags, 1u); return nullptr; }
     return g.resolved + base;
 }
 // count originals / their literals of a list (all lanes redundantly; lists are short)
-__device__ __forceinline__ void countOrgsLits(G& g, const u32* list, u32 n, u32& cls, u32& lits) {
+template <int GS> __device__ __forceinline__ void countOrgsLits(GT<GS>& g, const u32* list, u32 n, u32& cls, u32& lits) {
     u32 c = 0, l = 0;
-    for (u32 j = LANE; j < n; j += 32) { const uint4 h = g.hdr[list[j]]; if (C_ORIGINAL(h.w)) c++, l += h.y; }
-    cls = warpSum(c); lits = warpSum(l);
+    for (u32 j = LANE; j < n; j += GS) { const uint4 h = g.hdr[list[j]]; if (C_ORIGINAL(h.w)) c++, l += h.y; }
+    cls = gSum<GS>(c); lits = gSum<GS>(l);
 }
 // save the originals of `list` (witness literal first) followed by the witness unit of `wit`
 // `reserveCls`: clause count used for the reservation (the reference reserves pOrgs/nOrgs words
 //  in phase 1, elimination.cuh:455-476, which equals the number of originals except when learnt
 //  clauses sit in the list of a first-call run; reserve what the reference reserves)
-__device__ __forceinline__ void saveSide(G& g, const u32* list, u32 n, u32 witlit, u32 wit, u32 reserveCls) {
+template <int GS> __device__ __forceinline__ void saveSide(GT<GS>& g, const u32* list, u32 n, u32 witlit, u32 wit, u32 reserveCls) {
     u32 cls, lits;
     countOrgsLits(g, list, n, cls, lits);
     u32* saved = jumpResolved(g, reserveCls + lits + 2);
@@ -136,50 +157,50 @@ __device__ __forceinline__ void saveSide(G& g, const u32* list, u32 n, u32 witli
         saveWitness(g, saved, wit);
         while (saved < end) *saved++ = 0;  // unreachable unless reserveCls > #originals
     }
-    __syncwarp();
+    GSYNC();
 }
-__device__ __forceinline__ void deleteAll(G& g, const u32* list, u32 n) {
-    for (u32 j = LANE; j < n; j += 32) { const u32 ci = list[j]; const u32 w = g.hdr[ci].w; g.hdr[ci].w = (w & ~CB_ST_MASK) | CB_DELETED; }
-    __syncwarp();
+template <int GS> __device__ __forceinline__ void deleteAll(GT<GS>& g, const u32* list, u32 n) {
+    for (u32 j = LANE; j < n; j += GS) { const u32 ci = list[j]; const u32 w = g.hdr[ci].w; g.hdr[ci].w = (w & ~CB_ST_MASK) | CB_DELETED; }
+    GSYNC();
 }
 // toblivion with witness saving (elimination.cuh:443-492)
-__device__ void toblivionSave(G& g, u32 p, u32 n, u32 pOrgs, u32 nOrgs, const u32* P, u32 np, const u32* N, u32 nn) {
+template <int GS> __device__ void toblivionSave(GT<GS>& g, u32 p, u32 n, u32 pOrgs, u32 nOrgs, const u32* P, u32 np, const u32* N, u32 nn) {
     if (pOrgs > nOrgs) saveSide(g, N, nn, n, p, nOrgs);
     else saveSide(g, P, np, p, n, pOrgs);
     deleteAll(g, P, np);
     deleteAll(g, N, nn);
     if (LANE == 0) { g.otSize[p] = 0; g.otSize[n] = 0; }
-    __syncwarp();
+    GSYNC();
 }
-__device__ __forceinline__ void freezeBinaries(G& g, const u32* list, u32 n) {
-    for (u32 j = LANE; j < n; j += 32) { const u32 ci = list[j]; const uint4 h = g.hdr[ci]; if (C_ORIGINAL(h.w) && h.y == 2) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
-    __syncwarp();
+template <int GS> __device__ __forceinline__ void freezeBinaries(GT<GS>& g, const u32* list, u32 n) {
+    for (u32 j = LANE; j < n; j += GS) { const u32 ci = list[j]; const uint4 h = g.hdr[ci]; if (C_ORIGINAL(h.w) && h.y == 2) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
+    GSYNC();
 }
-__device__ __forceinline__ void freezeClauses(G& g, const u32* P, u32 np, const u32* N, u32 nn) {
-    for (u32 j = LANE; j < np; j += 32) { const u32 ci = P[j]; const u32 w = g.hdr[ci].w; if (C_ORIGINAL(w) && C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN; }
-    for (u32 j = LANE; j < nn; j += 32) { const u32 ci = N[j]; const u32 w = g.hdr[ci].w; if (C_ORIGINAL(w) && C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN; }
-    __syncwarp();
+template <int GS> __device__ __forceinline__ void freezeClauses(GT<GS>& g, const u32* P, u32 np, const u32* N, u32 nn) {
+    for (u32 j = LANE; j < np; j += GS) { const u32 ci = P[j]; const u32 w = g.hdr[ci].w; if (C_ORIGINAL(w) && C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN; }
+    for (u32 j = LANE; j < nn; j += GS) { const u32 ci = N[j]; const u32 w = g.hdr[ci].w; if (C_ORIGINAL(w) && C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN; }
+    GSYNC();
 }
-__device__ __forceinline__ void freezeArities(G& g, const u32* P, u32 np, const u32* N, u32 nn) {
-    for (u32 j = LANE; j < np; j += 32) { const u32 ci = P[j]; const uint4 h = g.hdr[ci]; if (h.y > 2 && C_MOLTEN(h.w)) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
-    for (u32 j = LANE; j < nn; j += 32) { const u32 ci = N[j]; const uint4 h = g.hdr[ci]; if (h.y > 2 && C_MOLTEN(h.w)) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
-    __syncwarp();
+template <int GS> __device__ __forceinline__ void freezeArities(GT<GS>& g, const u32* P, u32 np, const u32* N, u32 nn) {
+    for (u32 j = LANE; j < np; j += GS) { const u32 ci = P[j]; const uint4 h = g.hdr[ci]; if (h.y > 2 && C_MOLTEN(h.w)) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
+    for (u32 j = LANE; j < nn; j += GS) { const u32 ci = N[j]; const uint4 h = g.hdr[ci]; if (h.y > 2 && C_MOLTEN(h.w)) g.hdr[ci].w = h.w & ~CB_MOLTEN; }
+    GSYNC();
 }
 // append the unit clauses of a list to the units vector, list order (elimination.cuh:95-105)
-__device__ void appendUnits(G& g, const u32* list, u32 n, u32& cursor) {
-    for (u32 base = 0; base < n; base += 32) {
+template <int GS> __device__ void appendUnits(GT<GS>& g, const u32* list, u32 n, u32& cursor) {
+    for (u32 base = 0; base < n; base += GS) {
         const u32 j = base + LANE;
         u32 lit = 0; bool is = false;
         if (j < n) { const uint4 h = g.hdr[list[j]]; if (h.y == 1) { is = true; lit = g.pool[h.x]; } }
-        const u32 m = __ballot_sync(FULL, is);
-        if (is) { const u32 slot = cursor + __popc(m & lanemaskLt()); if (slot < g.unitsCap) g.units[slot] = lit; else atomicOr(&g.dc->flags, 2u); }
+        const u32 m = BALLOT(is);
+        if (is) { const u32 slot = cursor + __popc(m & LTMASK); if (slot < g.unitsCap) g.units[slot] = lit; else atomicOr(&g.dc->flags, 2u); }
         cursor += __popc(m);
     }
 }
-__device__ __forceinline__ u32 reserveUnits(G& g, u32 n) {
+template <int GS> __device__ __forceinline__ u32 reserveUnits(GT<GS>& g, u32 n) {
     u32 base = 0;
     if (LANE == 0) base = atomicAdd(&g.dc->numUnits, n);
-    return __shfl_sync(FULL, base, 0);
+    return __shfl_sync(FULL, base, 0, GS);
 }
 
 // ------------------------------------------------------------------ pair counting
@@ -188,7 +209,7 @@ __device__ __forceinline__ u32 reserveUnits(G& g, u32 n) {
 // mode 2: countSubstituted (elimination.cuh:365-441)     pairs with different molten flags
 // mode 3: countCoreSubstituted (function.cuh:181-257)    pairs not both molten
 // returns true when the elimination is NOT possible (bound / size / packing limits exceeded)
-__device__ bool countPairs(G& g, int mode, u32 x, const u32* M, u32 nm, const u32* O, u32 no, u32 nClsBefore,
+template <int GS> __device__ bool countPairs(GT<GS>& g, int mode, u32 x, const u32* M, u32 nm, const u32* O, u32 no, u32 nClsBefore,
                            u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     const u32 rlimit = g.k.ve_clause_max;
     u32 units = 0, cls = 0, lits = 0;
@@ -196,7 +217,7 @@ __device__ bool countPairs(G& g, int mode, u32 x, const u32* M, u32 nm, const u3
     const u64 total = (u64)nm * no;
     u32 iter = 0;
     bool fail = false;
-    for (u64 t0 = 0; t0 < total; t0 += 32, iter++) {
+    for (u64 t0 = 0; t0 < total; t0 += GS, iter++) {
         const u64 t = t0 + LANE;
         if (t < total) {
             const u32 i = (u32)(t / no), j = (u32)(t - (u64)i * no);
@@ -216,10 +237,10 @@ __device__ bool countPairs(G& g, int mode, u32 x, const u32* M, u32 nm, const u3
         }
         if ((iter & 7u) == 7u) {  // early exit like the serial loop's `return`
             if (__any_sync(FULL, big)) { fail = true; break; }
-            if (mode && warpSum(cls) > nClsBefore) { fail = true; break; }
+            if (mode && gSum<GS>(cls) > nClsBefore) { fail = true; break; }
         }
     }
-    nElements = warpSum(units); nAddedCls = warpSum(cls); nAddedLits = warpSum(lits);
+    nElements = gSum<GS>(units); nAddedCls = gSum<GS>(cls); nAddedLits = gSum<GS>(lits);
     if (__any_sync(FULL, big)) fail = true;
     if (mode && nAddedCls > nClsBefore) fail = true;
     if (fail) { if (!nAddedCls) nAddedCls = 1; return true; }
@@ -235,7 +256,7 @@ __device__ bool countPairs(G& g, int mode, u32 x, const u32* M, u32 nm, const u3
 
 // ------------------------------------------------------------------ gates (executed redundantly by all lanes)
 // equivalence.cuh:111-171
-__device__ u32 findEquGate(G& g, u32 p, u32 n, const u32* P, u32 np, const u32* N, u32 nn) {
+template <int GS> __device__ u32 findEquGate(GT<GS>& g, u32 p, u32 n, const u32* P, u32 np, const u32* N, u32 nn) {
     if (g.hdr[P[0]].y > 2 || g.hdr[N[0]].y > 2) return 0;
     // find_sfanin
     u32 imp = 0; int nImps = 0; bool multi = false;
@@ -261,13 +282,13 @@ __device__ u32 findEquGate(G& g, u32 p, u32 n, const u32* P, u32 np, const u32* 
     return 0;
 }
 
-__device__ __forceinline__ bool clauseHas(G& g, const uint4 h, u32 lit) {
+template <int GS> __device__ __forceinline__ bool clauseHas(GT<GS>& g, const uint4 h, u32 lit) {
     const u32* l = g.pool + h.x;
     for (u32 k = 0; k < h.y; k++) if (l[k] == lit) return true;
     return false;
 }
 // substitute_single on one clause (equivalence.cuh:28-57); lane 0 only
-__device__ void substituteClause(G& g, u32 ci, u32 dx, u32 def, u32& nUnits) {
+template <int GS> __device__ void substituteClause(GT<GS>& g, u32 ci, u32 dx, u32 def, u32& nUnits) {
     uint4 h = g.hdr[ci];
     u32* l = g.pool + h.x;
     if (LANE == 0) {
@@ -280,11 +301,11 @@ __device__ void substituteClause(G& g, u32 ci, u32 dx, u32 def, u32& nUnits) {
         }
         g.hdr[ci] = h;
     }
-    __syncwarp();
+    GSYNC();
     if (g.hdr[ci].y == 1) nUnits++;
 }
 // equivalence.cuh:59-109
-__device__ void substituteSingle(G& g, u32 p, u32 n, u32 def, const u32* P, u32 np, const u32* N, u32 nn) {
+template <int GS> __device__ void substituteSingle(GT<GS>& g, u32 p, u32 n, u32 def, const u32* P, u32 np, const u32* N, u32 nn) {
     const u32 def_f = LFLIP(def);
     u32 nNegUnits = 0, nPosUnits = 0;
     for (u32 j = 0; j < nn; j++) {
@@ -309,7 +330,7 @@ __device__ void substituteSingle(G& g, u32 p, u32 n, u32 def, const u32* P, u32 
 }
 
 // and.cuh:28-113 ; out_c lives in this warp's shared slice
-__device__ bool findAOGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
+template <int GS> __device__ bool findAOGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
                            u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     if (g.hdr[D[0]].y > 2 || g.hdr[F[nf - 1]].y < 3) return false;
     u32 sig = 0; u32 nImps = 0;
@@ -331,7 +352,7 @@ __device__ bool findAOGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32
         }
         nImps++;
         sig |= MAPHASH(fx);
-        __syncwarp();
+        GSYNC();
         for (u32 j = 0; j < nf; j++) {
             const u32 ci = F[j]; const uint4 h = g.hdr[ci];
             if (C_ORIGINAL(h.w) && h.y == nImps && SUBSIG(h.z, sig)) {
@@ -350,7 +371,7 @@ __device__ bool findAOGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32
 }
 
 // ifthenelse.cuh:28-50 ; returns clause index or NOVAR
-__device__ u32 fastEqualityCheck(G& g, u32 x, u32 y, u32 z) {
+template <int GS> __device__ u32 fastEqualityCheck(GT<GS>& g, u32 x, u32 y, u32 z) {
     u32 t;
     if (g.otSize[y] > g.otSize[z]) { t = y; y = z; z = t; }
     if (g.otSize[x] > g.otSize[y]) { t = x; x = y; y = t; }
@@ -361,7 +382,7 @@ __device__ u32 fastEqualityCheck(G& g, u32 x, u32 y, u32 z) {
     if (x > z) { t = x; x = z; z = t; }
     if (x > y) { t = x; x = y; y = t; }
     // first match in list order; lanes scan 32 entries at a time
-    for (u32 base = 0; base < n; base += 32) {
+    for (u32 base = 0; base < n; base += GS) {
         const u32 j = base + LANE;
         bool ok = false;
         if (j < n) {
@@ -371,13 +392,13 @@ __device__ u32 fastEqualityCheck(G& g, u32 x, u32 y, u32 z) {
                 ok = l[0] == x && l[1] == y && l[2] == z;
             }
         }
-        const u32 m = __ballot_sync(FULL, ok);
+        const u32 m = BALLOT(ok);
         if (m) return list[base + __ffs(m) - 1];
     }
     return NOVAR;
 }
 // ifthenelse.cuh:52-125
-__device__ bool findITEGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls,
+template <int GS> __device__ bool findITEGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls,
                             u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     if (g.hdr[D[nd - 1]].y == 2) return false;
     const u32 v = LABS(dx);
@@ -413,17 +434,17 @@ __device__ bool findITEGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u3
 }
 
 // xor.cuh:58-109 ; literals[] in this warp's shared slice (lane 0 writes)
-__device__ bool makeArity(G& g, u32& parity, u32* literals, int size) {
+template <int GS> __device__ bool makeArity(GT<GS>& g, u32& parity, u32* literals, int size) {
     const u32 oldparity = parity;
     while (__popc(++parity) & 1) {}
     if (LANE == 0)
         for (int k = 0; k < size; k++) { const u32 bit = 1u << k; if ((parity & bit) != (oldparity & bit)) literals[k] = LFLIP(literals[k]); }
-    __syncwarp();
+    GSYNC();
     u32 best = literals[0];
     u32 minsize = g.otSize[best];
     for (int k = 1; k < size; k++) { const u32 lit = literals[k]; const u32 ls = g.otSize[lit]; if (ls < minsize) { minsize = ls; best = lit; } }
     const u32* list = g.occurs + g.otStart[best];
-    for (u32 base = 0; base < minsize; base += 32) {
+    for (u32 base = 0; base < minsize; base += GS) {
         const u32 j = base + LANE;
         bool ok = false;
         if (j < minsize) {
@@ -438,13 +459,13 @@ __device__ bool makeArity(G& g, u32& parity, u32* literals, int size) {
                 }
             }
         }
-        const u32 m = __ballot_sync(FULL, ok);
+        const u32 m = BALLOT(ok);
         if (m) { melt(g, list[base + __ffs(m) - 1]); return true; }
     }
     return false;
 }
 // xor.cuh:111-185
-__device__ bool findXORGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
+template <int GS> __device__ bool findXORGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
                             u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     if (g.hdr[D[nd - 1]].y == 2 || g.hdr[F[nf - 1]].y == 2) return false;
     const int maxarity = (int)g.k.xor_max_arity;
@@ -455,9 +476,9 @@ __device__ bool findXORGate(G& g, u32 dx, const u32* D, u32 nd, u32 fx, const u3
         if (!C_ORIGINAL(h.w)) continue;
         const int size = (int)h.y, arity = size - 1;
         if (size < 3 || arity > maxarity) continue;
-        __syncwarp();
+        GSYNC();
         if (LANE == 0) for (int k = 0; k < size; k++) out_c[k] = g.pool[h.x + k];
-        __syncwarp();
+        GSYNC();
         u32 parity = 0;
         int itargets = 1 << arity;
         while (--itargets && makeArity(g, parity, out_c, size)) {}
@@ -485,7 +506,7 @@ __device__ __forceinline__ u64 funWord(int v, bool sign, u32 i) {  // clause2fun
     return ones ? ~0ULL : 0ULL;
 }
 // OR of the literals of clause h other than lit, as a table; false if a variable index >= 12
-__device__ __forceinline__ bool clauseFun(G& g, const uint4 h, u32 lit, Fun2& cls) {
+template <int GS> __device__ __forceinline__ bool clauseFun(GT<GS>& g, const uint4 h, u32 lit, Fun2& cls) {
     cls.a = cls.b = 0;
     const u32* l = g.pool + h.x;
     for (u32 k = 0; k < h.y; k++) {
@@ -498,7 +519,18 @@ __device__ __forceinline__ bool clauseFun(G& g, const uint4 h, u32 lit, Fun2& cl
     }
     return true;
 }
-__device__ bool buildFunAll(G& g, u32 lit, Fun2& f) {  // function.cuh:114-148
+// true iff buildFunAll(lit) would succeed: every non-learnt clause of the list only has mapped neighbours
+template <int GS> __device__ bool funPossible(GT<GS>& g, u32 lit, const u32* list, u32 n) {
+    bool bad = false;
+    for (u32 j = LANE; j < n; j += GS) {
+        const uint4 h = g.hdr[list[j]];
+        if (C_LEARNT(h.w)) continue;
+        const u32* l = g.pool + h.x;
+        for (u32 k = 0; k < h.y; k++) { const u32 other = l[k]; if (other != lit && g.varcore[LABS(other)] >= MAXFUNVAR) { bad = true; break; } }
+    }
+    return !__any_sync(FULL, bad);
+}
+template <int GS> __device__ bool buildFunAll(GT<GS>& g, u32 lit, Fun2& f) {  // function.cuh:114-148
     f.a = f.b = ~0ULL;
     const u32 n = g.otSize[lit];
     const u32* list = g.occurs + g.otStart[lit];
@@ -511,7 +543,7 @@ __device__ bool buildFunAll(G& g, u32 lit, Fun2& f) {  // function.cuh:114-148
     }
     return true;
 }
-__device__ void buildFunTail(G& g, u32 lit, u32 tail, const u32* list, Fun2& fun, bool& core) {  // function.cuh:150-179
+template <int GS> __device__ void buildFunTail(GT<GS>& g, u32 lit, u32 tail, const u32* list, Fun2& fun, bool& core) {  // function.cuh:150-179
     for (u32 j = 0; j < tail; j++) {
         const uint4 h = g.hdr[list[j]];
         if (C_LEARNT(h.w)) continue;
@@ -521,7 +553,7 @@ __device__ void buildFunTail(G& g, u32 lit, u32 tail, const u32* list, Fun2& fun
     }
     if (!__any_sync(FULL, (fun.a | fun.b) != 0)) { melt(g, list[tail]); core = true; }
 }
-__device__ bool findFunGate(G& g, u32 p, u32 n, u32 nOrgCls, const u32* P, u32 np, const u32* N, u32 nn,
+template <int GS> __device__ bool findFunGate(GT<GS>& g, u32 p, u32 n, u32 nOrgCls, const u32* P, u32 np, const u32* N, u32 nn,
                             u32& nElements, u32& nAddedCls, u32& nAddedLits) {  // function.cuh:275-327
     Fun2 pos, neg;
     if (buildFunAll(g, p, pos) && buildFunAll(g, n, neg)) {
@@ -548,13 +580,26 @@ __device__ bool findFunGate(G& g, u32 p, u32 n, u32 nOrgCls, const u32* P, u32 n
 }
 
 // ------------------------------------------------------------------ BVE phase 1 (bounded.cuh:282-394)
-#define VE_SLICE 256  // words of shared memory per warp (out_c of the gate searches, >= SH_MAX_BVE_OUT1)
+#define VE_SLICE 256       // words of shared memory per 32-lane group (out_c of the gate searches, >= SH_MAX_BVE_OUT1)
+#define VE_SLICE_SMALL 64  // per 4/8-lane group: those classes hold variables with <= BIN_T8 occurrences
+#define BIN_T4 12u         // occurrences (pos + neg) up to which a variable runs on a 4-lane group
+#define BIN_T8 48u         // ... on an 8-lane group; above: a full warp
 
-__global__ void __launch_bounds__(128) k_ve_phase1(G g) {
-    __shared__ u32 sh[4][VE_SLICE];
-    u32* out_c = sh[threadIdx.x >> 5];
-    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
+// `wl` = indices into elected[] of this group-size class (k_bin_elected).  Groups of fewer than 32
+// lanes do not carry the 4096-bit function tables: a variable that reaches the function-table step
+// with every neighbour mapped (varcore < 12; rare - only 12 variables are mapped per round) has
+// no side effects yet (failed gate attempts restore their marks) and is handed to the 32-lane
+// instance through `redo`.
+template <int GS>
+__global__ void __launch_bounds__(128) k_ve_phase1(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount,
+                                                   u32* __restrict__ redo, u32* redoCount) {
+    constexpr int SLICE = GS == 32 ? VE_SLICE : VE_SLICE_SMALL;
+    __shared__ u32 sh[128 / GS][SLICE];
+    u32* out_c = sh[threadIdx.x / GS];
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 count = *wlCount;
+    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
+        const u32 tid = wl[wi];
         const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
         const u32 np = g.otSize[p], nn = g.otSize[n];
         const u32* P = g.occurs + g.otStart[p];
@@ -592,9 +637,16 @@ __global__ void __launch_bounds__(128) k_ve_phase1(G g) {
                     else if (findXORGate(g, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
                     else if (!nAddedCls && findXORGate(g, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
                 }
-                if (g.k.ve_fun_en && !elimType && nClsBefore > 2 &&
-                    findFunGate(g, p, n, nClsBefore, P, np, N, nn, nElements, nAddedCls, nAddedLits))
-                    elimType = CORE_MASK;
+                bool funHit = false;
+                if (g.k.ve_fun_en && !elimType && nClsBefore > 2) {
+                    if constexpr (GS == 32) funHit = findFunGate(g, p, n, nClsBefore, P, np, N, nn, nElements, nAddedCls, nAddedLits);
+                    else if (funPossible(g, p, P, np) && funPossible(g, n, N, nn)) {
+                        if (LANE == 0) redo[atomicAdd(redoCount, 1u)] = tid;
+                        GSYNC();
+                        continue;
+                    }
+                }
+                if (funHit) elimType = CORE_MASK;
                 else if (!elimType && !nAddedCls && !countPairs(g, 1, x, P, np, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits))
                     elimType = RES_MASK;
                 if (!nAddedCls) { toblivionSave(g, p, n, pOrgs, nOrgs, P, np, N, nn); eliminatedNow = true; }
@@ -608,7 +660,7 @@ __global__ void __launch_bounds__(128) k_ve_phase1(G g) {
             } else { g.veType[tid] = 0; g.veUcnt[tid] = 0; g.veRpos[tid] = 0; g.veRref[tid] = 0; }
             if (eliminatedNow) g.eliminated[x] |= MELTING_MASK;
         }
-        __syncwarp();
+        GSYNC();
     }
 }
 
@@ -616,9 +668,13 @@ __global__ void __launch_bounds__(128) k_ve_phase1(G g) {
 // start values of the scans: CNF sizes before this BVE (elimination.cu:82-92)
 struct VEBase { u32 numCls0, poolUsed0; u64 dataSize0; };
 
-__global__ void __launch_bounds__(128) k_ve_phase3(G g, VEBase vb, u32* __restrict__ survivorFlag) {
-    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
+template <int GS>
+__global__ void __launch_bounds__(128) k_ve_phase3(GT<GS> g, VEBase vb, u32* __restrict__ survivorFlag, const u32* __restrict__ wl,
+                                                   const u32* __restrict__ wlCount) {
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 count = *wlCount;
+    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
+        const u32 tid = wl[wi];
         const u32 x = g.elected[tid];
         const u32 xinfo = g.veType[tid], elimType = RECOVERTYPE(xinfo);
         if (elimType) {
@@ -643,7 +699,7 @@ __global__ void __launch_bounds__(128) k_ve_phase3(G g, VEBase vb, u32* __restri
                 const u32 nUnitsExp = g.veUcnt[tid];
                 u32 ucursor = nUnitsExp ? reserveUnits(g, nUnitsExp) : 0;
                 const u64 total = (u64)np * nn;
-                for (u64 t0 = 0; t0 < total && clsOut < checksum; t0 += 32) {
+                for (u64 t0 = 0; t0 < total && clsOut < checksum; t0 += GS) {
                     const u64 t = t0 + LANE;
                     int rsize = 0;
                     uint4 hi = make_uint4(0, 0, 0, 0), hj = hi;
@@ -659,11 +715,11 @@ __global__ void __launch_bounds__(128) k_ve_phase3(G g, VEBase vb, u32* __restri
                         }
                     }
                     const bool isCls = rsize > 1, isUnit = rsize == 1;
-                    const u32 mc = __ballot_sync(FULL, isCls), mu = __ballot_sync(FULL, isUnit);
-                    const u32 myCls = __popc(mc & lanemaskLt());
-                    const u32 wordsIncl = warpIncl(isCls ? (u32)rsize : 0u);
+                    const u32 mc = BALLOT(isCls), mu = BALLOT(isUnit);
+                    const u32 myCls = __popc(mc & LTMASK);
+                    const u32 wordsIncl = gIncl<GS>(isCls ? (u32)rsize : 0u);
                     const u32 myWords = wordsIncl - (isCls ? (u32)rsize : 0u);
-                    const u32 totWords = __shfl_sync(FULL, wordsIncl, 31);
+                    const u32 totWords = __shfl_sync(FULL, wordsIncl, GS - 1, GS);
                     if (isCls && clsOut + myCls < checksum) {
                         u32 sig;
                         u32* out = g.pool + poolOut + myWords;
@@ -674,12 +730,12 @@ __global__ void __launch_bounds__(128) k_ve_phase3(G g, VEBase vb, u32* __restri
                     if (isUnit) {
                         u32 sig, lit;
                         mergeOut(g.pool + hi.x, (int)hi.y, g.pool + hj.x, (int)hj.y, x, &lit, sig);
-                        const u32 slot = ucursor + __popc(mu & lanemaskLt());
+                        const u32 slot = ucursor + __popc(mu & LTMASK);
                         if (slot < g.unitsCap) g.units[slot] = lit; else atomicOr(&g.dc->flags, 2u);
                     }
                     clsOut += __popc(mc); poolOut += totWords; ucursor += __popc(mu);
                 }
-                __syncwarp();
+                GSYNC();
                 deleteAll(g, P, np);
                 deleteAll(g, N, nn);
                 if (LANE == 0) {
@@ -687,7 +743,7 @@ __global__ void __launch_bounds__(128) k_ve_phase3(G g, VEBase vb, u32* __restri
                     g.eliminated[x] |= (MELTING_MASK | ADDING_MASK);
                     atomicMax(&g.dc->lastElimID, (int)tid);
                 }
-                __syncwarp();
+                GSYNC();
             }
             else {
                 if (LANE == 0) atomicOr(&g.dc->flags, 4u);
@@ -695,7 +751,7 @@ __global__ void __launch_bounds__(128) k_ve_phase3(G g, VEBase vb, u32* __restri
             }
         }
         if (LANE == 0) survivorFlag[tid] = g.eliminated[x] ? 0u : 1u;
-        __syncwarp();
+        GSYNC();
     }
 }
 
@@ -759,7 +815,7 @@ __device__ __forceinline__ bool subMerge(const u32* d1, int n1, const u32* d2, i
 }
 
 // one side of sub_k: every clause of M against the other list O, then against its predecessors in M
-__device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, u32 fx) {
+template <int GS> __device__ u32 subSide(GT<GS>& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, u32 fx) {
     u32 nUnits = 0;
     for (u32 i = 0; i < nm; i++) {
         const u32 ci = M[i];
@@ -768,7 +824,7 @@ __device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, 
         if (C_DELETED(h.w)) continue;
         // selfsubsume (subsume.cuh:344-400): first neg clause, in list order, that strengthens cand
         bool hit = false;
-        for (u32 base = 0; base < no; base += 32) {
+        for (u32 base = 0; base < no; base += GS) {
             const u32 j = base + LANE;
             bool brk = false, ok = false;
             if (j < no) {
@@ -777,7 +833,7 @@ __device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, 
                 else if (!C_DELETED(hj.w) && !C_MOLTEN(hj.w) && hj.y > 1 && selfsubSig(hj.z, h.z) &&
                          selfsubMerge(g.pool + hj.x, (int)hj.y, g.pool + h.x, (int)h.y, x, fx)) ok = true;
             }
-            const u32 bm = __ballot_sync(FULL, brk), om = __ballot_sync(FULL, ok);
+            const u32 bm = BALLOT(brk), om = BALLOT(ok);
             const u32 fb = bm ? (u32)__ffs(bm) - 1 : 32u, fo = om ? (u32)__ffs(om) - 1 : 32u;
             if (fo < fb) { hit = true; break; }
             if (bm) break;
@@ -801,13 +857,13 @@ __device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, 
                 h.w |= CB_MOLTEN;
                 g.hdr[ci] = h;
             }
-            __syncwarp();
+            GSYNC();
             h = g.hdr[ci];
             if (h.y == 1) nUnits++;
         }
         // subsume (subsume.cuh:305-342): first earlier clause of the same list that subsumes cand
         const bool candMolten = C_MOLTEN(h.w) != 0;
-        for (u32 base = 0; base < i; base += 32) {
+        for (u32 base = 0; base < i; base += GS) {
             const u32 j = base + LANE;
             bool ok = false;
             if (j < i) {
@@ -815,7 +871,7 @@ __device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, 
                 if (!C_DELETED(hj.w) && !(candMolten && hj.y > h.y) && hj.y > 1 && SUBSIG(hj.z, h.z) &&
                     subMerge(g.pool + hj.x, (int)hj.y, g.pool + h.x, (int)h.y)) ok = true;
             }
-            const u32 om = __ballot_sync(FULL, ok);
+            const u32 om = BALLOT(ok);
             if (om) {
                 const u32 cj = M[base + __ffs(om) - 1];
                 if (LANE == 0) {
@@ -823,7 +879,7 @@ __device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, 
                     if (C_LEARNT(wj) && C_ORIGINAL(h.w)) g.hdr[cj].w = wj & ~CB_ST_MASK;
                     g.hdr[ci].w = (h.w & ~CB_ST_MASK) | CB_DELETED;
                 }
-                __syncwarp();
+                GSYNC();
                 break;
             }
         }
@@ -831,12 +887,12 @@ __device__ u32 subSide(G& g, const u32* M, u32 nm, const u32* O, u32 no, u32 x, 
     return nUnits;
 }
 // updateOL (subsume.cuh:293-303): drop molten (un-melting them) and deleted clauses, keep order
-__device__ void updateOL(G& g, u32 lit) {
+template <int GS> __device__ void updateOL(GT<GS>& g, u32 lit) {
     const u32 n = g.otSize[lit];
     if (!n) return;
     u32* list = g.occurs + g.otStart[lit];
     u32 out = 0;
-    for (u32 base = 0; base < n; base += 32) {
+    for (u32 base = 0; base < n; base += GS) {
         const u32 j = base + LANE;
         u32 ci = 0; bool keep = false;
         if (j < n) {
@@ -845,20 +901,22 @@ __device__ void updateOL(G& g, u32 lit) {
             if (C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN;
             else if (!C_DELETED(w)) keep = true;
         }
-        const u32 m = __ballot_sync(FULL, keep);
-        __syncwarp();
-        if (keep) list[out + __popc(m & lanemaskLt())] = ci;
+        const u32 m = BALLOT(keep);
+        GSYNC();
+        if (keep) list[out + __popc(m & LTMASK)] = ci;
         out += __popc(m);
-        __syncwarp();
+        GSYNC();
     }
     if (LANE == 0) g.otSize[lit] = out;
-    __syncwarp();
+    GSYNC();
 }
 
-__global__ void __launch_bounds__(128) k_sub(G g) {
-    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
-        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
+template <int GS>
+__global__ void __launch_bounds__(128) k_sub(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount) {
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 count = *wlCount;
+    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
+        const u32 x = g.elected[wl[wi]], p = V2L(x), n = p | 1u;
         const u32 np = g.otSize[p], nn = g.otSize[n];
         if (np > g.k.sub_max_occurs || nn > g.k.sub_max_occurs) continue;
         const u32* P = g.occurs + g.otStart[p];
@@ -876,10 +934,12 @@ __global__ void __launch_bounds__(128) k_sub(G g) {
 }
 
 // ------------------------------------------------------------------ BCE (blocked.cuh:26-97)
-__global__ void __launch_bounds__(128) k_bce(G g) {
-    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < g.numElected; tid += warpsPerGrid) {
-        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
+template <int GS>
+__global__ void __launch_bounds__(128) k_bce(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount) {
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 count = *wlCount;
+    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
+        const u32 x = g.elected[wl[wi]], p = V2L(x), n = p | 1u;
         const u32 np = g.otSize[p], nn = g.otSize[n];
         if (np > g.k.bce_max_occurs || nn > g.k.bce_max_occurs) continue;
         const u32* P = g.occurs + g.otStart[p];
@@ -888,7 +948,7 @@ __global__ void __launch_bounds__(128) k_bce(G g) {
             const u32 ci = N[i]; const uint4 hi = g.hdr[ci];
             if (C_DELETED(hi.w) || C_LEARNT(hi.w)) continue;
             bool nonTaut = false;
-            for (u32 base = 0; base < np && !nonTaut; base += 32) {
+            for (u32 base = 0; base < np && !nonTaut; base += GS) {
                 const u32 j = base + LANE;
                 bool nt = false;
                 if (j < np) {
@@ -909,7 +969,8 @@ __global__ void __launch_bounds__(128) k_bce(G g) {
 
 // ------------------------------------------------------------------ ERE (redundancy.cuh:99-174)
 #define ERE_SLICE 256
-__global__ void __launch_bounds__(128) k_ere(G g) {
+__global__ void __launch_bounds__(128) k_ere(GT<32> g) {
+    constexpr int GS = 32;
     __shared__ u32 sh[4][ERE_SLICE];
     u32* m_c = sh[threadIdx.x >> 5];
     const int clause_max = g.k.ere_clause_max;
@@ -927,12 +988,12 @@ __global__ void __launch_bounds__(128) k_ere(G g) {
             for (u32 j = 0; j < fs; j++) {
                 const uint4 hn = g.hdr[N[j]];
                 if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
-                __syncwarp();
+                GSYNC();
                 u32 m_sig = 0; int m_len = 0;
                 if (LANE == 0) m_len = mergeOut(g.pool + hp.x, (int)hp.y, g.pool + hn.x, (int)hn.y, v, m_c, m_sig);
-                m_len = __shfl_sync(FULL, m_len, 0);
-                m_sig = __shfl_sync(FULL, m_sig, 0);
-                __syncwarp();
+                m_len = __shfl_sync(FULL, m_len, 0, GS);
+                m_sig = __shfl_sync(FULL, m_sig, 0, GS);
+                GSYNC();
                 if (m_len <= 1) continue;
                 const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
                 // forward_equ: smallest list among the resolvent's literals
@@ -940,7 +1001,7 @@ __global__ void __launch_bounds__(128) k_ere(G g) {
                 u32 minsize = g.otSize[best];
                 for (int k = 1; k < m_len; k++) { const u32 lit = m_c[k]; const u32 ls = g.otSize[lit]; if (ls < minsize) { minsize = ls; best = lit; } }
                 const u32* minList = g.occurs + g.otStart[best];
-                for (u32 e = LANE; e < minsize; e += 32) {
+                for (u32 e = LANE; e < minsize; e += GS) {
                     const u32 ci = minList[e];
                     const uint4 h = g.hdr[ci];
                     if ((int)h.y == m_len && (C_LEARNT(h.w) || (h.w & CB_ST_MASK) == type) && SUBSIG(m_sig, h.z) && !C_DELETED(h.w)) {
@@ -955,27 +1016,176 @@ __global__ void __launch_bounds__(128) k_ere(G g) {
     }
 }
 
+
+// ------------------------------------------------------------------ ERE, lane per resolvent
+// Same semantics as k_ere above (and ere_k, redundancy.cuh:136-174), different work mapping:
+//   * one warp per elected variable, one LANE per (pos, neg) pair - the 32 lanes build 32
+//     different resolvents at once instead of rebuilding the same one;
+//   * the resolvent is never stored: one merge pass yields its length, first/last literal,
+//     signature and the literal with the shortest occurrence list;
+//   * a clause equal to the resolvent has the same (size, first, last, sig), which is exactly the
+//     key the occurrence lists are sorted by (key.cuh:67-83), so the candidates are found by a
+//     binary search over the sorted list instead of scanning it: ~log2(n) key probes of 16 B
+//     replace n header reads;
+//   * the reference's rule "lane t checks entries t, t+32, ... and deletes its first match" is
+//     kept exactly: within the run of key-equal entries, the first matching entry of every
+//     residue class (position mod 32) is deleted.
+// Algorithmic bytes per resolvent: 2 clause reads (L1/L2 resident per variable) + 4 B per
+// resolvent literal (list sizes) + 20 B per binary-search probe.
+__device__ __forceinline__ int keyCmp(const uint4 k, u32 sz, u32 first, u32 last, u32 sig) {
+    if (k.x != sz) return k.x < sz ? -1 : 1;
+    if (k.y != first) return k.y < first ? -1 : 1;
+    if (k.z != last) return k.z < last ? -1 : 1;
+    if (k.w != sig) return k.w < sig ? -1 : 1;
+    return 0;
+}
+// does the resolvent of a and b on x equal cand[0..len)?  (same merge as mergeOut, streamed)
+__device__ __forceinline__ bool resolventEquals(const u32* a, int n1, const u32* b, int n2, u32 x, const u32* cand) {
+    int it1 = 0, it2 = 0, k = 0;
+    while (it1 < n1 && it2 < n2) {
+        const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
+        if (v1 == x) it1++;
+        else if (v2 == x) it2++;
+        else if (v1 < v2) { it1++; if (cand[k++] != lit1) return false; }
+        else if (v2 < v1) { it2++; if (cand[k++] != lit2) return false; }
+        else { it1++; it2++; if (cand[k++] != lit1) return false; }
+    }
+    while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != x && cand[k++] != l) return false; }
+    while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != x && cand[k++] != l) return false; }
+    return true;
+}
+
+template <int GS>
+__global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount) {
+    const int clause_max = g.k.ere_clause_max;
+    const u32 lane = LANE;
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 count = *wlCount;
+    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
+        const u32 v = g.elected[wl[wi]], p = V2L(v), n = p | 1u;
+        const u32 ds = g.otSize[p], fs = g.otSize[n];
+        if (!(ds && fs && ds <= g.k.ere_max_occurs && fs <= g.k.ere_max_occurs)) continue;
+        const u32* P = g.occurs + g.otStart[p];
+        const u32* N = g.occurs + g.otStart[n];
+        if ((int)g.hdr[P[0]].y > clause_max || (int)g.hdr[N[0]].y > clause_max) continue;
+        const u64 total = (u64)ds * fs;
+        for (u64 t = lane; t < total; t += GS) {
+            const u32 i = (u32)(t / fs), j = (u32)(t - (u64)i * fs);
+            const uint4 hp = g.hdr[P[i]];
+            if (C_DELETED(hp.w)) continue;
+            const uint4 hn = g.hdr[N[j]];
+            if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
+            const u32* a = g.pool + hp.x; const int n1 = (int)hp.y;
+            const u32* b = g.pool + hn.x; const int n2 = (int)hn.y;
+            // one merge pass: length, tautology, first / last literal, signature, shortest list
+            int it1 = 0, it2 = 0; u32 len = 0, first = 0, last = 0, sig = 0, best = 0, minsize = 0xFFFFFFFFu;
+            bool taut = false;
+#define ERE_EMIT(L_) do { const u32 l_ = (L_); if (!len) first = l_; last = l_; len++; sig |= MAPHASH(l_); \
+                          const u32 s_ = g.otSize[l_]; if (s_ < minsize) { minsize = s_; best = l_; } } while (0)
+            while (it1 < n1 && it2 < n2) {
+                const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
+                if (v1 == v) it1++;
+                else if (v2 == v) it2++;
+                else if (IS_TAUT(lit1, lit2)) { taut = true; break; }
+                else if (v1 < v2) { it1++; ERE_EMIT(lit1); }
+                else if (v2 < v1) { it2++; ERE_EMIT(lit2); }
+                else { it1++; it2++; ERE_EMIT(lit1); }
+            }
+            if (taut) continue;
+            while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != v) ERE_EMIT(l); }
+            while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
+#undef ERE_EMIT
+            if (len <= 1 || !minsize) continue;
+            const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
+            // lower bound of the key in the sorted list of `best`
+            const u32* list = g.occurs + g.otStart[best];
+            u32 lo = 0, hi = minsize;
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                if (keyCmp(g.key[list[mid]], len, first, last, sig) < 0) lo = mid + 1; else hi = mid;
+            }
+            u32 done = 0;
+            for (u32 e = lo; e < minsize; e++) {
+                const u32 ci = list[e];
+                if (keyCmp(g.key[ci], len, first, last, sig) != 0) break;
+                const u32 r = e & 31u;
+                if ((done >> r) & 1u) continue;
+                const uint4 h = g.hdr[ci];
+                if ((C_LEARNT(h.w) || (h.w & CB_ST_MASK) == type) && !C_DELETED(h.w) && h.y == len &&
+                    resolventEquals(a, n1, b, n2, v, g.pool + h.x)) {
+                    g.hdr[ci].w = (h.w & ~CB_ST_MASK) | CB_DELETED;
+                    done |= 1u << r;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ group-size classes
+// elected[] indices split by occurrence count of the variable; order inside a class is arbitrary
+// (nothing observable depends on it: scan offsets are indexed by the position in elected[])
+__global__ void k_bin_reset(DevCounters* dc) { dc->bin[0] = dc->bin[1] = dc->bin[2] = dc->bin[3] = 0; }
+__global__ void k_bin_elected(const u32* __restrict__ elected, const u32* nDev, u32 nHost, const u32* __restrict__ otSize, u32 t4, u32 t8,
+                              u32* __restrict__ wl4, u32* __restrict__ wl8, u32* __restrict__ wl32, DevCounters* dc) {
+    const u32 n = nDev ? *nDev : nHost;
+    for (u32 i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const u32 i = i0 + threadIdx.x;
+        int cls = -1;
+        if (i < n) {
+            const u32 x = elected[i];
+            const u32 deg = otSize[V2L(x)] + otSize[V2L(x) | 1u];
+            cls = deg <= t4 ? 0 : deg <= t8 ? 1 : 2;
+        }
+        for (int k = 0; k < 3; k++) {
+            const u32 m = __ballot_sync(0xffffffffu, cls == k);
+            if (!m) continue;
+            u32 base = 0;
+            const u32 leader = __ffs(m) - 1;
+            if (laneId() == leader) base = atomicAdd(&dc->bin[k], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cls == k) (k == 0 ? wl4 : k == 1 ? wl8 : wl32)[base + __popc(m & lanemaskLt())] = i;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host launchers
 static G makeG(Ctx* c, const KOpts& k) {
     G g;
     g.hdr = c->hdr[c->cur]; g.pool = c->pool[c->cur];
-    g.otStart = c->otStart; g.otSize = c->otSize; g.occurs = c->occurs;
+    g.otStart = c->otStart; g.otSize = c->otSize; g.occurs = c->occurs; g.key = c->key;
     g.elected = c->elected; g.eliminated = c->eliminated; g.vorg = c->vorg; g.varcore = c->varcore;
     g.units = c->units; g.unitsCap = 2 * (c->V + 1); g.resolved = c->resolved; g.resolvedCap = c->resolvedCap;
     g.veType = c->veType; g.veUcnt = c->veUcnt; g.veRpos = c->veRpos; g.veRref = c->veRref;
     g.dc = c->dc; g.k = k; g.numElected = c->numElected;
     return g;
 }
-static u32 warpGrid(u32 nWarps, u32 warpsPerBlock) {
-    u32 b = divup(nWarps, warpsPerBlock);
-    const u32 cap = 148u * 16;
-    return b > cap ? cap : (b ? b : 1);
+template <int GS> static GT<GS> asGroup(const G& g) { GT<GS> t; static_cast<G&>(t) = g; return t; }
+// enough CTAs for `n` groups of GS lanes, capped: the kernels stride over their worklist
+static u32 groupGrid(u32 nGroups, u32 GS, u32 block) {
+    const u64 b = ((u64)nGroups * GS + block - 1) / block;
+    const u64 cap = 148ull * 16;
+    return (u32)(b > cap ? cap : (b ? b : 1));
 }
+// worklists of the three classes live in the MIS scratch (free between election and the next round)
+static void binElected(Ctx* c, const KOpts& k, bool countOnDevice) {
+    // long XOR arities need the big shared-memory slice: everything runs on full warps then
+    const u32 t4 = k.xor_max_arity + 2 > VE_SLICE_SMALL ? 0 : BIN_T4, t8 = k.xor_max_arity + 2 > VE_SLICE_SMALL ? 0 : BIN_T8;
+    LAUNCH(c, k_bin_reset, 1, 1, 0, c->dc);
+    LAUNCH(c, k_bin_elected, gridFor(c->numElected, 256), 256, 0, c->elected, countOnDevice ? &c->dc->numElected : nullptr, c->numElected,
+           c->otSize, t4, t8, c->wlA, c->wlB, c->sortK, c->dc);
+}
+#define LAUNCH_CLASSES(c, kern, block, E, g, ...)                                                            \
+    do {                                                                                                     \
+        LAUNCH(c, kern<4>, groupGrid(E, 4, block), block, 0, asGroup<4>(g), ##__VA_ARGS__, c->wlA, &c->dc->bin[0]);   \
+        LAUNCH(c, kern<8>, groupGrid(E, 8, block), block, 0, asGroup<8>(g), ##__VA_ARGS__, c->wlB, &c->dc->bin[1]);   \
+        LAUNCH(c, kern<32>, groupGrid(E, 32, block), block, 0, asGroup<32>(g), ##__VA_ARGS__, c->sortK, &c->dc->bin[2]); \
+    } while (0)
 
 void launchSUB(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
-    LAUNCH(c, k_sub, warpGrid(c->numElected, 4), 128, 0, g);
+    binElected(c, k, false);
+    LAUNCH_CLASSES(c, k_sub, 128, c->numElected, g);
 }
 
 // veAsync + postVE (elimination.cu:131-154, 235-266)
@@ -984,13 +1194,19 @@ void launchVE(Ctx* c, const KOpts& k) {
     G g = makeG(c, k);
     const u32 E = c->numElected;
     LAUNCH(c, k_ve_reset, 1, 1, 0, c->dc);
-    LAUNCH(c, k_ve_phase1, warpGrid(E, 4), 128, 0, g);
+    binElected(c, k, false);   // SUB shrank the lists: classes by the current sizes
+    u32* redo = c->rank;       // rank[] is dead after the election
+    u32* redoCount = &c->dc->bin[3];
+    LAUNCH(c, k_ve_phase1<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
+    LAUNCH(c, k_ve_phase1<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
+    LAUNCH(c, k_ve_phase1<32>, groupGrid(E, 32, 128), 128, 0, asGroup<32>(g), c->sortK, &c->dc->bin[2], redo, redoCount);
+    LAUNCH(c, k_ve_phase1<32>, 148, 128, 0, asGroup<32>(g), redo, redoCount, redo, redoCount);   // variables handed over by the small groups
     // phase 2: exclusive scans seeded with the current CNF sizes
     VEBase vb;
     vb.numCls0 = c->hdc->numCls; vb.poolUsed0 = c->hdc->poolUsed; vb.dataSize0 = c->hdc->dataSize;
     scanExclusiveU32(c, c->veRpos, c->veRpos, E, vb.numCls0, nullptr);
     scanExclusiveU64(c, c->veRref, c->veRref, E, vb.dataSize0);
-    LAUNCH(c, k_ve_phase3, warpGrid(E, 4), 128, 0, g, vb, c->flagA);
+    LAUNCH_CLASSES(c, k_ve_phase3, 128, E, g, vb, c->flagA);
     LAUNCH(c, k_ve_resize, 1, 1, 0, g, vb);
     // elected := survivors, order kept (cub::DeviceSelect::If in postVE)
     scanExclusiveU32(c, c->flagA, c->flagB, E, 0, &c->dc->numElected);
@@ -1004,11 +1220,15 @@ void launchVE(Ctx* c, const KOpts& k) {
 void launchBCE(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
-    LAUNCH(c, k_bce, warpGrid(c->numElected, 4), 128, 0, g);
+    binElected(c, k, false);
+    LAUNCH_CLASSES(c, k_bce, 128, c->numElected, g);
 }
 
 void launchERE(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
-    LAUNCH(c, k_ere, warpGrid(c->numElected, 4), 128, 0, g);
+    static const bool v0 = getenv("SIGMA_ERE_V0") != nullptr;   // the warp-per-resolvent kernel, kept for A/B checks
+    if (v0) { LAUNCH(c, k_ere, groupGrid(c->numElected, 32, 128), 128, 0, asGroup<32>(g)); return; }
+    binElected(c, k, false);
+    LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g);
 }

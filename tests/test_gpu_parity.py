@@ -216,9 +216,11 @@ def test_reload_reuses_arena_and_is_idempotent():
     a = s.simplify(); da = to_dump(V, s.store(), a["cnfstate"])
     b = s.simplify(); db = to_dump(V, s.store(), b["cnfstate"])
     assert not sgd.compare(da, db)
-    V2, l2, o2 = helpers.gen_cnf("ksat", 11, [600, 2520, 3])
+    V2, l2, o2 = helpers.gen_cnf("ksat", 14, [500, 2000, 3])   # smaller: fits the arena already held
     s.load(V2, l2, o2)
-    s.simplify()
+    c = s.simplify()
+    od, _, _ = helpers.run_oracle(V2, l2, o2)
+    assert not sgd.compare(to_dump(V2, s.store(), c["cnfstate"]), od)
     assert s.memory()["cuda_mallocs"] == 1
     s.close()
 
