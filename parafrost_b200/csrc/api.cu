@@ -219,7 +219,8 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
     if (!c || !lits || !offs || !max_var) return SIGMA_BAD_ARGUMENT;
     CUDA_TRY(cudaSetDevice(c->device));
     const u64 L0 = offs[num_clauses];
-    if (max_var >= 0x7FFFFFFEu || num_clauses >= 0xFFFFFFF0ull) return SIGMA_BAD_ARGUMENT;
+    // election words carry a 27-bit rank (lcve.cu); clause indices are 32-bit
+    if (max_var >= (1u << 27) - 2 || num_clauses >= 0xFFFFFFF0ull) return SIGMA_BAD_ARGUMENT;
     // stats.clauses.original / stats.literals.original (solver.hpp:164-165)
     u64 orgC = num_clauses, orgL = L0;
     if (meta) {

@@ -62,7 +62,7 @@ void launchAwaken(Ctx* c) {
 // ------------------------------------------------------------------ histogram + sort keys
 // algorithmic bytes: read 16C + 4L, 4 per literal of atomic traffic on hist (L2 resident), write 16C keys
 __global__ void k_hist_key(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
-                           u32* __restrict__ hist, uint4* __restrict__ key) {
+                           u32* __restrict__ hist, uint4* __restrict__ key, u32* flags) {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint4 h = hdr[i];
         if (C_DELETED(h.w)) continue;
@@ -76,28 +76,35 @@ __global__ void k_hist_key(const uint4* __restrict__ hdr, const u32* __restrict_
             atomicAdd(&hist[lit], 1u);
         }
         key[i] = make_uint4(h.y, first, last, h.z);
+        if (sz >= (1 << 14)) atomicOr(flags, 8u);   // the list sort's folded key needs size < 2^14 (otsort.cu)
     }
 }
 
 void launchHistKey(Ctx* c) {
     cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
     const u32 n = c->hdc->numCls;
-    if (n) LAUNCH(c, k_hist_key, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->hist, c->key);
+    if (n) LAUNCH(c, k_hist_key, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->hist, c->key, &c->dc->flags);
 }
 
 // ------------------------------------------------------------------ scatter (occurrence lists)
 // algorithmic bytes: read 16C + 4L, write 4L list entries (random), one atomic per literal
-__global__ void k_scatter(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
-                          const u32* __restrict__ otStart, u32* __restrict__ otSize, u32* __restrict__ occurs) {
+__global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                                                 const u32* __restrict__ otStart, u32* __restrict__ otSize, u32* __restrict__ occurs) {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint4 h = hdr[i];
         if (C_DELETED(h.w)) continue;
         const u32* l = pool + h.x;
         const int sz = (int)h.y;
-        for (int k = 0; k < sz; k++) {
-            const u32 lit = l[k];
-            const u32 pos = atomicAdd(&otSize[lit], 1u);
-            occurs[otStart[lit] + pos] = i;
+        // 8 literals in flight per thread: the slot atomics and the list-start loads of a batch are
+        // independent, only the final stores wait for them
+        for (int k0 = 0; k0 < sz; k0 += 8) {
+            u32 lit[8], pos[8], st[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k0 + k < sz) lit[k] = l[k0 + k];
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k0 + k < sz) { st[k] = otStart[lit[k]]; pos[k] = atomicAdd(&otSize[lit[k]], 1u); }
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k0 + k < sz) occurs[st[k] + pos[k]] = i;
         }
     }
 }

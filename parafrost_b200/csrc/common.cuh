@@ -96,11 +96,13 @@ struct DevCounters {
     int lastElimID;    // lastEliminatedID (cnf.cu:29)
     u32 misStopRank;
     u32 wlNext;        // MIS worklist append cursor
-    u32 flags;         // bit0: resolved overflow, bit1: units overflow, bit2: hole after failed MEMORY_SAFE
+    u32 wlCnt[3];      // rotating MIS worklist sizes (lcve.cu)
+    u32 flags;         // bit0: resolved overflow, bit1: units overflow, bit2: hole after failed MEMORY_SAFE, bit3: a clause with >= 2^14 literals
     u32 bcpCurr, bcpNext, bcpConfl, bcpLevel;
     u32 nFrozen;       // number of first-frozen variables mapped into varcore (<= 12 needed)
     u32 unassignedDec; // variables assigned by prop()
-    u32 qMed, qBig, qHuge; // list-sort work queues
+    u32 qMed, qBig, qHuge; // (unused)
+    u32 sortCnt[9], sortCur[9];   // list-sort length classes (otsort.cu)
     u32 addedCls;      // resolvents appended by the last BVE
     u32 bin[4];        // group-size class sizes of the elected variables (elim.cu) + redo queue
     u32 scratch[8];

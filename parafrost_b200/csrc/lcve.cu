@@ -20,10 +20,15 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------ scores
+// Per-variable election word vinfo[v] = rank << 5 | class << 3 | state : one 4-byte load per
+// neighbour in the MIS rounds instead of three (state byte, class byte, rank word).
+#define VI_STATE(w) ((w) & 7u)
+#define VI_CLASS(w) (((w) >> 3) & 3u)
+#define VI_RANK(w) ((w) >> 5)
+
 __global__ void k_scores(const u32* __restrict__ hist, const unsigned char* __restrict__ vstate,
                          const unsigned char* __restrict__ assumed, u32 V, u32 pmax, u32 nmax, u32 maxoccurs,
-                         u32* __restrict__ keys, u32* __restrict__ vals, unsigned char* __restrict__ cstat,
-                         unsigned char* __restrict__ mis, DevCounters* dc) {
+                         u32* __restrict__ keys, u32* __restrict__ vals, unsigned char* __restrict__ cstat, DevCounters* dc) {
     for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < V; t += gridDim.x * blockDim.x) {
         const u32 v = t + 1;
         const u32 ps = hist[V2L(v)], ns = hist[V2L(v) | 1u];
@@ -33,9 +38,11 @@ __global__ void k_scores(const u32* __restrict__ hist, const unsigned char* __re
         if (!vstate[v] && !(assumed && assumed[v]) && (ps || ns))
             cs = (ps > maxoccurs || ns > maxoccurs || (ps >= pmax && ns >= nmax)) ? CS_STOP : CS_CAND;
         cstat[v] = cs;
-        mis[v] = cs ? MIS_UNDECIDED : MIS_NONE;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { dc->misStopRank = NOVAR; dc->numElected = 0; dc->wlNext = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dc->misStopRank = NOVAR; dc->numElected = 0; dc->wlNext = 0;
+        dc->wlCnt[0] = dc->wlCnt[1] = dc->wlCnt[2] = 0;
+    }
 }
 
 // ------------------------------------------------------------------ LSD radix sort (8-bit digits)
@@ -106,38 +113,52 @@ static void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2,
     }
 }
 
-__global__ void k_rank(const u32* __restrict__ eligible, u32 V, u32* __restrict__ rank) {
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < V; r += gridDim.x * blockDim.x) rank[eligible[r]] = r;
+__global__ void k_rank(const u32* __restrict__ eligible, const unsigned char* __restrict__ cstat, u32 V, u32* __restrict__ vinfo) {
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < V; r += gridDim.x * blockDim.x) {
+        const u32 v = eligible[r];
+        const u32 cs = cstat[v];
+        vinfo[v] = (r << 5) | (cs << 3) | (cs ? MIS_UNDECIDED : MIS_NONE);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) vinfo[0] = 0;
 }
 
 // ------------------------------------------------------------------ MIS
+// worklist counters rotate over three slots: round k reads wlCnt[k%3], appends to wlCnt[(k+1)%3]
+// and clears wlCnt[(k+2)%3], so several rounds can be queued without a host round-trip.
 __global__ void k_mis_fill(const u32* __restrict__ eligible, const unsigned char* __restrict__ cstat, u32 rBegin, u32 rEnd,
-                           u32* __restrict__ wl, DevCounters* dc) {
+                           u32* __restrict__ wl, DevCounters* dc, u32 slot) {
     for (u32 r = rBegin + blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x) {
         const u32 v = eligible[r];
-        if (cstat[v] != CS_NONE) wl[warpAggInc(&dc->wlNext)] = v;
+        if (cstat[v] != CS_NONE) wl[warpAggInc(&dc->wlCnt[slot])] = v;
     }
 }
 
-// one warp per undecided candidate; lanes stride over the clauses of its two lists
-__global__ void __launch_bounds__(256) k_mis_round(const u32* __restrict__ wlIn, u32 nIn, u32* __restrict__ wlOut, DevCounters* dc,
+// one group of GS lanes per undecided candidate; lanes stride over the clauses of its two lists
+template <int GS>
+__global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* __restrict__ wl1, u32 round, DevCounters* dc,
                                                    const uint4* __restrict__ hdr, const u32* __restrict__ pool,
                                                    const u32* __restrict__ otStart, const u32* __restrict__ otSize,
-                                                   const u32* __restrict__ occurs, const u32* __restrict__ rank,
-                                                   const unsigned char* __restrict__ cstat, volatile unsigned char* mis,
-                                                   int maxcsize) {
-    const u32 lane = threadIdx.x & 31u;
-    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < nIn; it += warpsPerGrid) {
+                                                   const u32* __restrict__ occurs, u32* vinfo, int maxcsize) {
+    const u32* wlIn = (round & 1u) ? wl1 : wl0;
+    u32* wlOut = (round & 1u) ? wl0 : wl1;
+    const u32 nIn = dc->wlCnt[round % 3u];
+    u32* outCnt = &dc->wlCnt[(round + 1u) % 3u];
+    if (blockIdx.x == 0 && threadIdx.x == 0) dc->wlCnt[(round + 2u) % 3u] = 0;
+    const u32 lane = threadIdx.x & (u32)(GS - 1);
+    const u32 gbase = (threadIdx.x & 31u) & ~(u32)(GS - 1);
+    const u32 gmask = GS == 32 ? 0xffffffffu : (((1u << (GS & 31)) - 1u) << gbase);
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) / GS; it < nIn; it += groupsPerGrid) {
         const u32 v = wlIn[it];
-        const u32 r = rank[v];
+        const u32 wv = vinfo[v];
+        const u32 r = VI_RANK(wv);
         if (r > dc->misStopRank) continue;  // beyond the cut: never looked at by the serial walk
         bool frozen = false, blocked = false, oversize = false;
         for (u32 side = 0; side < 2; side++) {
             const u32 lit = V2L(v) | side;
             const u32 n = otSize[lit];
             const u32* list = occurs + otStart[lit];
-            for (u32 j = lane; j < n; j += 32) {
+            for (u32 j = lane; j < n; j += GS) {
                 const uint4 h = hdr[list[j]];
                 if (C_DELETED(h.w)) continue;
                 if ((int)h.y > maxcsize) oversize = true;
@@ -145,37 +166,38 @@ __global__ void __launch_bounds__(256) k_mis_round(const u32* __restrict__ wlIn,
                 for (u32 k = 0; k < h.y; k++) {
                     const u32 u = LABS(l[k]);
                     if (u == v) continue;
-                    const unsigned char m = mis[u];
-                    if (m == MIS_ELECTED) { if (rank[u] < r) frozen = true; }
-                    else if (m == MIS_UNDECIDED && cstat[u] == CS_CAND && rank[u] < r) blocked = true;
+                    const u32 wu = vinfo[u];
+                    if (VI_RANK(wu) >= r) continue;
+                    const u32 m = VI_STATE(wu);
+                    if (m == MIS_ELECTED) frozen = true;
+                    else if (m == MIS_UNDECIDED && VI_CLASS(wu) == CS_CAND) blocked = true;
                 }
             }
         }
-        frozen = __any_sync(0xffffffffu, frozen);
-        blocked = __any_sync(0xffffffffu, blocked);
-        oversize = __any_sync(0xffffffffu, oversize);
+        frozen = __any_sync(gmask, frozen);
+        blocked = __any_sync(gmask, blocked);
+        oversize = __any_sync(gmask, oversize);
         if (lane == 0) {
-            if (frozen) mis[v] = MIS_FROZEN;
+            const u32 keep = wv & ~7u;
+            if (frozen) vinfo[v] = keep | MIS_FROZEN;
             else if (!blocked) {
-                if (cstat[v] == CS_STOP) { mis[v] = MIS_LIVESTOP; atomicMin(&dc->misStopRank, r); }
+                if (VI_CLASS(wv) == CS_STOP) { vinfo[v] = keep | MIS_LIVESTOP; atomicMin(&dc->misStopRank, r); }
                 // a clause longer than lcveclausemax makes depFreeze_d fail (lcve.cu:46-51): not elected, freezes nothing
-                else mis[v] = oversize ? MIS_FROZEN : MIS_ELECTED;
+                else vinfo[v] = keep | (oversize ? MIS_FROZEN : MIS_ELECTED);
             }
-            else wlOut[atomicAdd(&dc->wlNext, 1u)] = v;
+            else wlOut[atomicAdd(outCnt, 1u)] = v;
         }
     }
 }
 
-__global__ void k_elect_flags(const u32* __restrict__ eligible, const unsigned char* __restrict__ mis, u32 rEnd, u32* __restrict__ flags) {
+__global__ void k_elect_flags(const u32* __restrict__ eligible, const u32* __restrict__ vinfo, u32 rEnd, u32* __restrict__ flags) {
     for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x)
-        flags[r] = mis[eligible[r]] == MIS_ELECTED ? 1u : 0u;
+        flags[r] = VI_STATE(vinfo[eligible[r]]) == MIS_ELECTED ? 1u : 0u;
 }
-__global__ void k_elect_scatter(const u32* __restrict__ eligible, const unsigned char* __restrict__ mis, u32 rEnd,
+__global__ void k_elect_scatter(const u32* __restrict__ eligible, const u32* __restrict__ flags, u32 rEnd,
                                 const u32* __restrict__ pos, u32* __restrict__ elected) {
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x) {
-        const u32 v = eligible[r];
-        if (mis[v] == MIS_ELECTED) elected[pos[r]] = v;
-    }
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x)
+        if (flags[r]) elected[pos[r]] = eligible[r];
 }
 
 // ------------------------------------------------------------------ function-table indices
@@ -239,45 +261,54 @@ __global__ void __launch_bounds__(128) k_frozen12(const u32* __restrict__ electe
 }
 
 // ------------------------------------------------------------------ host driver
+#define MIS_BATCH 4   // MIS rounds queued per host round-trip
+
 int runLCVE(Ctx* c) {
     const u32 V = c->V;
     const u32 pmax = c->o.mu_pos << c->multiplier, nmax = c->o.mu_neg << c->multiplier;
+    u32* vinfo = c->rank;
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
-           c->scores, c->eligible, c->cstat, c->mis, c->dc);
+           c->scores, c->eligible, c->cstat, c->dc);
     radixSortPairs(c, c->scores, c->eligible, c->sortK, c->sortV, V);
-    LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, V, c->rank);
+    LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, c->cstat, V, vinfo);
+    // lanes per candidate: variables of Tseitin-like formulas have a handful of short clauses
+    const bool smallGroups = c->numLiterals <= (u64)24 * V;
 
     u32 hPrev = 0, stopRank = NOVAR, hEnd = 0;
-    u32* wlIn = c->wlA; u32* wlOut = c->wlB;
+    u32 round = 0;   // parity / counter slot of the next MIS round
     while (hPrev < V && stopRank == NOVAR) {
         u64 h64 = hPrev ? (u64)hPrev * 8 : 8192;
         const u32 H = (u32)(h64 > V ? V : h64);
-        LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, c->cstat, hPrev, H, wlIn, c->dc);
-        CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        u32 n = c->hdc->wlNext;
+        // the chunk's candidates go to the input list of round `round`
+        LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, c->cstat, hPrev, H, (round & 1u) ? c->wlB : c->wlA, c->dc, round % 3u);
+        u32 n = H - hPrev;   // upper bound of the worklist until the first read-back
         u32 guard = 0;
         while (n) {
             if (++guard > 100000u) { snprintf(c->err, sizeof c->err, "MIS did not converge"); return SIGMA_AWAKEN_FAIL; }
-            CUDA_TRY(cudaMemsetAsync(&c->dc->wlNext, 0, 4, c->stream));
-            const u32 warps = n, blocks = divup((u64)warps * 32, 256);
-            LAUNCH(c, k_mis_round, blocks > 148u * 32 ? 148u * 32 : blocks, 256, 0, wlIn, n, wlOut, c->dc, c->hdr[c->cur], c->pool[c->cur],
-                   c->otStart, c->otSize, c->occurs, c->rank, c->cstat, c->mis, c->o.lcve_clause_max);
+            const u32 gs = smallGroups ? 8u : 32u;
+            u64 blocks = ((u64)n * gs + 255) / 256;
+            if (blocks > 148ull * 32) blocks = 148ull * 32;
+            for (int b = 0; b < MIS_BATCH; b++, round++) {
+                if (smallGroups)
+                    LAUNCH(c, k_mis_round<8>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
+                           c->otSize, c->occurs, vinfo, c->o.lcve_clause_max);
+                else
+                    LAUNCH(c, k_mis_round<32>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
+                           c->otSize, c->occurs, vinfo, c->o.lcve_clause_max);
+            }
             CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
-            n = c->hdc->wlNext;
-            u32* t = wlIn; wlIn = wlOut; wlOut = t;
+            n = c->hdc->wlCnt[round % 3u];
         }
-        CUDA_TRY(cudaMemsetAsync(&c->dc->wlNext, 0, 4, c->stream));
         stopRank = c->hdc->misStopRank;
         hPrev = H;
         hEnd = H;
     }
     const u32 rEnd = stopRank < hEnd ? stopRank : hEnd;
     if (rEnd) {
-        LAUNCH(c, k_elect_flags, gridFor(rEnd, 256), 256, 0, c->eligible, c->mis, rEnd, c->flagA);
-        scanExclusiveU32(c, c->flagA, c->flagA, rEnd, 0, &c->dc->numElected);
-        LAUNCH(c, k_elect_scatter, gridFor(rEnd, 256), 256, 0, c->eligible, c->mis, rEnd, c->flagA, c->elected);
+        LAUNCH(c, k_elect_flags, gridFor(rEnd, 256), 256, 0, c->eligible, vinfo, rEnd, c->flagA);
+        scanExclusiveU32(c, c->flagA, c->flagB, rEnd, 0, &c->dc->numElected);
+        LAUNCH(c, k_elect_scatter, gridFor(rEnd, 256), 256, 0, c->eligible, c->flagA, rEnd, c->flagB, c->elected);
     }
     if (c->o.ve_fun_en)
         LAUNCH(c, k_frozen12, 1, 128, 0, c->elected, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart, c->otSize, c->occurs,

@@ -10,10 +10,10 @@
 // Algorithmic bytes: 4L (read entries) + 16L (key gather) + 4L (write) = 24L.
 #include "common.cuh"
 
-#define SORT_SMALL 16
 #define SORT_MED 512
 #define SORT_BIG 8192
 #define MED_WARPS 4
+#define NCLASS 9   // list-length classes: <=4 <=8 <=16 <=32 <=64 <=128 (registers), <=512 (warp smem), <=8192 (CTA smem), longer
 
 struct SKey { u64 a, b; u32 id; };
 __device__ __forceinline__ bool skLess(u64 a0, u64 b0, u32 i0, u64 a1, u64 b1, u32 i1) {
@@ -27,34 +27,118 @@ __device__ __forceinline__ void loadKey(const uint4* __restrict__ key, u32 id, u
     b = ((u64)k.z << 32) | k.w;
 }
 
-// thread per literal: sorts short lists in registers, queues the longer ones
-__global__ void k_sort_small(const uint4* __restrict__ key, const u32* __restrict__ otStart, const u32* __restrict__ otSize,
-                             u32* __restrict__ occurs, u32 ND, u32* __restrict__ qMed, u32* __restrict__ qBig,
-                             u32* __restrict__ qHuge, DevCounters* dc) {
+// ------------------------------------------------------------------ length classes
+__device__ __forceinline__ int sortClass(u32 n) {
+    if (n < 2) return -1;
+    if (n <= 4) return 0;
+    if (n <= 8) return 1;
+    if (n <= 16) return 2;
+    if (n <= 32) return 3;
+    if (n <= 64) return 4;
+    if (n <= 128) return 5;
+    if (n <= SORT_MED) return 6;
+    if (n <= SORT_BIG) return 7;
+    return 8;
+}
+// pass 1: class sizes (block-reduced, one atomic per class and block)
+__global__ void __launch_bounds__(256) k_sort_count(const u32* __restrict__ otSize, u32 ND, DevCounters* dc) {
+    __shared__ u32 cnt[NCLASS];
+    if (threadIdx.x < NCLASS) cnt[threadIdx.x] = 0;
+    __syncthreads();
     for (u32 lit = 2 + blockIdx.x * blockDim.x + threadIdx.x; lit < ND; lit += gridDim.x * blockDim.x) {
-        const u32 n = otSize[lit];
-        if (n < 2) continue;
-        if (n > SORT_SMALL) {
-            if (n <= SORT_MED) qMed[atomicAdd(&dc->qMed, 1u)] = lit;
-            else if (n <= SORT_BIG) qBig[atomicAdd(&dc->qBig, 1u)] = lit;
-            else qHuge[atomicAdd(&dc->qHuge, 1u)] = lit;
-            continue;
+        const int k = sortClass(otSize[lit]);
+        if (k >= 0) atomicAdd(&cnt[k], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < NCLASS && cnt[threadIdx.x]) atomicAdd(&dc->sortCnt[threadIdx.x], cnt[threadIdx.x]);
+}
+// pass 2: the literals of class k go to q[start_k ...), start = exclusive sum of the class sizes
+__global__ void __launch_bounds__(256) k_sort_fill(const u32* __restrict__ otSize, u32 ND, u32* __restrict__ q, DevCounters* dc) {
+    __shared__ u32 start[NCLASS];
+    if (threadIdx.x == 0) { u32 s = 0; for (int k = 0; k < NCLASS; k++) { start[k] = s; s += dc->sortCnt[k]; } }
+    __syncthreads();
+    for (u32 l0 = 2 + blockIdx.x * blockDim.x; l0 < ND; l0 += gridDim.x * blockDim.x) {
+        const u32 lit = l0 + threadIdx.x;
+        const int k = lit < ND ? sortClass(otSize[lit]) : -1;
+        for (int kk = 0; kk < NCLASS; kk++) {
+            const u32 m = __ballot_sync(0xffffffffu, k == kk);
+            if (!m) continue;
+            const u32 leader = __ffs(m) - 1;
+            u32 base = 0;
+            if (laneId() == leader) base = atomicAdd(&dc->sortCur[kk], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (k == kk) q[start[kk] + base + __popc(m & lanemaskLt())] = lit;
         }
-        u32* list = occurs + otStart[lit];
-        u64 ka[SORT_SMALL], kb[SORT_SMALL];
-        u32 id[SORT_SMALL];
-        for (u32 j = 0; j < n; j++) {
-            const u32 r = list[j];
-            u64 a, b;
-            loadKey(key, r, a, b);
-            int p = (int)j;
-            while (p > 0 && skLess(a, b, r, ka[p - 1], kb[p - 1], id[p - 1])) {
-                ka[p] = ka[p - 1]; kb[p] = kb[p - 1]; id[p] = id[p - 1];
-                p--;
+    }
+}
+
+// ------------------------------------------------------------------ register sort (lists of <= 128)
+// One group of GS lanes per list, ITEMS entries per lane (entry e lives in lane e % GS, slot
+// e / GS, so list reads and writes are coalesced).  The 16-byte OLIST_CMP key is folded into
+// 128 bits - size:14 | first literal:25 | last literal:25, then signature:32 | clause index:32 -
+// which is exact while every clause is shorter than 2^14 literals and literals are below 2^25
+// (checked on the host; otherwise the shared-memory kernels below sort everything).  Classical
+// bitonic network; exchanges between lanes are shuffles, exchanges between slots stay in the
+// thread.  Lists shorter than the network are padded with +inf.
+// Algorithmic bytes per entry: 4 (read) + 16 (key gather) + 4 (write).
+template <int GS, int ITEMS>
+__global__ void __launch_bounds__(256) k_sort_reg(const uint4* __restrict__ key, const u32* __restrict__ otStart,
+                                                  const u32* __restrict__ otSize, u32* __restrict__ occurs,
+                                                  const u32* __restrict__ q, const DevCounters* dc, int cls) {
+    u32 qStart = 0;
+    for (int k = 0; k < cls; k++) qStart += dc->sortCnt[k];
+    const u32 nq = dc->sortCnt[cls];
+    const u32 lane = threadIdx.x & (u32)(GS - 1);
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 rounds = (nq + groupsPerGrid - 1) / groupsPerGrid;   // every lane runs every round: shuffles are warp-wide
+    u32 gi = (blockIdx.x * blockDim.x + threadIdx.x) / GS;
+    for (u32 it = 0; it < rounds; it++, gi += groupsPerGrid) {
+        u32 n = 0; u32* list = nullptr;
+        if (gi < nq) { const u32 lit = q[qStart + gi]; n = otSize[lit]; list = occurs + otStart[lit]; }
+        u64 ka[ITEMS], kb[ITEMS];
+#pragma unroll
+        for (int s = 0; s < ITEMS; s++) {
+            const u32 e = s * GS + lane;
+            ka[s] = ~0ull; kb[s] = ~0ull;
+            if (e < n) {
+                const u32 r = list[e];
+                const uint4 k = key[r];
+                ka[s] = ((u64)k.x << 50) | ((u64)k.y << 25) | (u64)k.z;
+                kb[s] = ((u64)k.w << 32) | r;
             }
-            ka[p] = a; kb[p] = b; id[p] = r;
         }
-        for (u32 j = 0; j < n; j++) list[j] = id[j];
+#pragma unroll
+        for (int k = 2; k <= GS * ITEMS; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= GS) {   // partner in the same lane, slot s ^ (j / GS)
+#pragma unroll
+                    for (int s = 0; s < ITEMS; s++) {
+                        const int t = s ^ (j / GS);
+                        if (t > s) {
+                            const u32 e = s * GS + lane;
+                            const bool asc = (e & k) == 0;
+                            const bool gt = ka[s] > ka[t] || (ka[s] == ka[t] && kb[s] > kb[t]);
+                            if (gt == asc) { u64 x = ka[s]; ka[s] = ka[t]; ka[t] = x; x = kb[s]; kb[s] = kb[t]; kb[t] = x; }
+                        }
+                    }
+                } else {         // partner in lane ^ j, same slot
+#pragma unroll
+                    for (int s = 0; s < ITEMS; s++) {
+                        const u32 e = s * GS + lane;
+                        const u64 oa = __shfl_xor_sync(0xffffffffu, ka[s], j), ob = __shfl_xor_sync(0xffffffffu, kb[s], j);
+                        const bool asc = (e & k) == 0;
+                        const bool lower = (lane & j) == 0;           // this lane holds the lower index of the pair
+                        const bool gt = ka[s] > oa || (ka[s] == oa && kb[s] > ob);   // mine > partner's
+                        // the lower index keeps the smaller value when ascending
+                        const bool takeOther = (lower == asc) ? gt : !gt;
+                        if (takeOther) { ka[s] = oa; kb[s] = ob; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < ITEMS; s++) { const u32 e = s * GS + lane; if (e < n) list[e] = (u32)kb[s]; }
     }
 }
 
@@ -93,17 +177,19 @@ __device__ __forceinline__ void bitonicShared(u64* ka, u64* kb, u32* id, u32 n, 
 struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
 struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
-// one warp per list, 17..512 entries, shared-memory slice per warp
+// one warp per list, up to 512 entries, shared-memory slice per warp (exact 160-bit compare)
 __global__ void __launch_bounds__(MED_WARPS * 32) k_sort_med(const uint4* __restrict__ key, const u32* __restrict__ otStart,
                                                              const u32* __restrict__ otSize, u32* __restrict__ occurs,
-                                                             const u32* __restrict__ q, const DevCounters* dc) {
+                                                             const u32* __restrict__ q, const DevCounters* dc, int cls0, int cls1) {
     __shared__ u64 ska[MED_WARPS][SORT_MED];
     __shared__ u64 skb[MED_WARPS][SORT_MED];
     __shared__ u32 sid[MED_WARPS][SORT_MED];
     const u32 w = threadIdx.x >> 5, l = threadIdx.x & 31u;
-    const u32 nq = dc->qMed;
+    u32 qStart = 0, nq = 0;   // classes cls0..cls1 are contiguous in the queue
+    for (int k = 0; k < cls0; k++) qStart += dc->sortCnt[k];
+    for (int k = cls0; k <= cls1; k++) nq += dc->sortCnt[k];
     for (u32 qi = blockIdx.x * MED_WARPS + w; qi < nq; qi += gridDim.x * MED_WARPS) {
-        const u32 lit = q[qi], n = otSize[lit];
+        const u32 lit = q[qStart + qi], n = otSize[lit];
         u32* list = occurs + otStart[lit];
         for (u32 j = l; j < n; j += 32) {
             const u32 r = list[j];
@@ -125,9 +211,11 @@ __global__ void __launch_bounds__(512) k_sort_big(const uint4* __restrict__ key,
     u64* ska = dyn;
     u64* skb = dyn + SORT_BIG;
     u32* sid = (u32*)(dyn + 2 * SORT_BIG);
-    const u32 nq = dc->qBig;
+    u32 qStart = 0;
+    for (int k = 0; k < 7; k++) qStart += dc->sortCnt[k];
+    const u32 nq = dc->sortCnt[7];
     for (u32 qi = blockIdx.x; qi < nq; qi += gridDim.x) {
-        const u32 lit = q[qi], n = otSize[lit];
+        const u32 lit = q[qStart + qi], n = otSize[lit];
         u32* list = occurs + otStart[lit];
         for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
             const u32 r = list[j];
@@ -145,9 +233,11 @@ __global__ void __launch_bounds__(512) k_sort_big(const uint4* __restrict__ key,
 __global__ void __launch_bounds__(1024) k_sort_huge(const uint4* __restrict__ key, const u32* __restrict__ otStart,
                                                     const u32* __restrict__ otSize, u32* occurs,
                                                     const u32* __restrict__ q, const DevCounters* dc) {
-    const u32 nq = dc->qHuge;
+    u32 qStart = 0;
+    for (int k = 0; k < 8; k++) qStart += dc->sortCnt[k];
+    const u32 nq = dc->sortCnt[8];
     for (u32 qi = blockIdx.x; qi < nq; qi += gridDim.x) {
-        const u32 lit = q[qi], n = otSize[lit];
+        const u32 lit = q[qStart + qi], n = otSize[lit];
         volatile u32* list = occurs + otStart[lit];
         u32 P = 1;
         while (P < n) P <<= 1;
@@ -172,7 +262,9 @@ __global__ void __launch_bounds__(1024) k_sort_huge(const uint4* __restrict__ ke
     }
 }
 
-__global__ void k_sort_reset(DevCounters* dc) { dc->qMed = 0; dc->qBig = 0; dc->qHuge = 0; }
+__global__ void k_sort_reset(DevCounters* dc) {
+    for (int k = 0; k < NCLASS; k++) { dc->sortCnt[k] = 0; dc->sortCur[k] = 0; }
+}
 
 void launchSortOT(Ctx* c) {
     const size_t bigSmem = (size_t)SORT_BIG * (8 + 8 + 4);
@@ -180,9 +272,25 @@ void launchSortOT(Ctx* c) {
         cudaFuncSetAttribute(k_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigSmem);
         c->attrSort = true;
     }
+    u32* q = c->qMed;   // ND entries: the literals with >= 2 occurrences, grouped by length class
     LAUNCH(c, k_sort_reset, 1, 1, 0, c->dc);
-    LAUNCH(c, k_sort_small, gridFor(c->ND, 128), 128, 0, c->key, c->otStart, c->otSize, c->occurs, c->ND, c->qMed, c->qBig, c->qHuge, c->dc);
-    LAUNCH(c, k_sort_med, 148 * 4, MED_WARPS * 32, 0, c->key, c->otStart, c->otSize, c->occurs, c->qMed, c->dc);
-    LAUNCH(c, k_sort_big, 148, 512, bigSmem, c->key, c->otStart, c->otSize, c->occurs, c->qBig, c->dc);
-    LAUNCH(c, k_sort_huge, 32, 1024, 0, c->key, c->otStart, c->otSize, c->occurs, c->qHuge, c->dc);
+    LAUNCH(c, k_sort_count, gridFor(c->ND, 256, 4), 256, 0, c->otSize, c->ND, c->dc);
+    LAUNCH(c, k_sort_fill, gridFor(c->ND, 256, 4), 256, 0, c->otSize, c->ND, q, c->dc);
+    // the folded 128-bit key is exact while literals < 2^25 and clauses are shorter than 2^14 (flag 8: k_hist_key)
+    const bool fold = c->ND <= (1u << 25) && !(c->hdc->flags & 8u);
+    // grids: enough groups for every list of a class if all of them fell into it, capped
+    const u32 nLists = c->ND;
+    auto grid = [&](u32 gs) { u64 b = ((u64)nLists * gs + 255) / 256; return (u32)(b > 148ull * 16 ? 148ull * 16 : (b ? b : 1)); };
+    if (fold) {
+        LAUNCH(c, (k_sort_reg<4, 1>), grid(4), 256, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 0);
+        LAUNCH(c, (k_sort_reg<8, 1>), grid(8), 256, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 1);
+        LAUNCH(c, (k_sort_reg<16, 1>), grid(16), 256, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 2);
+        LAUNCH(c, (k_sort_reg<32, 1>), grid(32), 256, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 3);
+        LAUNCH(c, (k_sort_reg<32, 2>), grid(32), 256, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 4);
+        LAUNCH(c, (k_sort_reg<32, 4>), grid(32), 256, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 5);
+        LAUNCH(c, k_sort_med, 148 * 4, MED_WARPS * 32, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 6, 6);
+    } else
+        LAUNCH(c, k_sort_med, 148 * 4, MED_WARPS * 32, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc, 0, 6);
+    LAUNCH(c, k_sort_big, 148, 512, bigSmem, c->key, c->otStart, c->otSize, c->occurs, q, c->dc);
+    LAUNCH(c, k_sort_huge, 32, 1024, 0, c->key, c->otStart, c->otSize, c->occurs, q, c->dc);
 }
