@@ -97,6 +97,7 @@ struct DevCounters {
     u32 misStopRank;
     u32 wlNext;        // MIS worklist append cursor
     u32 wlCnt[3];      // rotating MIS worklist sizes (lcve.cu)
+    u32 firstStop;     // rank of the first bound-violating candidate (lcve.cu)
     u32 flags;         // bit0: resolved overflow, bit1: units overflow, bit2: hole after failed MEMORY_SAFE, bit3: a clause with >= 2^14 literals
     u32 bcpCurr, bcpNext, bcpConfl, bcpLevel;
     u32 nFrozen;       // number of first-frozen variables mapped into varcore (<= 12 needed)

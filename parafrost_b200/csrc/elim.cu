@@ -62,6 +62,19 @@ template <int GS> __device__ __forceinline__ void melt(GT<GS>& g, u32 ci) { setB
 template <int GS> __device__ __forceinline__ void freeze(GT<GS>& g, u32 ci) { setBits(g, ci, 0, CB_MOLTEN); }
 template <int GS> __device__ __forceinline__ void markDeleted(GT<GS>& g, u32 ci) { setBits(g, ci, CB_DELETED, CB_ST_MASK); }
 
+// Pull the clauses of a small variable into L1 up front: the gate searches below chase
+// list entry -> header -> literals serially, so without this every step is an L2/HBM round trip.
+template <int GS> __device__ __forceinline__ void prefetchLists(GT<GS>& g, const u32* P, u32 np, const u32* N, u32 nn) {
+    if (np + nn > 96u) return;
+    for (u32 j = LANE; j < np + nn; j += GS) {
+        const u32 ci = j < np ? P[j] : N[j - np];
+        const uint4 h = g.hdr[ci];
+        const u32* l = g.pool + h.x;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(l));
+        if (h.y > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(l + h.y - 1));
+    }
+}
+
 // resolvent length on x, 0 if tautology (elimination.cuh:180-205)
 __device__ __forceinline__ int mergeLen(const u32* __restrict__ a, int n1, const u32* __restrict__ b, int n2, u32 x) {
     int it1 = 0, it2 = 0, len = n1 + n2 - 2;
@@ -604,6 +617,7 @@ __global__ void __launch_bounds__(128) k_ve_phase1(GT<GS> g, const u32* __restri
         const u32 np = g.otSize[p], nn = g.otSize[n];
         const u32* P = g.occurs + g.otStart[p];
         const u32* N = g.occurs + g.otStart[n];
+        prefetchLists(g, P, np, N, nn);
         u32 pOrgs, nOrgs;
         if (g.k.in_mode) { u32 d; countOrgsLits(g, P, np, pOrgs, d); countOrgsLits(g, N, nn, nOrgs, d); }
         else { pOrgs = np; nOrgs = nn; }
@@ -921,6 +935,7 @@ __global__ void __launch_bounds__(128) k_sub(GT<GS> g, const u32* __restrict__ w
         if (np > g.k.sub_max_occurs || nn > g.k.sub_max_occurs) continue;
         const u32* P = g.occurs + g.otStart[p];
         const u32* N = g.occurs + g.otStart[n];
+        prefetchLists(g, P, np, N, nn);
         const u32 nPosUnits = subSide(g, P, np, N, nn, p, n);
         const u32 nNegUnits = subSide(g, N, nn, P, np, n, p);
         if (nPosUnits || nNegUnits) {

@@ -41,7 +41,7 @@ __global__ void k_scores(const u32* __restrict__ hist, const unsigned char* __re
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dc->misStopRank = NOVAR; dc->numElected = 0; dc->wlNext = 0;
-        dc->wlCnt[0] = dc->wlCnt[1] = dc->wlCnt[2] = 0;
+        dc->wlCnt[0] = dc->wlCnt[1] = dc->wlCnt[2] = 0; dc->firstStop = NOVAR;
     }
 }
 
@@ -113,12 +113,19 @@ static void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2,
     }
 }
 
-__global__ void k_rank(const u32* __restrict__ eligible, const unsigned char* __restrict__ cstat, u32 V, u32* __restrict__ vinfo) {
+__global__ void k_rank(const u32* __restrict__ eligible, const unsigned char* __restrict__ cstat, u32 V, u32* __restrict__ vinfo,
+                       u32* __restrict__ blocker, u32* __restrict__ nbr, unsigned char* __restrict__ ovs, DevCounters* dc) {
+    u32 firstStop = NOVAR;
     for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < V; r += gridDim.x * blockDim.x) {
         const u32 v = eligible[r];
         const u32 cs = cstat[v];
         vinfo[v] = (r << 5) | (cs << 3) | (cs ? MIS_UNDECIDED : MIS_NONE);
+        blocker[v] = 0; nbr[v] = NOVAR; ovs[v] = 0;
+        if (cs == CS_STOP && r < firstStop) firstStop = r;
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) firstStop = min(firstStop, __shfl_xor_sync(0xffffffffu, firstStop, o));
+    if ((threadIdx.x & 31u) == 0 && firstStop != NOVAR) atomicMin(&dc->firstStop, firstStop);
     if (blockIdx.x == 0 && threadIdx.x == 0) vinfo[0] = 0;
 }
 
@@ -133,12 +140,17 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const unsigned char
     }
 }
 
-// one group of GS lanes per undecided candidate; lanes stride over the clauses of its two lists
+// one group of GS lanes per undecided candidate; lanes stride over the clauses of its two lists.
+// blocker[v] remembers the lowest-ranked undecided candidate that shared a clause with v at its
+// last full scan: while that one is undecided v stays blocked, when it is elected v is frozen -
+// one 4-byte probe instead of walking the whole neighbourhood again; only when the blocker got
+// frozen itself is the neighbourhood rescanned.  (Decisions can come a round later than with a
+// full scan every round; the fixed point - the lexicographically first MIS - is the same.)
 template <int GS>
 __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* __restrict__ wl1, u32 round, DevCounters* dc,
                                                    const uint4* __restrict__ hdr, const u32* __restrict__ pool,
                                                    const u32* __restrict__ otStart, const u32* __restrict__ otSize,
-                                                   const u32* __restrict__ occurs, u32* vinfo, int maxcsize) {
+                                                   const u32* __restrict__ occurs, u32* vinfo, u32* __restrict__ blocker, int maxcsize) {
     const u32* wlIn = (round & 1u) ? wl1 : wl0;
     u32* wlOut = (round & 1u) ? wl0 : wl1;
     const u32 nIn = dc->wlCnt[round % 3u];
@@ -153,7 +165,14 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
         const u32 wv = vinfo[v];
         const u32 r = VI_RANK(wv);
         if (r > dc->misStopRank) continue;  // beyond the cut: never looked at by the serial walk
-        bool frozen = false, blocked = false, oversize = false;
+        const u32 b = blocker[v];
+        if (b) {
+            const u32 mb = VI_STATE(vinfo[b]);
+            if (mb == MIS_UNDECIDED) { if (lane == 0) wlOut[atomicAdd(outCnt, 1u)] = v; continue; }
+            if (mb == MIS_ELECTED) { if (lane == 0) vinfo[v] = (wv & ~7u) | MIS_FROZEN; continue; }
+        }
+        bool frozen = false, oversize = false;
+        u32 bRank = NOVAR, bVar = 0;
         for (u32 side = 0; side < 2; side++) {
             const u32 lit = V2L(v) | side;
             const u32 n = otSize[lit];
@@ -170,13 +189,17 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
                     if (VI_RANK(wu) >= r) continue;
                     const u32 m = VI_STATE(wu);
                     if (m == MIS_ELECTED) frozen = true;
-                    else if (m == MIS_UNDECIDED && VI_CLASS(wu) == CS_CAND) blocked = true;
+                    else if (m == MIS_UNDECIDED && VI_CLASS(wu) == CS_CAND && VI_RANK(wu) < bRank) { bRank = VI_RANK(wu); bVar = u; }
                 }
             }
         }
         frozen = __any_sync(gmask, frozen);
-        blocked = __any_sync(gmask, blocked);
         oversize = __any_sync(gmask, oversize);
+        u32 minRank = bRank;
+#pragma unroll
+        for (int o = GS / 2; o; o >>= 1) minRank = min(minRank, __shfl_xor_sync(gmask, minRank, o, GS));
+        const bool blocked = minRank != NOVAR;
+        if (blocked && !frozen && bRank == minRank) blocker[v] = bVar;   // ranks are unique: every writer holds the same variable
         if (lane == 0) {
             const u32 keep = wv & ~7u;
             if (frozen) vinfo[v] = keep | MIS_FROZEN;
@@ -186,6 +209,72 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
                 else vinfo[v] = keep | (oversize ? MIS_FROZEN : MIS_ELECTED);
             }
             else wlOut[atomicAdd(outCnt, 1u)] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ first MIS round, clause-centric
+// The first round of a chunk is the expensive one: every candidate would walk its whole
+// neighbourhood through the occurrence table (gathering headers and literals).  The same
+// information falls out of ONE streaming pass over the clause store: per clause the lowest elected
+// rank and the two lowest undecided candidate ranks; every undecided variable of the clause is
+// frozen (an elected variable of lower rank shares the clause) or gets the lowest-ranked other
+// undecided candidate min-reduced into nbr[].  k_mis_first then elects the local minima and
+// queues the rest with their blocker for the vertex-centric rounds above.
+// Algorithmic bytes: 16 C + 4 L (coalesced) + 4 L election words (L2 resident).
+__global__ void __launch_bounds__(256) k_mis_clauses(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n, u32* vinfo,
+                                                     u32* __restrict__ nbr, unsigned char* __restrict__ ovs, u32 H, int maxcsize) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w)) continue;
+        const u32* l = pool + h.x;
+        u32 eMin = NOVAR, u1 = NOVAR, u2 = NOVAR;
+        bool any = false;
+        for (u32 k = 0; k < h.y; k++) {
+            const u32 w = vinfo[LABS(l[k])];
+            const u32 r = VI_RANK(w), st = VI_STATE(w);
+            if (st == MIS_ELECTED) eMin = min(eMin, r);
+            else if (st == MIS_UNDECIDED && r < H) {
+                any = true;
+                if (VI_CLASS(w) == CS_CAND) { if (r < u1) { u2 = u1; u1 = r; } else if (r < u2) u2 = r; }
+            }
+        }
+        if (!any) continue;
+        const bool big = (int)h.y > maxcsize;
+        for (u32 k = 0; k < h.y; k++) {
+            const u32 u = LABS(l[k]);
+            const u32 w = vinfo[u];
+            const u32 r = VI_RANK(w);
+            if (VI_STATE(w) != MIS_UNDECIDED || r >= H) continue;
+            if (big) ovs[u] = 1;
+            if (eMin < r) vinfo[u] = (w & ~7u) | MIS_FROZEN;
+            else { const u32 other = (u1 == r) ? u2 : u1; if (other < r) atomicMin(&nbr[u], other); }
+        }
+    }
+}
+__global__ void k_mis_first(const u32* __restrict__ eligible, u32 rBegin, u32 rEnd, u32* vinfo, const u32* __restrict__ nbr,
+                            const unsigned char* __restrict__ ovs, u32* __restrict__ blocker, u32* __restrict__ wl, DevCounters* dc, u32 slot) {
+    for (u32 r0 = rBegin + blockIdx.x * blockDim.x; r0 < rEnd; r0 += gridDim.x * blockDim.x) {
+        const u32 r = r0 + threadIdx.x;
+        bool queue = false; u32 v = 0;
+        if (r < rEnd) {
+            v = eligible[r];
+            const u32 w = vinfo[v];
+            if (VI_STATE(w) == MIS_UNDECIDED) {
+                const u32 m = nbr[v];
+                if (m == NOVAR) {
+                    if (VI_CLASS(w) == CS_STOP) { vinfo[v] = (w & ~7u) | MIS_LIVESTOP; atomicMin(&dc->misStopRank, r); }
+                    else vinfo[v] = (w & ~7u) | (ovs[v] ? MIS_FROZEN : MIS_ELECTED);
+                } else { blocker[v] = eligible[m]; queue = true; }
+            }
+        }
+        const u32 mq = __ballot_sync(0xffffffffu, queue);
+        if (mq) {
+            const u32 leader = __ffs(mq) - 1;
+            u32 base = 0;
+            if (laneId() == leader) base = atomicAdd(&dc->wlCnt[slot], __popc(mq));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (queue) wl[base + __popc(mq & lanemaskLt())] = v;
         }
     }
 }
@@ -267,20 +356,35 @@ int runLCVE(Ctx* c) {
     const u32 V = c->V;
     const u32 pmax = c->o.mu_pos << c->multiplier, nmax = c->o.mu_neg << c->multiplier;
     u32* vinfo = c->rank;
+    u32* blocker = c->sortV;   // free once the radix sort is done
+    u32* nbr = c->sortK;
+    unsigned char* ovs = c->mis;
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
            c->scores, c->eligible, c->cstat, c->dc);
     radixSortPairs(c, c->scores, c->eligible, c->sortK, c->sortV, V);
-    LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, c->cstat, V, vinfo);
+    LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, c->cstat, V, vinfo, blocker, nbr, ovs, c->dc);
+    int rc = syncCounters(c);
+    if (rc) return rc;
+    const u32 firstStop = c->hdc->firstStop < V ? c->hdc->firstStop : V;   // everything ranked before it is walked for sure
+    const u32 nCls = c->hdc->numCls;
     // lanes per candidate: variables of Tseitin-like formulas have a handful of short clauses
     const bool smallGroups = c->numLiterals <= (u64)24 * V;
+    const u64 avgOcc = c->numLiterals / V + 1;
 
     u32 hPrev = 0, stopRank = NOVAR, hEnd = 0;
     u32 round = 0;   // parity / counter slot of the next MIS round
     while (hPrev < V && stopRank == NOVAR) {
-        u64 h64 = hPrev ? (u64)hPrev * 8 : 8192;
+        u64 h64 = hPrev ? (u64)hPrev * 8 : (firstStop > 8192 ? firstStop : 8192);
         const u32 H = (u32)(h64 > V ? V : h64);
-        // the chunk's candidates go to the input list of round `round`
-        LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, c->cstat, hPrev, H, (round & 1u) ? c->wlB : c->wlA, c->dc, round % 3u);
+        u32* wlIn = (round & 1u) ? c->wlB : c->wlA;
+        // first round of the chunk: one streaming pass over the clauses when the chunk is large,
+        // otherwise the candidates walk their own lists
+        const bool clausePass = (u64)(H - hPrev) * avgOcc * 2 > nCls;
+        if (clausePass) {
+            LAUNCH(c, k_mis_clauses, gridFor(nCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], nCls, vinfo, nbr, ovs, H, c->o.lcve_clause_max);
+            LAUNCH(c, k_mis_first, gridFor(H - hPrev, 256), 256, 0, c->eligible, hPrev, H, vinfo, nbr, ovs, blocker, wlIn, c->dc, round % 3u);
+        } else
+            LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, c->cstat, hPrev, H, wlIn, c->dc, round % 3u);
         u32 n = H - hPrev;   // upper bound of the worklist until the first read-back
         u32 guard = 0;
         while (n) {
@@ -291,10 +395,10 @@ int runLCVE(Ctx* c) {
             for (int b = 0; b < MIS_BATCH; b++, round++) {
                 if (smallGroups)
                     LAUNCH(c, k_mis_round<8>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
-                           c->otSize, c->occurs, vinfo, c->o.lcve_clause_max);
+                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max);
                 else
                     LAUNCH(c, k_mis_round<32>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
-                           c->otSize, c->occurs, vinfo, c->o.lcve_clause_max);
+                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max);
             }
             CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -52,23 +52,30 @@ __global__ void __launch_bounds__(256) k_sort_count(const u32* __restrict__ otSi
     __syncthreads();
     if (threadIdx.x < NCLASS && cnt[threadIdx.x]) atomicAdd(&dc->sortCnt[threadIdx.x], cnt[threadIdx.x]);
 }
-// pass 2: the literals of class k go to q[start_k ...), start = exclusive sum of the class sizes
+// pass 2: the literals of class k go to q[start_k ...), start = exclusive sum of the class sizes.
+// Each CTA owns a contiguous tile of literals, counts its classes in shared memory, reserves its
+// ranges with one global atomic per class, then places its literals with shared-memory atomics.
+#define FILL_TILE 4096
 __global__ void __launch_bounds__(256) k_sort_fill(const u32* __restrict__ otSize, u32 ND, u32* __restrict__ q, DevCounters* dc) {
-    __shared__ u32 start[NCLASS];
+    __shared__ u32 start[NCLASS], cnt[NCLASS], base[NCLASS];
     if (threadIdx.x == 0) { u32 s = 0; for (int k = 0; k < NCLASS; k++) { start[k] = s; s += dc->sortCnt[k]; } }
-    __syncthreads();
-    for (u32 l0 = 2 + blockIdx.x * blockDim.x; l0 < ND; l0 += gridDim.x * blockDim.x) {
-        const u32 lit = l0 + threadIdx.x;
-        const int k = lit < ND ? sortClass(otSize[lit]) : -1;
-        for (int kk = 0; kk < NCLASS; kk++) {
-            const u32 m = __ballot_sync(0xffffffffu, k == kk);
-            if (!m) continue;
-            const u32 leader = __ffs(m) - 1;
-            u32 base = 0;
-            if (laneId() == leader) base = atomicAdd(&dc->sortCur[kk], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (k == kk) q[start[kk] + base + __popc(m & lanemaskLt())] = lit;
+    for (u32 t0 = 2 + blockIdx.x * FILL_TILE; t0 < ND; t0 += gridDim.x * FILL_TILE) {
+        __syncthreads();
+        if (threadIdx.x < NCLASS) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int cls[FILL_TILE / 256]; u32 pos[FILL_TILE / 256];
+#pragma unroll
+        for (int k = 0; k < FILL_TILE / 256; k++) {
+            const u32 lit = t0 + k * 256 + threadIdx.x;
+            cls[k] = lit < ND ? sortClass(otSize[lit]) : -1;
+            if (cls[k] >= 0) pos[k] = atomicAdd(&cnt[cls[k]], 1u);
         }
+        __syncthreads();
+        if (threadIdx.x < NCLASS) base[threadIdx.x] = cnt[threadIdx.x] ? start[threadIdx.x] + atomicAdd(&dc->sortCur[threadIdx.x], cnt[threadIdx.x]) : 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < FILL_TILE / 256; k++)
+            if (cls[k] >= 0) q[base[cls[k]] + pos[k]] = t0 + k * 256 + threadIdx.x;
     }
 }
 
@@ -275,7 +282,7 @@ void launchSortOT(Ctx* c) {
     u32* q = c->qMed;   // ND entries: the literals with >= 2 occurrences, grouped by length class
     LAUNCH(c, k_sort_reset, 1, 1, 0, c->dc);
     LAUNCH(c, k_sort_count, gridFor(c->ND, 256, 4), 256, 0, c->otSize, c->ND, c->dc);
-    LAUNCH(c, k_sort_fill, gridFor(c->ND, 256, 4), 256, 0, c->otSize, c->ND, q, c->dc);
+    LAUNCH(c, k_sort_fill, gridFor(c->ND, 256, FILL_TILE / 256), 256, 0, c->otSize, c->ND, q, c->dc);
     // the folded 128-bit key is exact while literals < 2^25 and clauses are shorter than 2^14 (flag 8: k_hist_key)
     const bool fold = c->ND <= (1u << 25) && !(c->hdc->flags & 8u);
     // grids: enough groups for every list of a class if all of them fell into it, capped
