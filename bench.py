@@ -57,7 +57,8 @@ def workload_spec(name, rank=0, scale=1.0):
             args[0] = max(4, int(args[0] * scale)); args[1] = max(8, int(args[1] * scale))
         elif fam == "multpar":
             args[0] = max(4, int(args[0] * scale ** 0.5)); args[1] = max(8, int(args[1] * scale))
-    return fam, seed + 1000 * rank, args
+    from parafrost_b200 import replicas
+    return fam, replicas.rank_seed(seed, rank), args
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -108,7 +109,8 @@ def algorithmic_bytes(kernel, C, L, V, E=0):
         "k_awaken": 8 * C + 4 * L + 16 * C + 4 * L,
         "k_hist_key": 16 * C + 4 * L + 16 * C + 4 * ND,
         "k_hist": 16 * C + 4 * L + 4 * ND,
-        "k_scatter": 16 * C + 4 * L + 4 * L + 8 * ND,
+        "k_ot_part": 16 * C + 4 * L + 8 * L,
+        "k_ot_place": 8 * L + 4 * L + 12 * ND,
         "k_sort_small": 4 * L + 16 * L + 4 * L + 8 * ND,
         "k_sort_med": 4 * L + 16 * L + 4 * L,
         "k_sort_lists": 4 * L + 16 * L + 4 * L + 8 * ND,
@@ -334,13 +336,9 @@ def main():
     lit_step = sum(r["literals_in"] for r in rounds)
     nrounds = max(1, len(rounds))
     launches = sum(r["kernel_launches"] for r in reps)
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(lit_step)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    lit_all = float(tot[0])
+    from parafrost_b200 import replicas
+    ms, lit_all = replicas.reduce_timing(dist, ms, float(lit_step), device="cuda")      # max over ranks, units summed
+    ms_e2e, _ = replicas.reduce_timing(dist, ms_e2e, 0.0, device="cuda")
 
     if rank == 0:
         peaks = {}

@@ -187,6 +187,7 @@ static size_t carve(Ctx* c, char* base) {
     c->key = a.take<uint4>(capC + 1);
     c->hist = a.take<u32>(ND + 2); c->otStart = a.take<u32>(ND + 2); c->otSize = a.take<u32>(ND + 2);
     c->occurs = a.take<u32>(capW + 4);
+    c->otPairs = a.take<uint2>(capW + 4); c->otCur = a.take<u32>(8192 + 2);
     c->scores = a.take<u32>(V1); c->eligible = a.take<u32>(V1); c->rank = a.take<u32>(V1);
     c->sortK = a.take<u32>(V1); c->sortV = a.take<u32>(V1); c->elected = a.take<u32>(V1);
     c->units = a.take<u32>(2 * V1); c->trail = a.take<u32>(3 * V1);
@@ -228,6 +229,10 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
         for (u64 i = 0; i < num_clauses; i++) if (!(meta[i] & CB_LEARNT)) { orgC++; orgL += offs[i + 1] - offs[i]; }
     }
     c->V = max_var; c->ND = 2 * (max_var + 1);
+    // OT-build buckets: 2^otShift consecutive literals each, at most 1024 of them up to V = 2^24 (cnf.cu)
+    c->otShift = 8;
+    while (c->otShift < 15 && ((c->ND + (1u << c->otShift) - 1) >> c->otShift) > 1024) c->otShift++;
+    c->otNB = (c->ND + (1u << c->otShift) - 1) >> c->otShift;
     c->C0 = num_clauses; c->L0 = L0;
     c->orgClauses = orgC; c->orgLiterals = orgL;
     // logical capacities of awaken (simplify.cu:84-98); the physical buffers are sized for them
@@ -338,10 +343,10 @@ static void pushRound(Ctx* c, const sigma_round_report& r) {
     c->rounds[c->nRounds++] = r;
 }
 
-// histogram -> scan -> (GC) -> scatter : reallocOT + reallocCNF + createOTAsync (simplify.cu:164-167)
+// (GC) -> histogram -> scan -> partition/place : reallocOT + reallocCNF + createOTAsync (simplify.cu:164-167).
+// The reference counts before it compacts; compaction drops deleted clauses only, so the histogram
+// is the same either way and compacting first saves one pass over the clause store.
 static void buildOT(Ctx* c, bool withGC, bool* didGC) {
-    { StageTimer t(c, ST_VO); launchHistKey(c); }
-    { StageTimer t(c, ST_VO); scanExclusiveU32(c, c->hist, c->otStart, c->ND, 0, c->otStart + c->ND); }
     if (withGC) {
         StageTimer t(c, ST_GC);
         // reallocCNF(true), cnf.cu:129-144: new logical capacities, then compact
@@ -353,10 +358,10 @@ static void buildOT(Ctx* c, bool withGC, bool* didGC) {
         c->hdc->numCls = (u32)c->numClauses; c->hdc->poolUsed = (u32)c->numLiterals;
         c->hdc->dataSize = c->numClauses * NBUCKETS + c->numLiterals;
         c->compacted = true;
-        // clause indices changed: the keys gathered by the list sort must follow
-        launchHistKey(c);
         if (didGC) *didGC = true;
     }
+    { StageTimer t(c, ST_VO); launchHistKey(c); }
+    { StageTimer t(c, ST_VO); scanExclusiveU32(c, c->hist, c->otStart, c->ND, 0, c->otStart + c->ND); }
     { StageTimer t(c, ST_COT); launchScatter(c); }
 }
 
@@ -415,11 +420,13 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
         pushRound(c, r); if (rep) *rep = r;
         return SIGMA_OK;
     }
-    { StageTimer t(c, ST_SOT); launchSortOT(c); }
     const KOpts k = makeK(c);
     // stop() solver.hpp:748-753
     const bool stop = (c->phase == c->o.phases) || (c->simpstate == SIGMA_CNFALLOC_FAIL) || (!c->cdiff && !c->ldiff) ||
                       (c->phase > 2 && c->ldiff <= c->o.phase_lits_min);
+    // sortOT (segsort.cu:37-48).  ERE binary-searches the list of ANY literal, so the last round sorts
+    // every list; SUB/BVE/BCE only walk the lists of the elected variables in order.
+    if (!stop || (c->o.ere_en && c->numElected)) { StageTimer t(c, ST_SOT); launchSortOT(c, !stop); }
     if (stop) {
         r.kind = 1;
         if (c->o.ere_en && c->numElected) { StageTimer t(c, ST_ERE); launchERE(c, k); }

@@ -4,7 +4,7 @@
 // Reference behaviour being replaced (results must be identical):
 //   prep_cnf_k            src/gpu/cnf.cu:45-53        sort literals, 32-bit signature
 //   copy_if_k + histSimp  src/gpu/cnf.cu:33-43, histogram.cu:54-72  (thrust sort only to count!)
-//   create_ot_k           src/gpu/occurrence.cu:50-62
+//   create_ot_k           src/gpu/occurrence.cu:50-62   (k_ot_part + k_ot_place)
 //   cnt_cls_lits          src/gpu/count.cu:83-106
 //   scatter_k/compact_k   src/gpu/recycle.cu:34-105
 //   cacheCNF              src/gpu/cnf.cu:200-237
@@ -86,33 +86,113 @@ void launchHistKey(Ctx* c) {
     if (n) LAUNCH(c, k_hist_key, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->hist, c->key, &c->dc->flags);
 }
 
-// ------------------------------------------------------------------ scatter (occurrence lists)
-// algorithmic bytes: read 16C + 4L, write 4L list entries (random), one atomic per literal
-__global__ void __launch_bounds__(256) k_scatter(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
-                                                 const u32* __restrict__ otStart, u32* __restrict__ otSize, u32* __restrict__ occurs) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint4 h = hdr[i];
-        if (C_DELETED(h.w)) continue;
-        const u32* l = pool + h.x;
-        const int sz = (int)h.y;
-        // 8 literals in flight per thread: the slot atomics and the list-start loads of a batch are
-        // independent, only the final stores wait for them
-        for (int k0 = 0; k0 < sz; k0 += 8) {
-            u32 lit[8], pos[8], st[8];
+// ------------------------------------------------------------------ occurrence lists: partition + place
+// create_ot_k (occurrence.cu:50-62) appends every clause reference to the lists of its literals
+// with one global atomic and one random 8-byte store per literal.  Random 4-byte stores over an
+// occurs[] array far larger than L2 cost a DRAM sector each, so the lists are built in two
+// streaming passes instead (an MSD radix partition by literal, the histogram being known):
+//   k_ot_part   streams the clause store once; every CTA bins the (literal, clause) pairs of its
+//               tile by literal range ("bucket" = 2^shift consecutive literals, <= 1024 buckets for
+//               V <= 2^24), reserves one run per bucket with a single global atomic and writes the
+//               pairs into the bucket's segment of pairs[] (the segment bounds are otStart[] at the
+//               bucket borders: no extra histogram).  Runs of neighbouring CTAs complete each
+//               other's sectors in L2.
+//   k_ot_place  one CTA per bucket: list cursors of the bucket's literals in shared memory, pairs
+//               streamed once (coalesced), clause indices stored into occurs[] inside the bucket's
+//               window (<= a few hundred KB: the sectors are completed in L2 before they reach HBM).
+// The order inside a list is arbitrary (as in the reference); k_sort_* fixes it afterwards.
+// Algorithmic bytes: part 16C + 4L read + 8L written; place 8L read + 4L written + 12 ND.
+#define PART_THREADS 512
+#define PART_CPT 8
+#define PART_TILE (PART_THREADS * PART_CPT)
+
+__global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                                                          const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB,
+                                                          u32* __restrict__ gcur, uint2* __restrict__ pairs) {
+    extern __shared__ u32 sm[];
+    u32* cnt = sm;
+    u32* gbase = sm + NB;
+    const u32 tile0 = blockIdx.x * PART_TILE;
+    for (u32 b = threadIdx.x; b < NB; b += PART_THREADS) cnt[b] = 0;
+    __syncthreads();
+    u32 off[PART_CPT], sz[PART_CPT];
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (k0 + k < sz) lit[k] = l[k0 + k];
+    for (int k = 0; k < PART_CPT; k++) {
+        const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
+        sz[k] = 0; off[k] = 0;
+        if (i < n) {
+            const uint4 h = hdr[i];
+            if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; }
+        }
+    }
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (k0 + k < sz) { st[k] = otStart[lit[k]]; pos[k] = atomicAdd(&otSize[lit[k]], 1u); }
+    for (int k = 0; k < PART_CPT; k++) {
+        const u32* l = pool + off[k];
+        for (u32 q = 0; q < sz[k]; q++) atomicAdd(&cnt[l[q] >> shift], 1u);
+    }
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < NB; b += PART_THREADS) {
+        const u32 m = cnt[b];
+        if (m) {
+            const u32 lit0 = min(b << shift, ND);
+            gbase[b] = otStart[lit0] + atomicAdd(&gcur[b], m);
+        }
+        cnt[b] = 0;
+    }
+    __syncthreads();
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (k0 + k < sz) occurs[st[k] + pos[k]] = i;
+    for (int k = 0; k < PART_CPT; k++) {
+        const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
+        const u32* l = pool + off[k];
+        for (u32 q = 0; q < sz[k]; q++) {
+            const u32 lit = l[q];
+            const u32 b = lit >> shift;
+            const u32 r = atomicAdd(&cnt[b], 1u);
+            pairs[gbase[b] + r] = make_uint2(lit, i);
         }
     }
 }
 
+#define PLACE_THREADS 512
+__global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
+                                                            u32 shift, u32* __restrict__ otSize, u32* __restrict__ occurs) {
+    extern __shared__ u32 cur[];
+    const u32 W = 1u << shift;
+    const u32 lit0 = blockIdx.x << shift;
+    for (u32 k = threadIdx.x; k < W; k += PLACE_THREADS) cur[k] = (lit0 + k < ND) ? otStart[lit0 + k] : 0u;
+    __syncthreads();
+    const u32 p0 = otStart[min(lit0, ND)], p1 = otStart[min(lit0 + W, ND)];
+    u32 j = p0 + threadIdx.x;
+    // four independent pair loads in flight per thread
+    for (; j + 3 * PLACE_THREADS < p1; j += 4 * PLACE_THREADS) {
+        uint2 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = pairs[j + k * PLACE_THREADS];
+#pragma unroll
+        for (int k = 0; k < 4; k++) occurs[atomicAdd(&cur[p[k].x - lit0], 1u)] = p[k].y;
+    }
+    for (; j < p1; j += PLACE_THREADS) {
+        const uint2 p = pairs[j];
+        occurs[atomicAdd(&cur[p.x - lit0], 1u)] = p.y;
+    }
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < W; k += PLACE_THREADS)
+        if (lit0 + k < ND) otSize[lit0 + k] = cur[k] - otStart[lit0 + k];
+}
+
 void launchScatter(Ctx* c) {
-    cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream);
     const u32 n = c->hdc->numCls;
-    if (n) LAUNCH(c, k_scatter, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->otSize, c->occurs);
+    if (!n) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
+    const u32 NB = c->otNB, shift = c->otShift;
+    if (!c->attrOT) {
+        cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
+        c->attrOT = true;
+    }
+    cudaMemsetAsync(c->otCur, 0, (size_t)NB * 4, c->stream);
+    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 8 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
+           c->otCur, c->otPairs);
+    LAUNCH(c, k_ot_place, NB, PLACE_THREADS, 4u << shift, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs);
 }
 
 // ------------------------------------------------------------------ live counts

@@ -10,6 +10,7 @@
 //   key[capC]   uint4 {size, first lit, last lit, sig}: the OLIST_CMP key (src/gpu/key.cuh:67-83),
 //               rebuilt by the histogram pass so the list sort never chases clause pointers
 //   hist[2V+2], otStart[2V+3], otSize[2V+2], occurs[capW]  occurrence table with 4-byte entries
+//   otPairs[capW] uint2 {literal, clause}: the radix-partition buffer of the OT build (cnf.cu)
 //               (replaces OT/OL with 8-byte refs + 16-byte list headers, src/gpu/table.cuh:32-79)
 #pragma once
 
@@ -144,6 +145,7 @@ struct Ctx {
     uint4* key;
     // OT
     u32 *hist, *otStart, *otSize, *occurs;
+    uint2* otPairs; u32* otCur; u32 otShift, otNB;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
     // vars
     u32 *scores, *eligible, *rank, *sortK, *sortV, *elected, *units, *resolved, *trail, *vorg, *varcore;
     unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *eliminated;
@@ -167,7 +169,7 @@ struct Ctx {
     cudaEvent_t ev0, ev1, evRun0, evRun1; bool ownStream;
     double msTotal;
     u32 lastElectedCount;
-    bool varcoreDead, attrSort, attrElim;
+    bool varcoreDead, attrSort, attrElim, attrOT;
     i64 unassigned0;   // unassigned variables of the loaded formula (inf.unassigned)
     // per-kernel CUDA-event timing (sigma_kernel_profile): event pairs recorded on the launch stream
     bool ktOn; cudaEvent_t* ktEv; int* ktId; u32 ktUsed;
@@ -248,7 +250,7 @@ void launchCount(Ctx* c);
 void launchGC(Ctx* c);
 int  launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm);
 // otsort.cu
-void launchSortOT(Ctx* c);
+void launchSortOT(Ctx* c, bool electedOnly);
 // lcve.cu
 int  runLCVE(Ctx* c);
 // prop.cu

@@ -24,6 +24,7 @@ struct G {
     uint4* hdr; u32* pool;
     const u32* otStart; u32* otSize; u32* occurs;
     const uint4* key;   // OLIST_CMP keys of this round (k_hist_key); lists are sorted by (key, index)
+    const u32* bloom; u32 bloomMask;   // ERE: one bit per hashed key of a live clause (k_ere_bloom)
     const u32* elected; unsigned char* eliminated; const u32* vorg; const u32* varcore;
     u32* units; u32 unitsCap; u32* resolved; u32 resolvedCap;
     u32 *veType, *veUcnt, *veRpos; u64* veRref;
@@ -394,21 +395,21 @@ template <int GS> __device__ u32 fastEqualityCheck(GT<GS>& g, u32 x, u32 y, u32 
     if (y > z) { t = y; y = z; z = t; }
     if (x > z) { t = x; x = z; z = t; }
     if (x > y) { t = x; x = y; y = t; }
-    // first match in list order; lanes scan 32 entries at a time
-    for (u32 base = 0; base < n; base += GS) {
-        const u32 j = base + LANE;
-        bool ok = false;
-        if (j < n) {
-            const uint4 h = g.hdr[list[j]];
-            if (!C_MOLTEN(h.w) && C_ORIGINAL(h.w) && h.y == 3) {
-                const u32* l = g.pool + h.x;
-                ok = l[0] == x && l[1] == y && l[2] == z;
-            }
+    // The reference returns the first match in (sorted) list order.  All matches are copies of the
+    // same clause, i.e. they share the sort key and are ordered by clause index: the first match is
+    // the one with the smallest index, which does not need this (foreign) list to be sorted.
+    u32 found = NOVAR;
+    for (u32 j = LANE; j < n; j += GS) {
+        const u32 ci = list[j];
+        const uint4 h = g.hdr[ci];
+        if (!C_MOLTEN(h.w) && C_ORIGINAL(h.w) && h.y == 3) {
+            const u32* l = g.pool + h.x;
+            if (l[0] == x && l[1] == y && l[2] == z) found = min(found, ci);
         }
-        const u32 m = BALLOT(ok);
-        if (m) return list[base + __ffs(m) - 1];
     }
-    return NOVAR;
+#pragma unroll
+    for (int o = GS / 2; o; o >>= 1) found = min(found, __shfl_xor_sync(FULL, found, o, GS));
+    return found;
 }
 // ifthenelse.cuh:52-125
 template <int GS> __device__ bool findITEGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls,
@@ -457,24 +458,25 @@ template <int GS> __device__ bool makeArity(GT<GS>& g, u32& parity, u32* literal
     u32 minsize = g.otSize[best];
     for (int k = 1; k < size; k++) { const u32 lit = literals[k]; const u32 ls = g.otSize[lit]; if (ls < minsize) { minsize = ls; best = lit; } }
     const u32* list = g.occurs + g.otStart[best];
-    for (u32 base = 0; base < minsize; base += GS) {
-        const u32 j = base + LANE;
-        bool ok = false;
-        if (j < minsize) {
-            const uint4 h = g.hdr[list[j]];
-            if (C_ORIGINAL(h.w) && (int)h.y == size) {
-                ok = true;
-                const u32* l = g.pool + h.x;
-                for (int a = 0; a < size && ok; a++) {  // checkArity
-                    bool f = false;
-                    for (int b = 0; b < size; b++) if (l[a] == literals[b]) { f = true; break; }
-                    ok = f;
-                }
+    // first match in sorted order == the matching clause with the smallest index (see fastEqualityCheck)
+    u32 found = NOVAR;
+    for (u32 j = LANE; j < minsize; j += GS) {
+        const u32 ci = list[j];
+        const uint4 h = g.hdr[ci];
+        if (C_ORIGINAL(h.w) && (int)h.y == size) {
+            bool ok = true;
+            const u32* l = g.pool + h.x;
+            for (int a = 0; a < size && ok; a++) {  // checkArity
+                bool f = false;
+                for (int b = 0; b < size; b++) if (l[a] == literals[b]) { f = true; break; }
+                ok = f;
             }
+            if (ok) found = min(found, ci);
         }
-        const u32 m = BALLOT(ok);
-        if (m) { melt(g, list[base + __ffs(m) - 1]); return true; }
     }
+#pragma unroll
+    for (int o = GS / 2; o; o >>= 1) found = min(found, __shfl_xor_sync(FULL, found, o, GS));
+    if (found != NOVAR) { melt(g, found); return true; }
     return false;
 }
 // xor.cuh:111-185
@@ -1047,6 +1049,26 @@ __global__ void __launch_bounds__(128) k_ere(GT<32> g) {
 //     residue class (position mod 32) is deleted.
 // Algorithmic bytes per resolvent: 2 clause reads (L1/L2 resident per variable) + 4 B per
 // resolvent literal (list sizes) + 20 B per binary-search probe.
+//   * before any list is touched the resolvent's key is looked up in a Bloom filter over the keys of
+//     all live clauses (one bit each, <= 16 bits per clause: L2 resident).  A clause equal to the
+//     resolvent has the same key, so a clear bit proves there is none; only the few hits (false
+//     positives included) go on to the binary search.  The filter never changes a result.
+__device__ __forceinline__ u32 keyHash(u32 sz, u32 first, u32 last, u32 sig) {
+    u32 h = sz * 0x9E3779B1u;
+    h ^= first * 0x85EBCA6Bu + 0x7F4A7C15u + (h << 6) + (h >> 2);
+    h ^= last * 0xC2B2AE35u + (h << 6) + (h >> 2);
+    h ^= sig * 0x27D4EB2Fu + (h << 6) + (h >> 2);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+__global__ void k_ere_bloom(const uint4* __restrict__ hdr, const uint4* __restrict__ key, u32 n, u32* __restrict__ bloom, u32 mask) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (C_DELETED(hdr[i].w)) continue;
+        const uint4 k = key[i];
+        const u32 h = keyHash(k.x, k.y, k.z, k.w) & mask;
+        atomicOr(&bloom[h >> 5], 1u << (h & 31u));
+    }
+}
 __device__ __forceinline__ int keyCmp(const uint4 k, u32 sz, u32 first, u32 last, u32 sig) {
     if (k.x != sz) return k.x < sz ? -1 : 1;
     if (k.y != first) return k.y < first ? -1 : 1;
@@ -1111,6 +1133,7 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, const u32* __restri
             while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
 #undef ERE_EMIT
             if (len <= 1 || !minsize) continue;
+            { const u32 hb = keyHash(len, first, last, sig) & g.bloomMask; if (!((g.bloom[hb >> 5] >> (hb & 31u)) & 1u)) continue; }
             const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
             // lower bound of the key in the sorted list of `best`
             const u32* list = g.occurs + g.otStart[best];
@@ -1172,6 +1195,7 @@ static G makeG(Ctx* c, const KOpts& k) {
     g.units = c->units; g.unitsCap = 2 * (c->V + 1); g.resolved = c->resolved; g.resolvedCap = c->resolvedCap;
     g.veType = c->veType; g.veUcnt = c->veUcnt; g.veRpos = c->veRpos; g.veRref = c->veRref;
     g.dc = c->dc; g.k = k; g.numElected = c->numElected;
+    g.bloom = nullptr; g.bloomMask = 0;
     return g;
 }
 template <int GS> static GT<GS> asGroup(const G& g) { GT<GS> t; static_cast<G&>(t) = g; return t; }
@@ -1244,6 +1268,15 @@ void launchERE(Ctx* c, const KOpts& k) {
     G g = makeG(c, k);
     static const bool v0 = getenv("SIGMA_ERE_V0") != nullptr;   // the warp-per-resolvent kernel, kept for A/B checks
     if (v0) { LAUNCH(c, k_ere, groupGrid(c->numElected, 32, 128), 128, 0, asGroup<32>(g)); return; }
+    // Bloom filter over the keys of the live clauses, in the partition buffer of the OT build (free now)
+    const u32 n = c->hdc->numCls;
+    u64 bits = 256;
+    while (bits < 16ull * n && bits < (1ull << 30)) bits <<= 1;
+    while (bits > 32 && bits / 8 > ((u64)c->capW + 4) * sizeof(uint2)) bits >>= 1;
+    u32* bloom = (u32*)c->otPairs;
+    cudaMemsetAsync(bloom, 0, bits / 8, c->stream);
+    LAUNCH(c, k_ere_bloom, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->key, n, bloom, (u32)(bits - 1));
+    g.bloom = bloom; g.bloomMask = (u32)(bits - 1);
     binElected(c, k, false);
     LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g);
 }

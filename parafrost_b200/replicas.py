@@ -1,0 +1,75 @@
+"""Instance-parallel plumbing ("replicas only").
+
+A CNF does not shard - BVE/SUB/ERE need one occurrence table, one independent set and one clause
+arena (the reference never touches a second GPU, src/gpu/constants.cuh:27 MASTER_GPU) - so N GPUs
+simplify N independent formulas, one engine context per formula, and nothing crosses NVLink on the
+data path.  This module holds the host logic around that: which rank takes which instance of a
+batch (BASELINE.json config 5: 64 mixed CNFs over 1/2/4/8 GPUs) and how per-rank device timings are
+combined (max over ranks, units summed).  torch.distributed is used for the barrier and the two
+reductions only; it works the same on gloo (CPU tests) and nccl (GPU box)."""
+from __future__ import annotations
+
+# BASELINE.json config 5: 64 mixed synthetic CNFs of 1-50 M clauses.  (family, seed, args); the
+# clause counts follow a fixed geometric ladder so the batch is identical on every run.
+def batch_specs(n: int = 64, scale: float = 1.0):
+    specs = []
+    for i in range(n):
+        fam = ("ksat3", "ksat5", "miter", "multpar")[i % 4]
+        # 1 M .. 50 M clauses, geometric in i
+        target = int(1_000_000 * (50.0 ** (i / max(1, n - 1))) * scale)
+        target = max(target, 64)
+        if fam == "ksat3":
+            specs.append(("ksat", 500 + i, [max(8, int(target / 4.26)), target, 3]))
+        elif fam == "ksat5":
+            specs.append(("ksat", 500 + i, [max(8, target // 21), target, 5]))
+        elif fam == "miter":
+            # cfg3's generator: ~8 clauses per gate pair; inputs scale with the square root
+            gates = max(8, target // 8)
+            specs.append(("miter", 500 + i, [max(4, int(gates ** 0.5)), gates, 900, 100, 64]))
+        else:
+            # n x n array multiplier has ~17 n^2 clauses, the parity chain 4 per link: half / half
+            nbits = max(4, int((target / 2 / 17.0) ** 0.5))
+            specs.append(("multpar", 500 + i, [nbits, max(8, target // 8)]))
+    return specs
+
+
+def spec_weight(spec) -> int:
+    """Clause-count estimate used for the static schedule (no generation needed)."""
+    fam, _, a = spec
+    if fam == "ksat":
+        return int(a[1])
+    if fam == "miter":
+        return int(a[1]) * 8
+    if fam == "multpar":
+        return int(17 * a[0] * a[0] + 4 * a[1])
+    return 1
+
+
+def assign_longest_first(weights, world: int):
+    """Static longest-processing-time-first schedule: returns world lists of instance indices.
+    Deterministic (ties by index), every instance exactly once."""
+    order = sorted(range(len(weights)), key=lambda i: (-weights[i], i))
+    load = [0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += weights[i]
+    return out
+
+
+def reduce_timing(dist, ms_local: float, units_local: float, device="cpu"):
+    """(max over ranks of ms, sum over ranks of units).  `dist` is torch.distributed or None."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(ms_local), float(units_local)
+    import torch
+    t = torch.tensor([float(ms_local)], dtype=torch.float64, device=device)
+    u = torch.tensor([float(units_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(t[0]), float(u[0])
+
+
+def rank_seed(seed: int, rank: int) -> int:
+    """Replica r of a single-config bench simplifies its own formula of the same shape."""
+    return seed + 1000 * rank
