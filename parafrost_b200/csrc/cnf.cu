@@ -153,6 +153,87 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
     }
 }
 
+// The same partition with match-based ranking instead of shared-memory atomics (an ATOMS with
+// spread addresses costs ~2 cycles per lane, which made the atomic version LSU-bound at ~1.4 TB/s):
+// the lanes of a warp that hold the same bucket find each other with one ballot per bucket bit, the
+// lowest of them bumps the warp's PRIVATE counter with a plain read-modify-write, and a lane's slot
+// is counter + its rank among its peers - the ranking scheme of onesweep radix sorts.  Pass A counts,
+// the warps' counters are prefixed per bucket and one run per bucket is reserved with a global
+// atomic, pass B repeats the identical traversal and writes.  Needs warps x NB counters: NB <= 1024.
+#define PARTM_WARPS (PART_THREADS / 32)
+__device__ __forceinline__ u32 matchBucket(u32 b, u32 nbits, u32 validMask) {
+    u32 peers = validMask;
+    for (u32 i = 0; i < nbits; i++) {
+        const bool bit = (b >> i) & 1u;
+        const u32 m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+__global__ void __launch_bounds__(PART_THREADS) k_ot_part_m(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
+                                                            const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB, u32 nbits,
+                                                            u32* __restrict__ gcur, uint2* __restrict__ pairs) {
+    extern __shared__ u32 sm[];
+    u32* gbase = sm;                       // [NB]
+    u32* wc = sm + NB + (threadIdx.x >> 5) * NB;   // this warp's counters [NB]
+    const u32 lane = threadIdx.x & 31u;
+    const u32 tile0 = blockIdx.x * PART_TILE;
+    for (u32 z = threadIdx.x; z < (PARTM_WARPS + 1) * NB; z += PART_THREADS) sm[z] = 0;
+    u32 off[PART_CPT], sz[PART_CPT];
+#pragma unroll
+    for (int k = 0; k < PART_CPT; k++) {
+        // a warp owns 32 consecutive clauses per k: its literal loads cover one contiguous span
+        const u32 i = tile0 + ((threadIdx.x >> 5) * PART_CPT + k) * 32 + lane;
+        sz[k] = 0; off[k] = 0;
+        if (i < n) {
+            const uint4 h = hdr[i];
+            if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; }
+        }
+    }
+    __syncthreads();
+    // pass A: count
+#pragma unroll
+    for (int k = 0; k < PART_CPT; k++) {
+        const u32 maxsz = warpMax(sz[k]);
+        const u32* l = pool + off[k];
+        for (u32 q = 0; q < maxsz; q++) {
+            const bool valid = q < sz[k];
+            const u32 b = valid ? (l[q] >> shift) : 0u;
+            const u32 peers = matchBucket(b, nbits, __ballot_sync(0xffffffffu, valid));
+            if (valid && (peers & lanemaskLt()) == 0) wc[b] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < NB; b += PART_THREADS) {
+        u32 t = 0;
+#pragma unroll
+        for (int w = 0; w < PARTM_WARPS; w++) { u32* p = sm + NB + w * NB + b; const u32 m = *p; *p = t; t += m; }
+        if (t) gbase[b] = otStart[min(b << shift, ND)] + atomicAdd(&gcur[b], t);
+    }
+    __syncthreads();
+    // pass B: the identical traversal, now writing
+#pragma unroll
+    for (int k = 0; k < PART_CPT; k++) {
+        const u32 i = tile0 + ((threadIdx.x >> 5) * PART_CPT + k) * 32 + lane;
+        const u32 maxsz = warpMax(sz[k]);
+        const u32* l = pool + off[k];
+        for (u32 q = 0; q < maxsz; q++) {
+            const bool valid = q < sz[k];
+            const u32 lit = valid ? l[q] : 0u;
+            const u32 b = lit >> shift;
+            const u32 peers = matchBucket(b, nbits, __ballot_sync(0xffffffffu, valid));
+            const u32 rank = __popc(peers & lanemaskLt());
+            u32 pre = 0;
+            if (valid) pre = wc[b];
+            __syncwarp();
+            if (valid && rank == 0) wc[b] = pre + __popc(peers);
+            __syncwarp();
+            if (valid) pairs[gbase[b] + pre + rank] = make_uint2(lit, i);
+        }
+    }
+}
+
 #define PLACE_THREADS 512
 __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
                                                             u32 shift, u32* __restrict__ otSize, u32* __restrict__ occurs) {
@@ -182,16 +263,24 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restr
 
 void launchScatter(Ctx* c) {
     const u32 n = c->hdc->numCls;
-    if (!n) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
+    // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
+    if (!n || !c->numLiterals) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
     const u32 NB = c->otNB, shift = c->otShift;
     if (!c->attrOT) {
         cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_part_m, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PARTM_WARPS + 1) * 1024);
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
         c->attrOT = true;
     }
     cudaMemsetAsync(c->otCur, 0, (size_t)NB * 4, c->stream);
-    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 8 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
-           c->otCur, c->otPairs);
+    u32 nbits = 0;
+    while ((1u << nbits) < NB) nbits++;
+    if (NB <= 1024)
+        LAUNCH(c, k_ot_part_m, divup(n, PART_TILE), PART_THREADS, 4 * (PARTM_WARPS + 1) * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart,
+               c->ND, shift, NB, nbits, c->otCur, c->otPairs);
+    else   // more than 2^24 variables: the warp-private counters no longer fit, fall back to shared-memory atomics
+        LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 8 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
+               c->otCur, c->otPairs);
     LAUNCH(c, k_ot_place, NB, PLACE_THREADS, 4u << shift, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs);
 }
 

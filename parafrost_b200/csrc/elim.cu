@@ -1062,11 +1062,14 @@ __device__ __forceinline__ u32 keyHash(u32 sz, u32 first, u32 last, u32 sig) {
     return h;
 }
 __global__ void k_ere_bloom(const uint4* __restrict__ hdr, const uint4* __restrict__ key, u32 n, u32* __restrict__ bloom, u32 mask) {
+    u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sizes this thread has already reported (the 256-bit size mask follows the filter words)
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (C_DELETED(hdr[i].w)) continue;
         const uint4 k = key[i];
         const u32 h = keyHash(k.x, k.y, k.z, k.w) & mask;
         atomicOr(&bloom[h >> 5], 1u << (h & 31u));
+        const u32 sb = k.x < 255u ? k.x : 255u;
+        if (!((seen[sb >> 5] >> (sb & 31u)) & 1u)) { seen[sb >> 5] |= 1u << (sb & 31u); atomicOr(&bloom[(mask >> 5) + 1 + (sb >> 5)], 1u << (sb & 31u)); }
     }
 }
 __device__ __forceinline__ int keyCmp(const uint4 k, u32 sz, u32 first, u32 last, u32 sig) {
@@ -1098,6 +1101,9 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, const u32* __restri
     const u32 lane = LANE;
     const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
     const u32 count = *wlCount;
+    u32 sizeMask[8];   // bit s: some live clause has size s (255 = "255 or more"), k_ere_bloom
+#pragma unroll
+    for (int k = 0; k < 8; k++) sizeMask[k] = g.bloom[(g.bloomMask >> 5) + 1 + k];
     for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
         const u32 v = g.elected[wl[wi]], p = V2L(v), n = p | 1u;
         const u32 ds = g.otSize[p], fs = g.otSize[n];
@@ -1114,11 +1120,10 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, const u32* __restri
             if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
             const u32* a = g.pool + hp.x; const int n1 = (int)hp.y;
             const u32* b = g.pool + hn.x; const int n2 = (int)hn.y;
-            // one merge pass: length, tautology, first / last literal, signature, shortest list
-            int it1 = 0, it2 = 0; u32 len = 0, first = 0, last = 0, sig = 0, best = 0, minsize = 0xFFFFFFFFu;
+            // first merge pass: length, tautology, first / last literal, signature - enough for the filters
+            int it1 = 0, it2 = 0; u32 len = 0, first = 0, last = 0, sig = 0;
             bool taut = false;
-#define ERE_EMIT(L_) do { const u32 l_ = (L_); if (!len) first = l_; last = l_; len++; sig |= MAPHASH(l_); \
-                          const u32 s_ = g.otSize[l_]; if (s_ < minsize) { minsize = s_; best = l_; } } while (0)
+#define ERE_EMIT(L_) do { const u32 l_ = (L_); if (!len) first = l_; last = l_; len++; sig |= MAPHASH(l_); } while (0)
             while (it1 < n1 && it2 < n2) {
                 const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
                 if (v1 == v) it1++;
@@ -1132,8 +1137,26 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, const u32* __restri
             while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != v) ERE_EMIT(l); }
             while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
 #undef ERE_EMIT
-            if (len <= 1 || !minsize) continue;
+            if (len <= 1) continue;
+            // filters: is there a live clause of this size at all / with this key at all?
+            { const u32 sb = len < 255u ? len : 255u; if (!((sizeMask[sb >> 5] >> (sb & 31u)) & 1u)) continue; }
             { const u32 hb = keyHash(len, first, last, sig) & g.bloomMask; if (!((g.bloom[hb >> 5] >> (hb & 31u)) & 1u)) continue; }
+            // second pass (rare): the literal of the resolvent with the shortest occurrence list (forward_equ, redundancy.cuh:99-112)
+            u32 best = 0, minsize = 0xFFFFFFFFu;
+#define ERE_EMIT(L_) do { const u32 l_ = (L_); const u32 s_ = g.otSize[l_]; if (s_ < minsize) { minsize = s_; best = l_; } } while (0)
+            it1 = 0; it2 = 0;
+            while (it1 < n1 && it2 < n2) {
+                const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
+                if (v1 == v) it1++;
+                else if (v2 == v) it2++;
+                else if (v1 < v2) { it1++; ERE_EMIT(lit1); }
+                else if (v2 < v1) { it2++; ERE_EMIT(lit2); }
+                else { it1++; it2++; ERE_EMIT(lit1); }
+            }
+            while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != v) ERE_EMIT(l); }
+            while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
+#undef ERE_EMIT
+            if (!minsize) continue;
             const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
             // lower bound of the key in the sorted list of `best`
             const u32* list = g.occurs + g.otStart[best];
@@ -1271,10 +1294,10 @@ void launchERE(Ctx* c, const KOpts& k) {
     // Bloom filter over the keys of the live clauses, in the partition buffer of the OT build (free now)
     const u32 n = c->hdc->numCls;
     u64 bits = 256;
-    while (bits < 16ull * n && bits < (1ull << 30)) bits <<= 1;
-    while (bits > 32 && bits / 8 > ((u64)c->capW + 4) * sizeof(uint2)) bits >>= 1;
+    while (bits < 8ull * n && bits < (1ull << 30)) bits <<= 1;   // >= 8 bits per clause: the filter stays L2 resident
+    while (bits > 32 && bits / 8 + 32 > ((u64)c->capW + 4) * sizeof(uint2)) bits >>= 1;
     u32* bloom = (u32*)c->otPairs;
-    cudaMemsetAsync(bloom, 0, bits / 8, c->stream);
+    cudaMemsetAsync(bloom, 0, bits / 8 + 32, c->stream);   // + the 256-bit clause-size mask
     LAUNCH(c, k_ere_bloom, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->key, n, bloom, (u32)(bits - 1));
     g.bloom = bloom; g.bloomMask = (u32)(bits - 1);
     binElected(c, k, false);

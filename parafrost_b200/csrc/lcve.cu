@@ -146,6 +146,47 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const unsigned char
 // one 4-byte probe instead of walking the whole neighbourhood again; only when the blocker got
 // frozen itself is the neighbourhood rescanned.  (Decisions can come a round later than with a
 // full scan every round; the fixed point - the lexicographically first MIS - is the same.)
+// An elected variable freezes its higher-ranked undecided neighbours at once (push) instead of
+// letting each of them find out by rescanning its own neighbourhood: every concurrent writer of a
+// neighbour's state word agrees on FROZEN (a neighbour of a just-elected variable can neither be
+// elected nor become the live stopper in the same launch: it sees this variable undecided or elected).
+template <int GS>
+__device__ __forceinline__ void pushFreeze(u32 v, u32 r, u32 lane, const uint4* __restrict__ hdr, const u32* __restrict__ pool,
+                                           const u32* __restrict__ otStart, const u32* __restrict__ otSize,
+                                           const u32* __restrict__ occurs, u32* vinfo) {
+    for (u32 side = 0; side < 2; side++) {
+        const u32 lit = V2L(v) | side;
+        const u32 n = otSize[lit];
+        const u32* list = occurs + otStart[lit];
+        for (u32 j = lane; j < n; j += GS) {
+            const uint4 h = hdr[list[j]];
+            if (C_DELETED(h.w)) continue;
+            const u32* l = pool + h.x;
+            for (u32 k = 0; k < h.y; k++) {
+                const u32 u = LABS(l[k]);
+                if (u == v) continue;
+                const u32 wu = vinfo[u];
+                if (VI_STATE(wu) == MIS_UNDECIDED && VI_RANK(wu) > r) vinfo[u] = (wu & ~7u) | MIS_FROZEN;
+            }
+        }
+    }
+}
+
+// push for the variables elected by k_mis_first (thread-per-variable there: no group to walk the lists)
+template <int GS>
+__global__ void __launch_bounds__(256) k_mis_push(const u32* __restrict__ list, const u32* __restrict__ count,
+                                                  const uint4* __restrict__ hdr, const u32* __restrict__ pool,
+                                                  const u32* __restrict__ otStart, const u32* __restrict__ otSize,
+                                                  const u32* __restrict__ occurs, u32* vinfo) {
+    const u32 n = *count;
+    const u32 lane = threadIdx.x & (u32)(GS - 1);
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) / GS; it < n; it += groupsPerGrid) {
+        const u32 v = list[it];
+        pushFreeze<GS>(v, VI_RANK(vinfo[v]), lane, hdr, pool, otStart, otSize, occurs, vinfo);
+    }
+}
+
 template <int GS>
 __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* __restrict__ wl1, u32 round, DevCounters* dc,
                                                    const uint4* __restrict__ hdr, const u32* __restrict__ pool,
@@ -164,6 +205,7 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
         const u32 v = wlIn[it];
         const u32 wv = vinfo[v];
         const u32 r = VI_RANK(wv);
+        if (VI_STATE(wv) != MIS_UNDECIDED) continue;   // frozen by an elected neighbour's push
         if (r > dc->misStopRank) continue;  // beyond the cut: never looked at by the serial walk
         const u32 b = blocker[v];
         if (b) {
@@ -210,6 +252,8 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
             }
             else wlOut[atomicAdd(outCnt, 1u)] = v;
         }
+        if (!frozen && !blocked && !oversize && VI_CLASS(wv) == CS_CAND)   // just elected (uniform over the group)
+            pushFreeze<GS>(v, r, lane, hdr, pool, otStart, otSize, occurs, vinfo);
     }
 }
 
@@ -230,30 +274,36 @@ __global__ void __launch_bounds__(256) k_mis_clauses(const uint4* __restrict__ h
         const u32* l = pool + h.x;
         u32 eMin = NOVAR, u1 = NOVAR, u2 = NOVAR;
         bool any = false;
-        for (u32 k = 0; k < h.y; k++) {
-            const u32 w = vinfo[LABS(l[k])];
-            const u32 r = VI_RANK(w), st = VI_STATE(w);
-            if (st == MIS_ELECTED) eMin = min(eMin, r);
-            else if (st == MIS_UNDECIDED && r < H) {
-                any = true;
-                if (VI_CLASS(w) == CS_CAND) { if (r < u1) { u2 = u1; u1 = r; } else if (r < u2) u2 = r; }
-            }
-        }
+        // election words of the first 8 literals stay in registers for the second loop
+        u32 lv[8], wv[8];
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) if (k < h.y) lv[k] = LABS(l[k]);
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) if (k < h.y) wv[k] = vinfo[lv[k]];
+#define MC_SCAN(W_) do { const u32 w = (W_); const u32 r = VI_RANK(w), st = VI_STATE(w); \
+            if (st == MIS_ELECTED) eMin = min(eMin, r); \
+            else if (st == MIS_UNDECIDED && r < H) { any = true; \
+                if (VI_CLASS(w) == CS_CAND) { if (r < u1) { u2 = u1; u1 = r; } else if (r < u2) u2 = r; } } } while (0)
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) if (k < h.y) MC_SCAN(wv[k]);
+        for (u32 k = 8; k < h.y; k++) MC_SCAN(vinfo[LABS(l[k])]);
+#undef MC_SCAN
         if (!any) continue;
         const bool big = (int)h.y > maxcsize;
-        for (u32 k = 0; k < h.y; k++) {
-            const u32 u = LABS(l[k]);
-            const u32 w = vinfo[u];
-            const u32 r = VI_RANK(w);
-            if (VI_STATE(w) != MIS_UNDECIDED || r >= H) continue;
-            if (big) ovs[u] = 1;
-            if (eMin < r) vinfo[u] = (w & ~7u) | MIS_FROZEN;
-            else { const u32 other = (u1 == r) ? u2 : u1; if (other < r) atomicMin(&nbr[u], other); }
-        }
+#define MC_APPLY(U_, W_) do { const u32 u_ = (U_), w_ = (W_); const u32 r_ = VI_RANK(w_); \
+            if (VI_STATE(w_) == MIS_UNDECIDED && r_ < H) { \
+                if (big) ovs[u_] = 1; \
+                if (eMin < r_) vinfo[u_] = (w_ & ~7u) | MIS_FROZEN; \
+                else { const u32 other = (u1 == r_) ? u2 : u1; if (other < r_) atomicMin(&nbr[u_], other); } } } while (0)
+#pragma unroll
+        for (u32 k = 0; k < 8; k++) if (k < h.y) MC_APPLY(lv[k], wv[k]);
+        for (u32 k = 8; k < h.y; k++) { const u32 uu = LABS(l[k]); MC_APPLY(uu, vinfo[uu]); }
+#undef MC_APPLY
     }
 }
 __global__ void k_mis_first(const u32* __restrict__ eligible, u32 rBegin, u32 rEnd, u32* vinfo, const u32* __restrict__ nbr,
-                            const unsigned char* __restrict__ ovs, u32* __restrict__ blocker, u32* __restrict__ wl, DevCounters* dc, u32 slot) {
+                            const unsigned char* __restrict__ ovs, u32* __restrict__ blocker, u32* __restrict__ wl, DevCounters* dc, u32 slot,
+                            u32* __restrict__ pushList, u32* pushCount) {
     for (u32 r0 = rBegin + blockIdx.x * blockDim.x; r0 < rEnd; r0 += gridDim.x * blockDim.x) {
         const u32 r = r0 + threadIdx.x;
         bool queue = false; u32 v = 0;
@@ -264,7 +314,8 @@ __global__ void k_mis_first(const u32* __restrict__ eligible, u32 rBegin, u32 rE
                 const u32 m = nbr[v];
                 if (m == NOVAR) {
                     if (VI_CLASS(w) == CS_STOP) { vinfo[v] = (w & ~7u) | MIS_LIVESTOP; atomicMin(&dc->misStopRank, r); }
-                    else vinfo[v] = (w & ~7u) | (ovs[v] ? MIS_FROZEN : MIS_ELECTED);
+                    else if (ovs[v]) vinfo[v] = (w & ~7u) | MIS_FROZEN;
+                    else { vinfo[v] = (w & ~7u) | MIS_ELECTED; pushList[atomicAdd(pushCount, 1u)] = v; }
                 } else { blocker[v] = eligible[m]; queue = true; }
             }
         }
@@ -382,7 +433,16 @@ int runLCVE(Ctx* c) {
         const bool clausePass = (u64)(H - hPrev) * avgOcc * 2 > nCls;
         if (clausePass) {
             LAUNCH(c, k_mis_clauses, gridFor(nCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], nCls, vinfo, nbr, ovs, H, c->o.lcve_clause_max);
-            LAUNCH(c, k_mis_first, gridFor(H - hPrev, 256), 256, 0, c->eligible, hPrev, H, vinfo, nbr, ovs, blocker, wlIn, c->dc, round % 3u);
+            u32* pushCount = &c->dc->scratch[2];
+            CUDA_TRY(cudaMemsetAsync(pushCount, 0, 4, c->stream));
+            LAUNCH(c, k_mis_first, gridFor(H - hPrev, 256), 256, 0, c->eligible, hPrev, H, vinfo, nbr, ovs, blocker, wlIn, c->dc, round % 3u,
+                   c->flagA, pushCount);
+            if (smallGroups)
+                LAUNCH(c, k_mis_push<8>, gridFor((u64)(H - hPrev) * 8, 256), 256, 0, c->flagA, pushCount, c->hdr[c->cur], c->pool[c->cur],
+                       c->otStart, c->otSize, c->occurs, vinfo);
+            else
+                LAUNCH(c, k_mis_push<32>, gridFor((u64)(H - hPrev) * 32, 256), 256, 0, c->flagA, pushCount, c->hdr[c->cur], c->pool[c->cur],
+                       c->otStart, c->otSize, c->occurs, vinfo);
         } else
             LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, c->cstat, hPrev, H, wlIn, c->dc, round % 3u);
         u32 n = H - hPrev;   // upper bound of the worklist until the first read-back

@@ -15,6 +15,9 @@ for w in $what; do
       echo "pytest rc=$?"; tail -3 gpurun_out/${tag}_pytest_gpu.log ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" ;;
+    sanitize)  # memcheck of the small smoke formulas (slow: tiny inputs only)
+      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/${tag}_sanitize.log 2>&1
+      echo "sanitize rc=$?"; grep -E "ERROR SUMMARY|Invalid|smoke" gpurun_out/${tag}_sanitize.log | head -8 ;;
     bench)
       timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench_cfg2.json 2> gpurun_out/${tag}_bench_cfg2.err
       echo "bench rc=$?"; cut -c1-600 gpurun_out/${tag}_bench_cfg2.json ;;
@@ -36,6 +39,9 @@ for w in $what; do
       echo "full rc=$?"
       ncu -i /tmp/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
       python tools/ncu_digest.py gpurun_out/${tag}_full_raw.csv > gpurun_out/${tag}_full_digest.txt 2>&1; head -40 gpurun_out/${tag}_full_digest.txt
+      for kn in ${NCU_SRC:-}; do   # per-instruction stall samples of selected kernels (first captured launch each)
+        ncu -i /tmp/${tag}_full.ncu-rep --page source --csv --kernel-name regex:$kn --launch-count 1 > gpurun_out/${tag}_src_${kn}.csv 2>/dev/null
+      done
       sz=$(stat -c %s /tmp/${tag}_full.ncu-rep 2>/dev/null || echo 0)
       if [ "$sz" -gt 0 ] && [ "$sz" -lt 30000000 ]; then cp /tmp/${tag}_full.ncu-rep gpurun_out/; fi ;;
   esac
