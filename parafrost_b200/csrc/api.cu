@@ -196,6 +196,7 @@ static size_t carve(Ctx* c, char* base) {
     c->mis = a.take<unsigned char>(V1); c->cstat = a.take<unsigned char>(V1);
     c->vstate = a.take<unsigned char>(V1); c->vstate0 = a.take<unsigned char>(V1);
     c->assumed = a.take<unsigned char>(V1); c->eliminated = a.take<unsigned char>(V1);
+    c->needSort = a.take<unsigned char>(ND + 4);
     c->wlA = a.take<u32>(V1); c->wlB = a.take<u32>(V1);
     c->veType = a.take<u32>(V1); c->veUcnt = a.take<u32>(V1); c->veRpos = a.take<u32>(V1); c->veRref = a.take<u64>(V1);
     const size_t maxScan = (nflag > ND + 2 ? nflag : ND + 2);
@@ -311,7 +312,7 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     c->cur = 0;
     c->phase = c->multiplier = 0; c->simpstate = SIGMA_OK; c->cnfstate = SIGMA_UNSOLVED; c->compacted = false;
     c->nUnits = 0; c->numElected = 0; c->currMelted = 0; c->varcoreDead = false;
-    c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0;
+    c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0; c->otValid = false;
     memset(c->stageMs, 0, sizeof c->stageMs);
     c->unassigned = c->unassigned0;
     memset(c->hdc, 0, sizeof(DevCounters));
@@ -383,7 +384,23 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     const int times = c->phase + 1;
     const bool gc = times > 1 && times != c->o.phases && c->o.shrink_rate > 0 && (times % c->o.shrink_rate) == 0;
     if (!gc) c->compacted = false;
-    buildOT(c, gc, &didGC);
+    // A round that changed nothing (no elimination, resolvent, unit, deletion or strengthening) leaves
+    // the clause store, and with it the occurrence table, exactly as this round would rebuild them -
+    // the usual way into the last round (stop(): !cdiff && !ldiff).  Compacting a store without
+    // deleted slots or shrunken clauses is the identity, so a due GC does not invalidate the table.
+    const bool gcIdentity = c->hdc->numCls == c->numClauses && c->hdc->poolUsed == c->numLiterals &&
+                            c->hdc->dataSize == c->numClauses * NBUCKETS + c->numLiterals;
+    if (c->otValid && !c->nUnits && (!gc || gcIdentity)) {
+        if (gc) {   // reallocCNF(true), cnf.cu:129-144: the logical capacities move as if it had compacted
+            const u64 maxAddedCls = c->o.ve_en ? c->numClauses : 0;
+            const u64 maxAddedLits = c->o.ve_en ? (u64)((double)c->orgLiterals * c->o.lits_mul) : 0;
+            c->refsCap = c->numClauses + maxAddedCls;
+            c->dataCap = c->refsCap * NBUCKETS + (c->numLiterals + maxAddedLits);
+            c->compacted = true; didGC = true;
+        }
+    } else
+        buildOT(c, gc, &didGC);
+    c->otValid = false;
     r.gc = didGC;
     // prop (elimbcp.cu:144-215)
     if (c->nUnits) {
@@ -424,9 +441,9 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     // stop() solver.hpp:748-753
     const bool stop = (c->phase == c->o.phases) || (c->simpstate == SIGMA_CNFALLOC_FAIL) || (!c->cdiff && !c->ldiff) ||
                       (c->phase > 2 && c->ldiff <= c->o.phase_lits_min);
-    // sortOT (segsort.cu:37-48).  ERE binary-searches the list of ANY literal, so the last round sorts
-    // every list; SUB/BVE/BCE only walk the lists of the elected variables in order.
-    if (!stop || (c->o.ere_en && c->numElected)) { StageTimer t(c, ST_SOT); launchSortOT(c, !stop); }
+    // sortOT (segsort.cu:37-48).  SUB/BVE/BCE only walk the lists of the elected variables in order;
+    // the last round's ERE sorts the lists it is going to search by itself (launchERE).
+    if (!stop) { StageTimer t(c, ST_SOT); launchSortOT(c, 1); }
     if (stop) {
         r.kind = 1;
         if (c->o.ere_en && c->numElected) { StageTimer t(c, ST_ERE); launchERE(c, k); }
@@ -460,6 +477,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     c->ldiff = c->litsbefore - (i64)c->numLiterals; c->litsbefore = (i64)c->numLiterals;
     c->nUnits = c->hdc->numUnits;
     r.units = c->nUnits;
+    c->otValid = !r.eliminated && !r.resolvents && !c->nUnits && !c->cdiff && !c->ldiff;   // structure untouched: table reusable
     c->phase++; c->multiplier++;
     c->multiplier += (c->phase == c->o.phases);
     r.clauses = c->numClauses; r.literals = c->numLiterals;

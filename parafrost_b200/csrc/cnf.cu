@@ -101,6 +101,11 @@ void launchHistKey(Ctx* c) {
 //               streamed once (coalesced), clause indices stored into occurs[] inside the bucket's
 //               window (<= a few hundred KB: the sectors are completed in L2 before they reach HBM).
 // The order inside a list is arbitrary (as in the reference); k_sort_* fixes it afterwards.
+// Measured (profiles/r01_ncu_full_cfg2_v3.txt): both kernels are bound by the LSU/MIO path - one
+// shared-memory atomic (~2 cycles per lane) and one 4/8-byte store to its own sector per pair - not
+// by HBM.  A warp-match ranking variant (ballots + warp-private counters, no atomics) was measured
+// 10-100 % slower on cfg2-cfg4 and dropped; clause-local formulas (Tseitin, multiplier) already
+// write long runs per bucket and partition at ~3x the speed of uniform random k-SAT.
 // Algorithmic bytes: part 16C + 4L read + 8L written; place 8L read + 4L written + 12 ND.
 #define PART_THREADS 512
 #define PART_CPT 8
@@ -153,87 +158,6 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
     }
 }
 
-// The same partition with match-based ranking instead of shared-memory atomics (an ATOMS with
-// spread addresses costs ~2 cycles per lane, which made the atomic version LSU-bound at ~1.4 TB/s):
-// the lanes of a warp that hold the same bucket find each other with one ballot per bucket bit, the
-// lowest of them bumps the warp's PRIVATE counter with a plain read-modify-write, and a lane's slot
-// is counter + its rank among its peers - the ranking scheme of onesweep radix sorts.  Pass A counts,
-// the warps' counters are prefixed per bucket and one run per bucket is reserved with a global
-// atomic, pass B repeats the identical traversal and writes.  Needs warps x NB counters: NB <= 1024.
-#define PARTM_WARPS (PART_THREADS / 32)
-__device__ __forceinline__ u32 matchBucket(u32 b, u32 nbits, u32 validMask) {
-    u32 peers = validMask;
-    for (u32 i = 0; i < nbits; i++) {
-        const bool bit = (b >> i) & 1u;
-        const u32 m = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? m : ~m;
-    }
-    return peers;
-}
-__global__ void __launch_bounds__(PART_THREADS) k_ot_part_m(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
-                                                            const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB, u32 nbits,
-                                                            u32* __restrict__ gcur, uint2* __restrict__ pairs) {
-    extern __shared__ u32 sm[];
-    u32* gbase = sm;                       // [NB]
-    u32* wc = sm + NB + (threadIdx.x >> 5) * NB;   // this warp's counters [NB]
-    const u32 lane = threadIdx.x & 31u;
-    const u32 tile0 = blockIdx.x * PART_TILE;
-    for (u32 z = threadIdx.x; z < (PARTM_WARPS + 1) * NB; z += PART_THREADS) sm[z] = 0;
-    u32 off[PART_CPT], sz[PART_CPT];
-#pragma unroll
-    for (int k = 0; k < PART_CPT; k++) {
-        // a warp owns 32 consecutive clauses per k: its literal loads cover one contiguous span
-        const u32 i = tile0 + ((threadIdx.x >> 5) * PART_CPT + k) * 32 + lane;
-        sz[k] = 0; off[k] = 0;
-        if (i < n) {
-            const uint4 h = hdr[i];
-            if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; }
-        }
-    }
-    __syncthreads();
-    // pass A: count
-#pragma unroll
-    for (int k = 0; k < PART_CPT; k++) {
-        const u32 maxsz = warpMax(sz[k]);
-        const u32* l = pool + off[k];
-        for (u32 q = 0; q < maxsz; q++) {
-            const bool valid = q < sz[k];
-            const u32 b = valid ? (l[q] >> shift) : 0u;
-            const u32 peers = matchBucket(b, nbits, __ballot_sync(0xffffffffu, valid));
-            if (valid && (peers & lanemaskLt()) == 0) wc[b] += __popc(peers);
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    for (u32 b = threadIdx.x; b < NB; b += PART_THREADS) {
-        u32 t = 0;
-#pragma unroll
-        for (int w = 0; w < PARTM_WARPS; w++) { u32* p = sm + NB + w * NB + b; const u32 m = *p; *p = t; t += m; }
-        if (t) gbase[b] = otStart[min(b << shift, ND)] + atomicAdd(&gcur[b], t);
-    }
-    __syncthreads();
-    // pass B: the identical traversal, now writing
-#pragma unroll
-    for (int k = 0; k < PART_CPT; k++) {
-        const u32 i = tile0 + ((threadIdx.x >> 5) * PART_CPT + k) * 32 + lane;
-        const u32 maxsz = warpMax(sz[k]);
-        const u32* l = pool + off[k];
-        for (u32 q = 0; q < maxsz; q++) {
-            const bool valid = q < sz[k];
-            const u32 lit = valid ? l[q] : 0u;
-            const u32 b = lit >> shift;
-            const u32 peers = matchBucket(b, nbits, __ballot_sync(0xffffffffu, valid));
-            const u32 rank = __popc(peers & lanemaskLt());
-            u32 pre = 0;
-            if (valid) pre = wc[b];
-            __syncwarp();
-            if (valid && rank == 0) wc[b] = pre + __popc(peers);
-            __syncwarp();
-            if (valid) pairs[gbase[b] + pre + rank] = make_uint2(lit, i);
-        }
-    }
-}
-
 #define PLACE_THREADS 512
 __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
                                                             u32 shift, u32* __restrict__ otSize, u32* __restrict__ occurs) {
@@ -268,19 +192,12 @@ void launchScatter(Ctx* c) {
     const u32 NB = c->otNB, shift = c->otShift;
     if (!c->attrOT) {
         cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-        cudaFuncSetAttribute(k_ot_part_m, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PARTM_WARPS + 1) * 1024);
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
         c->attrOT = true;
     }
     cudaMemsetAsync(c->otCur, 0, (size_t)NB * 4, c->stream);
-    u32 nbits = 0;
-    while ((1u << nbits) < NB) nbits++;
-    if (NB <= 1024)
-        LAUNCH(c, k_ot_part_m, divup(n, PART_TILE), PART_THREADS, 4 * (PARTM_WARPS + 1) * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart,
-               c->ND, shift, NB, nbits, c->otCur, c->otPairs);
-    else   // more than 2^24 variables: the warp-private counters no longer fit, fall back to shared-memory atomics
-        LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 8 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
-               c->otCur, c->otPairs);
+    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 8 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
+           c->otCur, c->otPairs);
     LAUNCH(c, k_ot_place, NB, PLACE_THREADS, 4u << shift, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs);
 }
 

@@ -148,7 +148,7 @@ struct Ctx {
     uint2* otPairs; u32* otCur; u32 otShift, otNB;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
     // vars
     u32 *scores, *eligible, *rank, *sortK, *sortV, *elected, *units, *resolved, *trail, *vorg, *varcore;
-    unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *eliminated;
+    unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *eliminated, *needSort;
     u32 *wlA, *wlB;
     // BVE arrays
     u32 *veType, *veUcnt, *veRpos, *veRes, *veUoff, *veResOff; u64* veRref;
@@ -170,6 +170,7 @@ struct Ctx {
     double msTotal;
     u32 lastElectedCount;
     bool varcoreDead, attrSort, attrElim, attrOT;
+    bool otValid;      // the occurrence table built last round still describes the clause store (api.cu)
     i64 unassigned0;   // unassigned variables of the loaded formula (inf.unassigned)
     // per-kernel CUDA-event timing (sigma_kernel_profile): event pairs recorded on the launch stream
     bool ktOn; cudaEvent_t* ktEv; int* ktId; u32 ktUsed;
@@ -250,7 +251,7 @@ void launchCount(Ctx* c);
 void launchGC(Ctx* c);
 int  launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm);
 // otsort.cu
-void launchSortOT(Ctx* c, bool electedOnly);
+void launchSortOT(Ctx* c, int mode);   // 0 all lists, 1 elected variables, 2 lists flagged in needSort
 // lcve.cu
 int  runLCVE(Ctx* c);
 // prop.cu

@@ -1061,16 +1061,29 @@ __device__ __forceinline__ u32 keyHash(u32 sz, u32 first, u32 last, u32 sig) {
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
     return h;
 }
-__global__ void k_ere_bloom(const uint4* __restrict__ hdr, const uint4* __restrict__ key, u32 n, u32* __restrict__ bloom, u32 mask) {
-    u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sizes this thread has already reported (the 256-bit size mask follows the filter words)
+__global__ void __launch_bounds__(256) k_ere_bloom(const uint4* __restrict__ hdr, const uint4* __restrict__ key, u32 n, u32* __restrict__ bloom, u32 mask) {
+    __shared__ u32 sizes[8];   // 256-bit mask of the clause sizes seen by this CTA; stored after the filter words
+    if (threadIdx.x < 8) sizes[threadIdx.x] = 0;
+    __syncthreads();
+    u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (C_DELETED(hdr[i].w)) continue;
         const uint4 k = key[i];
         const u32 h = keyHash(k.x, k.y, k.z, k.w) & mask;
         atomicOr(&bloom[h >> 5], 1u << (h & 31u));
         const u32 sb = k.x < 255u ? k.x : 255u;
-        if (!((seen[sb >> 5] >> (sb & 31u)) & 1u)) { seen[sb >> 5] |= 1u << (sb & 31u); atomicOr(&bloom[(mask >> 5) + 1 + (sb >> 5)], 1u << (sb & 31u)); }
+#pragma unroll
+        for (int w = 0; w < 8; w++) if ((sb >> 5) == (u32)w) seen[w] |= 1u << (sb & 31u);
     }
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        u32 m = seen[w];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+        if ((threadIdx.x & 31u) == 0 && m) atomicOr(&sizes[w], m);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sizes[threadIdx.x]) atomicOr(&bloom[(mask >> 5) + 1 + threadIdx.x], sizes[threadIdx.x]);
 }
 __device__ __forceinline__ int keyCmp(const uint4 k, u32 sz, u32 first, u32 last, u32 sig) {
     if (k.x != sz) return k.x < sz ? -1 : 1;
@@ -1095,8 +1108,77 @@ __device__ __forceinline__ bool resolventEquals(const u32* a, int n1, const u32*
     return true;
 }
 
+// One merge pass over the resolvent of a and b on variable v: length, first / last literal and
+// signature - everything the filters and the key search need.  Returns false for a tautology.
+__device__ __forceinline__ bool ereKey(const u32* a, int n1, const u32* b, int n2, u32 v, u32& len, u32& first, u32& last, u32& sig) {
+    int it1 = 0, it2 = 0;
+    len = 0; first = 0; last = 0; sig = 0;
+#define ERE_EMIT(L_) do { const u32 l_ = (L_); if (!len) first = l_; last = l_; len++; sig |= MAPHASH(l_); } while (0)
+    while (it1 < n1 && it2 < n2) {
+        const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
+        if (v1 == v) it1++;
+        else if (v2 == v) it2++;
+        else if (IS_TAUT(lit1, lit2)) return false;
+        else if (v1 < v2) { it1++; ERE_EMIT(lit1); }
+        else if (v2 < v1) { it2++; ERE_EMIT(lit2); }
+        else { it1++; it2++; ERE_EMIT(lit1); }
+    }
+    while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != v) ERE_EMIT(l); }
+    while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
+#undef ERE_EMIT
+    return true;
+}
+// the literal of the (non-tautological) resolvent with the shortest occurrence list (forward_equ, redundancy.cuh:99-112)
+__device__ __forceinline__ u32 ereBest(const u32* __restrict__ otSize, const u32* a, int n1, const u32* b, int n2, u32 v, u32& minsize) {
+    int it1 = 0, it2 = 0;
+    u32 best = 0;
+    minsize = 0xFFFFFFFFu;
+#define ERE_EMIT(L_) do { const u32 l_ = (L_); const u32 s_ = otSize[l_]; if (s_ < minsize) { minsize = s_; best = l_; } } while (0)
+    while (it1 < n1 && it2 < n2) {
+        const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
+        if (v1 == v) it1++;
+        else if (v2 == v) it2++;
+        else if (v1 < v2) { it1++; ERE_EMIT(lit1); }
+        else if (v2 < v1) { it2++; ERE_EMIT(lit2); }
+        else { it1++; it2++; ERE_EMIT(lit1); }
+    }
+    while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != v) ERE_EMIT(l); }
+    while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
+#undef ERE_EMIT
+    return best;
+}
+// key search in the SORTED list of `best` + the reference's residue-class deletion rule
 template <int GS>
-__global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount) {
+__device__ __forceinline__ void ereSearchDelete(GT<GS>& g, const u32* a, int n1, const u32* b, int n2, u32 v, u32 len, u32 first, u32 last,
+                                                u32 sig, u32 type, u32 best, u32 minsize) {
+    const u32* list = g.occurs + g.otStart[best];
+    u32 lo = 0, hi = minsize;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (keyCmp(g.key[list[mid]], len, first, last, sig) < 0) lo = mid + 1; else hi = mid;
+    }
+    u32 done = 0;
+    for (u32 e = lo; e < minsize; e++) {
+        const u32 ci = list[e];
+        if (keyCmp(g.key[ci], len, first, last, sig) != 0) break;
+        const u32 r = e & 31u;
+        if ((done >> r) & 1u) continue;
+        const uint4 h = g.hdr[ci];
+        if ((C_LEARNT(h.w) || (h.w & CB_ST_MASK) == type) && !C_DELETED(h.w) && h.y == len &&
+            resolventEquals(a, n1, b, n2, v, g.pool + h.x)) {
+            g.hdr[ci].w = (h.w & ~CB_ST_MASK) | CB_DELETED;
+            done |= 1u << r;
+        }
+    }
+}
+
+// Phase A: enumerate the resolvents, keep the few that pass the filters.  With `queue` the survivors
+// are only recorded (clause pair + variable) and the list they will be searched in is flagged, so
+// that ONLY those lists have to be sorted before phase B (k_ere_apply); without it the search runs
+// here, on lists the caller has sorted already.
+struct EreQueue { u32* items; u32 cap; u32* count; unsigned char* need; u32* overflow; };
+template <int GS>
+__global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, EreQueue Q, const u32* __restrict__ wl, const u32* __restrict__ wlCount) {
     const int clause_max = g.k.ere_clause_max;
     const u32 lane = LANE;
     const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
@@ -1110,75 +1192,61 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, const u32* __restri
         if (!(ds && fs && ds <= g.k.ere_max_occurs && fs <= g.k.ere_max_occurs)) continue;
         const u32* P = g.occurs + g.otStart[p];
         const u32* N = g.occurs + g.otStart[n];
-        if ((int)g.hdr[P[0]].y > clause_max || (int)g.hdr[N[0]].y > clause_max) continue;
+        // the reference tests the FIRST clause of the sorted lists, i.e. the smallest size of each list
+        // (redundancy.cuh:151-154); the minimum does not need the lists sorted
+        u32 minP = 0xFFFFFFFFu, minN = 0xFFFFFFFFu;
+        for (u32 i = lane; i < ds; i += GS) minP = min(minP, g.hdr[P[i]].y);
+        for (u32 j = lane; j < fs; j += GS) minN = min(minN, g.hdr[N[j]].y);
+#pragma unroll
+        for (int o = GS / 2; o; o >>= 1) { minP = min(minP, __shfl_xor_sync(FULL, minP, o, GS)); minN = min(minN, __shfl_xor_sync(FULL, minN, o, GS)); }
+        if ((int)minP > clause_max || (int)minN > clause_max) continue;
         const u64 total = (u64)ds * fs;
         for (u64 t = lane; t < total; t += GS) {
             const u32 i = (u32)(t / fs), j = (u32)(t - (u64)i * fs);
-            const uint4 hp = g.hdr[P[i]];
+            const u32 ciP = P[i], ciN = N[j];
+            const uint4 hp = g.hdr[ciP];
             if (C_DELETED(hp.w)) continue;
-            const uint4 hn = g.hdr[N[j]];
+            const uint4 hn = g.hdr[ciN];
             if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
             const u32* a = g.pool + hp.x; const int n1 = (int)hp.y;
             const u32* b = g.pool + hn.x; const int n2 = (int)hn.y;
-            // first merge pass: length, tautology, first / last literal, signature - enough for the filters
-            int it1 = 0, it2 = 0; u32 len = 0, first = 0, last = 0, sig = 0;
-            bool taut = false;
-#define ERE_EMIT(L_) do { const u32 l_ = (L_); if (!len) first = l_; last = l_; len++; sig |= MAPHASH(l_); } while (0)
-            while (it1 < n1 && it2 < n2) {
-                const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
-                if (v1 == v) it1++;
-                else if (v2 == v) it2++;
-                else if (IS_TAUT(lit1, lit2)) { taut = true; break; }
-                else if (v1 < v2) { it1++; ERE_EMIT(lit1); }
-                else if (v2 < v1) { it2++; ERE_EMIT(lit2); }
-                else { it1++; it2++; ERE_EMIT(lit1); }
-            }
-            if (taut) continue;
-            while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != v) ERE_EMIT(l); }
-            while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
-#undef ERE_EMIT
-            if (len <= 1) continue;
+            u32 len, first, last, sig;
+            if (!ereKey(a, n1, b, n2, v, len, first, last, sig) || len <= 1) continue;
             // filters: is there a live clause of this size at all / with this key at all?
             { const u32 sb = len < 255u ? len : 255u; if (!((sizeMask[sb >> 5] >> (sb & 31u)) & 1u)) continue; }
             { const u32 hb = keyHash(len, first, last, sig) & g.bloomMask; if (!((g.bloom[hb >> 5] >> (hb & 31u)) & 1u)) continue; }
-            // second pass (rare): the literal of the resolvent with the shortest occurrence list (forward_equ, redundancy.cuh:99-112)
-            u32 best = 0, minsize = 0xFFFFFFFFu;
-#define ERE_EMIT(L_) do { const u32 l_ = (L_); const u32 s_ = g.otSize[l_]; if (s_ < minsize) { minsize = s_; best = l_; } } while (0)
-            it1 = 0; it2 = 0;
-            while (it1 < n1 && it2 < n2) {
-                const u32 lit1 = a[it1], lit2 = b[it2], v1 = LABS(lit1), v2 = LABS(lit2);
-                if (v1 == v) it1++;
-                else if (v2 == v) it2++;
-                else if (v1 < v2) { it1++; ERE_EMIT(lit1); }
-                else if (v2 < v1) { it2++; ERE_EMIT(lit2); }
-                else { it1++; it2++; ERE_EMIT(lit1); }
-            }
-            while (it1 < n1) { const u32 l = a[it1++]; if (LABS(l) != v) ERE_EMIT(l); }
-            while (it2 < n2) { const u32 l = b[it2++]; if (LABS(l) != v) ERE_EMIT(l); }
-#undef ERE_EMIT
+            u32 minsize;
+            const u32 best = ereBest(g.otSize, a, n1, b, n2, v, minsize);
             if (!minsize) continue;
-            const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
-            // lower bound of the key in the sorted list of `best`
-            const u32* list = g.occurs + g.otStart[best];
-            u32 lo = 0, hi = minsize;
-            while (lo < hi) {
-                const u32 mid = (lo + hi) >> 1;
-                if (keyCmp(g.key[list[mid]], len, first, last, sig) < 0) lo = mid + 1; else hi = mid;
-            }
-            u32 done = 0;
-            for (u32 e = lo; e < minsize; e++) {
-                const u32 ci = list[e];
-                if (keyCmp(g.key[ci], len, first, last, sig) != 0) break;
-                const u32 r = e & 31u;
-                if ((done >> r) & 1u) continue;
-                const uint4 h = g.hdr[ci];
-                if ((C_LEARNT(h.w) || (h.w & CB_ST_MASK) == type) && !C_DELETED(h.w) && h.y == len &&
-                    resolventEquals(a, n1, b, n2, v, g.pool + h.x)) {
-                    g.hdr[ci].w = (h.w & ~CB_ST_MASK) | CB_DELETED;
-                    done |= 1u << r;
-                }
+            if (Q.items) {
+                const u32 slot = atomicAdd(Q.count, 1u);
+                if (slot < Q.cap) { Q.items[3 * slot] = ciP; Q.items[3 * slot + 1] = ciN; Q.items[3 * slot + 2] = v; Q.need[best] = 1; }
+                else *Q.overflow = 1u;
+            } else {
+                const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
+                ereSearchDelete(g, a, n1, b, n2, v, len, first, last, sig, type, best, minsize);
             }
         }
+    }
+}
+// Phase B: one thread per recorded resolvent, in queue order
+__global__ void __launch_bounds__(256) k_ere_apply(GT<32> g, const u32* __restrict__ items, const u32* __restrict__ count) {
+    const int clause_max = g.k.ere_clause_max;
+    const u32 nq = *count;
+    for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const u32 ciP = items[3 * q], ciN = items[3 * q + 1], v = items[3 * q + 2];
+        const uint4 hp = g.hdr[ciP];
+        if (C_DELETED(hp.w)) continue;
+        const uint4 hn = g.hdr[ciN];
+        if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
+        const u32* a = g.pool + hp.x; const int n1 = (int)hp.y;
+        const u32* b = g.pool + hn.x; const int n2 = (int)hn.y;
+        u32 len, first, last, sig, minsize;
+        if (!ereKey(a, n1, b, n2, v, len, first, last, sig) || len <= 1) continue;
+        const u32 best = ereBest(g.otSize, a, n1, b, n2, v, minsize);
+        if (!minsize) continue;
+        const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
+        ereSearchDelete(g, a, n1, b, n2, v, len, first, last, sig, type, best, minsize);
     }
 }
 
@@ -1290,16 +1358,37 @@ void launchERE(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
     static const bool v0 = getenv("SIGMA_ERE_V0") != nullptr;   // the warp-per-resolvent kernel, kept for A/B checks
-    if (v0) { LAUNCH(c, k_ere, groupGrid(c->numElected, 32, 128), 128, 0, asGroup<32>(g)); return; }
+    if (v0) { launchSortOT(c, 0); LAUNCH(c, k_ere, groupGrid(c->numElected, 32, 128), 128, 0, asGroup<32>(g)); return; }
     // Bloom filter over the keys of the live clauses, in the partition buffer of the OT build (free now)
     const u32 n = c->hdc->numCls;
+    const u64 bufBytes = ((u64)c->capW + 4) * sizeof(uint2);
     u64 bits = 256;
     while (bits < 8ull * n && bits < (1ull << 30)) bits <<= 1;   // >= 8 bits per clause: the filter stays L2 resident
-    while (bits > 32 && bits / 8 + 32 > ((u64)c->capW + 4) * sizeof(uint2)) bits >>= 1;
+    while (bits > 32 && bits / 8 + 32 > bufBytes / 2) bits >>= 1;
     u32* bloom = (u32*)c->otPairs;
     cudaMemsetAsync(bloom, 0, bits / 8 + 32, c->stream);   // + the 256-bit clause-size mask
     LAUNCH(c, k_ere_bloom, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->key, n, bloom, (u32)(bits - 1));
     g.bloom = bloom; g.bloomMask = (u32)(bits - 1);
     binElected(c, k, false);
-    LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g);
+    // Phase A records the resolvents that pass the filters; only the lists they will be searched in
+    // get sorted (sortOT, segsort.cu:37-48, restricted), then phase B searches and deletes.
+    EreQueue Q;
+    const u64 qOff = (bits / 8 + 32 + 255) & ~255ull;
+    Q.items = (u32*)((char*)c->otPairs + qOff);
+    const u64 qCap = (bufBytes - qOff) / 12;
+    Q.cap = (u32)(qCap > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : qCap);
+    Q.count = &c->dc->scratch[3]; Q.overflow = &c->dc->scratch[4]; Q.need = c->needSort;
+    cudaMemsetAsync(Q.count, 0, 8, c->stream);
+    cudaMemsetAsync(c->needSort, 0, c->ND, c->stream);
+    LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g, Q);
+    if (syncCounters(c)) return;
+    const u32 nq = c->hdc->scratch[3];
+    if (c->hdc->scratch[4]) {   // more survivors than the queue holds: sort everything, search in place (nothing was deleted yet)
+        launchSortOT(c, 0);
+        Q.items = nullptr;
+        LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g, Q);
+    } else if (nq) {
+        launchSortOT(c, 2);
+        LAUNCH(c, k_ere_apply, gridFor(nq, 256), 256, 0, asGroup<32>(g), Q.items, Q.count);
+    }
 }

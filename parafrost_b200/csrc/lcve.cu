@@ -132,11 +132,11 @@ __global__ void k_rank(const u32* __restrict__ eligible, const unsigned char* __
 // ------------------------------------------------------------------ MIS
 // worklist counters rotate over three slots: round k reads wlCnt[k%3], appends to wlCnt[(k+1)%3]
 // and clears wlCnt[(k+2)%3], so several rounds can be queued without a host round-trip.
-__global__ void k_mis_fill(const u32* __restrict__ eligible, const unsigned char* __restrict__ cstat, u32 rBegin, u32 rEnd,
+__global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restrict__ vinfo, u32 rBegin, u32 rEnd,
                            u32* __restrict__ wl, DevCounters* dc, u32 slot) {
     for (u32 r = rBegin + blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x) {
         const u32 v = eligible[r];
-        if (cstat[v] != CS_NONE) wl[warpAggInc(&dc->wlCnt[slot])] = v;
+        if (VI_STATE(vinfo[v]) == MIS_UNDECIDED) wl[warpAggInc(&dc->wlCnt[slot])] = v;   // candidates not yet frozen by an earlier chunk's push
     }
 }
 
@@ -422,15 +422,30 @@ int runLCVE(Ctx* c) {
     const bool smallGroups = c->numLiterals <= (u64)24 * V;
     const u64 avgOcc = c->numLiterals / V + 1;
 
+    // Dense neighbourhoods (uniform k-SAT with many occurrences: hundreds of neighbours per variable):
+    // a few thousand elected variables freeze almost everything by push, so the walk starts with a
+    // short rank prefix and later chunks only queue what is still undecided.
+    const u64 avgK = c->numClauses ? c->numLiterals / c->numClauses + 1 : 2;
+    const bool dense = 2 * avgOcc * (avgK > 1 ? avgK - 1 : 1) >= 128;
+
     u32 hPrev = 0, stopRank = NOVAR, hEnd = 0;
     u32 round = 0;   // parity / counter slot of the next MIS round
     while (hPrev < V && stopRank == NOVAR) {
         u64 h64 = hPrev ? (u64)hPrev * 8 : (firstStop > 8192 ? firstStop : 8192);
+        if (dense && !hPrev) { const u64 pre = V / 64 > 8192 ? V / 64 : 8192; if (h64 > pre) h64 = pre; }
         const u32 H = (u32)(h64 > V ? V : h64);
         u32* wlIn = (round & 1u) ? c->wlB : c->wlA;
-        // first round of the chunk: one streaming pass over the clauses when the chunk is large,
-        // otherwise the candidates walk their own lists
-        const bool clausePass = (u64)(H - hPrev) * avgOcc * 2 > nCls;
+        u32 n = H - hPrev;   // upper bound of the worklist until the first read-back
+        // first round of the chunk: one streaming pass over the clauses when many candidates are
+        // undecided, otherwise the candidates walk their own lists
+        bool clausePass = (u64)n * avgOcc * 2 > nCls;
+        if (dense && hPrev) {   // most of the chunk is frozen already: count what is left before choosing
+            LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, vinfo, hPrev, H, wlIn, c->dc, round % 3u);
+            if ((rc = syncCounters(c))) return rc;
+            n = c->hdc->wlCnt[round % 3u];
+            clausePass = (u64)n * avgOcc * 2 > nCls;
+            if (clausePass) CUDA_TRY(cudaMemsetAsync(&c->dc->wlCnt[round % 3u], 0, 4, c->stream));   // k_mis_first refills the slot
+        }
         if (clausePass) {
             LAUNCH(c, k_mis_clauses, gridFor(nCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], nCls, vinfo, nbr, ovs, H, c->o.lcve_clause_max);
             u32* pushCount = &c->dc->scratch[2];
@@ -443,9 +458,9 @@ int runLCVE(Ctx* c) {
             else
                 LAUNCH(c, k_mis_push<32>, gridFor((u64)(H - hPrev) * 32, 256), 256, 0, c->flagA, pushCount, c->hdr[c->cur], c->pool[c->cur],
                        c->otStart, c->otSize, c->occurs, vinfo);
-        } else
-            LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, c->cstat, hPrev, H, wlIn, c->dc, round % 3u);
-        u32 n = H - hPrev;   // upper bound of the worklist until the first read-back
+            n = H - hPrev;
+        } else if (!(dense && hPrev))
+            LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, vinfo, hPrev, H, wlIn, c->dc, round % 3u);
         u32 guard = 0;
         while (n) {
             if (++guard > 100000u) { snprintf(c->err, sizeof c->err, "MIS did not converge"); return SIGMA_AWAKEN_FAIL; }

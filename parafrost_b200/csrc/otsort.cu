@@ -41,17 +41,23 @@ __device__ __forceinline__ int sortClass(u32 n) {
     return 8;
 }
 // pass 1: class sizes (block-reduced, one atomic per class and block)
-// `vinfo` (lcve.cu election words), when given, restricts the sort to the lists of elected variables:
-// in a SUB/BVE/BCE round no kernel observes the order of any other list (the gate searches that
-// scan foreign lists take the match with the smallest clause index, elim.cu), and the table is
-// rebuilt before the next round.
-__device__ __forceinline__ bool sortWanted(const u32* __restrict__ vinfo, u32 lit) { return !vinfo || (vinfo[lit >> 1] & 7u) == MIS_ELECTED; }
-__global__ void __launch_bounds__(256) k_sort_count(const u32* __restrict__ otSize, u32 ND, DevCounters* dc, const u32* __restrict__ vinfo) {
+// The sort can be restricted to the lists somebody will read in order:
+//   vinfo (lcve.cu election words): only the lists of elected variables - in a SUB/BVE/BCE round no
+//         kernel observes the order of any other list (the gate searches that scan foreign lists take
+//         the match with the smallest clause index, elim.cu), and the table is rebuilt next round;
+//   need  (one byte per literal): only the lists ERE is going to binary-search (elim.cu, k_ere_pairs).
+__device__ __forceinline__ bool sortWanted(const u32* __restrict__ vinfo, const unsigned char* __restrict__ need, u32 lit) {
+    if (vinfo) return (vinfo[lit >> 1] & 7u) == MIS_ELECTED;
+    if (need) return need[lit] != 0;
+    return true;
+}
+__global__ void __launch_bounds__(256) k_sort_count(const u32* __restrict__ otSize, u32 ND, DevCounters* dc, const u32* __restrict__ vinfo,
+                                                    const unsigned char* __restrict__ need) {
     __shared__ u32 cnt[NCLASS];
     if (threadIdx.x < NCLASS) cnt[threadIdx.x] = 0;
     __syncthreads();
     for (u32 lit = 2 + blockIdx.x * blockDim.x + threadIdx.x; lit < ND; lit += gridDim.x * blockDim.x) {
-        const int k = sortWanted(vinfo, lit) ? sortClass(otSize[lit]) : -1;
+        const int k = sortWanted(vinfo, need, lit) ? sortClass(otSize[lit]) : -1;
         if (k >= 0) atomicAdd(&cnt[k], 1u);
     }
     __syncthreads();
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(256) k_sort_count(const u32* __restrict__ otSi
 // ranges with one global atomic per class, then places its literals with shared-memory atomics.
 #define FILL_TILE 4096
 __global__ void __launch_bounds__(256) k_sort_fill(const u32* __restrict__ otSize, u32 ND, u32* __restrict__ q, DevCounters* dc,
-                                                   const u32* __restrict__ vinfo) {
+                                                   const u32* __restrict__ vinfo, const unsigned char* __restrict__ need) {
     __shared__ u32 start[NCLASS], cnt[NCLASS], base[NCLASS];
     if (threadIdx.x == 0) { u32 s = 0; for (int k = 0; k < NCLASS; k++) { start[k] = s; s += dc->sortCnt[k]; } }
     for (u32 t0 = 2 + blockIdx.x * FILL_TILE; t0 < ND; t0 += gridDim.x * FILL_TILE) {
@@ -73,7 +79,7 @@ __global__ void __launch_bounds__(256) k_sort_fill(const u32* __restrict__ otSiz
 #pragma unroll
         for (int k = 0; k < FILL_TILE / 256; k++) {
             const u32 lit = t0 + k * 256 + threadIdx.x;
-            cls[k] = (lit < ND && sortWanted(vinfo, lit)) ? sortClass(otSize[lit]) : -1;
+            cls[k] = (lit < ND && sortWanted(vinfo, need, lit)) ? sortClass(otSize[lit]) : -1;
             if (cls[k] >= 0) pos[k] = atomicAdd(&cnt[cls[k]], 1u);
         }
         __syncthreads();
@@ -279,8 +285,10 @@ __global__ void k_sort_reset(DevCounters* dc) {
     for (int k = 0; k < NCLASS; k++) { dc->sortCnt[k] = 0; dc->sortCur[k] = 0; }
 }
 
-void launchSortOT(Ctx* c, bool electedOnly) {
-    const u32* vinfo = electedOnly ? c->rank : nullptr;
+// mode 0: every list, 1: lists of elected variables, 2: lists flagged in needSort
+void launchSortOT(Ctx* c, int mode) {
+    const u32* vinfo = mode == 1 ? c->rank : nullptr;
+    const unsigned char* need = mode == 2 ? c->needSort : nullptr;
     const size_t bigSmem = (size_t)SORT_BIG * (8 + 8 + 4);
     if (!c->attrSort) {
         cudaFuncSetAttribute(k_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigSmem);
@@ -288,8 +296,8 @@ void launchSortOT(Ctx* c, bool electedOnly) {
     }
     u32* q = c->qMed;   // ND entries: the literals with >= 2 occurrences, grouped by length class
     LAUNCH(c, k_sort_reset, 1, 1, 0, c->dc);
-    LAUNCH(c, k_sort_count, gridFor(c->ND, 256, 4), 256, 0, c->otSize, c->ND, c->dc, vinfo);
-    LAUNCH(c, k_sort_fill, gridFor(c->ND, 256, FILL_TILE / 256), 256, 0, c->otSize, c->ND, q, c->dc, vinfo);
+    LAUNCH(c, k_sort_count, gridFor(c->ND, 256, 4), 256, 0, c->otSize, c->ND, c->dc, vinfo, need);
+    LAUNCH(c, k_sort_fill, gridFor(c->ND, 256, FILL_TILE / 256), 256, 0, c->otSize, c->ND, q, c->dc, vinfo, need);
     // the folded 128-bit key is exact while literals < 2^25 and clauses are shorter than 2^14 (flag 8: k_hist_key)
     const bool fold = c->ND <= (1u << 25) && !(c->hdc->flags & 8u);
     // grids: enough groups for every list of a class if all of them fell into it, capped
