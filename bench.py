@@ -122,28 +122,51 @@ def algorithmic_bytes(kernel, C, L, V, E=0):
     return f.get(kernel)
 
 
-def roofline(ktimes, C, L, V, peaks):
+def ncu_traffic(workload):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of this workload's kernels
+    from the newest committed `ncu --set full` capture (profiles/*_ncu_traffic_<workload>.json,
+    written by tools/ncu_digest.py --json)."""
+    import glob
+    best = {}
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_ncu_traffic_{workload}*.json"))):
+        try:
+            best.update(json.load(open(f)).get("kernels", {}))
+        except (OSError, ValueError):
+            pass
+    return best
+
+
+def roofline(ktimes, C, L, V, peaks, workload="cfg2"):
+    """Roofline of the dominant kernel.  Streaming kernels have closed-form algorithmic bytes
+    (DESIGN.md 3); the per-variable kernels (MIS rounds, BVE, SUB, ERE) are latency / instruction
+    bound gather kernels whose bytes depend on the elected set - when one of those leads, the line
+    names it (`dominant`) and carries the roofline of the largest kernel that HAS a byte formula."""
     if not ktimes:
         return None
-    name, (ms, cnt) = max(ktimes.items(), key=lambda kv: kv[1][0])
     peak = peaks.get("hbm_gbs")
     src = "measured (MEASURED_PEAKS.json)"
     if not peak:
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
-    b = algorithmic_bytes(name.split("<")[0], C, L, V)
     total = sum(v[0] for v in ktimes.values())
+    order = sorted(ktimes.items(), key=lambda kv: -kv[1][0])
+    dom_name, (dom_ms, dom_cnt) = order[0]
+    name, (ms, cnt) = next(((k, v) for k, v in order if algorithmic_bytes(k.split("<")[0], C, L, V)), order[0])
+    traffic = ncu_traffic(workload)
+    b = algorithmic_bytes(name.split("<")[0], C, L, V)
     out = {"bound": "hbm", "kernel": name, "launches": cnt, "ms_per_launch": ms / cnt, "share_of_kernel_time": ms / total if total else None,
-           "peak": peak, "peak_source": src, "unit": "GB/s", "traffic": None}
+           "peak": peak, "peak_source": src, "unit": "GB/s", "traffic": traffic.get(name.split("<")[0])}
     if b:
         ach = b / (ms / cnt * 1e-3) / 1e9
         out.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": b})
     else:
-        out.update({"achieved": None, "frac": None, "algorithmic_bytes_per_launch": None,
-                    "note": "irregular per-variable kernel: bytes depend on the elected set; see DESIGN.md"})
-    top = sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:8]
-    out["top_kernels"] = [{"kernel": k, "ms": round(v[0], 3), "launches": v[1],
+        out.update({"achieved": None, "frac": None, "algorithmic_bytes_per_launch": None})
+    if dom_name != name:
+        out["dominant"] = {"kernel": dom_name, "ms_per_launch": dom_ms / dom_cnt, "launches": dom_cnt, "share_of_kernel_time": dom_ms / total,
+                           "traffic": traffic.get(dom_name.split("<")[0]),
+                           "note": "per-variable gather kernel: latency/instruction bound, no closed-form bytes (DESIGN.md 3)"}
+    out["top_kernels"] = [{"kernel": k, "ms": round(v[0], 3), "launches": v[1], "share": round(v[0] / total, 3),
                            "gbs": (lambda bb: round(bb / (v[0] / v[1] * 1e-3) / 1e9, 1) if bb else None)(algorithmic_bytes(k.split("<")[0], C, L, V))}
-                          for k, v in top]
+                          for k, v in order[:8]]
     return out
 
 
@@ -232,6 +255,96 @@ def reference_arm(a):
     return 0
 
 
+# ----------------------------------------------------------------------------- config 5: instance-parallel batch
+def batch_main(a, torch, dist, barrier, rank, world, local):
+    """BASELINE.json config 5: a batch of mixed CNFs, one engine context per instance, instances
+    dealt to the ranks longest-first (parafrost_b200/replicas.py), no collective on the data path.
+    Metric CNFs/s; `value` counts the sigma_run time of each instance with its formula resident,
+    `e2e` the whole load -> run -> store sequence from / to pinned host memory.  "scaling": "strong"
+    (the batch is fixed, ranks share it)."""
+    import cnfgen
+    from parafrost_b200 import replicas, sigma
+    specs = replicas.batch_specs(a.batch, a.scale)
+    weights = [replicas.spec_weight(sp) for sp in specs]
+    mine = replicas.assign_longest_first(weights, world)[rank]
+    stream = torch.cuda.Stream()
+    s = sigma.Simplifier(local)
+    s.set_stream(stream.cuda_stream)
+    inst = []
+    for i in mine:   # generated once, kept in pinned host memory for every step
+        fam, seed, args = specs[i]
+        keep = []
+
+        def alloc(n, dt, keep=keep):
+            t = torch.empty(int(n), dtype={np.uint32: torch.int32, np.uint64: torch.int64}[dt], pin_memory=True)
+            keep.append(t)
+            return t.numpy().view(dt)
+        V, lits, offs = cnfgen.gen_cnf(fam, seed, args, alloc=alloc)
+        inst.append((V, lits, offs, keep))
+    maxC = max((len(x[2]) - 1 for x in inst), default=1)
+    maxL = max((len(x[1]) for x in inst), default=1)
+    maxV = max((x[0] for x in inst), default=1)
+    pin = []
+
+    def palloc(n, dt):
+        t = torch.empty(int(n), dtype={np.uint32: torch.int32, np.uint64: torch.int64}[dt], pin_memory=True)
+        pin.append(t)
+        return t.numpy().view(dt)
+    outbuf = {"bits": palloc(2 * maxC + 16, np.uint32), "sig": palloc(2 * maxC + 16, np.uint32), "offs": palloc(2 * maxC + 17, np.uint64),
+              "lits": palloc(2 * maxL + 16, np.uint32), "eliminated": np.zeros(maxV + 1, np.uint8), "resolved": palloc(maxC + maxL + 2, np.uint32),
+              "trail": palloc(3 * (maxV + 1), np.uint32)}
+
+    def one_pass(timed):
+        """-> (ms of sigma_run summed over my instances, ms of the whole pass, launches, literals, h2d, d2h)"""
+        run_ms, launches, lit, h2d, d2h = 0.0, 0, 0, 0, 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for V, lits, offs, _ in inst:
+            s.load(V, lits, offs)
+            rep = s.simplify()
+            outbuf["eliminated"] = np.zeros(V + 1, np.uint8)
+            st = s.store(into=outbuf)
+            run_ms += rep["ms_device"]; launches += rep["kernel_launches"]
+            lit += sum(r["literals_in"] for r in s.rounds())
+            h2d += int(lits.nbytes + offs.nbytes); d2h += sum(int(v.nbytes) for v in st.values())
+        e1.record(stream)
+        stream.synchronize()
+        return run_ms, e0.elapsed_time(e1), launches, lit, h2d, d2h
+
+    for _ in range(a.warmup):
+        one_pass(False)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    tot = [one_pass(True) for _ in range(a.steps)]
+    barrier()
+    clk = clocks.stop()
+    run_ms = sum(t[0] for t in tot); all_ms = sum(t[1] for t in tot)
+    n_mine = len(inst) * a.steps
+    run_ms, n_all = replicas.reduce_timing(dist, run_ms, float(n_mine), device="cuda")
+    all_ms, lit_all = replicas.reduce_timing(dist, all_ms, float(sum(t[3] for t in tot)), device="cuda")
+    if rank == 0:
+        line = {
+            "metric": "batch_cnfs_per_s", "value": n_all / (run_ms * 1e-3), "unit": "CNFs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": run_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "cfg5" + ("" if a.scale == 1.0 else f" x{a.scale}"), "instances": a.batch,
+                       "clauses_min": min(weights), "clauses_max": max(weights), "families": "ksat3 / ksat5 / miter / multpar, round robin",
+                       "schedule": "static longest-first over ranks (replicas.assign_longest_first)", "flags": "reference defaults",
+                       "l2": "each instance is simplified once per step: cold caches", "parallelism": f"instance-parallel x{world}, no collective"},
+            "literals_per_s": lit_all / (run_ms * 1e-3),
+            "e2e": {"value": n_all / (all_ms * 1e-3), "unit": "CNFs/s", "ms_per_step": all_ms / a.steps,
+                    "h2d_bytes_per_step": tot[-1][4], "d2h_bytes_per_step": tot[-1][5]},
+            "gpu_launches": int(sum(t[2] for t in tot)), "clocks": clk,
+            "roofline": None, "cpu_baseline": {"value": None, "unit": "CNFs/s", "cores": 0, "kind": "reference", "sample": "not run for the batch workload (see cfg2)"},
+        }
+        print(json.dumps(line))
+    s.close()
+    if dist is not None:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    return 0
+
+
 # ----------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -239,7 +352,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sigma-b200", choices=["sigma-b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--batch", type=int, default=64, help="cfg5: number of instances in the batch")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", default="", help="reference CLI flags for the engine, space separated (e.g. '--phases=5 -no-ere')")
@@ -269,6 +383,9 @@ def main():
         if dist is not None:
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
+
+    if a.workload == "cfg5":
+        return batch_main(a, torch, dist, barrier, rank, world, local)
 
     # ---- synthetic input of the named shape, in pinned host memory
     fam, seed, args = workload_spec(a.workload, rank, a.scale)
@@ -361,7 +478,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clk,
             "result": {"clauses_out": reps[-1]["clauses"], "literals_out": reps[-1]["literals"], "eliminated_vars": reps[-1]["eliminated_vars"],
                        "cnfstate": reps[-1]["cnfstate"]},
-            "roofline": roofline(ktimes, meanC, meanL, V, peaks),
+            "roofline": roofline(ktimes, meanC, meanL, V, peaks, a.workload),
         }
         if world == 1 and not a.no_cpu_baseline and os.path.exists(REF_CPU):
             try:

@@ -230,10 +230,6 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
         for (u64 i = 0; i < num_clauses; i++) if (!(meta[i] & CB_LEARNT)) { orgC++; orgL += offs[i + 1] - offs[i]; }
     }
     c->V = max_var; c->ND = 2 * (max_var + 1);
-    // OT-build buckets: 2^otShift consecutive literals each, at most 1024 of them up to V = 2^24 (cnf.cu)
-    c->otShift = 8;
-    while (c->otShift < 15 && ((c->ND + (1u << c->otShift) - 1) >> c->otShift) > 1024) c->otShift++;
-    c->otNB = (c->ND + (1u << c->otShift) - 1) >> c->otShift;
     c->C0 = num_clauses; c->L0 = L0;
     c->orgClauses = orgC; c->orgLiterals = orgL;
     // logical capacities of awaken (simplify.cu:84-98); the physical buffers are sized for them

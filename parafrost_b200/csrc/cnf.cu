@@ -107,20 +107,25 @@ void launchHistKey(Ctx* c) {
 // 10-100 % slower on cfg2-cfg4 and dropped; clause-local formulas (Tseitin, multiplier) already
 // write long runs per bucket and partition at ~3x the speed of uniform random k-SAT.
 // Algorithmic bytes: part 16C + 4L read + 8L written; place 8L read + 4L written + 12 ND.
-#define PART_THREADS 512
-#define PART_CPT 8
+#define PART_THREADS 1024
+#define PART_CPT 4
 #define PART_TILE (PART_THREADS * PART_CPT)
+#define PART_SHORT 8   // clauses up to this size keep the ranks of their literals in registers
 
+// One shared-memory atomic per pair: the rank the counting sweep hands out IS the pair's slot in the
+// tile's run of its bucket, so it is kept (16 bits per literal, four registers per clause) and the
+// writing sweep needs no second atomic.  Literals of longer clauses are counted separately and take
+// the tail of the run with a second atomic.
 __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
                                                           const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB,
                                                           u32* __restrict__ gcur, uint2* __restrict__ pairs) {
     extern __shared__ u32 sm[];
-    u32* cnt = sm;
-    u32* gbase = sm + NB;
+    u32* cntS = sm;            // literals of short clauses per bucket
+    u32* cntL = sm + NB;       // literals of long clauses per bucket, then their running slot
+    u32* gbase = sm + 2 * NB;  // start of this tile's run in the bucket's segment
     const u32 tile0 = blockIdx.x * PART_TILE;
-    for (u32 b = threadIdx.x; b < NB; b += PART_THREADS) cnt[b] = 0;
-    __syncthreads();
-    u32 off[PART_CPT], sz[PART_CPT];
+    for (u32 b = threadIdx.x; b < 2 * NB; b += PART_THREADS) sm[b] = 0;
+    u32 off[PART_CPT], sz[PART_CPT], rk[PART_CPT][PART_SHORT / 2];
 #pragma unroll
     for (int k = 0; k < PART_CPT; k++) {
         const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
@@ -130,75 +135,147 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
             if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; }
         }
     }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < PART_CPT; k++) {
         const u32* l = pool + off[k];
-        for (u32 q = 0; q < sz[k]; q++) atomicAdd(&cnt[l[q] >> shift], 1u);
+#pragma unroll
+        for (int q = 0; q < PART_SHORT / 2; q++) rk[k][q] = 0;
+        if (sz[k] <= PART_SHORT) {
+#pragma unroll
+            for (int q = 0; q < PART_SHORT; q++)
+                if ((u32)q < sz[k]) rk[k][q >> 1] |= atomicAdd(&cntS[l[q] >> shift], 1u) << ((q & 1) * 16);
+        } else
+            for (u32 q = 0; q < sz[k]; q++) atomicAdd(&cntL[l[q] >> shift], 1u);
     }
     __syncthreads();
+#pragma unroll 4
     for (u32 b = threadIdx.x; b < NB; b += PART_THREADS) {
-        const u32 m = cnt[b];
-        if (m) {
-            const u32 lit0 = min(b << shift, ND);
-            gbase[b] = otStart[lit0] + atomicAdd(&gcur[b], m);
-        }
-        cnt[b] = 0;
+        const u32 tS = cntS[b], tL = cntL[b];
+        if (tS + tL) gbase[b] = otStart[min(b << shift, ND)] + atomicAdd(&gcur[b], tS + tL);
+        cntL[b] = tS;   // long-clause literals follow the short ones
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < PART_CPT; k++) {
         const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
         const u32* l = pool + off[k];
-        for (u32 q = 0; q < sz[k]; q++) {
-            const u32 lit = l[q];
-            const u32 b = lit >> shift;
-            const u32 r = atomicAdd(&cnt[b], 1u);
-            pairs[gbase[b] + r] = make_uint2(lit, i);
-        }
+        if (sz[k] <= PART_SHORT) {
+#pragma unroll
+            for (int q = 0; q < PART_SHORT; q++)
+                if ((u32)q < sz[k]) {
+                    const u32 lit = l[q];
+                    pairs[gbase[lit >> shift] + ((rk[k][q >> 1] >> ((q & 1) * 16)) & 0xFFFFu)] = make_uint2(lit, i);
+                }
+        } else
+            for (u32 q = 0; q < sz[k]; q++) {
+                const u32 lit = l[q];
+                const u32 b = lit >> shift;
+                pairs[gbase[b] + atomicAdd(&cntL[b], 1u)] = make_uint2(lit, i);
+            }
     }
 }
 
 #define PLACE_THREADS 512
+#define PLACE_SPLIT 8            // a bucket with many pairs is shared by up to 8 CTAs (grid.y) ...
+#define PLACE_UNIT (128u << 10)  // ... of about this many pairs each
+#define PLACE_WINDOW (40u << 10) // entries of a bucket's occurs[] window that can be staged in shared memory
+// first literal l in [lo, hi] with otStart[l] >= target (uniform over the CTA: broadcast loads)
+__device__ __forceinline__ u32 litLowerBound(const u32* __restrict__ otStart, u32 lo, u32 hi, u32 target) {
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (otStart[mid] < target) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// Staged mode (the normal case, buckets are sized for it): the whole occurs[] window of the bucket is
+// assembled in shared memory - one shared-memory atomic and one shared-memory store per pair - and
+// written out with coalesced full-sector stores.  Scattering the 4-byte entries straight into global
+// memory costs one L2 write transaction per entry, and ~65 G transactions/s chip-wide was the
+// measured ceiling of the unstaged kernel (profiles/r01_ncu_full_cfg2_v3.txt).
+// Direct mode (a bucket too large for the window: hot literal ranges of structured formulas):
+// buckets are literal RANGES, so their pair counts follow the formula's structure (multiplier
+// inputs: one bucket with 28x the mean).  CTA (b, s) owns the literal sub-range of bucket b that
+// holds the s-th share of its pairs (boundaries read off otStart), streams all pairs of the bucket
+// and places the ones in its sub-range directly.
 __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
-                                                            u32 shift, u32* __restrict__ otSize, u32* __restrict__ occurs) {
-    extern __shared__ u32 cur[];
+                                                            u32 shift, u32 window, u32* __restrict__ otSize, u32* __restrict__ occurs) {
+    extern __shared__ u32 smem[];
     const u32 W = 1u << shift;
+    u32* cur = smem;          // [W] list cursors
+    u32* win = smem + W;      // [window] staged entries
     const u32 lit0 = blockIdx.x << shift;
-    for (u32 k = threadIdx.x; k < W; k += PLACE_THREADS) cur[k] = (lit0 + k < ND) ? otStart[lit0 + k] : 0u;
-    __syncthreads();
-    const u32 p0 = otStart[min(lit0, ND)], p1 = otStart[min(lit0 + W, ND)];
-    u32 j = p0 + threadIdx.x;
-    // four independent pair loads in flight per thread
-    for (; j + 3 * PLACE_THREADS < p1; j += 4 * PLACE_THREADS) {
-        uint2 p[4];
+    const u32 litEnd = min(lit0 + W, ND);
+    const u32 p0 = otStart[lit0], p1 = otStart[litEnd];
+    const u32 len = p1 - p0;
+    const u32 s = blockIdx.y;
+    if (len <= window) {
+        if (s) return;
+        const u32 nl = litEnd - lit0;
+        for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) cur[k] = otStart[lit0 + k] - p0;
+        __syncthreads();
+        u32 j = p0 + threadIdx.x;
+        for (; j + 3 * PLACE_THREADS < p1; j += 4 * PLACE_THREADS) {
+            uint2 p[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) p[k] = pairs[j + k * PLACE_THREADS];
+            for (int k = 0; k < 4; k++) p[k] = pairs[j + k * PLACE_THREADS];
 #pragma unroll
-        for (int k = 0; k < 4; k++) occurs[atomicAdd(&cur[p[k].x - lit0], 1u)] = p[k].y;
+            for (int k = 0; k < 4; k++) win[atomicAdd(&cur[p[k].x - lit0], 1u)] = p[k].y;
+        }
+        for (; j < p1; j += PLACE_THREADS) { const uint2 p = pairs[j]; win[atomicAdd(&cur[p.x - lit0], 1u)] = p.y; }
+        __syncthreads();
+        for (u32 k = threadIdx.x; k < len; k += PLACE_THREADS) occurs[p0 + k] = win[k];
+        for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) otSize[lit0 + k] = cur[k] - (otStart[lit0 + k] - p0);
+        return;
     }
-    for (; j < p1; j += PLACE_THREADS) {
-        const uint2 p = pairs[j];
-        occurs[atomicAdd(&cur[p.x - lit0], 1u)] = p.y;
+    u32 S = (len + PLACE_UNIT - 1) / PLACE_UNIT;
+    S = S < 1 ? 1 : (S > PLACE_SPLIT ? PLACE_SPLIT : S);
+    if (s >= S) return;
+    const u32 la = s == 0 ? lit0 : litLowerBound(otStart, lit0, litEnd, p0 + (u32)((u64)len * s / S));
+    const u32 lb = s == S - 1 ? litEnd : litLowerBound(otStart, lit0, litEnd, p0 + (u32)((u64)len * (s + 1) / S));
+    const u32 nl = lb - la;
+    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) cur[k] = otStart[la + k];
+    __syncthreads();
+    if (nl) {
+        u32 j = p0 + threadIdx.x;
+        for (; j + 3 * PLACE_THREADS < p1; j += 4 * PLACE_THREADS) {
+            uint2 p[4]; u32 pos[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) p[k] = pairs[j + k * PLACE_THREADS];
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (p[k].x - la < nl) pos[k] = atomicAdd(&cur[p[k].x - la], 1u);
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (p[k].x - la < nl) occurs[pos[k]] = p[k].y;
+        }
+        for (; j < p1; j += PLACE_THREADS) {
+            const uint2 p = pairs[j];
+            if (p.x - la < nl) occurs[atomicAdd(&cur[p.x - la], 1u)] = p.y;
+        }
     }
     __syncthreads();
-    for (u32 k = threadIdx.x; k < W; k += PLACE_THREADS)
-        if (lit0 + k < ND) otSize[lit0 + k] = cur[k] - otStart[lit0 + k];
+    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) otSize[la + k] = cur[k] - otStart[la + k];
 }
 
 void launchScatter(Ctx* c) {
     const u32 n = c->hdc->numCls;
     // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
     if (!n || !c->numLiterals) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
-    const u32 NB = c->otNB, shift = c->otShift;
     if (!c->attrOT) {
-        cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-        cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
+        cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 8192);
+        cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
         c->attrOT = true;
     }
+    // bucket = 2^shift consecutive literals, sized so that an average bucket fills at most ~70 % of a
+    // staging window; at most 8192 buckets (shared-memory counters of k_ot_part)
+    u32 shift = 6;
+    while (shift < 12 && ((u64)c->numLiterals << (shift + 1)) / c->ND <= PLACE_WINDOW * 7 / 10) shift++;
+    while (shift < 15 && ((c->ND + (1u << shift) - 1) >> shift) > 8192) shift++;
+    const u32 NB = (c->ND + (1u << shift) - 1) >> shift;
+    c->otShift = shift; c->otNB = NB;
+    // beyond 2^12 literals per bucket (more than 2^25 literals in all) the cursors alone fill the shared memory: direct mode only
+    const u32 window = shift <= 12 ? PLACE_WINDOW : 0;
+    const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
     cudaMemsetAsync(c->otCur, 0, (size_t)NB * 4, c->stream);
-    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 8 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
+    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 12 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
            c->otCur, c->otPairs);
-    LAUNCH(c, k_ot_place, NB, PLACE_THREADS, 4u << shift, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs);
+    LAUNCH(c, k_ot_place, dim3(NB, PLACE_SPLIT), PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs);
 }
 
 // ------------------------------------------------------------------ live counts

@@ -1183,9 +1183,9 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, EreQueue Q, const u
     const u32 lane = LANE;
     const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
     const u32 count = *wlCount;
-    u32 sizeMask[8];   // bit s: some live clause has size s (255 = "255 or more"), k_ere_bloom
-#pragma unroll
-    for (int k = 0; k < 8; k++) sizeMask[k] = g.bloom[(g.bloomMask >> 5) + 1 + k];
+    __shared__ u32 sizeMask[8];   // bit s: some live clause has size s (255 = "255 or more"), k_ere_bloom
+    if (threadIdx.x < 8) sizeMask[threadIdx.x] = g.bloom[(g.bloomMask >> 5) + 1 + threadIdx.x];
+    __syncthreads();
     for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
         const u32 v = g.elected[wl[wi]], p = V2L(v), n = p | 1u;
         const u32 ds = g.otSize[p], fs = g.otSize[n];
@@ -1210,6 +1210,18 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, EreQueue Q, const u
             if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
             const u32* a = g.pool + hp.x; const int n1 = (int)hp.y;
             const u32* b = g.pool + hn.x; const int n2 = (int)hn.y;
+            {   // cheapest filter first: bounds of the resolvent length from the two signatures alone.  A literal
+                // of a can only be shared with b if its hash bit is set in b's signature, so at most U
+                // literals merge and the length lies in [n1+n2-2-U, n1+n2-2]; no live clause of such a
+                // size -> nothing can equal this resolvent (most pairs of a uniform k-SAT formula stop here)
+                u32 U = 0;
+                for (int q = 0; q < n1; q++) { const u32 l = a[q]; if (LABS(l) != v) U += (hn.z >> (l & 31u)) & 1u; }
+                const u32 lenMax = (u32)(n1 + n2 - 2);
+                if (U > (u32)(n2 - 1)) U = (u32)(n2 - 1);
+                bool any = false;
+                for (u32 sN = lenMax - U; sN <= lenMax; sN++) { const u32 sb = sN < 255u ? sN : 255u; any |= (sizeMask[sb >> 5] >> (sb & 31u)) & 1u; }
+                if (!any) continue;
+            }
             u32 len, first, last, sig;
             if (!ereKey(a, n1, b, n2, v, len, first, last, sig) || len <= 1) continue;
             // filters: is there a live clause of this size at all / with this key at all?

@@ -63,5 +63,31 @@ def main(path):
         print(f"{name:34s} {ms:8.3f} {rdb / 1e6:10.1f} {wrb / 1e6:10.1f} {gbs:8.0f} {rest[0]:6.1f} {rest[1]:7.1f} {rest[2]:6.1f} {rest[3]:6.1f} {rest[4]:5.0f} {rest[5]:8.0f} {rest[6]:6.0f}")
 
 
+def traffic_json(path, out):
+    """--json: mean DRAM bytes per launch and duration per kernel -> profiles/*_ncu_traffic_<cfg>.json (bench.py `traffic`)."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    h, units = rows[hi], rows[hi + 1]
+    col = {n: i for i, n in enumerate(h)}
+    agg = {}
+    for r in rows[hi + 2:]:
+        if len(r) <= col["Kernel Name"]:
+            continue
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].strip()
+        try:
+            rd = to_bytes(float(r[col["dram__bytes_read.sum"]].replace(",", "")), units[col["dram__bytes_read.sum"]])
+            wr = to_bytes(float(r[col["dram__bytes_write.sum"]].replace(",", "")), units[col["dram__bytes_write.sum"]])
+        except (ValueError, KeyError):
+            continue
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1; a[1] += rd + wr
+    json.dump({"source": path, "how": "ncu --set full --clock-control none: dram__bytes_read.sum + dram__bytes_write.sum, mean per captured launch",
+               "kernels": {k: v[1] / v[0] for k, v in agg.items()}}, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 3 and sys.argv[2] == "--json":
+        traffic_json(sys.argv[1], sys.argv[3])
+    else:
+        main(sys.argv[1])
