@@ -108,23 +108,34 @@ void launchHistKey(Ctx* c) {
 // write long runs per bucket and partition at ~3x the speed of uniform random k-SAT.
 // Algorithmic bytes: part 16C + 4L read + 8L written; place 8L read + 4L written + 12 ND.
 #define PART_THREADS 1024
-#define PART_CPT 4
+#define PART_CPT 3
 #define PART_TILE (PART_THREADS * PART_CPT)
-#define PART_SHORT 8   // clauses up to this size keep the ranks of their literals in registers
+#define PART_SHORT 8       // clauses up to this size keep the ranks of their literals in registers
+#define PART_STAGE 16384u  // pairs of a tile staged in shared memory (128 KB)
 
 // One shared-memory atomic per pair: the rank the counting sweep hands out IS the pair's slot in the
 // tile's run of its bucket, so it is kept (16 bits per literal, four registers per clause) and the
 // writing sweep needs no second atomic.  Literals of longer clauses are counted separately and take
 // the tail of the run with a second atomic.
+// The writing sweep goes through shared memory: the tile's pairs are laid out bucket by bucket
+// (tileOff = exclusive scan of the tile's bucket counts) and copied out in that order, so that
+// neighbouring lanes store to neighbouring addresses of a run.  Per-lane scattered 8-byte stores cost
+// one L2 write transaction each, and that transaction rate - not HBM - bounded the unstaged kernel.
+// A tile with more pairs than the stage holds (long clauses) writes directly.
 __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
-                                                          const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB,
+                                                          const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB, u32 stageCap,
                                                           u32* __restrict__ gcur, uint2* __restrict__ pairs) {
     extern __shared__ u32 sm[];
-    u32* cntS = sm;            // literals of short clauses per bucket
-    u32* cntL = sm + NB;       // literals of long clauses per bucket, then their running slot
-    u32* gbase = sm + 2 * NB;  // start of this tile's run in the bucket's segment
+    u32* cntS = sm;             // literals of short clauses per bucket
+    u32* cntL = sm + NB;        // literals of long clauses per bucket, then their running slot
+    u32* gbase = sm + 2 * NB;   // start of this tile's run in the bucket's segment
+    u32* tileOff = sm + 3 * NB; // start of the bucket inside the staged tile
+    uint2* stage = (uint2*)(sm + 4 * NB);   // 16 NB bytes: 8-byte aligned
+    __shared__ u32 warpTot[32];
+    __shared__ u32 tileTotal, nonEmpty;
     const u32 tile0 = blockIdx.x * PART_TILE;
     for (u32 b = threadIdx.x; b < 2 * NB; b += PART_THREADS) sm[b] = 0;
+    if (threadIdx.x == 0) nonEmpty = 0;
     u32 off[PART_CPT], sz[PART_CPT], rk[PART_CPT][PART_SHORT / 2];
 #pragma unroll
     for (int k = 0; k < PART_CPT; k++) {
@@ -149,13 +160,39 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
             for (u32 q = 0; q < sz[k]; q++) atomicAdd(&cntL[l[q] >> shift], 1u);
     }
     __syncthreads();
-#pragma unroll 4
-    for (u32 b = threadIdx.x; b < NB; b += PART_THREADS) {
-        const u32 tS = cntS[b], tL = cntL[b];
-        if (tS + tL) gbase[b] = otStart[min(b << shift, ND)] + atomicAdd(&gcur[b], tS + tL);
-        cntL[b] = tS;   // long-clause literals follow the short ones
+    // per bucket: reserve the run (one global atomic), exclusive scan of the tile's bucket counts
+    const u32 per = (NB + PART_THREADS - 1) / PART_THREADS;   // consecutive buckets per thread
+    const u32 b0 = threadIdx.x * per;
+    u32 mine = 0, used = 0;
+    for (u32 q = 0; q < per; q++) {
+        const u32 b = b0 + q;
+        if (b < NB) {
+            const u32 tS = cntS[b], tL = cntL[b];
+            if (tS + tL) { gbase[b] = otStart[min(b << shift, ND)] + atomicAdd(&gcur[b], tS + tL); used++; }
+            cntL[b] = tS;   // long-clause literals follow the short ones
+            tileOff[b] = mine;
+            mine += tS + tL;
+        }
+    }
+    const u32 incl = warpIncl(mine);
+    used = warpSum(used);
+    if ((threadIdx.x & 31u) == 0 && used) atomicAdd(&nonEmpty, used);
+    if ((threadIdx.x & 31u) == 31u) warpTot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const u32 t = warpTot[threadIdx.x];
+        const u32 ti = warpIncl(t);
+        warpTot[threadIdx.x] = ti - t;
+        if (threadIdx.x == 31) tileTotal = ti;
     }
     __syncthreads();
+    const u32 base = warpTot[threadIdx.x >> 5] + incl - mine;
+    for (u32 q = 0; q < per; q++) { const u32 b = b0 + q; if (b < NB) tileOff[b] += base; }
+    __syncthreads();
+    // Staging pays when the tile's runs are short (uniform random formulas: ~4 pairs per bucket).  In
+    // clause-local formulas (Tseitin, arithmetic) neighbouring clauses fall into the same bucket with
+    // consecutive ranks, so the direct stores of a warp already coalesce and staging only adds a pass.
+    const bool staged = tileTotal <= stageCap && tileTotal < 12u * nonEmpty;
 #pragma unroll
     for (int k = 0; k < PART_CPT; k++) {
         const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
@@ -165,14 +202,27 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
             for (int q = 0; q < PART_SHORT; q++)
                 if ((u32)q < sz[k]) {
                     const u32 lit = l[q];
-                    pairs[gbase[lit >> shift] + ((rk[k][q >> 1] >> ((q & 1) * 16)) & 0xFFFFu)] = make_uint2(lit, i);
+                    const u32 b = lit >> shift;
+                    const u32 r = (rk[k][q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
+                    if (staged) stage[tileOff[b] + r] = make_uint2(lit, i);
+                    else pairs[gbase[b] + r] = make_uint2(lit, i);
                 }
         } else
             for (u32 q = 0; q < sz[k]; q++) {
                 const u32 lit = l[q];
                 const u32 b = lit >> shift;
-                pairs[gbase[b] + atomicAdd(&cntL[b], 1u)] = make_uint2(lit, i);
+                const u32 r = atomicAdd(&cntL[b], 1u);
+                if (staged) stage[tileOff[b] + r] = make_uint2(lit, i);
+                else pairs[gbase[b] + r] = make_uint2(lit, i);
             }
+    }
+    if (!staged) return;
+    __syncthreads();
+    const u32 total = tileTotal;
+    for (u32 t = threadIdx.x; t < total; t += PART_THREADS) {
+        const uint2 pr = stage[t];
+        const u32 b = pr.x >> shift;
+        pairs[gbase[b] + (t - tileOff[b])] = pr;
     }
 }
 
@@ -258,7 +308,7 @@ void launchScatter(Ctx* c) {
     // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
     if (!n || !c->numLiterals) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
     if (!c->attrOT) {
-        cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 8192);
+        cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
         c->attrOT = true;
     }
@@ -273,8 +323,11 @@ void launchScatter(Ctx* c) {
     const u32 window = shift <= 12 ? PLACE_WINDOW : 0;
     const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
     cudaMemsetAsync(c->otCur, 0, (size_t)NB * 4, c->stream);
-    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, 12 * NB, c->hdr[c->cur], c->pool[c->cur], n, c->otStart, c->ND, shift, NB,
-           c->otCur, c->otPairs);
+    // shared memory of k_ot_part: 4 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
+    const size_t partFixed = 16 * (size_t)NB + 8;
+    u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
+    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n, c->otStart,
+           c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
     LAUNCH(c, k_ot_place, dim3(NB, PLACE_SPLIT), PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs);
 }
 
