@@ -128,7 +128,10 @@ def ncu_traffic(workload):
     written by tools/ncu_digest.py --json)."""
     import glob
     best = {}
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_ncu_traffic_{workload}*.json"))):
+    def version(f):   # ..._vNN.json, natural order
+        m = re.search(r"_v(\d+)[a-z]*\.json$", f)
+        return int(m.group(1)) if m else -1
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_ncu_traffic_{workload}*.json")), key=version):
         try:
             best.update(json.load(open(f)).get("kernels", {}))
         except (OSError, ValueError):

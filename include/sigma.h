@@ -130,6 +130,15 @@ int  sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses,
                 const uint32_t* lits, const uint64_t* offs, const uint32_t* meta,
                 const uint32_t* vorg, const uint8_t* vstate, const uint8_t* assumed);
 
+/* The same from the reference's own host mirror `hcnf` (CNF::newClause, cnf.cuh:82-97): the SCLAUSE
+ * record stream {word 0 = st:2 f:1 a:1 u:2 lbd:26, sig, size, literals...} of num_words words and the
+ * uint64 word offsets `refs[num_clauses]`, gap-free in ref order - exactly the two buffers
+ * Solver::reflectCNF copies to the device (cnf.cu:166-174); unpacked on the device.  The inverse of
+ * sigma_store_sclauses. */
+int  sigma_load_sclauses(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, const uint32_t* data_words,
+                         uint64_t num_words, const uint64_t* refs, const uint32_t* vorg, const uint8_t* vstate,
+                         const uint8_t* assumed);
+
 /* Solver::simplifying (simplify.cu:136-241): awaken's device half (prep_cnf_k) + the round
  * loop.  Can be called repeatedly on the loaded formula (each call restarts from it). */
 int  sigma_run(sigma_ctx* c, sigma_report* rep);

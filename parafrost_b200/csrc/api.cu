@@ -215,20 +215,10 @@ __global__ void k_iota(u32* __restrict__ a, u32 n) {
 }
 
 // ------------------------------------------------------------------ load
-extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, const uint32_t* lits,
-                          const uint64_t* offs, const uint32_t* meta, const uint32_t* vorg, const uint8_t* vstate,
-                          const uint8_t* assumed) {
-    if (!c || !lits || !offs || !max_var) return SIGMA_BAD_ARGUMENT;
-    CUDA_TRY(cudaSetDevice(c->device));
-    const u64 L0 = offs[num_clauses];
+// sizes the logical capacities and the arena for a formula of num_clauses clauses / L0 literals
+static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u64 orgC, u64 orgL) {
     // election words carry a 27-bit rank (lcve.cu); clause indices are 32-bit
     if (max_var >= (1u << 27) - 2 || num_clauses >= 0xFFFFFFF0ull) return SIGMA_BAD_ARGUMENT;
-    // stats.clauses.original / stats.literals.original (solver.hpp:164-165)
-    u64 orgC = num_clauses, orgL = L0;
-    if (meta) {
-        orgC = 0; orgL = 0;
-        for (u64 i = 0; i < num_clauses; i++) if (!(meta[i] & CB_LEARNT)) { orgC++; orgL += offs[i + 1] - offs[i]; }
-    }
     c->V = max_var; c->ND = 2 * (max_var + 1);
     c->C0 = num_clauses; c->L0 = L0;
     c->orgClauses = orgC; c->orgLiterals = orgL;
@@ -257,24 +247,96 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
     }
     c->arenaUsed = carve(c, c->arena);
     if (c->arenaUsed > c->arenaPeak) c->arenaPeak = c->arenaUsed;
-    // host -> device (extractCNF + reflectCNF, cnf.cu:166-184)
-    CUDA_TRY(cudaMemcpyAsync(c->inLits, lits, L0 * 4, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->inOffs, offs, (num_clauses + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    if (meta) CUDA_TRY(cudaMemcpyAsync(c->inMeta, meta, num_clauses * 4, cudaMemcpyHostToDevice, c->stream));
-    else c->inMeta = nullptr;
-    const size_t V1 = (size_t)max_var + 1;
+    return SIGMA_OK;
+}
+// per-variable inputs + completion of a load
+static int finishLoad(Ctx* c, const uint32_t* vorg, const uint8_t* vstate, const uint8_t* assumed) {
+    const size_t V1 = (size_t)c->V + 1;
     if (vorg) CUDA_TRY(cudaMemcpyAsync(c->vorg, vorg, V1 * 4, cudaMemcpyHostToDevice, c->stream));
     else LAUNCH(c, k_iota, gridFor(V1, 256), 256, 0, c->vorg, (u32)V1);
     if (vstate) CUDA_TRY(cudaMemcpyAsync(c->vstate0, vstate, V1, cudaMemcpyHostToDevice, c->stream));
     else CUDA_TRY(cudaMemsetAsync(c->vstate0, 0, V1, c->stream));
     if (assumed) CUDA_TRY(cudaMemcpyAsync(c->assumed, assumed, V1, cudaMemcpyHostToDevice, c->stream));
     else c->assumed = nullptr;
-    i64 un = max_var;
+    i64 un = c->V;
     if (vstate) for (size_t v = 1; v < V1; v++) if (vstate[v]) un--;
     c->unassigned0 = un;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->loaded = true; c->begun = false;
     return SIGMA_OK;
+}
+
+extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, const uint32_t* lits,
+                          const uint64_t* offs, const uint32_t* meta, const uint32_t* vorg, const uint8_t* vstate,
+                          const uint8_t* assumed) {
+    if (!c || !lits || !offs || !max_var) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const u64 L0 = offs[num_clauses];
+    // stats.clauses.original / stats.literals.original (solver.hpp:164-165)
+    u64 orgC = num_clauses, orgL = L0;
+    if (meta) {
+        orgC = 0; orgL = 0;
+        for (u64 i = 0; i < num_clauses; i++) if (!(meta[i] & CB_LEARNT)) { orgC++; orgL += offs[i + 1] - offs[i]; }
+    }
+    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL);
+    if (rc) return rc;
+    // host -> device (extractCNF + reflectCNF, cnf.cu:166-184)
+    CUDA_TRY(cudaMemcpyAsync(c->inLits, lits, L0 * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->inOffs, offs, (num_clauses + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (meta) CUDA_TRY(cudaMemcpyAsync(c->inMeta, meta, num_clauses * 4, cudaMemcpyHostToDevice, c->stream));
+    else c->inMeta = nullptr;
+    return finishLoad(c, vorg, vstate, assumed);
+}
+
+// SCLAUSE records {word 0, sig, size, literals...} at refs[i] -> the engine's input arrays
+__global__ void k_unpack_sclauses(const u32* __restrict__ data, const u64* __restrict__ refs, u64 C, u64 numWords,
+                                  u32* __restrict__ inLits, u64* __restrict__ inOffs, u32* __restrict__ inMeta, u32* bad) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (u64)gridDim.x * blockDim.x) {
+        const u64 r = refs[i];
+        // records are appended in ref order without gaps (cnf.cuh:82-97): literal offset = ref - 3 i
+        if (r < NBUCKETS * i || r + NBUCKETS > numWords) { atomicOr(bad, 1u); continue; }
+        const u32 sz = data[r + 2];
+        if (data[r] & CB_DELETED) { atomicOr(bad, 1u); continue; }   // extractCNF never mirrors deleted clauses (cnf.cu:176-184)
+        const u64 next = i + 1 < C ? refs[i + 1] : numWords;
+        if (r + NBUCKETS + sz != next) { atomicOr(bad, 1u); continue; }
+        const u64 o = r - NBUCKETS * i;
+        inOffs[i] = o;
+        if (i + 1 == C) inOffs[C] = o + sz;
+        inMeta[i] = data[r] & ~(CB_DELETED | CB_MOLTEN | CB_ADDED);
+        for (u32 k = 0; k < sz; k++) inLits[o + k] = data[r + NBUCKETS + k];
+    }
+}
+
+extern "C" int sigma_load_sclauses(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, const uint32_t* data_words,
+                                   uint64_t num_words, const uint64_t* refs, const uint32_t* vorg, const uint8_t* vstate,
+                                   const uint8_t* assumed) {
+    if (!c || !data_words || !refs || !max_var || num_words < NBUCKETS * num_clauses) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const u64 L0 = num_words - NBUCKETS * num_clauses;
+    u64 orgC = 0, orgL = 0;
+    for (u64 i = 0; i < num_clauses; i++) {
+        const u64 r = refs[i];
+        if (r + NBUCKETS > num_words) return SIGMA_BAD_ARGUMENT;
+        if ((data_words[r] & CB_ST_MASK) == 0) { orgC++; orgL += data_words[r + 2]; }
+    }
+    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL);
+    if (rc) return rc;
+    // the reference's own two copies (reflectCNF, cnf.cu:166-174): record stream and refs, staged in
+    // the inactive clause buffer, then unpacked on the device
+    u32* dData = c->pool[1];
+    u64* dRefs = c->flag64;
+    u32* bad = &c->dc->scratch[5];
+    CUDA_TRY(cudaMemcpyAsync(dData, data_words, num_words * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dRefs, refs, num_clauses * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(bad, 0, 4, c->stream));
+    if (num_clauses)
+        LAUNCH(c, k_unpack_sclauses, gridFor(num_clauses, 256), 256, 0, dData, dRefs, num_clauses, num_words, c->inLits, c->inOffs, c->inMeta, bad);
+    else CUDA_TRY(cudaMemsetAsync(c->inOffs, 0, 8, c->stream));
+    u32 hbad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (hbad) { snprintf(c->err, sizeof c->err, "SCLAUSE stream is not a gap-free sequence of records in ref order"); return SIGMA_BAD_ARGUMENT; }
+    return finishLoad(c, vorg, vstate, assumed);
 }
 
 // ------------------------------------------------------------------ round loop

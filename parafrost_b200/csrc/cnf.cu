@@ -108,8 +108,6 @@ void launchHistKey(Ctx* c) {
 // write long runs per bucket and partition at ~3x the speed of uniform random k-SAT.
 // Algorithmic bytes: part 16C + 4L read + 8L written; place 8L read + 4L written + 12 ND.
 #define PART_THREADS 1024
-#define PART_CPT 3
-#define PART_TILE (PART_THREADS * PART_CPT)
 #define PART_SHORT 8       // clauses up to this size keep the ranks of their literals in registers
 #define PART_STAGE 16384u  // pairs of a tile staged in shared memory (128 KB)
 
@@ -122,6 +120,7 @@ void launchHistKey(Ctx* c) {
 // neighbouring lanes store to neighbouring addresses of a run.  Per-lane scattered 8-byte stores cost
 // one L2 write transaction each, and that transaction rate - not HBM - bounded the unstaged kernel.
 // A tile with more pairs than the stage holds (long clauses) writes directly.
+template <int PART_CPT>   // clauses per thread: 3 (tiles of 3072 clauses) or 5 for short clauses, so that a tile fills the stage
 __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
                                                           const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB, u32 stageCap,
                                                           u32* __restrict__ gcur, uint2* __restrict__ pairs) {
@@ -133,7 +132,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
     uint2* stage = (uint2*)(sm + 4 * NB);   // 16 NB bytes: 8-byte aligned
     __shared__ u32 warpTot[32];
     __shared__ u32 tileTotal, nonEmpty;
-    const u32 tile0 = blockIdx.x * PART_TILE;
+    const u32 tile0 = blockIdx.x * (PART_THREADS * PART_CPT);
     for (u32 b = threadIdx.x; b < 2 * NB; b += PART_THREADS) sm[b] = 0;
     if (threadIdx.x == 0) nonEmpty = 0;
     u32 off[PART_CPT], sz[PART_CPT], rk[PART_CPT][PART_SHORT / 2];
@@ -308,7 +307,8 @@ void launchScatter(Ctx* c) {
     // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
     if (!n || !c->numLiterals) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
     if (!c->attrOT) {
-        cudaFuncSetAttribute(k_ot_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
         c->attrOT = true;
     }
@@ -326,8 +326,12 @@ void launchScatter(Ctx* c) {
     // shared memory of k_ot_part: 4 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
     const size_t partFixed = 16 * (size_t)NB + 8;
     u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
-    LAUNCH(c, k_ot_part, divup(n, PART_TILE), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n, c->otStart,
-           c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
+    if (c->numLiterals <= 3 * c->numClauses)   // short clauses: more of them per tile
+        LAUNCH(c, k_ot_part<5>, divup(n, PART_THREADS * 5), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
+               c->otStart, c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
+    else
+        LAUNCH(c, k_ot_part<3>, divup(n, PART_THREADS * 3), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
+               c->otStart, c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
     LAUNCH(c, k_ot_place, dim3(NB, PLACE_SPLIT), PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs);
 }
 

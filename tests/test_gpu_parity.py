@@ -316,3 +316,55 @@ def test_full_size_properties_cfg2_shape():
     gone = (st["eliminated"] != 0)
     touched = np.bitwise_or.reduceat(gone[lits >> 1].astype(np.uint8), offs[:-1].astype(np.int64))
     assert int((touched == 0).sum()) <= fin["clauses"]
+
+
+def sclause_stream(lits, offs, meta=None):
+    """Host mirror of the reference (CNF::newClause, cnf.cuh:82-97): records {word0, sig, size, lits...} + uint64 refs."""
+    n = len(offs) - 1
+    sz = np.diff(offs.astype(np.int64))
+    refs = (offs[:-1].astype(np.int64) + 3 * np.arange(n, dtype=np.int64)).astype(np.uint64)
+    data = np.zeros(int(offs[-1]) + 3 * n, np.uint32)
+    r = refs.astype(np.int64)
+    data[r] = 0 if meta is None else meta
+    data[r + 2] = sz
+    pos = np.arange(len(lits), dtype=np.int64) + 3 * (np.repeat(np.arange(n, dtype=np.int64), sz) + 1)
+    data[pos] = lits
+    return data, refs
+
+
+def test_load_from_reference_host_mirror():
+    """sigma_load_sclauses (the SCLAUSE record stream + refs the reference copies in reflectCNF) gives the
+    same result as the CSR load, with and without learnt clauses; a store_sclauses() result can be fed
+    back as the input of the next call; a stream with a gap is refused."""
+    S = sigma()
+    rng = np.random.default_rng(3)
+    for fam, seed, args, with_meta in (("ksat", 12, [800, 2400, 3], False), ("miter", 21, [30, 600, 900, 100, 8], True), ("mult", 32, [10], False)):
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        meta = None
+        if with_meta:
+            meta = np.zeros(len(offs) - 1, np.uint32)
+            lrn = rng.random(len(meta)) < 0.15
+            meta[lrn] = 1 | (1 << 4) | (rng.integers(2, 7, int(lrn.sum())).astype(np.uint32) << 6)
+        calls = 2 if with_meta else 1
+        a = S.Simplifier(0, sigma_calls=calls); a.load(V, lits, offs, meta=meta); ra = a.simplify(); da = to_dump(V, a.store(), ra["cnfstate"])
+        data, refs = sclause_stream(lits, offs, meta)
+        b = S.Simplifier(0, sigma_calls=calls); b.load_sclauses(V, data, refs); rb = b.simplify(); db = to_dump(V, b.store(), rb["cnfstate"])
+        assert not sgd.compare(da, db), fam
+        assert (da.bits == db.bits).all() and (da.sig == db.sig).all()
+        # second call on the simplified formula, fed through the reference's own record format
+        d2, r2 = a.store_sclauses()
+        st = a.store()
+        vstate = (st["eliminated"] != 0).astype(np.uint8)
+        meta2 = (st["bits"] & np.uint32(~(2 | 4 | 8) & 0xFFFFFFFF)).astype(np.uint32)
+        x = S.Simplifier(0, sigma_calls=2); x.load(V, st["lits"], st["offs"], meta=meta2, vstate=vstate); rx = x.simplify(); dx = to_dump(V, x.store(), rx["cnfstate"])
+        y = S.Simplifier(0, sigma_calls=2); y.load_sclauses(V, d2, r2, vstate=vstate); ry = y.simplify(); dy = to_dump(V, y.store(), ry["cnfstate"])
+        assert not sgd.compare(dx, dy), fam
+        for s_ in (a, b, x, y):
+            s_.close()
+    V, lits, offs = helpers.gen_cnf("ksat", 12, [800, 2400, 3])
+    data, refs = sclause_stream(lits, offs)
+    refs[5] += 1
+    s_ = S.Simplifier(0)
+    with pytest.raises(S.SigmaError):
+        s_.load_sclauses(V, data, refs)
+    s_.close()
