@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
     }
 }
 
-#define PLACE_THREADS 512
+#define PLACE_THREADS 1024
 #define PLACE_SPLIT 8            // a bucket with many pairs is shared by up to 8 CTAs (grid.y) ...
 #define PLACE_UNIT (128u << 10)  // ... of about this many pairs each
 #define PLACE_WINDOW (40u << 10) // entries of a bucket's occurs[] window that can be staged in shared memory
