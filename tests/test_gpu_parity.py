@@ -368,3 +368,32 @@ def test_load_from_reference_host_mirror():
     with pytest.raises(S.SigmaError):
         s_.load_sclauses(V, data, refs)
     s_.close()
+
+
+FULLSIZE = os.path.join(HERE, "golden", "fullsize_fingerprints.json")
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg4", "cfg2", "cfg3"])
+def test_full_size_matches_oracle_fingerprint(name):
+    """BASELINE.json configs 1-4 at FULL size: the engine's result against the fingerprint of the CPU
+    oracle computed in the build container (tests/golden/make_fullsize_fingerprints.py; the oracle needs
+    minutes there, the GPU box only runs the engine): same clause list in the same order with the
+    same flag words, same eliminated set, witness groups and units, same per-round counters."""
+    gold = json.load(open(FULLSIZE))
+    if name not in gold:
+        pytest.skip(f"no committed fingerprint for {name}")
+    g = gold[name]
+    V, lits, offs = helpers.gen_cnf(g["family"], g["seed"], g["args"])
+    assert (V, len(offs) - 1, len(lits)) == (g["vars"], g["clauses_in"], g["literals_in"])
+    S = sigma()
+    s = S.Simplifier(0, flags=g["flags"])
+    s.load(V, lits, offs)
+    fin = s.simplify()
+    rounds = [r for r in s.rounds() if r["kind"] == 0]
+    st = s.store()
+    s.close()
+    got = [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds]
+    assert got == g["rounds"]
+    fp = to_dump(V, st, fin["cnfstate"]).fingerprint()
+    diff = {k: (fp[k], v) for k, v in g["fingerprint"].items() if fp[k] != v}
+    assert not diff, diff
