@@ -370,7 +370,7 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     c->cur = 0;
     c->phase = c->multiplier = 0; c->simpstate = SIGMA_OK; c->cnfstate = SIGMA_UNSOLVED; c->compacted = false;
     c->nUnits = 0; c->numElected = 0; c->currMelted = 0; c->varcoreDead = false;
-    c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0; c->otValid = false;
+    c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0; c->otValid = false; c->countsFresh = false;
     memset(c->stageMs, 0, sizeof c->stageMs);
     c->unassigned = c->unassigned0;
     memset(c->hdc, 0, sizeof(DevCounters));
@@ -438,6 +438,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     const double t0 = nowMs();
     int rc;
     bool didGC = false;
+    c->countsFresh = false;
     // cnf.cu:146-150
     const int times = c->phase + 1;
     const bool gc = times > 1 && times != c->o.phases && c->o.shrink_rate > 0 && (times % c->o.shrink_rate) == 0;
@@ -508,6 +509,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
         c->loopDone = true;
         launchCount(c);
         if ((rc = syncCounters(c))) return rc;
+        c->countsFresh = true;
         r.clauses = c->hdc->liveCls; r.literals = c->hdc->liveLits;
         r.ms = (float)(nowMs() - t0);
         pushRound(c, r); if (rep) *rep = r;
@@ -523,6 +525,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     }
     { StageTimer t(c, ST_CNT); launchCount(c); }
     if ((rc = syncCounters(c))) return rc;
+    c->countsFresh = true;
     if (c->hdc->flags & 3u) { snprintf(c->err, sizeof c->err, "device vector overflow (flags %u)", c->hdc->flags); return SIGMA_OVERFLOW; }
     // updateNumPVs (simplify.cu:35-41)
     const u32 remained = c->o.ve_en ? c->hdc->numElected : c->numElected;
@@ -551,8 +554,10 @@ extern "C" int sigma_finish(sigma_ctx* c, sigma_report* rep) {
     if (!c->begun) return SIGMA_NOT_LOADED;
     CUDA_TRY(cudaSetDevice(c->device));
     int rc;
-    launchCount(c);
-    if ((rc = syncCounters(c))) return rc;
+    if (!c->countsFresh) {   // the last round ended with a count and nothing touched the clause store since
+        launchCount(c);
+        if ((rc = syncCounters(c))) return rc;
+    }
     c->numClauses = c->hdc->liveCls; c->numLiterals = c->hdc->liveLits;
     // simplify.cu:198-209
     if (c->cnfstate == SIGMA_UNSOLVED && (c->unassigned <= 0 || !c->numClauses)) c->cnfstate = SIGMA_SAT;

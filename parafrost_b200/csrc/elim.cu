@@ -1172,6 +1172,11 @@ __device__ __forceinline__ void ereSearchDelete(GT<GS>& g, const u32* a, int n1,
     }
 }
 
+__device__ __forceinline__ void ereAdvance(u32& i, u32& j, u32 step, u32 fs) {
+    j += step;
+    if (fs >= step) { if (j >= fs) { j -= fs; i++; } }   // at most one wrap
+    else { i += j / fs; j %= fs; }
+}
 // Phase A: enumerate the resolvents, keep the few that pass the filters.  With `queue` the survivors
 // are only recorded (clause pair + variable) and the list they will be searched in is flagged, so
 // that ONLY those lists have to be sorted before phase B (k_ere_apply); without it the search runs
@@ -1200,9 +1205,9 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, EreQueue Q, const u
 #pragma unroll
         for (int o = GS / 2; o; o >>= 1) { minP = min(minP, __shfl_xor_sync(FULL, minP, o, GS)); minN = min(minN, __shfl_xor_sync(FULL, minN, o, GS)); }
         if ((int)minP > clause_max || (int)minN > clause_max) continue;
-        const u64 total = (u64)ds * fs;
-        for (u64 t = lane; t < total; t += GS) {
-            const u32 i = (u32)(t / fs), j = (u32)(t - (u64)i * fs);
+        // pairs (i, j) in pos-major order, lane-strided; the indices advance without a division
+        u32 i = lane / fs, j = lane - i * fs;
+        for (; i < ds; ereAdvance(i, j, (u32)GS, fs)) {
             const u32 ciP = P[i], ciN = N[j];
             const uint4 hp = g.hdr[ciP];
             if (C_DELETED(hp.w)) continue;
