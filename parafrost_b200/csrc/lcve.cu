@@ -146,6 +146,54 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
 // one 4-byte probe instead of walking the whole neighbourhood again; only when the blocker got
 // frozen itself is the neighbourhood rescanned.  (Decisions can come a round later than with a
 // full scan every round; the fixed point - the lexicographically first MIS - is the same.)
+// the plain walk: right for the 8-lane groups of formulas with a handful of short clauses per
+// variable, where batching only adds predicated loads (measured on cfg3: +45 %)
+#define MIS_WALK_SIMPLE(GS_, V_, LANE_, APPLY_)                                                        \
+    for (u32 side_ = 0; side_ < 2; side_++) {                                                          \
+        const u32 lit_ = V2L(V_) | side_;                                                              \
+        const u32 n_ = otSize[lit_];                                                                   \
+        const u32* list_ = occurs + otStart[lit_];                                                     \
+        for (u32 j_ = (LANE_); j_ < n_; j_ += (GS_)) {                                                 \
+            const uint4 h_ = hdr[list_[j_]];                                                           \
+            if (C_DELETED(h_.w)) continue;                                                             \
+            const u32 csize = h_.y; (void)csize;                                                       \
+            const u32* l_ = pool + h_.x;                                                               \
+            for (u32 k_ = 0; k_ < h_.y; k_++) { const u32 u = LABS(l_[k_]); if (u != (V_)) { const u32 wu = vinfo[u]; APPLY_ } } \
+        }                                                                                              \
+    }
+#define MIS_WALK_ANY(GS_, V_, LANE_, APPLY_) \
+    if constexpr ((GS_) == 32) { MIS_WALK(GS_, V_, LANE_, APPLY_) } else { MIS_WALK_SIMPLE(GS_, V_, LANE_, APPLY_) }
+
+// An elected variable freezes its higher-ranked undecided neighbours at once (push) instead of
+// letting each of them find out by rescanning its own neighbourhood: every concurrent writer of a
+// neighbour's state word agrees on FROZEN (a neighbour of a just-elected variable can neither be
+// elected nor become the live stopper in the same launch: it sees this variable undecided or elected).
+// Walk over the neighbourhood of v (both occurrence lists, every literal of every live clause).  The
+// chain list entry -> header -> literals -> election words is four dependent loads deep; with small
+// worklists a MIS round is pure latency, so each lane keeps four clauses in flight (entries and
+// headers loaded as a batch) and loads the literals and the election words of a clause as batches of 8.
+#define MIS_WALK(GS_, V_, LANE_, APPLY_)                                                               \
+    for (u32 side_ = 0; side_ < 2; side_++) {                                                          \
+        const u32 lit_ = V2L(V_) | side_;                                                              \
+        const u32 n_ = otSize[lit_];                                                                   \
+        const u32* list_ = occurs + otStart[lit_];                                                     \
+        for (u32 j0_ = (LANE_); j0_ < n_; j0_ += 4 * (GS_)) {                                          \
+            u32 ci_[4]; uint4 h_[4];                                                                   \
+            _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) { const u32 j_ = j0_ + u_ * (GS_); ci_[u_] = j_ < n_ ? list_[j_] : NOVAR; } \
+            _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) h_[u_] = ci_[u_] != NOVAR ? hdr[ci_[u_]] : make_uint4(0, 0, 0, CB_DELETED);  \
+            _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) {                                         \
+                if (C_DELETED(h_[u_].w)) continue;                                                     \
+                const u32 csize = h_[u_].y; (void)csize;                                               \
+                const u32* l_ = pool + h_[u_].x;                                                       \
+                u32 lv_[8], wv_[8];                                                                    \
+                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) lv_[k_] = (u32)k_ < h_[u_].y ? LABS(l_[k_]) : (V_); \
+                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) wv_[k_] = lv_[k_] != (V_) ? vinfo[lv_[k_]] : 0u;    \
+                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) if (lv_[k_] != (V_)) { const u32 u = lv_[k_], wu = wv_[k_]; APPLY_ } \
+                for (u32 k_ = 8; k_ < h_[u_].y; k_++) { const u32 u = LABS(l_[k_]); if (u != (V_)) { const u32 wu = vinfo[u]; APPLY_ } } \
+            }                                                                                          \
+        }                                                                                              \
+    }
+
 // An elected variable freezes its higher-ranked undecided neighbours at once (push) instead of
 // letting each of them find out by rescanning its own neighbourhood: every concurrent writer of a
 // neighbour's state word agrees on FROZEN (a neighbour of a just-elected variable can neither be
@@ -154,22 +202,7 @@ template <int GS>
 __device__ __forceinline__ void pushFreeze(u32 v, u32 r, u32 lane, const uint4* __restrict__ hdr, const u32* __restrict__ pool,
                                            const u32* __restrict__ otStart, const u32* __restrict__ otSize,
                                            const u32* __restrict__ occurs, u32* vinfo) {
-    for (u32 side = 0; side < 2; side++) {
-        const u32 lit = V2L(v) | side;
-        const u32 n = otSize[lit];
-        const u32* list = occurs + otStart[lit];
-        for (u32 j = lane; j < n; j += GS) {
-            const uint4 h = hdr[list[j]];
-            if (C_DELETED(h.w)) continue;
-            const u32* l = pool + h.x;
-            for (u32 k = 0; k < h.y; k++) {
-                const u32 u = LABS(l[k]);
-                if (u == v) continue;
-                const u32 wu = vinfo[u];
-                if (VI_STATE(wu) == MIS_UNDECIDED && VI_RANK(wu) > r) vinfo[u] = (wu & ~7u) | MIS_FROZEN;
-            }
-        }
-    }
+    MIS_WALK_ANY(GS, v, lane, { if (VI_STATE(wu) == MIS_UNDECIDED && VI_RANK(wu) > r) vinfo[u] = (wu & ~7u) | MIS_FROZEN; })
 }
 
 // push for the variables elected by k_mis_first (thread-per-variable there: no group to walk the lists)
@@ -215,26 +248,14 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
         }
         bool frozen = false, oversize = false;
         u32 bRank = NOVAR, bVar = 0;
-        for (u32 side = 0; side < 2; side++) {
-            const u32 lit = V2L(v) | side;
-            const u32 n = otSize[lit];
-            const u32* list = occurs + otStart[lit];
-            for (u32 j = lane; j < n; j += GS) {
-                const uint4 h = hdr[list[j]];
-                if (C_DELETED(h.w)) continue;
-                if ((int)h.y > maxcsize) oversize = true;
-                const u32* l = pool + h.x;
-                for (u32 k = 0; k < h.y; k++) {
-                    const u32 u = LABS(l[k]);
-                    if (u == v) continue;
-                    const u32 wu = vinfo[u];
-                    if (VI_RANK(wu) >= r) continue;
-                    const u32 m = VI_STATE(wu);
-                    if (m == MIS_ELECTED) frozen = true;
-                    else if (m == MIS_UNDECIDED && VI_CLASS(wu) == CS_CAND && VI_RANK(wu) < bRank) { bRank = VI_RANK(wu); bVar = u; }
-                }
+        MIS_WALK_ANY(GS, v, lane, {
+            if ((int)csize > maxcsize) oversize = true;
+            if (VI_RANK(wu) < r) {
+                const u32 m = VI_STATE(wu);
+                if (m == MIS_ELECTED) frozen = true;
+                else if (m == MIS_UNDECIDED && VI_CLASS(wu) == CS_CAND && VI_RANK(wu) < bRank) { bRank = VI_RANK(wu); bVar = u; }
             }
-        }
+        })
         frozen = __any_sync(gmask, frozen);
         oversize = __any_sync(gmask, oversize);
         u32 minRank = bRank;
