@@ -1313,13 +1313,81 @@ static u32 groupGrid(u32 nGroups, u32 GS, u32 block) {
     const u64 cap = 148ull * 16;
     return (u32)(b > cap ? cap : (b ? b : 1));
 }
+// ------------------------------------------------------------------ shape order inside a class
+// A 4- or 8-lane group shares its warp with 7 or 3 other variables; what a variable does in SUB/BVE
+// (which gate pattern matches, how many pairs are merged) follows from the shape of its two lists,
+// so the worklist of a class is grouped by (|pos|, |neg|): warps run one code path instead of
+// eight (the BVE kernel is ~270 KB of SASS - divergent groups also thrash the instruction cache).
+// Counting sort with 256 keys, tile-local ranks + one global atomic per (tile, key); the order inside
+// a key is arbitrary, which nothing observes (results are indexed by the position in elected[]).
+#define SHAPE_TILE 2048
+__device__ __forceinline__ u32 shapeKey(const u32* __restrict__ elected, const u32* __restrict__ otSize, u32 item) {
+    const u32 x = elected[item];
+    const u32 np = otSize[V2L(x)], nn = otSize[V2L(x) | 1u];
+    return (min(np, 15u) << 4) | min(nn, 15u);
+}
+__global__ void __launch_bounds__(256) k_shape_hist(const u32* __restrict__ wl, const u32* __restrict__ count, const u32* __restrict__ elected,
+                                                    const u32* __restrict__ otSize, u32* __restrict__ hist) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 n = *count;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&h[shapeKey(elected, otSize, wl[i])], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_shape_scan(u32* __restrict__ hist) {   // hist[0..255] -> exclusive starts in hist[256..511]
+    __shared__ u32 s[256];
+    s[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) { u32 run = 0; for (int k = 0; k < 256; k++) { const u32 t = s[k]; s[k] = run; run += t; } }
+    __syncthreads();
+    hist[256 + threadIdx.x] = s[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) k_shape_scatter(const u32* __restrict__ wl, const u32* __restrict__ count, const u32* __restrict__ elected,
+                                                       const u32* __restrict__ otSize, u32* __restrict__ cursor, u32* __restrict__ out) {
+    __shared__ u32 cnt[256], base[256];
+    const u32 n = *count;
+    for (u32 t0 = blockIdx.x * SHAPE_TILE; t0 < n; t0 += gridDim.x * SHAPE_TILE) {
+        __syncthreads();
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+        u32 item[SHAPE_TILE / 256], key[SHAPE_TILE / 256], rank[SHAPE_TILE / 256];
+#pragma unroll
+        for (int k = 0; k < SHAPE_TILE / 256; k++) {
+            const u32 i = t0 + k * 256 + threadIdx.x;
+            key[k] = 0xFFFFFFFFu;
+            if (i < n) { item[k] = wl[i]; key[k] = shapeKey(elected, otSize, item[k]); rank[k] = atomicAdd(&cnt[key[k]], 1u); }
+        }
+        __syncthreads();
+        base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SHAPE_TILE / 256; k++) if (key[k] != 0xFFFFFFFFu) out[base[key[k]] + rank[k]] = item[k];
+    }
+}
+static void shapeSort(Ctx* c, u32* wl, const u32* count, u32 upperBound) {
+    if (upperBound < 64) return;   // a couple of warps: nothing to group
+    u32* hist = c->radixHist;      // 512 words, free after the election's radix sort
+    u32* tmp = c->flagA;           // free until BVE phase 3 writes the survivor flags
+    cudaMemsetAsync(hist, 0, 256 * 4, c->stream);
+    LAUNCH(c, k_shape_hist, gridFor(upperBound, 256, 4), 256, 0, wl, count, c->elected, c->otSize, hist);
+    LAUNCH(c, k_shape_scan, 1, 256, 0, hist);
+    LAUNCH(c, k_shape_scatter, gridFor(upperBound, 256, SHAPE_TILE / 256), 256, 0, wl, count, c->elected, c->otSize, hist + 256, tmp);
+    LAUNCH(c, k_copy_u32, gridFor(upperBound, 256), 256, 0, tmp, wl, count);
+}
+
 // worklists of the three classes live in the MIS scratch (free between election and the next round)
-static void binElected(Ctx* c, const KOpts& k, bool countOnDevice) {
+static void binElected(Ctx* c, const KOpts& k, bool countOnDevice, bool byShape = false) {
     // long XOR arities need the big shared-memory slice: everything runs on full warps then
     const u32 t4 = k.xor_max_arity + 2 > VE_SLICE_SMALL ? 0 : BIN_T4, t8 = k.xor_max_arity + 2 > VE_SLICE_SMALL ? 0 : BIN_T8;
     LAUNCH(c, k_bin_reset, 1, 1, 0, c->dc);
     LAUNCH(c, k_bin_elected, gridFor(c->numElected, 256), 256, 0, c->elected, countOnDevice ? &c->dc->numElected : nullptr, c->numElected,
            c->otSize, t4, t8, c->wlA, c->wlB, c->sortK, c->dc);
+    if (byShape) {
+        shapeSort(c, c->wlA, &c->dc->bin[0], c->numElected);
+        shapeSort(c, c->wlB, &c->dc->bin[1], c->numElected);
+    }
 }
 #define LAUNCH_CLASSES(c, kern, block, E, g, ...)                                                            \
     do {                                                                                                     \
@@ -1331,7 +1399,7 @@ static void binElected(Ctx* c, const KOpts& k, bool countOnDevice) {
 void launchSUB(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
-    binElected(c, k, false);
+    binElected(c, k, false, true);
     LAUNCH_CLASSES(c, k_sub, 128, c->numElected, g);
 }
 
@@ -1341,7 +1409,7 @@ void launchVE(Ctx* c, const KOpts& k) {
     G g = makeG(c, k);
     const u32 E = c->numElected;
     LAUNCH(c, k_ve_reset, 1, 1, 0, c->dc);
-    binElected(c, k, false);   // SUB shrank the lists: classes by the current sizes
+    binElected(c, k, false, true);   // SUB shrank the lists: classes by the current sizes
     u32* redo = c->rank;       // rank[] is dead after the election
     u32* redoCount = &c->dc->bin[3];
     LAUNCH(c, k_ve_phase1<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
