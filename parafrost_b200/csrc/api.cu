@@ -370,7 +370,7 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     c->cur = 0;
     c->phase = c->multiplier = 0; c->simpstate = SIGMA_OK; c->cnfstate = SIGMA_UNSOLVED; c->compacted = false;
     c->nUnits = 0; c->numElected = 0; c->currMelted = 0; c->varcoreDead = false;
-    c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0; c->otValid = false; c->countsFresh = false;
+    c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0; c->otValid = false; c->countsFresh = false; c->histFresh = false;
     memset(c->stageMs, 0, sizeof c->stageMs);
     c->unassigned = c->unassigned0;
     memset(c->hdc, 0, sizeof(DevCounters));
@@ -419,7 +419,8 @@ static void buildOT(Ctx* c, bool withGC, bool* didGC) {
         c->compacted = true;
         if (didGC) *didGC = true;
     }
-    { StageTimer t(c, ST_VO); launchHistKey(c); }
+    if (!c->histFresh || withGC) { StageTimer t(c, ST_VO); launchHistKey(c); }
+    c->histFresh = false;
     { StageTimer t(c, ST_VO); scanExclusiveU32(c, c->hist, c->otStart, c->ND, 0, c->otStart + c->ND); }
     { StageTimer t(c, ST_COT); launchScatter(c); }
 }

@@ -13,8 +13,10 @@
 
 // ------------------------------------------------------------------ awaken + prep
 // algorithmic bytes: read 8(C+1) offsets + 4L literals [+4C meta], write 16C headers + 4L literals
+// With hist != NULL the first round's histogram + sort-key pass (k_hist_key) is fused in: the sorted
+// literals are in registers anyway, so the clause store is not read again before the partition.
 __global__ void k_awaken(const u32* __restrict__ inLits, const u64* __restrict__ inOffs, const u32* __restrict__ inMeta,
-                         u64 C, uint4* __restrict__ hdr, u32* __restrict__ pool) {
+                         u64 C, uint4* __restrict__ hdr, u32* __restrict__ pool, u32* __restrict__ hist, uint4* __restrict__ key, u32* flags) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (u64)gridDim.x * blockDim.x) {
         const u64 b = inOffs[i], e = inOffs[i + 1];
         const int sz = (int)(e - b);
@@ -51,12 +53,20 @@ __global__ void k_awaken(const u32* __restrict__ inLits, const u64* __restrict__
             if (m & CB_LEARNT) bits = m & ~(CB_DELETED | CB_MOLTEN | CB_ADDED);
         }
         hdr[i] = make_uint4((u32)b, (u32)sz, sig, bits);
+        if (hist) {
+            for (int k = 0; k < sz; k++) atomicAdd(&hist[dst[k]], 1u);
+            key[i] = make_uint4((u32)sz, sz ? dst[0] : 0u, sz ? dst[sz - 1] : 0u, sig);
+            if (sz >= (1 << 14)) atomicOr(flags, 8u);
+        }
     }
 }
 
 void launchAwaken(Ctx* c) {
     if (!c->C0) return;
-    LAUNCH(c, k_awaken, gridFor(c->C0, 256), 256, 0, c->inLits, c->inOffs, c->inMeta, c->C0, c->hdr[c->cur], c->pool[c->cur]);
+    cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
+    LAUNCH(c, k_awaken, gridFor(c->C0, 256), 256, 0, c->inLits, c->inOffs, c->inMeta, c->C0, c->hdr[c->cur], c->pool[c->cur], c->hist, c->key,
+           &c->dc->flags);
+    c->histFresh = true;   // hist[] and key[] describe the store until a kernel changes it (api.cu: buildOT)
 }
 
 // ------------------------------------------------------------------ histogram + sort keys

@@ -170,6 +170,7 @@ struct Ctx {
     double msTotal;
     u32 lastElectedCount;
     bool varcoreDead, attrSort, attrElim, attrOT;
+    bool histFresh;    // hist[] / key[] were produced by k_awaken and the store is untouched since
     bool countsFresh;  // hdc->liveCls / liveLits describe the clause store as it is now
     bool otValid;      // the occurrence table built last round still describes the clause store (api.cu)
     i64 unassigned0;   // unassigned variables of the loaded formula (inf.unassigned)
