@@ -29,16 +29,20 @@
 __global__ void k_scores(const u32* __restrict__ hist, const unsigned char* __restrict__ vstate,
                          const unsigned char* __restrict__ assumed, u32 V, u32 pmax, u32 nmax, u32 maxoccurs,
                          u32* __restrict__ keys, u32* __restrict__ vals, unsigned char* __restrict__ cstat, DevCounters* dc) {
+    u32 kmax = 0;   // largest score: tells the host how many radix digits the sort needs
     for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < V; t += gridDim.x * blockDim.x) {
         const u32 v = t + 1;
         const u32 ps = hist[V2L(v)], ns = hist[V2L(v) | 1u];
         keys[t] = ps * ns;
+        kmax = max(kmax, ps * ns);
         vals[t] = v;
         unsigned char cs = CS_NONE;
         if (!vstate[v] && !(assumed && assumed[v]) && (ps || ns))
             cs = (ps > maxoccurs || ns > maxoccurs || (ps >= pmax && ns >= nmax)) ? CS_STOP : CS_CAND;
         cstat[v] = cs;
     }
+    kmax = warpMax(kmax);
+    if ((threadIdx.x & 31u) == 0 && kmax) atomicMax(&dc->scratch[6], kmax);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         dc->misStopRank = NOVAR; dc->numElected = 0; dc->wlNext = 0;
         dc->wlCnt[0] = dc->wlCnt[1] = dc->wlCnt[2] = 0; dc->firstStop = NOVAR;
@@ -100,11 +104,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const u32* __restr
     }
 }
 
-// sorts (keys, vals) ascending by key, stable; result ends in (keys, vals) after 4 passes
-static void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, u32 n) {
+// sorts (keys, vals) ascending by key, stable; only the digits below `bits` are sorted (all keys are
+// < 2^bits) in an EVEN number of 8-bit passes, so that the result ends in (keys, vals)
+static void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, u32 n, u32 bits) {
     const u32 nblocks = divup(n, RS_TILE);
     u32 *ki = keys, *vi = vals, *ko = keys2, *vo = vals2;
-    for (u32 shift = 0; shift < 32; shift += 8) {
+    u32 passes = (bits + 7) / 8;
+    passes = (passes + 1) & ~1u;
+    if (passes > 4) passes = 4;
+    for (u32 shift = 0; shift < 8 * passes; shift += 8) {
         LAUNCH(c, k_radix_hist, nblocks, RS_THREADS, 0, ki, n, shift, c->radixHist, nblocks);
         scanExclusiveU32(c, c->radixHist, c->radixHist, (u64)256 * nblocks, 0, nullptr);
         LAUNCH(c, k_radix_scatter, nblocks, RS_THREADS, 0, ki, vi, ko, vo, n, shift, c->radixHist, nblocks);
@@ -114,13 +122,12 @@ static void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2,
 }
 
 __global__ void k_rank(const u32* __restrict__ eligible, const unsigned char* __restrict__ cstat, u32 V, u32* __restrict__ vinfo,
-                       u32* __restrict__ blocker, u32* __restrict__ nbr, unsigned char* __restrict__ ovs, DevCounters* dc) {
+                       DevCounters* dc) {
     u32 firstStop = NOVAR;
     for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < V; r += gridDim.x * blockDim.x) {
         const u32 v = eligible[r];
         const u32 cs = cstat[v];
         vinfo[v] = (r << 5) | (cs << 3) | (cs ? MIS_UNDECIDED : MIS_NONE);
-        blocker[v] = 0; nbr[v] = NOVAR; ovs[v] = 0;
         if (cs == CS_STOP && r < firstStop) firstStop = r;
     }
 #pragma unroll
@@ -431,11 +438,20 @@ int runLCVE(Ctx* c) {
     u32* blocker = c->sortV;   // free once the radix sort is done
     u32* nbr = c->sortK;
     unsigned char* ovs = c->mis;
+    CUDA_TRY(cudaMemsetAsync(&c->dc->scratch[6], 0, 4, c->stream));
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
            c->scores, c->eligible, c->cstat, c->dc);
-    radixSortPairs(c, c->scores, c->eligible, c->sortK, c->sortV, V);
-    LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, c->cstat, V, vinfo, blocker, nbr, ovs, c->dc);
-    int rc = syncCounters(c);
+    int rc = syncCounters(c);   // the largest score decides how many radix passes the sort needs (usually 2 of 4)
+    if (rc) return rc;
+    u32 bits = 0;
+    while (bits < 32 && (c->hdc->scratch[6] >> bits)) bits++;
+    radixSortPairs(c, c->scores, c->eligible, c->sortK, c->sortV, V, bits);
+    // the per-variable MIS scratch is cleared with coalesced memsets; k_rank only scatters the election words
+    CUDA_TRY(cudaMemsetAsync(blocker, 0, (size_t)(V + 1) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(nbr, 0xFF, (size_t)(V + 1) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(ovs, 0, (size_t)V + 1, c->stream));
+    LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, c->cstat, V, vinfo, c->dc);
+    rc = syncCounters(c);
     if (rc) return rc;
     const u32 firstStop = c->hdc->firstStop < V ? c->hdc->firstStop : V;   // everything ranked before it is walked for sure
     const u32 nCls = c->hdc->numCls;
