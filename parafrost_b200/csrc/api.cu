@@ -188,6 +188,7 @@ static size_t carve(Ctx* c, char* base) {
     c->hist = a.take<u32>(ND + 2); c->otStart = a.take<u32>(ND + 2); c->otSize = a.take<u32>(ND + 2);
     c->occurs = a.take<u32>(capW + 4);
     c->otPairs = a.take<uint2>(capW + 4); c->otCur = a.take<u32>(8192 + 2);
+    c->otBig = a.take<u32>(8192 + capW / 32768 + 64);   // work units of oversized buckets (k_ot_place_big)
     c->scores = a.take<u32>(V1); c->eligible = a.take<u32>(V1); c->rank = a.take<u32>(V1);
     c->sortK = a.take<u32>(V1); c->sortV = a.take<u32>(V1); c->elected = a.take<u32>(V1);
     c->units = a.take<u32>(2 * V1); c->trail = a.take<u32>(3 * V1);

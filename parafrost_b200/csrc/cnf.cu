@@ -9,6 +9,8 @@
 //   scatter_k/compact_k   src/gpu/recycle.cu:34-105
 //   cacheCNF              src/gpu/cnf.cu:200-237
 // All of them stream the clause store once: they are HBM-bound, one coalesced pass each.
+#include <cstdlib>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------ awaken + prep
@@ -130,7 +132,10 @@ void launchHistKey(Ctx* c) {
 // neighbouring lanes store to neighbouring addresses of a run.  Per-lane scattered 8-byte stores cost
 // one L2 write transaction each, and that transaction rate - not HBM - bounded the unstaged kernel.
 // A tile with more pairs than the stage holds (long clauses) writes directly.
-template <int PART_CPT>   // clauses per thread: 3 (tiles of 3072 clauses) or 5 for short clauses, so that a tile fills the stage
+// PART_CPT clauses per thread: 3 (tiles of 3072 clauses) or 5 for short clauses, so that a tile fills the stage;
+// the first PART_KEEP literals of a clause stay in registers between the two sweeps (the 220 KB of shared
+// memory leave almost no L1, a second read would come from L2)
+template <int PART_CPT, int PART_KEEP>
 __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
                                                           const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB, u32 stageCap,
                                                           u32* __restrict__ gcur, uint2* __restrict__ pairs) {
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
     const u32 tile0 = blockIdx.x * (PART_THREADS * PART_CPT);
     for (u32 b = threadIdx.x; b < 2 * NB; b += PART_THREADS) sm[b] = 0;
     if (threadIdx.x == 0) nonEmpty = 0;
-    u32 off[PART_CPT], sz[PART_CPT], rk[PART_CPT][PART_SHORT / 2];
+    u32 off[PART_CPT], sz[PART_CPT], rk[PART_CPT][PART_SHORT / 2], lk[PART_CPT][PART_KEEP];
 #pragma unroll
     for (int k = 0; k < PART_CPT; k++) {
         const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
@@ -164,7 +169,11 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
         if (sz[k] <= PART_SHORT) {
 #pragma unroll
             for (int q = 0; q < PART_SHORT; q++)
-                if ((u32)q < sz[k]) rk[k][q >> 1] |= atomicAdd(&cntS[l[q] >> shift], 1u) << ((q & 1) * 16);
+                if ((u32)q < sz[k]) {
+                    const u32 lit = l[q];
+                    if (q < PART_KEEP) lk[k][q < PART_KEEP ? q : 0] = lit;
+                    rk[k][q >> 1] |= atomicAdd(&cntS[lit >> shift], 1u) << ((q & 1) * 16);
+                }
         } else
             for (u32 q = 0; q < sz[k]; q++) atomicAdd(&cntL[l[q] >> shift], 1u);
     }
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
 #pragma unroll
             for (int q = 0; q < PART_SHORT; q++)
                 if ((u32)q < sz[k]) {
-                    const u32 lit = l[q];
+                    const u32 lit = q < PART_KEEP ? lk[k][q < PART_KEEP ? q : 0] : l[q];
                     const u32 b = lit >> shift;
                     const u32 r = (rk[k][q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
                     if (staged) stage[tileOff[b] + r] = make_uint2(lit, i);
@@ -236,26 +245,20 @@ __global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restric
 }
 
 #define PLACE_THREADS 1024
-#define PLACE_SPLIT 8            // a bucket with many pairs is shared by up to 8 CTAs (grid.y) ...
-#define PLACE_UNIT (128u << 10)  // ... of about this many pairs each
+#define PLACE_SPLIT 64           // a bucket too large for the window is shared by up to 64 work units ...
+#define PLACE_UNIT (32u << 10)   // ... of about this many pairs each
 #define PLACE_WINDOW (40u << 10) // entries of a bucket's occurs[] window that can be staged in shared memory
-// first literal l in [lo, hi] with otStart[l] >= target (uniform over the CTA: broadcast loads)
-__device__ __forceinline__ u32 litLowerBound(const u32* __restrict__ otStart, u32 lo, u32 hi, u32 target) {
-    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (otStart[mid] < target) lo = mid + 1; else hi = mid; }
-    return lo;
-}
 // Staged mode (the normal case, buckets are sized for it): the whole occurs[] window of the bucket is
 // assembled in shared memory - one shared-memory atomic and one shared-memory store per pair - and
 // written out with coalesced full-sector stores.  Scattering the 4-byte entries straight into global
 // memory costs one L2 write transaction per entry, and ~65 G transactions/s chip-wide was the
 // measured ceiling of the unstaged kernel (profiles/r01_ncu_full_cfg2_v3.txt).
-// Direct mode (a bucket too large for the window: hot literal ranges of structured formulas):
-// buckets are literal RANGES, so their pair counts follow the formula's structure (multiplier
-// inputs: one bucket with 28x the mean).  CTA (b, s) owns the literal sub-range of bucket b that
-// holds the s-th share of its pairs (boundaries read off otStart), streams all pairs of the bucket
-// and places the ones in its sub-range directly.
+// A bucket too large for the window (hot literal ranges of structured formulas: buckets are literal
+// RANGES, so their pair counts follow the formula's structure - multiplier inputs: one bucket with
+// 28x the mean) is queued as work units for k_ot_place_big.
 __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
-                                                            u32 shift, u32 window, u32* __restrict__ otSize, u32* __restrict__ occurs) {
+                                                            u32 shift, u32 window, u32* __restrict__ otSize, u32* __restrict__ occurs,
+                                                            u32* __restrict__ big, u32* nBig) {
     extern __shared__ u32 smem[];
     const u32 W = 1u << shift;
     u32* cur = smem;          // [W] list cursors
@@ -264,52 +267,62 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restr
     const u32 litEnd = min(lit0 + W, ND);
     const u32 p0 = otStart[lit0], p1 = otStart[litEnd];
     const u32 len = p1 - p0;
-    const u32 s = blockIdx.y;
-    if (len <= window) {
-        if (s) return;
-        const u32 nl = litEnd - lit0;
-        for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) cur[k] = otStart[lit0 + k] - p0;
-        __syncthreads();
-        u32 j = p0 + threadIdx.x;
-        for (; j + 3 * PLACE_THREADS < p1; j += 4 * PLACE_THREADS) {
-            uint2 p[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) p[k] = pairs[j + k * PLACE_THREADS];
-#pragma unroll
-            for (int k = 0; k < 4; k++) win[atomicAdd(&cur[p[k].x - lit0], 1u)] = p[k].y;
+    if (len > window) {
+        if (threadIdx.x == 0) {
+            u32 S = (len + PLACE_UNIT - 1) / PLACE_UNIT;
+            S = S > PLACE_SPLIT ? PLACE_SPLIT : S;
+            const u32 base = atomicAdd(nBig, S);
+            for (u32 s = 0; s < S; s++) big[base + s] = blockIdx.x | (s << 13) | (S << 19);   // bucket < 2^13, s < 2^6, S <= 2^6
         }
-        for (; j < p1; j += PLACE_THREADS) { const uint2 p = pairs[j]; win[atomicAdd(&cur[p.x - lit0], 1u)] = p.y; }
-        __syncthreads();
-        for (u32 k = threadIdx.x; k < len; k += PLACE_THREADS) occurs[p0 + k] = win[k];
-        for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) otSize[lit0 + k] = cur[k] - (otStart[lit0 + k] - p0);
+        for (u32 k = threadIdx.x; lit0 + k < litEnd; k += PLACE_THREADS) otSize[lit0 + k] = 0;   // global list cursors of the work units
         return;
     }
-    u32 S = (len + PLACE_UNIT - 1) / PLACE_UNIT;
-    S = S < 1 ? 1 : (S > PLACE_SPLIT ? PLACE_SPLIT : S);
-    if (s >= S) return;
-    const u32 la = s == 0 ? lit0 : litLowerBound(otStart, lit0, litEnd, p0 + (u32)((u64)len * s / S));
-    const u32 lb = s == S - 1 ? litEnd : litLowerBound(otStart, lit0, litEnd, p0 + (u32)((u64)len * (s + 1) / S));
-    const u32 nl = lb - la;
-    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) cur[k] = otStart[la + k];
+    const u32 nl = litEnd - lit0;
+    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) cur[k] = otStart[lit0 + k] - p0;
     __syncthreads();
-    if (nl) {
-        u32 j = p0 + threadIdx.x;
-        for (; j + 3 * PLACE_THREADS < p1; j += 4 * PLACE_THREADS) {
+    u32 j = p0 + threadIdx.x;
+    for (; j + 3 * PLACE_THREADS < p1; j += 4 * PLACE_THREADS) {
+        uint2 p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = pairs[j + k * PLACE_THREADS];
+#pragma unroll
+        for (int k = 0; k < 4; k++) win[atomicAdd(&cur[p[k].x - lit0], 1u)] = p[k].y;
+    }
+    for (; j < p1; j += PLACE_THREADS) { const uint2 p = pairs[j]; win[atomicAdd(&cur[p.x - lit0], 1u)] = p.y; }
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < len; k += PLACE_THREADS) occurs[p0 + k] = win[k];
+    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) otSize[lit0 + k] = cur[k] - (otStart[lit0 + k] - p0);
+}
+// Work unit (b, s of S): the s-th share of the PAIRS of an oversized bucket.  The list cursors of such a
+// bucket live in global memory (otSize[], zeroed by k_ot_place; L2 resident: the bucket is one
+// literal range), so every pair is read once and placed with one L2 atomic.
+__global__ void __launch_bounds__(PLACE_THREADS) k_ot_place_big(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
+                                                                u32 shift, u32* __restrict__ otSize, u32* __restrict__ occurs,
+                                                                const u32* __restrict__ big, const u32* nBig) {
+    const u32 W = 1u << shift;
+    const u32 nItems = *nBig;
+    for (u32 item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const u32 code = big[item];
+        const u32 b = code & 0x1FFFu, s = (code >> 13) & 0x3Fu, S = code >> 19;
+        const u32 lit0 = b << shift;
+        const u32 p0 = otStart[lit0], p1 = otStart[min(lit0 + W, ND)];
+        const u32 len = p1 - p0;
+        const u32 q0 = p0 + (u32)((u64)len * s / S), q1 = p0 + (u32)((u64)len * (s + 1) / S);
+        u32 j = q0 + threadIdx.x;
+        for (; j + 3 * PLACE_THREADS < q1; j += 4 * PLACE_THREADS) {
             uint2 p[4]; u32 pos[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) p[k] = pairs[j + k * PLACE_THREADS];
 #pragma unroll
-            for (int k = 0; k < 4; k++) if (p[k].x - la < nl) pos[k] = atomicAdd(&cur[p[k].x - la], 1u);
+            for (int k = 0; k < 4; k++) pos[k] = otStart[p[k].x] + atomicAdd(&otSize[p[k].x], 1u);
 #pragma unroll
-            for (int k = 0; k < 4; k++) if (p[k].x - la < nl) occurs[pos[k]] = p[k].y;
+            for (int k = 0; k < 4; k++) occurs[pos[k]] = p[k].y;
         }
-        for (; j < p1; j += PLACE_THREADS) {
+        for (; j < q1; j += PLACE_THREADS) {
             const uint2 p = pairs[j];
-            if (p.x - la < nl) occurs[atomicAdd(&cur[p.x - la], 1u)] = p.y;
+            occurs[otStart[p.x] + atomicAdd(&otSize[p.x], 1u)] = p.y;
         }
     }
-    __syncthreads();
-    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) otSize[la + k] = cur[k] - otStart[la + k];
 }
 
 void launchScatter(Ctx* c) {
@@ -317,8 +330,8 @@ void launchScatter(Ctx* c) {
     // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
     if (!n || !c->numLiterals) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
     if (!c->attrOT) {
-        cudaFuncSetAttribute(k_ot_part<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
         c->attrOT = true;
     }
@@ -330,19 +343,23 @@ void launchScatter(Ctx* c) {
     const u32 NB = (c->ND + (1u << shift) - 1) >> shift;
     c->otShift = shift; c->otNB = NB;
     // beyond 2^12 literals per bucket (more than 2^25 literals in all) the cursors alone fill the shared memory: direct mode only
-    const u32 window = shift <= 12 ? PLACE_WINDOW : 0;
+    u32 window = shift <= 12 ? PLACE_WINDOW : 0;
+    if (const char* w = getenv("SIGMA_OT_WINDOW")) { const u32 v = (u32)atoi(w); if (v < window) window = v; }   // tests: force the work-unit path
     const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
     cudaMemsetAsync(c->otCur, 0, (size_t)NB * 4, c->stream);
     // shared memory of k_ot_part: 4 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
     const size_t partFixed = 16 * (size_t)NB + 8;
     u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
     if (c->numLiterals <= 3 * c->numClauses)   // short clauses: more of them per tile
-        LAUNCH(c, k_ot_part<5>, divup(n, PART_THREADS * 5), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
+        LAUNCH(c, (k_ot_part<5, 3>), divup(n, PART_THREADS * 5), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
                c->otStart, c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
     else
-        LAUNCH(c, k_ot_part<3>, divup(n, PART_THREADS * 3), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
+        LAUNCH(c, (k_ot_part<3, 5>), divup(n, PART_THREADS * 3), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
                c->otStart, c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
-    LAUNCH(c, k_ot_place, dim3(NB, PLACE_SPLIT), PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs);
+    u32* nBig = &c->dc->scratch[7];
+    cudaMemsetAsync(nBig, 0, 4, c->stream);
+    LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
+    LAUNCH(c, k_ot_place_big, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs, c->otBig, nBig);
 }
 
 // ------------------------------------------------------------------ live counts

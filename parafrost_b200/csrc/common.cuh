@@ -145,7 +145,7 @@ struct Ctx {
     uint4* key;
     // OT
     u32 *hist, *otStart, *otSize, *occurs;
-    uint2* otPairs; u32* otCur; u32 otShift, otNB;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
+    uint2* otPairs; u32* otCur; u32* otBig; u32 otShift, otNB;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
     // vars
     u32 *scores, *eligible, *rank, *sortK, *sortV, *elected, *units, *resolved, *trail, *vorg, *varcore;
     unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *eliminated, *needSort;

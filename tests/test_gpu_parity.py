@@ -397,3 +397,20 @@ def test_full_size_matches_oracle_fingerprint(name):
     fp = to_dump(V, st, fin["cnfstate"]).fingerprint()
     diff = {k: (fp[k], v) for k, v in g["fingerprint"].items() if fp[k] != v}
     assert not diff, diff
+
+
+def test_oversized_bucket_path(monkeypatch):
+    """k_ot_place_big (buckets too large for the shared-memory window: hot literal ranges, or more than
+    2^25 literals) on small inputs: SIGMA_OT_WINDOW=0 sends every bucket through the work-unit path."""
+    monkeypatch.setenv("SIGMA_OT_WINDOW", "0")
+    for name in ("k3_r30", "miter_x", "mult10", "k5_r10"):
+        fam, seed, args = SMALL[name]
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True)
+        ed, fin, _, _ = run_engine_rounds(V, lits, offs, [], ors, osnaps)
+        assert not sgd.compare(ed, od), name
+    fam, seed, args = MEDIUM["k5_20k"]
+    V, lits, offs = helpers.gen_cnf(fam, seed, args)
+    od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True)
+    ed, fin, _, _ = run_engine_rounds(V, lits, offs, [], ors, osnaps)
+    assert not sgd.compare(ed, od)
