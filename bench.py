@@ -106,7 +106,7 @@ def algorithmic_bytes(kernel, C, L, V, E=0):
     V variables; 16-byte clause headers, 4-byte literals and occurrence entries."""
     ND = 2 * V + 2
     f = {
-        "k_awaken": 8 * C + 4 * L + 16 * C + 4 * L,
+        "k_awaken": 8 * C + 4 * L + 16 * C + 4 * L + 16 * C + 4 * ND,   # prep + the fused first-round histogram and sort keys
         "k_hist_key": 16 * C + 4 * L + 16 * C + 4 * ND,
         "k_hist": 16 * C + 4 * L + 4 * ND,
         "k_ot_part": 16 * C + 4 * L + 8 * L,

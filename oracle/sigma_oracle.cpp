@@ -84,7 +84,7 @@ struct oracle_ctx {
     std::vector<OL> ot;
     std::vector<u32> hist;
     std::vector<u32> eligible, scores, elected, units, resolved, frozenList, trail, vorg;
-    std::vector<uint8_t> eliminated, vstate, frozen;
+    std::vector<uint8_t> eliminated, vstate, frozen, assumed;   // assumed: incremental assumption mask (lcve.cu:316-323), may be empty
     const u32* varcore = nullptr;
     bool varcore_dead = false;
     int phase = 0, multiplier = 0, simpstate = AWAKEN_SUCC, cnfstate = UNSOLVED;
@@ -310,6 +310,7 @@ bool LCVE(S& s) {
         const u32 cand = s.eligible[ei];
         if (s.frozen[cand]) continue;
         if (s.vstate[cand]) continue;
+        if (!s.assumed.empty() && s.assumed[cand]) continue;   // lcve.cu:88
         const u32 p = V2L(cand), n = NEG(p);
         const u32 ps = s.hist[p], ns = s.hist[n];
         if (!ps && !ns) continue;
@@ -1422,6 +1423,10 @@ void oracle_copy_result(const oracle_ctx* s, uint32_t* bits, uint32_t* sig, uint
 }
 
 void oracle_keep_snapshots(oracle_ctx* s, int keep) { s->keep_snaps = keep != 0; }
+// incremental solving: variables under assumption are never candidates (Solver::LCVE, lcve.cu:316-323, lcve_k :88)
+void oracle_set_assumed(oracle_ctx* s, const uint8_t* assumed) {
+    if (assumed) s->assumed.assign(assumed, assumed + s->V + 1); else s->assumed.clear();
+}
 uint64_t oracle_snapshot_clauses(const oracle_ctx* s, int r) { return s->snaps[r].bits.size(); }
 uint64_t oracle_snapshot_literals(const oracle_ctx* s, int r) { return s->snaps[r].lits.size(); }
 void oracle_copy_snapshot(const oracle_ctx* s, int r, uint32_t* bits, uint32_t* sig, uint64_t* offs, uint32_t* lits) {

@@ -74,6 +74,8 @@ void oracle_copy_result(const oracle_ctx* c, uint32_t* bits, uint32_t* sig, uint
                         uint32_t* lits, uint8_t* eliminated, uint32_t* resolved, uint32_t* trail);
 /* snapshot of the live clauses after round r (only kept when keep_snapshots != 0) */
 void oracle_keep_snapshots(oracle_ctx* c, int keep);
+/* assumed[max_var+1]: variables under assumption (incremental mode) are never elected; NULL clears */
+void oracle_set_assumed(oracle_ctx* c, const uint8_t* assumed);
 uint64_t oracle_snapshot_clauses(const oracle_ctx* c, int round);
 uint64_t oracle_snapshot_literals(const oracle_ctx* c, int round);
 void oracle_copy_snapshot(const oracle_ctx* c, int round, uint32_t* bits, uint32_t* sig,

@@ -75,6 +75,7 @@ def oracle_lib():
             getattr(lib, f).argtypes = [P]; getattr(lib, f).restype = C.c_uint64
         lib.oracle_copy_result.argtypes = [P, _u32p, _u32p, _u64p, _u32p, _u8p, _u32p, _u32p]
         lib.oracle_keep_snapshots.argtypes = [P, C.c_int]
+        lib.oracle_set_assumed.argtypes = [P, P]
         lib.oracle_snapshot_clauses.argtypes = [P, C.c_int]; lib.oracle_snapshot_clauses.restype = C.c_uint64
         lib.oracle_snapshot_literals.argtypes = [P, C.c_int]; lib.oracle_snapshot_literals.restype = C.c_uint64
         lib.oracle_copy_snapshot.argtypes = [P, C.c_int, _u32p, _u32p, _u64p, _u32p]
@@ -119,7 +120,7 @@ def make_oracle_opts(**over) -> OracleOpts:
     return o
 
 
-def run_oracle(max_var, lits, offs, meta=None, snapshots=False, **over):
+def run_oracle(max_var, lits, offs, meta=None, snapshots=False, vorg=None, vstate=None, assumed=None, **over):
     """Run the CPU oracle -> (Dump, round_stats uint64[R,5], [snapshot Dumps])."""
     lib = oracle_lib()
     o = make_oracle_opts(**over)
@@ -130,9 +131,13 @@ def run_oracle(max_var, lits, offs, meta=None, snapshots=False, **over):
     if meta is not None:
         meta = np.ascontiguousarray(meta, np.uint32)
         meta_p = meta.ctypes.data_as(C.c_void_p)
-    lib.oracle_create(C.byref(o), max_var, len(offs) - 1, lits, offs, meta_p, None, None, C.byref(h))
+    keep = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in ((vorg, np.uint32), (vstate, np.uint8), (assumed, np.uint8))]
+    ptr = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep]
+    lib.oracle_create(C.byref(o), max_var, len(offs) - 1, lits, offs, meta_p, ptr[0], ptr[1], C.byref(h))
     try:
         lib.oracle_keep_snapshots(h, int(snapshots))
+        if keep[2] is not None:
+            lib.oracle_set_assumed(h, ptr[2])
         state = lib.oracle_run(h)
         nc, nl = lib.oracle_num_clauses(h), lib.oracle_num_literals(h)
         nr, nt = lib.oracle_num_resolved(h), lib.oracle_num_trail(h)

@@ -414,3 +414,39 @@ def test_oversized_bucket_path(monkeypatch):
     od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True)
     ed, fin, _, _ = run_engine_rounds(V, lits, offs, [], ors, osnaps)
     assert not sgd.compare(ed, od)
+
+
+def test_per_variable_inputs_vorg_vstate_assumed():
+    """The per-variable inputs Solver::simplify() reads (SURVEY 8b): vorg (current -> original variable
+    map: the witness stack is written in original names, model.cuh), sp->vstate (inactive variables
+    are never candidates, lcve.cu:87) and the incremental assumption mask (lcve.cu:88, 316-323)."""
+    S = sigma()
+    rng = np.random.default_rng(17)
+    for name in ("k3_r30", "miter_x", "mult10", "multpar"):
+        fam, seed, args = SMALL[name]
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        vorg = np.zeros(V + 1, np.uint32)
+        vorg[1:] = rng.permutation(V).astype(np.uint32) + 1 + 1000      # arbitrary original names
+        used = np.zeros(V + 1, bool); used[lits >> 1] = True
+        vstate = np.zeros(V + 1, np.uint8)
+        vstate[~used] = 1                                                # variables without clauses: inactive, as after a host BCP
+        vstate[0] = 0
+        frozen_like = rng.random(V + 1) < 0.03
+        vstate[frozen_like] = 3                                          # a few occurring variables marked inactive as well
+        assumed = (rng.random(V + 1) < 0.05).astype(np.uint8)
+        for flags in ([], ["--phases=3", "-no-ere"], ["-all"]):
+            od, ors, osn = helpers.run_oracle(V, lits, offs, snapshots=True, vorg=vorg, vstate=vstate, assumed=assumed,
+                                              **helpers.opts_from_flags(flags))
+            s = S.Simplifier(0, flags=flags)
+            s.load(V, lits, offs, vorg=vorg, vstate=vstate, assumed=assumed)
+            fin = s.simplify()
+            ed = to_dump(V, s.store(), fin["cnfstate"])
+            rounds = [r for r in s.rounds() if r["kind"] == 0]
+            s.close()
+            assert not sgd.compare(ed, od), (name, flags)
+            assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
+                   [[int(x) for x in row] for row in ors], (name, flags)
+            # no assumed or inactive variable was eliminated
+            elim = ed.eliminated_vars()
+            assert not (set(elim) & set(np.nonzero(assumed)[0].tolist())), name
+            assert not (set(elim) & set(np.nonzero(vstate)[0].tolist())), name
