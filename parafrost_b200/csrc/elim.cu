@@ -1462,6 +1462,7 @@ void launchERE(Ctx* c, const KOpts& k) {
     Q.items = (u32*)((char*)c->otPairs + qOff);
     const u64 qCap = (bufBytes - qOff) / 12;
     Q.cap = (u32)(qCap > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : qCap);
+    if (const char* e = getenv("SIGMA_ERE_QUEUE_CAP")) { const u32 v = (u32)atoi(e); if (v < Q.cap) Q.cap = v; }   // tests: force the overflow fallback
     Q.count = &c->dc->scratch[3]; Q.overflow = &c->dc->scratch[4]; Q.need = c->needSort;
     cudaMemsetAsync(Q.count, 0, 8, c->stream);
     cudaMemsetAsync(c->needSort, 0, c->ND, c->stream);

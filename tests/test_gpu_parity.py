@@ -450,3 +450,16 @@ def test_per_variable_inputs_vorg_vstate_assumed():
             elim = ed.eliminated_vars()
             assert not (set(elim) & set(np.nonzero(assumed)[0].tolist())), name
             assert not (set(elim) & set(np.nonzero(vstate)[0].tolist())), name
+
+
+def test_ere_queue_overflow_fallback(monkeypatch):
+    """More resolvents pass the ERE filters than the queue holds: the engine sorts every list and
+    searches in place (the path of the reference) - same result.  SIGMA_ERE_QUEUE_CAP=1 forces it."""
+    monkeypatch.setenv("SIGMA_ERE_QUEUE_CAP", "1")
+    for name in ("miter_x", "miter_a", "mult10", "k3_r42"):
+        fam, seed, args = SMALL[name]
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        for flags in ([], ["-all"]):
+            od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True, **helpers.opts_from_flags(flags))
+            ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags, ors, osnaps)
+            assert not sgd.compare(ed, od), (name, flags)
