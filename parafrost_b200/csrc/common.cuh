@@ -75,6 +75,8 @@ typedef int64_t i64;
 #define MIS_ELECTED 2
 #define MIS_FROZEN 3
 #define MIS_LIVESTOP 4
+#define MIS_HALF 5      // not elected, but its positive-list neighbours are frozen: depFreeze_d succeeded on the positive list and hit a
+                        // clause longer than lcveclausemax in the negative one, whose freezes alone are rolled back (lcve.cu:33-62, :96-98)
 // candidate class
 #define CS_NONE 0
 #define CS_CAND 1
@@ -107,7 +109,7 @@ struct DevCounters {
     u32 sortCnt[9], sortCur[9];   // list-sort length classes (otsort.cu)
     u32 addedCls;      // resolvents appended by the last BVE
     u32 bin[4];        // group-size class sizes of the elected variables (elim.cu) + redo queue
-    u32 scratch[8];
+    u32 scratch[16];   // 0,1 scan totals; 2 MIS push count; 3,4 ERE queue count / overflow; 5 load check; 6 max score; 7 big-bucket units; 8 MIS_HALF count; 9 freezer count
     u32 froz12[12];    // variables currently holding a function-table index in varcore
 };
 

@@ -155,8 +155,8 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
 // full scan every round; the fixed point - the lexicographically first MIS - is the same.)
 // the plain walk: right for the 8-lane groups of formulas with a handful of short clauses per
 // variable, where batching only adds predicated loads (measured on cfg3: +45 %)
-#define MIS_WALK_SIMPLE(GS_, V_, LANE_, APPLY_)                                                        \
-    for (u32 side_ = 0; side_ < 2; side_++) {                                                          \
+#define MIS_WALK_SIMPLE(GS_, V_, LANE_, NSIDES_, APPLY_)                                               \
+    for (u32 side_ = 0; side_ < (NSIDES_); side_++) {                                                          \
         const u32 lit_ = V2L(V_) | side_;                                                              \
         const u32 n_ = otSize[lit_];                                                                   \
         const u32* list_ = occurs + otStart[lit_];                                                     \
@@ -165,11 +165,13 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
             if (C_DELETED(h_.w)) continue;                                                             \
             const u32 csize = h_.y; (void)csize;                                                       \
             const u32* l_ = pool + h_.x;                                                               \
-            for (u32 k_ = 0; k_ < h_.y; k_++) { const u32 u = LABS(l_[k_]); if (u != (V_)) { const u32 wu = vinfo[u]; APPLY_ } } \
+            for (u32 k_ = 0; k_ < h_.y; k_++) { const u32 ul_ = l_[k_]; const u32 u = LABS(ul_); if (u != (V_)) { const bool upos = !LSIGN(ul_); (void)upos; const u32 wu = vinfo[u]; APPLY_ } } \
         }                                                                                              \
     }
-#define MIS_WALK_ANY(GS_, V_, LANE_, APPLY_) \
-    if constexpr ((GS_) == 32) { MIS_WALK(GS_, V_, LANE_, APPLY_) } else { MIS_WALK_SIMPLE(GS_, V_, LANE_, APPLY_) }
+// APPLY_ sees: u (neighbour variable), upos (its literal in the shared clause is positive), wu (its
+// election word), csize (clause size), side_ (0: the clause is in v's positive list)
+#define MIS_WALK_ANY(GS_, V_, LANE_, NSIDES_, APPLY_) \
+    if constexpr ((GS_) == 32) { MIS_WALK(GS_, V_, LANE_, NSIDES_, APPLY_) } else { MIS_WALK_SIMPLE(GS_, V_, LANE_, NSIDES_, APPLY_) }
 
 // An elected variable freezes its higher-ranked undecided neighbours at once (push) instead of
 // letting each of them find out by rescanning its own neighbourhood: every concurrent writer of a
@@ -179,8 +181,8 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
 // chain list entry -> header -> literals -> election words is four dependent loads deep; with small
 // worklists a MIS round is pure latency, so each lane keeps four clauses in flight (entries and
 // headers loaded as a batch) and loads the literals and the election words of a clause as batches of 8.
-#define MIS_WALK(GS_, V_, LANE_, APPLY_)                                                               \
-    for (u32 side_ = 0; side_ < 2; side_++) {                                                          \
+#define MIS_WALK(GS_, V_, LANE_, NSIDES_, APPLY_)                                                      \
+    for (u32 side_ = 0; side_ < (NSIDES_); side_++) {                                                          \
         const u32 lit_ = V2L(V_) | side_;                                                              \
         const u32 n_ = otSize[lit_];                                                                   \
         const u32* list_ = occurs + otStart[lit_];                                                     \
@@ -193,10 +195,10 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
                 const u32 csize = h_[u_].y; (void)csize;                                               \
                 const u32* l_ = pool + h_[u_].x;                                                       \
                 u32 lv_[8], wv_[8];                                                                    \
-                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) lv_[k_] = (u32)k_ < h_[u_].y ? LABS(l_[k_]) : (V_); \
-                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) wv_[k_] = lv_[k_] != (V_) ? vinfo[lv_[k_]] : 0u;    \
-                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) if (lv_[k_] != (V_)) { const u32 u = lv_[k_], wu = wv_[k_]; APPLY_ } \
-                for (u32 k_ = 8; k_ < h_[u_].y; k_++) { const u32 u = LABS(l_[k_]); if (u != (V_)) { const u32 wu = vinfo[u]; APPLY_ } } \
+                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) lv_[k_] = (u32)k_ < h_[u_].y ? l_[k_] : V2L(V_); /* literals */ \
+                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) wv_[k_] = LABS(lv_[k_]) != (V_) ? vinfo[LABS(lv_[k_])] : 0u;    \
+                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) if (LABS(lv_[k_]) != (V_)) { const u32 u = LABS(lv_[k_]), wu = wv_[k_]; const bool upos = !LSIGN(lv_[k_]); (void)upos; APPLY_ } \
+                for (u32 k_ = 8; k_ < h_[u_].y; k_++) { const u32 ul_ = l_[k_]; const u32 u = LABS(ul_); if (u != (V_)) { const bool upos = !LSIGN(ul_); (void)upos; const u32 wu = vinfo[u]; APPLY_ } } \
             }                                                                                          \
         }                                                                                              \
     }
@@ -208,8 +210,9 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
 template <int GS>
 __device__ __forceinline__ void pushFreeze(u32 v, u32 r, u32 lane, const uint4* __restrict__ hdr, const u32* __restrict__ pool,
                                            const u32* __restrict__ otStart, const u32* __restrict__ otSize,
-                                           const u32* __restrict__ occurs, u32* vinfo) {
-    MIS_WALK_ANY(GS, v, lane, { if (VI_STATE(wu) == MIS_UNDECIDED && VI_RANK(wu) > r) vinfo[u] = (wu & ~7u) | MIS_FROZEN; })
+                                           const u32* __restrict__ occurs, u32* vinfo, u32 nsides) {
+    // nsides = 1 for a MIS_HALF variable: only the clauses of its positive list freeze their variables
+    MIS_WALK_ANY(GS, v, lane, nsides, { if (VI_STATE(wu) == MIS_UNDECIDED && VI_RANK(wu) > r) vinfo[u] = (wu & ~7u) | MIS_FROZEN; })
 }
 
 // push for the variables elected by k_mis_first (thread-per-variable there: no group to walk the lists)
@@ -222,8 +225,9 @@ __global__ void __launch_bounds__(256) k_mis_push(const u32* __restrict__ list, 
     const u32 lane = threadIdx.x & (u32)(GS - 1);
     const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
     for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) / GS; it < n; it += groupsPerGrid) {
-        const u32 v = list[it];
-        pushFreeze<GS>(v, VI_RANK(vinfo[v]), lane, hdr, pool, otStart, otSize, occurs, vinfo);
+        const u32 e = list[it];
+        const u32 v = e & 0x7FFFFFFFu;   // bit 31: MIS_HALF
+        pushFreeze<GS>(v, VI_RANK(vinfo[v]), lane, hdr, pool, otStart, otSize, occurs, vinfo, (e >> 31) ? 1u : 2u);
     }
 }
 
@@ -253,18 +257,20 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
             if (mb == MIS_UNDECIDED) { if (lane == 0) wlOut[atomicAdd(outCnt, 1u)] = v; continue; }
             if (mb == MIS_ELECTED) { if (lane == 0) vinfo[v] = (wv & ~7u) | MIS_FROZEN; continue; }
         }
-        bool frozen = false, oversize = false;
+        bool frozen = false, overP = false, overN = false;
         u32 bRank = NOVAR, bVar = 0;
-        MIS_WALK_ANY(GS, v, lane, {
-            if ((int)csize > maxcsize) oversize = true;
+        MIS_WALK_ANY(GS, v, lane, 2u, {
+            if ((int)csize > maxcsize) { if (side_ == 0) overP = true; else overN = true; }
             if (VI_RANK(wu) < r) {
                 const u32 m = VI_STATE(wu);
-                if (m == MIS_ELECTED) frozen = true;
+                // an elected neighbour freezes v; a MIS_HALF one only through a clause of ITS positive list
+                if (m == MIS_ELECTED || (m == MIS_HALF && upos)) frozen = true;
                 else if (m == MIS_UNDECIDED && VI_CLASS(wu) == CS_CAND && VI_RANK(wu) < bRank) { bRank = VI_RANK(wu); bVar = u; }
             }
         })
         frozen = __any_sync(gmask, frozen);
-        oversize = __any_sync(gmask, oversize);
+        overP = __any_sync(gmask, overP);
+        overN = __any_sync(gmask, overN);
         u32 minRank = bRank;
 #pragma unroll
         for (int o = GS / 2; o; o >>= 1) minRank = min(minRank, __shfl_xor_sync(gmask, minRank, o, GS));
@@ -275,13 +281,16 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
             if (frozen) vinfo[v] = keep | MIS_FROZEN;
             else if (!blocked) {
                 if (VI_CLASS(wv) == CS_STOP) { vinfo[v] = keep | MIS_LIVESTOP; atomicMin(&dc->misStopRank, r); }
-                // a clause longer than lcveclausemax makes depFreeze_d fail (lcve.cu:46-51): not elected, freezes nothing
-                else vinfo[v] = keep | (oversize ? MIS_FROZEN : MIS_ELECTED);
+                // a clause longer than lcveclausemax makes depFreeze_d fail (lcve.cu:46-51): in the positive list -> not
+                // elected, freezes nothing; only in the negative list -> not elected, the positive list's freezes stay
+                else if (overP) vinfo[v] = keep | MIS_FROZEN;
+                else if (overN) { vinfo[v] = keep | MIS_HALF; atomicAdd(&dc->scratch[8], 1u); }
+                else vinfo[v] = keep | MIS_ELECTED;
             }
             else wlOut[atomicAdd(outCnt, 1u)] = v;
         }
-        if (!frozen && !blocked && !oversize && VI_CLASS(wv) == CS_CAND)   // just elected (uniform over the group)
-            pushFreeze<GS>(v, r, lane, hdr, pool, otStart, otSize, occurs, vinfo);
+        if (!frozen && !blocked && !overP && VI_CLASS(wv) == CS_CAND)   // just elected or MIS_HALF (uniform over the group)
+            pushFreeze<GS>(v, r, lane, hdr, pool, otStart, otSize, occurs, vinfo, overN ? 1u : 2u);
     }
 }
 
@@ -302,30 +311,32 @@ __global__ void __launch_bounds__(256) k_mis_clauses(const uint4* __restrict__ h
         const u32* l = pool + h.x;
         u32 eMin = NOVAR, u1 = NOVAR, u2 = NOVAR;
         bool any = false;
-        // election words of the first 8 literals stay in registers for the second loop
+        // literals and election words of the first 8 literals stay in registers for the second loop
         u32 lv[8], wv[8];
 #pragma unroll
-        for (u32 k = 0; k < 8; k++) if (k < h.y) lv[k] = LABS(l[k]);
+        for (u32 k = 0; k < 8; k++) if (k < h.y) lv[k] = l[k];
 #pragma unroll
-        for (u32 k = 0; k < 8; k++) if (k < h.y) wv[k] = vinfo[lv[k]];
-#define MC_SCAN(W_) do { const u32 w = (W_); const u32 r = VI_RANK(w), st = VI_STATE(w); \
-            if (st == MIS_ELECTED) eMin = min(eMin, r); \
+        for (u32 k = 0; k < 8; k++) if (k < h.y) wv[k] = vinfo[LABS(lv[k])];
+        // a MIS_HALF variable freezes through the clauses of its positive list only (see MIS_HALF, common.cuh)
+#define MC_SCAN(L_, W_) do { const u32 w = (W_); const u32 r = VI_RANK(w), st = VI_STATE(w); \
+            if (st == MIS_ELECTED || (st == MIS_HALF && !LSIGN(L_))) eMin = min(eMin, r); \
             else if (st == MIS_UNDECIDED && r < H) { any = true; \
                 if (VI_CLASS(w) == CS_CAND) { if (r < u1) { u2 = u1; u1 = r; } else if (r < u2) u2 = r; } } } while (0)
 #pragma unroll
-        for (u32 k = 0; k < 8; k++) if (k < h.y) MC_SCAN(wv[k]);
-        for (u32 k = 8; k < h.y; k++) MC_SCAN(vinfo[LABS(l[k])]);
+        for (u32 k = 0; k < 8; k++) if (k < h.y) MC_SCAN(lv[k], wv[k]);
+        for (u32 k = 8; k < h.y; k++) { const u32 ll = l[k]; MC_SCAN(ll, vinfo[LABS(ll)]); }
 #undef MC_SCAN
         if (!any) continue;
         const bool big = (int)h.y > maxcsize;
-#define MC_APPLY(U_, W_) do { const u32 u_ = (U_), w_ = (W_); const u32 r_ = VI_RANK(w_); \
+        // ovs[u]: bit 0 = an oversized clause in u's positive list, bit 1 = in its negative list (byte inside an atomically or-ed word)
+#define MC_APPLY(L_, W_) do { const u32 u_ = LABS(L_), w_ = (W_); const u32 r_ = VI_RANK(w_); \
             if (VI_STATE(w_) == MIS_UNDECIDED && r_ < H) { \
-                if (big) ovs[u_] = 1; \
+                if (big) atomicOr((u32*)(ovs + (u_ & ~3u)), (LSIGN(L_) ? 2u : 1u) << (8u * (u_ & 3u))); \
                 if (eMin < r_) vinfo[u_] = (w_ & ~7u) | MIS_FROZEN; \
                 else { const u32 other = (u1 == r_) ? u2 : u1; if (other < r_) atomicMin(&nbr[u_], other); } } } while (0)
 #pragma unroll
         for (u32 k = 0; k < 8; k++) if (k < h.y) MC_APPLY(lv[k], wv[k]);
-        for (u32 k = 8; k < h.y; k++) { const u32 uu = LABS(l[k]); MC_APPLY(uu, vinfo[uu]); }
+        for (u32 k = 8; k < h.y; k++) { const u32 ll = l[k]; MC_APPLY(ll, vinfo[LABS(ll)]); }
 #undef MC_APPLY
     }
 }
@@ -342,7 +353,8 @@ __global__ void k_mis_first(const u32* __restrict__ eligible, u32 rBegin, u32 rE
                 const u32 m = nbr[v];
                 if (m == NOVAR) {
                     if (VI_CLASS(w) == CS_STOP) { vinfo[v] = (w & ~7u) | MIS_LIVESTOP; atomicMin(&dc->misStopRank, r); }
-                    else if (ovs[v]) vinfo[v] = (w & ~7u) | MIS_FROZEN;
+                    else if (ovs[v] & 1) vinfo[v] = (w & ~7u) | MIS_FROZEN;                 // oversized clause in the positive list
+                    else if (ovs[v] & 2) { vinfo[v] = (w & ~7u) | MIS_HALF; atomicAdd(&dc->scratch[8], 1u); pushList[atomicAdd(pushCount, 1u)] = v | 0x80000000u; }
                     else { vinfo[v] = (w & ~7u) | MIS_ELECTED; pushList[atomicAdd(pushCount, 1u)] = v; }
                 } else { blocker[v] = eligible[m]; queue = true; }
             }
@@ -358,9 +370,12 @@ __global__ void k_mis_first(const u32* __restrict__ eligible, u32 rBegin, u32 rE
     }
 }
 
-__global__ void k_elect_flags(const u32* __restrict__ eligible, const u32* __restrict__ vinfo, u32 rEnd, u32* __restrict__ flags) {
-    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x)
-        flags[r] = VI_STATE(vinfo[eligible[r]]) == MIS_ELECTED ? 1u : 0u;
+// withHalf: also the MIS_HALF variables - the walk order of everything that froze something (k_frozen12)
+__global__ void k_elect_flags(const u32* __restrict__ eligible, const u32* __restrict__ vinfo, u32 rEnd, u32* __restrict__ flags, int withHalf) {
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < rEnd; r += gridDim.x * blockDim.x) {
+        const u32 st = VI_STATE(vinfo[eligible[r]]);
+        flags[r] = (st == MIS_ELECTED || (withHalf && st == MIS_HALF)) ? 1u : 0u;
+    }
 }
 __global__ void k_elect_scatter(const u32* __restrict__ eligible, const u32* __restrict__ flags, u32 rEnd,
                                 const u32* __restrict__ pos, u32* __restrict__ elected) {
@@ -372,19 +387,21 @@ __global__ void k_elect_scatter(const u32* __restrict__ eligible, const u32* __r
 // Walks the elected variables like depFreeze_d (lcve.cu:33-62) - positive list then negative
 // list, clauses in clause-index order (the unsorted-list policy), literals in
 // clause order - until 12 distinct frozen variables are known.  One CTA; tiny.
-__global__ void __launch_bounds__(128) k_frozen12(const u32* __restrict__ elected, DevCounters* dc, const uint4* __restrict__ hdr,
+__global__ void __launch_bounds__(128) k_frozen12(const u32* __restrict__ elected, const u32* nList, const u32* __restrict__ vinfo,
+                                                  DevCounters* dc, const uint4* __restrict__ hdr,
                                                   const u32* __restrict__ pool, const u32* __restrict__ otStart,
                                                   const u32* __restrict__ otSize, const u32* __restrict__ occurs,
                                                   u32* __restrict__ varcore, u32* __restrict__ prev12) {
     __shared__ u32 fv[MAXFUNVAR];
     __shared__ u32 nf, sMin[4], cur;
-    const u32 nE = dc->numElected;
+    const u32 nE = *nList;
     if (threadIdx.x < MAXFUNVAR) { const u32 old = prev12[threadIdx.x]; if (old != NOVAR) varcore[old] = NOVAR; }
     if (threadIdx.x == 0) nf = 0;
     __syncthreads();
     for (u32 ei = 0; ei < nE && nf < MAXFUNVAR; ei++) {
         const u32 x = elected[ei];
-        for (u32 side = 0; side < 2 && nf < MAXFUNVAR; side++) {
+        const u32 nsides = VI_STATE(vinfo[x]) == MIS_HALF ? 1u : 2u;   // MIS_HALF: only its positive list froze anything
+        for (u32 side = 0; side < nsides && nf < MAXFUNVAR; side++) {
             const u32 lit = V2L(x) | side;
             const u32 n = otSize[lit];
             const u32* list = occurs + otStart[lit];
@@ -439,6 +456,7 @@ int runLCVE(Ctx* c) {
     u32* nbr = c->sortK;
     unsigned char* ovs = c->mis;
     CUDA_TRY(cudaMemsetAsync(&c->dc->scratch[6], 0, 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(&c->dc->scratch[8], 0, 4, c->stream));   // number of MIS_HALF decisions
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
            c->scores, c->eligible, c->cstat, c->dc);
     int rc = syncCounters(c);   // the largest score decides how many radix passes the sort needs (usually 2 of 4)
@@ -522,12 +540,20 @@ int runLCVE(Ctx* c) {
     }
     const u32 rEnd = stopRank < hEnd ? stopRank : hEnd;
     if (rEnd) {
-        LAUNCH(c, k_elect_flags, gridFor(rEnd, 256), 256, 0, c->eligible, vinfo, rEnd, c->flagA);
+        LAUNCH(c, k_elect_flags, gridFor(rEnd, 256), 256, 0, c->eligible, vinfo, rEnd, c->flagA, 0);
         scanExclusiveU32(c, c->flagA, c->flagB, rEnd, 0, &c->dc->numElected);
         LAUNCH(c, k_elect_scatter, gridFor(rEnd, 256), 256, 0, c->eligible, c->flagA, rEnd, c->flagB, c->elected);
     }
-    if (c->o.ve_fun_en)
-        LAUNCH(c, k_frozen12, 1, 128, 0, c->elected, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart, c->otSize, c->occurs,
+    if (c->o.ve_fun_en) {
+        const u32* walk = c->elected; const u32* nWalk = &c->dc->numElected;
+        if (rEnd && c->hdc->scratch[8]) {   // some variables froze only their positive side: the walk order includes them
+            LAUNCH(c, k_elect_flags, gridFor(rEnd, 256), 256, 0, c->eligible, vinfo, rEnd, c->flagA, 1);
+            scanExclusiveU32(c, c->flagA, c->flagB, rEnd, 0, &c->dc->scratch[9]);
+            LAUNCH(c, k_elect_scatter, gridFor(rEnd, 256), 256, 0, c->eligible, c->flagA, rEnd, c->flagB, blocker);
+            walk = blocker; nWalk = &c->dc->scratch[9];
+        }
+        LAUNCH(c, k_frozen12, 1, 128, 0, walk, nWalk, vinfo, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart, c->otSize, c->occurs,
                c->varcore, c->dc->froz12);
+    }
     return syncCounters(c);
 }

@@ -22,16 +22,20 @@ KEYS = ["cnfstate", "clauses", "literals", "eliminated", "forced", "resolved_wor
 
 
 def main():
-    names = [a for a in sys.argv[1:] if a in helpers.CONFIGS] or ["cfg1", "cfg4", "cfg2", "cfg3"]
+    """argv: config names, optionally `name:flag,flag` for a flag variant (key `name__flag_flag`)."""
+    specs = [a for a in sys.argv[1:] if a.split(":")[0] in helpers.CONFIGS] or ["cfg1", "cfg4", "cfg2", "cfg3"]
     res = json.load(open(OUT)) if os.path.exists(OUT) else {}
-    for name in names:
-        fam, seed, args = helpers.CONFIGS[name]
+    for spec in specs:
+        cfg, _, fl = spec.partition(":")
+        flags = [f for f in fl.split(",") if f]
+        name = cfg if not flags else cfg + "__" + "_".join(f.strip("-").replace("=", "") for f in flags)
+        fam, seed, args = helpers.CONFIGS[cfg]
         t0 = time.time()
         V, lits, offs = helpers.gen_cnf(fam, seed, args)
-        od, stats, _ = helpers.run_oracle(V, lits, offs)
+        od, stats, _ = helpers.run_oracle(V, lits, offs, **helpers.opts_from_flags(flags))
         fp = od.fingerprint()
         res[name] = {"family": fam, "seed": seed, "args": list(args), "vars": int(V), "clauses_in": len(offs) - 1, "literals_in": len(lits),
-                     "flags": [], "rounds": [[int(x) for x in r] for r in stats],
+                     "flags": flags, "rounds": [[int(x) for x in r] for r in stats],
                      "fingerprint": {k: fp[k] for k in KEYS}, "oracle_seconds": round(time.time() - t0, 1)}
         print(name, res[name]["oracle_seconds"], "s", res[name]["fingerprint"]["clauses"], "clauses", flush=True)
         json.dump(res, open(OUT, "w"), indent=1)

@@ -91,20 +91,29 @@ def oracle_lib():
     return _orc
 
 
-FLAG_MAP = {  # reference CLI flag -> option override
-    "-no-ere": {"ere_en": 0}, "-no-vefunction": {"ve_fun_en": 0}, "-bce": {"bce_en": 1}, "-all": {"all_en": 1},
-    "-no-sub": {"sub_en": 0}, "-no-veextend": {"ve_plus_en": 0}, "-no-ve": {"ve_en": 0},
+FLAG_MAP = {  # reference CLI flag -> option override (src/gpu/options.cpp:24-43, options.cu:36-60)
+    "-no-ere": {"ere_en": 0}, "-ere": {"ere_en": 1}, "-no-vefunction": {"ve_fun_en": 0}, "-bce": {"bce_en": 1}, "-all": {"all_en": 1},
+    "-no-sub": {"sub_en": 0}, "-no-veextend": {"ve_plus_en": 0}, "-no-ve": {"ve_en": 0}, "-velitsbound": {"ve_lbound_en": 1},
     "-no-lcvefast": {}, "-quiet": {},
+}
+VALUE_FLAGS = {
+    "--phases": "phases", "--mupos": "mu_pos", "--muneg": "mu_neg", "--electionsmin": "lcve_min_vars",
+    "--electionsmax": "lcve_max_occurs", "--lcveclausemax": "lcve_clause_max", "--eliminatedlitsmin": "phase_lits_min",
+    "--collectfreq": "shrink_rate", "--literalsmul": "lits_mul", "--resolventmax": "ve_clause_max",
+    "--xormaxarity": "xor_max_arity", "--ereclausemax": "ere_clause_max", "--eremaxoccurs": "ere_max_occurs",
+    "--submaxoccurs": "sub_max_occurs", "--bcemaxoccurs": "bce_max_occurs",
 }
 
 
 def opts_from_flags(flags) -> dict:
     o = {}
     for f in flags:
-        if f.startswith("--phases="):
-            o["phases"] = int(f.split("=")[1])
-        elif f.startswith("--mapperc="):
-            pass
+        if "=" in f:
+            k, v = f.split("=", 1)
+            if k in VALUE_FLAGS:
+                o[VALUE_FLAGS[k]] = float(v) if k == "--literalsmul" else int(v)
+            elif k != "--mapperc":
+                raise ValueError(f"unknown flag {f}")
         else:
             o.update(FLAG_MAP[f])
     return o

@@ -373,7 +373,10 @@ def test_load_from_reference_host_mirror():
 FULLSIZE = os.path.join(HERE, "golden", "fullsize_fingerprints.json")
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg4", "cfg2", "cfg3"])
+FULLSIZE_KEYS = sorted(json.load(open(FULLSIZE))) if os.path.exists(FULLSIZE) else []
+
+
+@pytest.mark.parametrize("name", FULLSIZE_KEYS)
 def test_full_size_matches_oracle_fingerprint(name):
     """BASELINE.json configs 1-4 at FULL size: the engine's result against the fingerprint of the CPU
     oracle computed in the build container (tests/golden/make_fullsize_fingerprints.py; the oracle needs
@@ -463,3 +466,65 @@ def test_ere_queue_overflow_fallback(monkeypatch):
             od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True, **helpers.opts_from_flags(flags))
             ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags, ors, osnaps)
             assert not sgd.compare(ed, od), (name, flags)
+
+
+OPTION_SETS = [
+    ["-velitsbound"],
+    ["--resolventmax=6", "--phases=4"],
+    ["--xormaxarity=70"],                       # beyond the small shared-memory slice: every variable runs on a full warp
+    ["--xormaxarity=3", "-no-ere"],
+    ["--mupos=4", "--muneg=4"],
+    ["--mupos=1", "--muneg=1", "--phases=6"],   # the occurrence bound doubles per round (lcve.cu:309-311)
+    ["--electionsmax=6"],
+    ["--electionsmin=50"],
+    ["--collectfreq=1"],
+    ["--collectfreq=3", "--phases=7", "--eliminatedlitsmin=0"],
+    ["--literalsmul=0.02"],                     # tight literal capacity: MEMORY_SAFE failures (bounded.cuh:266-276)
+    ["--lcveclausemax=3"],
+    ["--ereclausemax=4"],
+    ["--eremaxoccurs=3", "--submaxoccurs=3"],
+    ["-no-ve", "-no-veextend"],
+    ["-no-sub", "-bce"],
+    ["--phases=0"],
+    ["--phases=1"],
+]
+
+
+@pytest.mark.parametrize("flags", OPTION_SETS, ids=lambda f: " ".join(f))
+def test_option_matrix(flags):
+    """The simplifier options of the reference CLI (options.cpp:24-43, options.cu:36-60), one set at a
+    time, on a 3-SAT, a miter and a multiplier instance: every round equals the oracle's."""
+    for name in ("k3_r42", "miter_a", "mult10", "k5_r10", "multpar", "miter_x"):
+        fam, seed, args = SMALL[name]
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True, **helpers.opts_from_flags(flags))
+        ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags, ors, osnaps)
+        assert not sgd.compare(ed, od), (name, flags)
+
+
+@pytest.mark.parametrize("flags", [[], ["-all"], ["--lcveclausemax=4"], ["--mupos=8", "--muneg=8", "--phases=6"], ["-no-vefunction", "--resolventmax=5"]],
+                         ids=lambda f: " ".join(f) or "default")
+def test_inprocessing_call_with_learnts(flags):
+    """A later inprocessing call (stats.sigma.calls > 1: learnt clauses in the store, original-only
+    counting in BVE, bounded.cuh / elimination.cuh `in_mode` paths) on formulas with 20 % learnt clauses."""
+    S = sigma()
+    rng = np.random.default_rng(23)
+    for name in ("k3_r30", "miter_a", "mult10", "k4_r7"):
+        fam, seed, args = SMALL[name]
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        meta = np.zeros(len(offs) - 1, np.uint32)
+        lrn = rng.random(len(meta)) < 0.2
+        meta[lrn] = 1 | (rng.integers(0, 3, int(lrn.sum())).astype(np.uint32) << 4) | (rng.integers(2, 9, int(lrn.sum())).astype(np.uint32) << 6)
+        over = helpers.opts_from_flags(flags)
+        over["sigma_calls"] = 3
+        od, ors, osn = helpers.run_oracle(V, lits, offs, meta=meta, snapshots=True, **over)
+        s = S.Simplifier(0, flags=flags, sigma_calls=3)
+        s.load(V, lits, offs, meta=meta)
+        fin = s.simplify()
+        ed = to_dump(V, s.store(), fin["cnfstate"])
+        rounds = [r for r in s.rounds() if r["kind"] == 0]
+        s.close()
+        assert not sgd.compare(ed, od), (name, flags)
+        assert (ed.bits == od.bits).all() and (ed.sig == od.sig).all(), (name, flags)
+        assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
+               [[int(x) for x in row] for row in ors], (name, flags)
