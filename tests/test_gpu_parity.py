@@ -528,3 +528,71 @@ def test_inprocessing_call_with_learnts(flags):
         assert (ed.bits == od.bits).all() and (ed.sig == od.sig).all(), (name, flags)
         assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
                [[int(x) for x in row] for row in ors], (name, flags)
+
+
+FUZZ_FLAGS = [[], ["-all"], ["-bce"], ["--lcveclausemax=5"], ["--mupos=6", "--muneg=6"], ["--phases=7", "--eliminatedlitsmin=0"],
+              ["-no-vefunction"], ["--resolventmax=7"], ["--xormaxarity=4"], ["--collectfreq=1"], ["-velitsbound"],
+              ["--electionsmax=8"], ["--literalsmul=0.1"], ["-no-sub"], ["-no-ere", "--phases=3"], ["--ereclausemax=6"]]
+
+
+def random_cnf(rng, V, C, kmin, kmax, dup=0.02):
+    """Mixed clause sizes, no tautologies, a few duplicate clauses, a few units."""
+    cls = []
+    for _ in range(C):
+        k = int(rng.integers(kmin, kmax + 1))
+        vs = rng.choice(V, size=min(k, V), replace=False) + 1
+        cls.append((2 * vs + rng.integers(0, 2, len(vs))).astype(np.uint32))
+    for _ in range(int(C * dup)):
+        cls.append(cls[int(rng.integers(0, len(cls)))].copy())
+    order = rng.permutation(len(cls))
+    cls = [cls[i] for i in order]
+    lits = np.concatenate(cls).astype(np.uint32)
+    offs = np.zeros(len(cls) + 1, np.uint64)
+    np.cumsum([len(c) for c in cls], out=offs[1:])
+    return lits, offs
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("SIGMA_FUZZ_SEEDS", "64")))))
+def test_random_fuzz(seed):
+    """Random small formulas (mixed clause sizes 2-12, duplicates, optional learnt clauses, inactive and
+    assumed variables) under a random option set: every round and the final result equal the oracle's."""
+    S = sigma()
+    rng = np.random.default_rng(1000 + seed)
+    V = int(rng.integers(30, 500))
+    ratio = float(rng.choice([1.5, 2.5, 4.0, 6.0, 10.0]))
+    kmin = int(rng.integers(2, 4)); kmax = int(rng.integers(kmin, 13))
+    lits, offs = random_cnf(rng, V, max(8, int(V * ratio)), kmin, kmax)
+    flags = list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    if rng.random() < 0.3:
+        flags += list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    calls = int(rng.integers(1, 4))
+    meta = None
+    if calls > 1 and rng.random() < 0.7:
+        meta = np.zeros(len(offs) - 1, np.uint32)
+        sz = np.diff(offs.astype(np.int64))
+        lrn = (rng.random(len(meta)) < 0.25) & (sz > 1)
+        meta[lrn] = 1 | (rng.integers(0, 3, int(lrn.sum())).astype(np.uint32) << 4) | (rng.integers(2, 9, int(lrn.sum())).astype(np.uint32) << 6)
+    vstate = assumed = None
+    if rng.random() < 0.4:
+        vstate = (rng.random(V + 1) < 0.04).astype(np.uint8) * 3; vstate[0] = 0
+    if rng.random() < 0.4:
+        assumed = (rng.random(V + 1) < 0.06).astype(np.uint8)
+    try:
+        over = helpers.opts_from_flags(flags)
+    except KeyError:
+        pytest.skip("flag combination not expressible")
+    over["sigma_calls"] = calls
+    od, ors, _ = helpers.run_oracle(V, lits, offs, meta=meta, vstate=vstate, assumed=assumed, **over)
+    s = S.Simplifier(0, flags=flags, sigma_calls=calls)
+    try:
+        s.load(V, lits, offs, meta=meta, vstate=vstate, assumed=assumed)
+        fin = s.simplify()
+        ed = to_dump(V, s.store(), fin["cnfstate"])
+        rounds = [r for r in s.rounds() if r["kind"] == 0]
+    finally:
+        s.close()
+    ctx = (seed, V, len(offs) - 1, kmin, kmax, flags, calls)
+    assert od.cnfstate == fin["cnfstate"], ctx
+    assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
+           [[int(x) for x in row] for row in ors], ctx
+    assert not sgd.compare(ed, od), ctx
