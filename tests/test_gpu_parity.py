@@ -596,3 +596,53 @@ def test_random_fuzz(seed):
     assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
            [[int(x) for x in row] for row in ors], ctx
     assert not sgd.compare(ed, od), ctx
+
+
+def skewed_cnf(rng, V, C, kmax, hubs, hub_p):
+    """Hub variables (occurrence lists of hundreds to thousands of entries: every list-sort class, the
+    32-lane groups, electionsmax / submaxoccurs bounds) and clause sizes up to kmax (> 8: the long-clause
+    paths of prep, partition and the MIS walk)."""
+    hub = rng.choice(V, size=hubs, replace=False) + 1
+    cls = []
+    for _ in range(C):
+        k = int(min(V - 1, max(2, rng.geometric(0.35) + 1 if rng.random() < 0.8 else rng.integers(9, kmax + 1))))
+        vs = set((rng.choice(V, size=k, replace=False) + 1).tolist())
+        if rng.random() < hub_p:
+            vs.add(int(hub[int(rng.integers(0, hubs))]))
+        vs = np.array(sorted(vs), np.uint32)
+        cls.append((2 * vs + rng.integers(0, 2, len(vs))).astype(np.uint32))
+    lits = np.concatenate(cls).astype(np.uint32)
+    offs = np.zeros(len(cls) + 1, np.uint64)
+    np.cumsum([len(c) for c in cls], out=offs[1:])
+    return lits, offs
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("SIGMA_FUZZ2_SEEDS", "24")))))
+def test_random_fuzz_skewed(seed):
+    S = sigma()
+    rng = np.random.default_rng(5000 + seed)
+    V = int(rng.integers(300, 4000))
+    C = int(V * float(rng.choice([2.0, 3.5, 5.0])))
+    lits, offs = skewed_cnf(rng, V, C, int(rng.integers(12, 60)), int(rng.integers(1, 6)), float(rng.choice([0.05, 0.3, 0.8])))
+    flags = list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    if rng.random() < 0.5:
+        flags += [str(rng.choice(["--electionsmax=40", "--submaxoccurs=20", "--eremaxoccurs=30", "--mupos=256", "--bcemaxoccurs=25"]))]
+        if flags[-1] == "--mupos=256":
+            flags.append("--muneg=256")
+    calls = int(rng.integers(1, 3))
+    over = helpers.opts_from_flags(flags); over["sigma_calls"] = calls
+    od, ors, _ = helpers.run_oracle(V, lits, offs, **over)
+    s = S.Simplifier(0, flags=flags, sigma_calls=calls)
+    try:
+        s.load(V, lits, offs)
+        fin = s.simplify()
+        ed = to_dump(V, s.store(), fin["cnfstate"])
+        rounds = [r for r in s.rounds() if r["kind"] == 0]
+    finally:
+        s.close()
+    ctx = (seed, V, C, flags, calls)
+    assert od.cnfstate == fin["cnfstate"], ctx
+    if od.cnfstate != 0:
+        assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
+               [[int(x) for x in row] for row in ors], ctx
+    assert not sgd.compare(ed, od), ctx
