@@ -646,3 +646,43 @@ def test_random_fuzz_skewed(seed):
         assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
                [[int(x) for x in row] for row in ors], ctx
     assert not sgd.compare(ed, od), ctx
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("SIGMA_FUZZ3_SEEDS", "24")))))
+def test_random_fuzz_structured(seed):
+    """Gate-rich formulas (Tseitin miters with a random AND/XOR mix and rewriting rate, array multipliers,
+    parity chains) of random size under random options: equivalence / AND-OR / ITE / XOR / function-table
+    substitution paths of BVE, SUB on gate clauses, ERE on redundant resolvents."""
+    S = sigma()
+    rng = np.random.default_rng(9000 + seed)
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        fam, args = "miter", [int(rng.integers(8, 80)), int(rng.integers(60, 2500)), int(rng.integers(0, 1001)), int(rng.integers(0, 400)), int(rng.integers(1, 33))]
+    elif kind == 1:
+        fam, args = "mult", [int(rng.integers(3, 15))]
+    elif kind == 2:
+        fam, args = "parity", [int(rng.integers(10, 800))]
+    else:
+        fam, args = "multpar", [int(rng.integers(3, 9)), int(rng.integers(10, 400))]
+    V, lits, offs = helpers.gen_cnf(fam, 7000 + seed, args)
+    flags = list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    if rng.random() < 0.4:
+        flags += list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    calls = int(rng.integers(1, 3))
+    over = helpers.opts_from_flags(flags); over["sigma_calls"] = calls
+    od, ors, osn = helpers.run_oracle(V, lits, offs, snapshots=True, **over)
+    ed, fin, _, _ = (None, None, None, None)
+    s = S.Simplifier(0, flags=flags, sigma_calls=calls)
+    try:
+        s.load(V, lits, offs)
+        fin = s.simplify()
+        ed = to_dump(V, s.store(), fin["cnfstate"])
+        rounds = [r for r in s.rounds() if r["kind"] == 0]
+    finally:
+        s.close()
+    ctx = (seed, fam, args, flags, calls)
+    assert od.cnfstate == fin["cnfstate"], ctx
+    if od.cnfstate != 0:
+        assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
+               [[int(x) for x in row] for row in ors], ctx
+    assert not sgd.compare(ed, od), ctx
