@@ -686,3 +686,39 @@ def test_random_fuzz_structured(seed):
         assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
                [[int(x) for x in row] for row in ors], ctx
     assert not sgd.compare(ed, od), ctx
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("SIGMA_FUZZ4_SEEDS", "10")))))
+def test_random_fuzz_medium(seed):
+    """Medium instances (20 k - 150 k variables): several partition tiles and buckets, staged and direct
+    partition tiles, chunked (dense) and clause-pass (sparse) election, all list-sort classes."""
+    S = sigma()
+    rng = np.random.default_rng(12000 + seed)
+    kind = int(rng.integers(0, 5))
+    if kind <= 2:
+        k = int(rng.choice([3, 4, 5, 7]))
+        n = int(rng.integers(20000, 150000))
+        ratio = {3: 4.26, 4: 9.0, 5: float(rng.choice([12.0, 21.0])), 7: 40.0}[k] * float(rng.choice([0.6, 1.0]))
+        fam, args = "ksat", [n, int(n * ratio), k]
+    elif kind == 3:
+        fam, args = "miter", [int(rng.integers(200, 1500)), int(rng.integers(20000, 120000)), int(rng.integers(0, 1001)), int(rng.integers(0, 300)), 32]
+    else:
+        fam, args = "multpar", [int(rng.integers(24, 64)), int(rng.integers(5000, 60000))]
+    V, lits, offs = helpers.gen_cnf(fam, 300 + seed, args)
+    flags = list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    over = helpers.opts_from_flags(flags)
+    od, ors, _ = helpers.run_oracle(V, lits, offs, **over)
+    s = S.Simplifier(0, flags=flags)
+    try:
+        s.load(V, lits, offs)
+        fin = s.simplify()
+        ed = to_dump(V, s.store(), fin["cnfstate"])
+        rounds = [r for r in s.rounds() if r["kind"] == 0]
+    finally:
+        s.close()
+    ctx = (seed, fam, args, flags)
+    assert od.cnfstate == fin["cnfstate"], ctx
+    if od.cnfstate != 0:
+        assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
+               [[int(x) for x in row] for row in ors], ctx
+    assert not sgd.compare(ed, od), ctx
