@@ -66,6 +66,7 @@ typedef struct sigma_opts {
     int32_t  sigma_calls;       /* stats.sigma.calls of this call: 1 = preprocessing */
     int32_t  final_gc;          /* compact before store (simplify(skip_transfer_to_host)) */
     int32_t  profile;           /* -profilegpu: per-stage CUDA-event times */
+    int32_t  aggr_cnf_sort;     /* -aggresivesort (off): clauses leave in OLIST_CMP order (cnf.cu:232-233, key.cuh:67-83) */
 } sigma_opts;
 
 /* Per-round report; replaces the LOG2 lines + inf.* updates of simplify.cu:163-186. */

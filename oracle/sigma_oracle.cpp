@@ -1328,7 +1328,7 @@ void oracle_default_opts(oracle_opts* o) {
     o->phase_lits_min = 500; o->shrink_rate = 2; o->lits_mul = 1.0;
     o->ve_fun_en = 1; o->ve_lbound_en = 0; o->ve_clause_max = 100; o->xor_max_arity = 10;
     o->ere_clause_max = 250; o->ere_max_occurs = 3000; o->sub_max_occurs = 3000; o->bce_max_occurs = 3000;
-    o->sh_max_bve_out1 = 250; o->sigma_calls = 1; o->final_gc = 1;
+    o->sh_max_bve_out1 = 250; o->sigma_calls = 1; o->final_gc = 1; o->aggr_cnf_sort = 0;
 }
 
 void oracle_normalize_opts(oracle_opts* o) {  // options.cpp:291-296
@@ -1408,15 +1408,30 @@ void oracle_copy_result(const oracle_ctx* s, uint32_t* bits, uint32_t* sig, uint
                         uint8_t* eliminated, uint32_t* resolved, uint32_t* trail) {
     u64 i = 0, l = 0;
     offs[0] = 0;
-    if (live_result(s))
-        for (const Clause& c : s->cls) {
-            if (c.deleted()) continue;
+    if (live_result(s)) {
+        std::vector<u32> order;
+        for (u32 k = 0; k < u32(s->cls.size()); k++) if (!s->cls[k].deleted()) order.push_back(k);
+        // cacheCNF, cnf.cu:232-233: thrust::stable_sort of the refs with OLIST_CMP (key.cuh:67-83):
+        // size, first literal, last literal, signature, ref
+        if (s->o.aggr_cnf_sort && s->simpstate != OTALLOC_FAIL && s->simpstate != CNFALLOC_FAIL)   // !reallocFailed()
+            std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) {
+                const Clause& x = s->cls[a]; const Clause& y = s->cls[b];
+                if (x.sz != y.sz) return x.sz < y.sz;
+                const u32 *lx = s->L(x), *ly = s->L(y);
+                if (lx[0] != ly[0]) return lx[0] < ly[0];
+                if (lx[x.sz - 1] != ly[y.sz - 1]) return lx[x.sz - 1] < ly[y.sz - 1];
+                if (x.sig != y.sig) return x.sig < y.sig;
+                return a < b;
+            });
+        for (u32 k : order) {
+            const Clause& c = s->cls[k];
             bits[i] = c.st | (c.molten << 2) | (c.added << 3) | (c.usage << 4) | (c.lbd << 6);
             sig[i] = c.sig;
             memcpy(lits + l, s->L(c), size_t(c.sz) * 4);
             l += c.sz;
             offs[++i] = l;
         }
+    }
     memcpy(eliminated, s->eliminated.data(), s->eliminated.size());
     if (!s->resolved.empty()) memcpy(resolved, s->resolved.data(), s->resolved.size() * 4);
     if (!s->trail.empty()) memcpy(trail, s->trail.data(), s->trail.size() * 4);

@@ -45,6 +45,7 @@ typedef struct oracle_opts {
     uint32_t sh_max_bve_out1;   /* 250 with EXTSHMEM, 190 without (gate eligibility) */
     int32_t  sigma_calls;       /* stats.sigma.calls: 1 = preprocessing call */
     int32_t  final_gc;          /* 1: compact at the end like simplify(skip_transfer_to_host) */
+    int32_t  aggr_cnf_sort;     /* -aggresivesort: refs stable-sorted by OLIST_CMP before the write-back (cnf.cu:232-233) */
 } oracle_opts;
 
 void oracle_default_opts(oracle_opts* o);

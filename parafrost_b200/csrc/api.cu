@@ -201,7 +201,7 @@ static size_t carve(Ctx* c, char* base) {
     c->wlA = a.take<u32>(V1); c->wlB = a.take<u32>(V1);
     c->veType = a.take<u32>(V1); c->veUcnt = a.take<u32>(V1); c->veRpos = a.take<u32>(V1); c->veRref = a.take<u64>(V1);
     const size_t maxScan = (nflag > ND + 2 ? nflag : ND + 2);
-    const size_t radixBlocks = V1 / 4096 + 2;
+    const size_t radixBlocks = (V1 > capC ? V1 : capC) / 4096 + 2;   // the election sorts V scores, -aggresivesort up to capC clause keys
     const size_t scanTiles = (maxScan > 256 * radixBlocks ? maxScan : 256 * radixBlocks) / 2048 + 4;
     c->scanTmp = a.take<u32>(scanTiles); c->scanTmp64 = a.take<u64>(scanTiles);
     c->flagA = a.take<u32>(nflag); c->flagB = a.take<u32>(nflag); c->flag64 = a.take<u64>(capC + 2);
@@ -612,7 +612,7 @@ extern "C" int sigma_snapshot(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num
     int rc = syncCounters(c);
     if (rc) return rc;
     u64 nc, nl;
-    if ((rc = launchStore(c, &nc, &nl, false))) return rc;
+    if ((rc = launchStore(c, &nc, &nl, false, false))) return rc;
     if (num_clauses) *num_clauses = nc;
     if (num_literals) *num_literals = nl;
     return SIGMA_OK;
@@ -636,7 +636,8 @@ extern "C" int sigma_store(sigma_ctx* c, uint32_t* bits, uint32_t* sig, uint64_t
     int rc = syncCounters(c);
     if (rc) return rc;
     u64 nc = 0, nl = 0;
-    if ((rc = launchStore(c, &nc, &nl, false))) return rc;
+    // -aggresivesort orders the final write-back only (cacheCNF); a store between two sigma_round calls is a snapshot in ref order
+    if ((rc = launchStore(c, &nc, &nl, false, c->loopDone))) return rc;
     const int dst = 1 - c->cur;
     const bool live = c->cnfstate == SIGMA_UNSOLVED;
     if (offs) {
@@ -664,7 +665,7 @@ extern "C" int sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t
     int rc = syncCounters(c);
     if (rc) return rc;
     u64 nc = 0, nl = 0;
-    if ((rc = launchStore(c, &nc, &nl, true))) return rc;
+    if ((rc = launchStore(c, &nc, &nl, true, c->loopDone))) return rc;
     if (c->cnfstate != SIGMA_UNSOLVED || !nc) return SIGMA_OK;
     const int dst = 1 - c->cur;
     if (data_words) CUDA_TRY(cudaMemcpyAsync(data_words, c->pool[dst], (nc * NBUCKETS + nl) * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -469,8 +469,52 @@ __global__ void k_store_sclause(const uint4* __restrict__ hdr, const u32* __rest
     }
 }
 
+// -aggresivesort (cacheCNF, cnf.cu:232-233): thrust::stable_sort of the refs with OLIST_CMP, i.e. the
+// clauses leave ordered by (size, first literal, last literal, signature, ref).  Done as an LSD chain
+// of stable radix sorts over the four key words (the initial order is the ref order), then the output
+// position and literal offset of every clause are scattered back so that the store kernels run as usual.
+__global__ void k_as_init(const uint4* __restrict__ hdr, u32 n, const u32* __restrict__ pCls, u32* __restrict__ order) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (!C_DELETED(hdr[i].w)) order[pCls[i]] = i;
+}
+__global__ void k_as_word(const uint4* __restrict__ hdr, const u32* __restrict__ pool, const u32* __restrict__ order, u32 m, int word,
+                          u32* __restrict__ keys) {
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[order[j]];
+        keys[j] = word == 3 ? h.z : word == 2 ? (h.y ? pool[h.x + h.y - 1] : 0u) : word == 1 ? (h.y ? pool[h.x] : 0u) : h.y;
+    }
+}
+__global__ void k_as_sizes(const uint4* __restrict__ hdr, const u32* __restrict__ order, u32 m, u32* __restrict__ sz) {
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) sz[j] = hdr[order[j]].y;
+}
+__global__ void k_as_back(const u32* __restrict__ order, const u32* __restrict__ offS, u32 m, u32* __restrict__ pCls, u32* __restrict__ pLits) {
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) { const u32 i = order[j]; pCls[i] = j; pLits[i] = offS[j]; }
+}
+static int aggressiveOrder(Ctx* c, u32 n) {
+    // live count first (host): the radix launches are sized by it
+    u32 m = 0;
+    cudaError_t e = cudaMemcpyAsync(&m, c->dc->scratch, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return -(int)e;
+    if (m < 2) return 0;
+    u32* base = (u32*)c->otPairs;   // free outside the OT build: 8 capW bytes >= 5 capC words
+    u32 *order = base, *order2 = base + c->capC, *keys = base + 2 * (size_t)c->capC, *keys2 = base + 3 * (size_t)c->capC, *offS = base + 4 * (size_t)c->capC;
+    LAUNCH(c, k_as_init, gridFor(n, 256), 256, 0, c->hdr[c->cur], n, c->flagA, order);
+    u32 litBits = 0;
+    while (litBits < 32 && (c->ND >> litBits)) litBits++;
+    const u32 bits[4] = {(c->hdc->flags & 8u) ? 32u : 14u, litBits, litBits, 32u};   // size, first, last, sig
+    for (int word = 3; word >= 0; word--) {   // least significant key word first
+        LAUNCH(c, k_as_word, gridFor(m, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], order, m, word, keys);
+        radixSortPairs(c, keys, order, keys2, order2, m, bits[word]);
+    }
+    LAUNCH(c, k_as_sizes, gridFor(m, 256), 256, 0, c->hdr[c->cur], order, m, keys);
+    scanExclusiveU32(c, keys, offS, m, 0, nullptr);
+    LAUNCH(c, k_as_back, gridFor(m, 256), 256, 0, order, offS, m, c->flagA, c->flagB);
+    return 0;
+}
+
 // Selects the live clauses into the staging buffers (the inactive CNF buffer); returns sizes.
-int launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm) {
+int launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm, bool writeBackOrder) {
     const u32 n = c->hdc->numCls;
     const int src = c->cur, dst = 1 - c->cur;
     u32* tot = c->dc->scratch;
@@ -479,6 +523,10 @@ int launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm) {
     LAUNCH(c, k_gc_flags, gridFor(n, 256), 256, 0, c->hdr[src], n, c->flagA, c->flagB);
     scanExclusiveU32(c, c->flagA, c->flagA, n, 0, tot);
     scanExclusiveU32(c, c->flagB, c->flagB, n, 0, tot + 1);
+    if (writeBackOrder && c->o.aggr_cnf_sort && c->simpstate != SIGMA_CNFALLOC_FAIL && c->simpstate != SIGMA_OTALLOC_FAIL) {   // !reallocFailed()
+        const int rc = aggressiveOrder(c, n);
+        if (rc) return rc;
+    }
     if (sclauseForm)
         LAUNCH(c, k_store_sclause, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, c->pool[dst], c->flag64);
     else {

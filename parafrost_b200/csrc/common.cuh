@@ -253,11 +253,13 @@ void launchHistKey(Ctx* c);
 void launchScatter(Ctx* c);
 void launchCount(Ctx* c);
 void launchGC(Ctx* c);
-int  launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm);
+int  launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm, bool writeBackOrder);   // writeBackOrder: apply -aggresivesort (cacheCNF only)
 // otsort.cu
 void launchSortOT(Ctx* c, int mode);   // 0 all lists, 1 elected variables, 2 lists flagged in needSort
 // lcve.cu
 int  runLCVE(Ctx* c);
+// stable LSD radix sort of (key, value) pairs on the low `bits` bits; result in (keys, vals); n <= max(V + 1, capC)
+void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, u32 n, u32 bits);
 // prop.cu
 int  runProp(Ctx* c, bool* conflict);
 // elim.cu

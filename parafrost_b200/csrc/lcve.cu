@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const u32* __restr
 
 // sorts (keys, vals) ascending by key, stable; only the digits below `bits` are sorted (all keys are
 // < 2^bits) in an EVEN number of 8-bit passes, so that the result ends in (keys, vals)
-static void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, u32 n, u32 bits) {
+void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, u32 n, u32 bits) {
     const u32 nblocks = divup(n, RS_TILE);
     u32 *ki = keys, *vi = vals, *ko = keys2, *vo = vals2;
     u32 passes = (bits + 7) / 8;

@@ -59,6 +59,8 @@ VARIANTS = {
     "all": ["-all"],
     "p1_ere": ["--phases=1"],
     "nosub_p2": ["-no-sub", "-no-veextend", "--phases=2", "-no-ere"],
+    "aggr_p3": ["-aggresivesort", "--phases=3", "-no-ere"],
+    "aggr_bce_p2": ["-aggresivesort", "-bce", "--phases=2", "-no-ere"],
 }
 MEDIUM_VARIANTS = ["p1", "p2", "def", "nofun"]
 
@@ -68,6 +70,11 @@ def sh(cmd, **kw):
 
 
 def main():
+    """`--only v1,v2` runs just those variants (small instances) and merges them into the summary."""
+    only = None
+    for i, a in enumerate(sys.argv):
+        if a == "--only":
+            only = sys.argv[i + 1].split(",")
     os.makedirs(OUT, exist_ok=True)
     os.makedirs(TMP, exist_ok=True)
     gen = os.path.join(ROOT, "build", "cnfgen")
@@ -76,8 +83,11 @@ def main():
     assert r.returncode == 0, r.stdout
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     summary = {}
+    if only:
+        summary = json.load(open(os.path.join(ROOT, "tests", "golden", "summary.json")))
     log = open(os.path.join(OUT, "runs.log"), "w")
-    for group, variants, keep in ((SMALL, list(VARIANTS), True), (MEDIUM, MEDIUM_VARIANTS, False)):
+    groups = ((SMALL, only, True),) if only else ((SMALL, list(VARIANTS), True), (MEDIUM, MEDIUM_VARIANTS, False))
+    for group, variants, keep in groups:
         for name, (fam, seed, args) in group.items():
             cnf = os.path.join(TMP, name + ".cnf")
             r = sh([gen, fam, str(seed), cnf] + [str(a) for a in args])

@@ -722,3 +722,27 @@ def test_random_fuzz_medium(seed):
         assert [[r["elected"], r["eliminated"], r["resolvents"], r["clauses"], r["literals"]] for r in rounds] == \
                [[int(x) for x in row] for row in ors], ctx
     assert not sgd.compare(ed, od), ctx
+
+
+@pytest.mark.parametrize("flags", [["-aggresivesort"], ["-aggresivesort", "-all"], ["-aggresivesort", "--phases=2", "-no-ere"]], ids=lambda f: " ".join(f))
+def test_aggressive_write_back_order(flags):
+    """-aggresivesort (cacheCNF, cnf.cu:232-233): the clauses leave sorted by OLIST_CMP (size, first literal,
+    last literal, signature, ref); per-round snapshots stay in ref order.  CSR and SCLAUSE-stream outputs."""
+    S = sigma()
+    for name in ("k3_r30", "miter_x", "mult10", "k5_r10", "multpar"):
+        fam, seed, args = SMALL[name]
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        od, ors, osnaps = helpers.run_oracle(V, lits, offs, snapshots=True, **helpers.opts_from_flags(flags))
+        ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags, ors, osnaps)
+        assert not sgd.compare(ed, od), (name, flags)
+        assert ed.ordered_clauses() == od.ordered_clauses()
+        oc = ed.ordered_clauses()
+        key = [(len(c), c[0], c[-1]) for c in oc]
+        assert key == sorted(key), name                      # the order really is the OLIST_CMP order
+        s = S.Simplifier(0, flags=flags)
+        s.load(V, lits, offs)
+        s.simplify()
+        data, refs = s.store_sclauses()
+        s.close()
+        rec = [tuple(data[int(r) + 3:int(r) + 3 + int(data[int(r) + 2])].tolist()) for r in refs]
+        assert rec == oc, name
