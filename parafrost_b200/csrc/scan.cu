@@ -1,7 +1,8 @@
 // parafrost_b200/csrc/scan.cu -- device-wide exclusive scans (hand-written; replaces the
 // cub::DeviceScan calls at src/gpu/memory.cu:429-430, elimination.cu:85-92, recycle.cu:84-93).
 //
-// Three launches: per-tile reduce -> single-CTA scan of the tile sums -> per-tile downsweep.
+// Three launches: per-tile reduce -> single-CTA scan of the tile sums -> per-tile downsweep
+// (one launch for short ranges, k_scan_small).
 // Algorithmic bytes: read n + write n (+ the tile sums); HBM-bound.
 #include "common.cuh"
 
@@ -78,9 +79,35 @@ __global__ void k_scan_down(const T* in, T* out, u64 n, const T* __restrict__ ti
     for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
 }
 
+// Short ranges (worklists, radix digit tables, elected variables: most scans of a round) in ONE launch:
+// a single CTA walks the range in chunks of 1024 x 4 elements with a running carry.
+#define SCAN_SMALL_MAX (32u << 10)
+template <typename T>
+__global__ void __launch_bounds__(1024) k_scan_small(const T* in, T* out, u32 n, T init, T* totalOut) {
+    __shared__ T sm[32];
+    __shared__ T carry;
+    if (threadIdx.x == 0) carry = init;
+    __syncthreads();
+    for (u32 b = 0; b < n; b += 4096) {
+        const u32 i0 = b + threadIdx.x * 4;
+        T v[4]; T s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : T(0); s += v[k]; }
+        T total;
+        T ex = blockExclusive<T>(s, sm, total) + carry;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (i0 + k < n) out[i0 + k] = ex; ex += v[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && totalOut) *totalOut = carry;
+}
+
 template <typename T>
 static void scanImpl(Ctx* c, const T* in, T* out, u64 n, T init, T* tmp, T* totalOut) {
     if (!n) return;  // callers never scan empty ranges with a total
+    if (n <= SCAN_SMALL_MAX) { LAUNCH(c, k_scan_small<T>, 1, 1024, 0, in, out, (u32)n, init, totalOut); return; }
     const u32 ntiles = divup(n, SCAN_TILE);
     LAUNCH(c, k_scan_reduce<T>, ntiles, SCAN_THREADS, 0, in, n, tmp);
     LAUNCH(c, k_scan_tiles<T>, 1, 1024, 0, tmp, ntiles, init, totalOut);
