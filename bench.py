@@ -139,6 +139,11 @@ def ncu_traffic(workload):
     return best
 
 
+def kbase(name):
+    """'(k_ot_part<3, 5>)' / 'void k_sub<4>' -> 'k_ot_part' / 'k_sub' (the LAUNCH macro stringifies its argument)."""
+    return name.replace("void ", "").strip("() ").split("<")[0]
+
+
 def roofline(ktimes, C, L, V, peaks, workload="cfg2"):
     """Roofline of the dominant kernel.  Streaming kernels have closed-form algorithmic bytes
     (DESIGN.md 3); the per-variable kernels (MIS rounds, BVE, SUB, ERE) are latency / instruction
@@ -153,11 +158,11 @@ def roofline(ktimes, C, L, V, peaks, workload="cfg2"):
     total = sum(v[0] for v in ktimes.values())
     order = sorted(ktimes.items(), key=lambda kv: -kv[1][0])
     dom_name, (dom_ms, dom_cnt) = order[0]
-    name, (ms, cnt) = next(((k, v) for k, v in order if algorithmic_bytes(k.split("<")[0], C, L, V)), order[0])
+    name, (ms, cnt) = next(((k, v) for k, v in order if algorithmic_bytes(kbase(k), C, L, V)), order[0])
     traffic = ncu_traffic(workload)
-    b = algorithmic_bytes(name.split("<")[0], C, L, V)
+    b = algorithmic_bytes(kbase(name), C, L, V)
     out = {"bound": "hbm", "kernel": name, "launches": cnt, "ms_per_launch": ms / cnt, "share_of_kernel_time": ms / total if total else None,
-           "peak": peak, "peak_source": src, "unit": "GB/s", "traffic": traffic.get(name.split("<")[0])}
+           "peak": peak, "peak_source": src, "unit": "GB/s", "traffic": traffic.get(kbase(name))}
     if b:
         ach = b / (ms / cnt * 1e-3) / 1e9
         out.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": b})
@@ -165,10 +170,10 @@ def roofline(ktimes, C, L, V, peaks, workload="cfg2"):
         out.update({"achieved": None, "frac": None, "algorithmic_bytes_per_launch": None})
     if dom_name != name:
         out["dominant"] = {"kernel": dom_name, "ms_per_launch": dom_ms / dom_cnt, "launches": dom_cnt, "share_of_kernel_time": dom_ms / total,
-                           "traffic": traffic.get(dom_name.split("<")[0]),
+                           "traffic": traffic.get(kbase(dom_name)),
                            "note": "per-variable gather kernel: latency/instruction bound, no closed-form bytes (DESIGN.md 3)"}
     out["top_kernels"] = [{"kernel": k, "ms": round(v[0], 3), "launches": v[1], "share": round(v[0] / total, 3),
-                           "gbs": (lambda bb: round(bb / (v[0] / v[1] * 1e-3) / 1e9, 1) if bb else None)(algorithmic_bytes(k.split("<")[0], C, L, V))}
+                           "gbs": (lambda bb: round(bb / (v[0] / v[1] * 1e-3) / 1e9, 1) if bb else None)(algorithmic_bytes(kbase(k), C, L, V))}
                           for k, v in order[:8]]
     return out
 

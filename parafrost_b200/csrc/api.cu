@@ -22,7 +22,12 @@ static double nowMs() {
 static std::mutex gKtMutex;
 static char gKtNames[KT_MAX_KERNELS][64];
 static int gKtN = 0;
-int ktRegister(const char* name) {
+int ktRegister(const char* rawName) {
+    // the LAUNCH macro stringifies its argument: "(k_ot_part<3, 5>)" -> "k_ot_part<3, 5>"
+    char name[64];
+    const size_t len = strlen(rawName);
+    const bool paren = len >= 2 && rawName[0] == '(' && rawName[len - 1] == ')';
+    snprintf(name, sizeof name, "%.*s", (int)(paren ? len - 2 : len), rawName + (paren ? 1 : 0));
     std::lock_guard<std::mutex> lk(gKtMutex);
     for (int i = 0; i < gKtN; i++) if (!strncmp(gKtNames[i], name, 63)) return i;
     if (gKtN == KT_MAX_KERNELS - 1) return KT_MAX_KERNELS - 1;   // overflow bucket
