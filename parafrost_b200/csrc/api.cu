@@ -211,7 +211,7 @@ static size_t carve(Ctx* c, char* base) {
     c->scanTmp = a.take<u32>(scanTiles); c->scanTmp64 = a.take<u64>(scanTiles);
     c->flagA = a.take<u32>(nflag); c->flagB = a.take<u32>(nflag); c->flag64 = a.take<u64>(capC + 2);
     c->radixHist = a.take<u32>(256 * radixBlocks);
-    c->qMed = a.take<u32>(ND); c->qBig = a.take<u32>(ND / 512 + 64); c->qHuge = a.take<u32>(ND / 8192 + 64);
+    c->qMed = a.take<u32>(ND);
     c->dc = a.take<DevCounters>(1);
     return a.off + 256;
 }

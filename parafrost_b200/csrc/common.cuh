@@ -105,7 +105,6 @@ struct DevCounters {
     u32 bcpCurr, bcpNext, bcpConfl, bcpLevel;
     u32 nFrozen;       // number of first-frozen variables mapped into varcore (<= 12 needed)
     u32 unassignedDec; // variables assigned by prop()
-    u32 qMed, qBig, qHuge; // (unused)
     u32 sortCnt[9], sortCur[9];   // list-sort length classes (otsort.cu)
     u32 addedCls;      // resolvents appended by the last BVE
     u32 bin[4];        // group-size class sizes of the elected variables (elim.cu) + redo queue
@@ -156,8 +155,7 @@ struct Ctx {
     u32 *veType, *veUcnt, *veRpos, *veRes, *veUoff, *veResOff; u64* veRref;
     // scan / misc scratch
     u32 *scanTmp; u64* scanTmp64; u32 *flagA, *flagB; u64* flag64;
-    u32 *radixHist; u32 *qMed, *qBig, *qHuge;
-    u32 *frontA, *frontB; unsigned char* bcpState;
+    u32 *radixHist; u32 *qMed;   // qMed: literals grouped by list-length class (otsort.cu)
     DevCounters* dc; DevCounters* hdc;   // device + pinned host mirror
     // host-side loop state (simplify.cu:136-241)
     int phase, multiplier, simpstate, cnfstate; bool compacted;

@@ -984,58 +984,8 @@ __global__ void __launch_bounds__(128) k_bce(GT<GS> g, const u32* __restrict__ w
     }
 }
 
-// ------------------------------------------------------------------ ERE (redundancy.cuh:99-174)
-#define ERE_SLICE 256
-__global__ void __launch_bounds__(128) k_ere(GT<32> g) {
-    constexpr int GS = 32;
-    __shared__ u32 sh[4][ERE_SLICE];
-    u32* m_c = sh[threadIdx.x >> 5];
-    const int clause_max = g.k.ere_clause_max;
-    const u32 warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    for (u32 gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gid < g.numElected; gid += warpsPerGrid) {
-        const u32 v = g.elected[gid], p = V2L(v), n = p | 1u;
-        const u32 ds = g.otSize[p], fs = g.otSize[n];
-        if (!(ds && fs && ds <= g.k.ere_max_occurs && fs <= g.k.ere_max_occurs)) continue;
-        const u32* P = g.occurs + g.otStart[p];
-        const u32* N = g.occurs + g.otStart[n];
-        if ((int)g.hdr[P[0]].y > clause_max || (int)g.hdr[N[0]].y > clause_max) continue;
-        for (u32 i = 0; i < ds; i++) {
-            const uint4 hp = g.hdr[P[i]];
-            if (C_DELETED(hp.w)) continue;
-            for (u32 j = 0; j < fs; j++) {
-                const uint4 hn = g.hdr[N[j]];
-                if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
-                GSYNC();
-                u32 m_sig = 0; int m_len = 0;
-                if (LANE == 0) m_len = mergeOut(g.pool + hp.x, (int)hp.y, g.pool + hn.x, (int)hn.y, v, m_c, m_sig);
-                m_len = __shfl_sync(FULL, m_len, 0, GS);
-                m_sig = __shfl_sync(FULL, m_sig, 0, GS);
-                GSYNC();
-                if (m_len <= 1) continue;
-                const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
-                // forward_equ: smallest list among the resolvent's literals
-                u32 best = m_c[0];
-                u32 minsize = g.otSize[best];
-                for (int k = 1; k < m_len; k++) { const u32 lit = m_c[k]; const u32 ls = g.otSize[lit]; if (ls < minsize) { minsize = ls; best = lit; } }
-                const u32* minList = g.occurs + g.otStart[best];
-                for (u32 e = LANE; e < minsize; e += GS) {
-                    const u32 ci = minList[e];
-                    const uint4 h = g.hdr[ci];
-                    if ((int)h.y == m_len && (C_LEARNT(h.w) || (h.w & CB_ST_MASK) == type) && SUBSIG(m_sig, h.z) && !C_DELETED(h.w)) {
-                        const u32* l = g.pool + h.x;
-                        bool eq = true;
-                        for (int k = 0; k < m_len; k++) if (l[k] != m_c[k]) { eq = false; break; }
-                        if (eq) { g.hdr[ci].w = (h.w & ~CB_ST_MASK) | CB_DELETED; break; }
-                    }
-                }
-            }
-        }
-    }
-}
-
-
 // ------------------------------------------------------------------ ERE, lane per resolvent
-// Same semantics as k_ere above (and ere_k, redundancy.cuh:136-174), different work mapping:
+// Same semantics as ere_k (redundancy.cuh:99-174), different work mapping:
 //   * one warp per elected variable, one LANE per (pos, neg) pair - the 32 lanes build 32
 //     different resolvents at once instead of rebuilding the same one;
 //   * the resolvent is never stored: one merge pass yields its length, first/last literal,
@@ -1442,8 +1392,6 @@ void launchBCE(Ctx* c, const KOpts& k) {
 void launchERE(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
-    static const bool v0 = getenv("SIGMA_ERE_V0") != nullptr;   // the warp-per-resolvent kernel, kept for A/B checks
-    if (v0) { launchSortOT(c, 0); LAUNCH(c, k_ere, groupGrid(c->numElected, 32, 128), 128, 0, asGroup<32>(g)); return; }
     // Bloom filter over the keys of the live clauses, in the partition buffer of the OT build (free now)
     const u32 n = c->hdc->numCls;
     const u64 bufBytes = ((u64)c->capW + 4) * sizeof(uint2);
