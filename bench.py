@@ -509,5 +509,17 @@ def main():
     return 0
 
 
+def _only_json_on_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on
+    stdout.  Everything but our own print goes to stderr from here on."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    _only_json_on_stdout()
+    rc = main()
+    sys.stdout.flush()
+    sys.exit(rc)
