@@ -1,0 +1,57 @@
+"""CPU-side checks of bench.py's contract: the reference arm prints exactly one JSON line with the agreed
+keys (it times the reference's CPU simplifier, oracle/_ref/parafrost_cpu), and the roofline helper maps
+the timer's kernel names to their byte formulas."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_bench():
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_reference_arm_prints_one_json_line():
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "parafrost_cpu")):
+        pytest.skip("reference CPU build not present (make -f oracle/Makefile ref)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "simplify_literals_per_s" and d["unit"] == "literals/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["config"]["workload"] == "cfg1"
+
+
+def test_roofline_picks_a_kernel_with_a_byte_formula():
+    b = load_bench()
+    assert b.kbase("(k_ot_part<3, 5>)") == "k_ot_part" and b.kbase("void k_sub<4>") == "k_sub" and b.kbase("k_count") == "k_count"
+    C, L, V = 21e6, 105e6, 1_000_000
+    kt = {"k_mis_round<32>": (9.0, 100), "(k_ot_part<3, 5>)": (5.0, 5), "k_awaken": (4.0, 5), "k_ere_pairs<32>": (2.5, 5)}
+    r = b.roofline(kt, C, L, V, {"hbm_gbs": 6551.4})
+    assert r["kernel"] == "(k_ot_part<3, 5>)" and r["dominant"]["kernel"] == "k_mis_round<32>"
+    assert r["algorithmic_bytes_per_launch"] == 16 * C + 4 * L + 8 * L
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / 1e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / 6551.4) < 1e-12
+    r2 = b.roofline({"k_awaken": (4.0, 5)}, C, L, V, {})
+    assert r2["peak"] == 6650.0 and "fallback" in r2["peak_source"] and "dominant" not in r2
+
+
+def test_batch_specs_cover_the_config5_range():
+    sys.path.insert(0, ROOT)
+    from parafrost_b200 import replicas
+    specs = replicas.batch_specs(64)
+    w = [replicas.spec_weight(s) for s in specs]
+    assert len(specs) == 64 and 0.9e6 <= min(w) <= 1.1e6 and 4.0e7 <= max(w) <= 6.0e7
+    assert {s[0] for s in specs} == {"ksat", "miter", "multpar"}
