@@ -753,7 +753,7 @@ bool makeArity(S& s, u32& parity, u32* literals, int size) {
     const u32 oldparity = parity;
     while (__builtin_popcount(++parity) & 1) {}
     for (int k = 0; k < size; k++) {
-        const u32 bit = 1u << k;
+        const u32 bit = k < 32 ? (1u << k) : 0u;   // xor.cuh:78 `(1UL << k)` truncated to 32 bits: 0 from bit 32 on
         if ((parity & bit) != (oldparity & bit)) literals[k] = FLIP(literals[k]);
     }
     u32 best = literals[0];
@@ -784,7 +784,9 @@ bool find_xor_gate(S& s, u32 dx, const OL& dx_list, u32 fx, const OL& fx_list, u
         if (size < 3 || arity > maxarity) continue;
         out_c.assign(s.L(ci), s.L(ci) + size);
         u32 parity = 0;
-        int itargets = 1 << arity;
+        // xor.cuh:148 `1 << arity` runs on the GPU: a 32-bit shift by 32 or more gives 0 there (PTX shl clamps the
+        // amount), not the x86 result; only reachable with --xormaxarity > 31
+        int itargets = arity >= 32 ? 0 : int(1u << arity);
         while (--itargets && makeArity(s, parity, out_c.data(), size)) {}
         if (itargets) freeze_arities(s, dx_list, fx_list);
         else {

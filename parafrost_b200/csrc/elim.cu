@@ -452,7 +452,7 @@ template <int GS> __device__ bool makeArity(GT<GS>& g, u32& parity, u32* literal
     const u32 oldparity = parity;
     while (__popc(++parity) & 1) {}
     if (LANE == 0)
-        for (int k = 0; k < size; k++) { const u32 bit = 1u << k; if ((parity & bit) != (oldparity & bit)) literals[k] = LFLIP(literals[k]); }
+        for (int k = 0; k < size; k++) { const u32 bit = k < 32 ? 1u << k : 0u; if ((parity & bit) != (oldparity & bit)) literals[k] = LFLIP(literals[k]); }   // xor.cuh:78: (1UL << k) truncated
     GSYNC();
     u32 best = literals[0];
     u32 minsize = g.otSize[best];
@@ -495,7 +495,7 @@ template <int GS> __device__ bool findXORGate(GT<GS>& g, u32 dx, const u32* D, u
         if (LANE == 0) for (int k = 0; k < size; k++) out_c[k] = g.pool[h.x + k];
         GSYNC();
         u32 parity = 0;
-        int itargets = 1 << arity;
+        int itargets = arity >= 32 ? 0 : (int)(1u << arity);   // what `1 << arity` yields on the device (shl clamps); explicit, no UB
         while (--itargets && makeArity(g, parity, out_c, size)) {}
         if (itargets) freezeArities(g, D, nd, F, nf);
         else {

@@ -532,7 +532,8 @@ def test_inprocessing_call_with_learnts(flags):
 
 FUZZ_FLAGS = [[], ["-all"], ["-bce"], ["--lcveclausemax=5"], ["--mupos=6", "--muneg=6"], ["--phases=7", "--eliminatedlitsmin=0"],
               ["-no-vefunction"], ["--resolventmax=7"], ["--xormaxarity=4"], ["--collectfreq=1"], ["-velitsbound"],
-              ["--electionsmax=8"], ["--literalsmul=0.1"], ["-no-sub"], ["-no-ere", "--phases=3"], ["--ereclausemax=6"]]
+              ["--electionsmax=8"], ["--literalsmul=0.1"], ["-no-sub"], ["-no-ere", "--phases=3"], ["--ereclausemax=6"],
+              ["-aggresivesort"], ["--lcveclausemax=3", "--phases=6"], ["--xormaxarity=70"]]
 
 
 def random_cnf(rng, V, C, kmin, kmax, dup=0.02):
