@@ -573,20 +573,30 @@ def test_random_fuzz(seed):
         sz = np.diff(offs.astype(np.int64))
         lrn = (rng.random(len(meta)) < 0.25) & (sz > 1)
         meta[lrn] = 1 | (rng.integers(0, 3, int(lrn.sum())).astype(np.uint32) << 4) | (rng.integers(2, 9, int(lrn.sum())).astype(np.uint32) << 6)
-    vstate = assumed = None
+    vstate = assumed = vorg = None
     if rng.random() < 0.4:
         vstate = (rng.random(V + 1) < 0.04).astype(np.uint8) * 3; vstate[0] = 0
     if rng.random() < 0.4:
         assumed = (rng.random(V + 1) < 0.06).astype(np.uint8)
+    if seed >= 64 and rng.random() < 0.3:      # (seeds < 64 keep the formulas of the first sweeps)
+        vorg = np.zeros(V + 1, np.uint32); vorg[1:] = rng.permutation(V).astype(np.uint32) + 1 + int(rng.integers(0, 5000))
+    if seed >= 64 and rng.random() < 0.15:     # a few unit clauses in the input (the host normally propagates them first)
+        nu = int(rng.integers(1, 4))
+        uv = rng.choice(V, size=nu, replace=False) + 1
+        ul = (2 * uv + rng.integers(0, 2, nu)).astype(np.uint32)
+        lits = np.concatenate([lits, ul]).astype(np.uint32)
+        offs = np.concatenate([offs, offs[-1] + np.arange(1, nu + 1, dtype=np.uint64)]).astype(np.uint64)
+        if meta is not None:
+            meta = np.concatenate([meta, np.zeros(nu, np.uint32)])
     try:
         over = helpers.opts_from_flags(flags)
     except KeyError:
         pytest.skip("flag combination not expressible")
     over["sigma_calls"] = calls
-    od, ors, _ = helpers.run_oracle(V, lits, offs, meta=meta, vstate=vstate, assumed=assumed, **over)
+    od, ors, _ = helpers.run_oracle(V, lits, offs, meta=meta, vorg=vorg, vstate=vstate, assumed=assumed, **over)
     s = S.Simplifier(0, flags=flags, sigma_calls=calls)
     try:
-        s.load(V, lits, offs, meta=meta, vstate=vstate, assumed=assumed)
+        s.load(V, lits, offs, meta=meta, vorg=vorg, vstate=vstate, assumed=assumed)
         fin = s.simplify()
         ed = to_dump(V, s.store(), fin["cnfstate"])
         rounds = [r for r in s.rounds() if r["kind"] == 0]
