@@ -1,5 +1,6 @@
-// parafrost_b200/csrc/cnf.cu -- clause store kernels: awaken/prep, literal histogram + sort keys,
-// occurrence scatter, live counts, garbage-collecting compaction, result store.
+// parafrost_b200/csrc/cnf.cu -- clause store kernels: awaken/prep (+ the first round's histogram), literal
+// histogram + sort keys, occurrence-table construction (radix partition + staged placement), live counts,
+// garbage-collecting compaction, result store (+ the -aggresivesort write-back order).
 //
 // Reference behaviour being replaced (results must be identical):
 //   prep_cnf_k            src/gpu/cnf.cu:45-53        sort literals, 32-bit signature
@@ -8,7 +9,8 @@
 //   cnt_cls_lits          src/gpu/count.cu:83-106
 //   scatter_k/compact_k   src/gpu/recycle.cu:34-105
 //   cacheCNF              src/gpu/cnf.cu:200-237
-// All of them stream the clause store once: they are HBM-bound, one coalesced pass each.
+//   thrust::stable_sort   src/gpu/cnf.cu:232-233      (-aggresivesort: aggressiveOrder)
+// All of them stream the clause store once, coalesced; what bounds each is measured in DESIGN.md 7.
 #include <cstdlib>
 
 #include "common.cuh"

@@ -12,7 +12,10 @@
 //   3. rank-priority MIS rounds over a shrinking worklist, a candidate decides once no
 //      lower-ranked undecided candidate shares a clause with it; "stoppers" (bound
 //      violators) never block or freeze others, the first one that stays unfrozen cuts the
-//      schedule                                                   k_mis_round
+//      schedule.  The first round of a rank chunk is one streaming pass over the clauses
+//      (k_mis_clauses / k_mis_first), later rounds probe a memorised blocker (k_mis_round);
+//      a newly elected variable freezes its neighbours by push; a candidate with a clause
+//      longer than lcveclausemax in its negative list only becomes MIS_HALF (common.cuh)
 //   4. elected = decided-elected candidates below the cut, in rank order   k_elect_*
 //   5. the first 12 frozen variables in the serial walk's order get their function-table
 //      index (mapfrozen_k, lcve.cu:253-260; only indices < 12 are observable,
