@@ -44,7 +44,8 @@ enum { AWAKEN_SUCC = 0, AWAKEN_FAIL = 1, CNFALLOC_FAIL = 2, OTALLOC_FAIL = 3 };
 // src/gpu/constants.cuh:33-62
 const uint8_t MELTING_MASK = 1, ADDING_MASK = 2, FORCED_MASK = 4;
 const u32 RES_MASK = 1, AOIX_MASK = 2, CORE_MASK = 3;
-const u32 ADDEDCLS_MAX = 0x3FFF, ADDEDLITS_MAX = 0xFFFF;
+const u32 ADDEDCLS_MAX = 0x3FFF, ADDEDLITS_MAX = 0xFFFF, ADDEDPROOF_MAX = 0x3FFFF;
+const uint8_t PROOF_ADDED = 'a', PROOF_DELETED = 'd';   // constants.hpp:45-46
 const int SH_MAX_BVE_OUT2 = 120;  // irrelevant to results (same clause either path)
 const int SUB_MAX_CL_SIZE = 1000;
 const u32 NBUCKETS = 3;           // sizeof(SCLAUSE)/4, sclause.cuh:206-209
@@ -99,6 +100,11 @@ struct oracle_ctx {
     // BVE phase arrays (elimination.cu:146-149)
     std::vector<u32> ve_type, ve_ucnt, ve_rpos;
     std::vector<u64> ve_rref;
+    // device DRAT stream (proof.cu, proofutils.cuh): one chunk per cacheProof/writeProof pair
+    bool proof_en = false;
+    std::vector<uint8_t> proofCur;
+    std::vector<std::vector<uint8_t>> proofChunks;
+    u32 proofCap = 0;
 
     u32* L(const Clause& c) { return pool.data() + c.off; }
     const u32* L(const Clause& c) const { return pool.data() + c.off; }
@@ -465,10 +471,52 @@ void freezeClauses(S& s, const OL& poss, const OL& negs) {  // elimination.cuh:8
     for (u32 ci : negs) { Clause& c = s.cls[ci]; if (c.original() && c.molten) c.molten = 0; }
 }
 
+// ------------------------------------------------------------------ device DRAT stream (proofutils.cuh)
+// bytes of the 7-bit variable-length encoding of the ORIGINAL literal (proof.cu:31-41 BLUT, :57-63)
+u32 proofLitBytes(const S& s, u32 lit) {
+    u32 org = V2L(s.vorg[ABS(lit)]) | SIGN(lit);
+    u32 n = 1;
+    while (org & 0xFFFFFF80u) { n++; org >>= 7; }
+    return n;
+}
+// proofutils.cuh:96-121
+void saveProofLiteral(S& s, u32 lit) {
+    u32 org = V2L(s.vorg[ABS(lit)]) | SIGN(lit);
+    while (org & 0xFFFFFF80u) { s.proofCur.push_back(uint8_t((org & 0x7Fu) | 0x80u)); org >>= 7; }
+    s.proofCur.push_back(uint8_t(org));
+}
+// proofutils.cuh:123-170
+void saveProofClause(S& s, const u32* lits, int n, uint8_t state) {
+    s.proofCur.push_back(state);
+    for (int k = 0; k < n; k++) saveProofLiteral(s, lits[k]);
+    s.proofCur.push_back(0);
+}
+void saveProofClause(S& s, const Clause& c, uint8_t state) { saveProofClause(s, s.L(c), c.sz, state); }
+// mergeProof (elimination.cuh:162-215): proof bytes of the resolvent of c1 and c2 on x (prefix + literals + suffix)
+u32 mergeProofBytes(const S& s, u32 x, const Clause& c1, const Clause& c2) {
+    std::vector<u32> out(size_t(c1.sz) + c2.sz);
+    const int n = merge_out(s, x, s.L(c1), c1.sz, s.L(c2), c2.sz, out.data());
+    if (!n) return 0;
+    u32 bytes = 2;
+    for (int k = 0; k < n; k++) bytes += proofLitBytes(s, out[k]);
+    return bytes;
+}
+// the proof guard of the four counting functions (resolve.cuh:66-70, :152-154, elimination.cuh:445-447, function.cuh:232-235)
+bool proofGuard(const S& s, u32 nElements, u32 proofBytes) {
+    return s.proof_en && (nElements > ADDEDCLS_MAX || proofBytes > ADDEDPROOF_MAX);
+}
+// cacheProof + writeProof (proof.cu:160-199, 232-247): the device stream leaves as one chunk
+void flushProof(S& s) {
+    if (!s.proof_en) return;
+    s.proofChunks.push_back(s.proofCur);
+    s.proofCur.clear();
+}
+
 // ------------------------------------------------------------------ resolvent counting
 // resolve.cuh:28-109 (no clause bound) ; returns true if resolvable
 bool countResolvents_simple(S& s, u32 x, const OL& me, const OL& other, u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     const int rlimit = int(s.o.ve_clause_max);
+    u32 proofBytes = 0;
     for (u32 i : me) {
         const Clause& ci = s.cls[i];
         if (ci.learnt()) continue;
@@ -476,6 +524,7 @@ bool countResolvents_simple(S& s, u32 x, const OL& me, const OL& other, u32& nEl
             const Clause& cj = s.cls[j];
             if (cj.learnt()) continue;
             const int rsize = merge_len(s, x, ci, cj);
+            if (rsize && s.proof_en) proofBytes += mergeProofBytes(s, x, ci, cj);
             if (rsize == 1) nElements++;
             else if (rsize) {
                 if (rlimit && rsize > rlimit) return false;
@@ -484,6 +533,7 @@ bool countResolvents_simple(S& s, u32 x, const OL& me, const OL& other, u32& nEl
             }
         }
     }
+    if (proofGuard(s, nElements, proofBytes)) return false;
     if (nAddedCls > ADDEDCLS_MAX || nAddedLits > ADDEDLITS_MAX) return false;
     return true;
 }
@@ -491,6 +541,7 @@ bool countResolvents_simple(S& s, u32 x, const OL& me, const OL& other, u32& nEl
 bool countResolvents(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other, u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     nElements = 0, nAddedCls = 0, nAddedLits = 0;
     const int rlimit = int(s.o.ve_clause_max);
+    u32 proofBytes = 0;
     for (u32 i : me) {
         const Clause& ci = s.cls[i];
         if (ci.learnt()) continue;
@@ -498,6 +549,7 @@ bool countResolvents(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other,
             const Clause& cj = s.cls[j];
             if (cj.learnt()) continue;
             const int rsize = merge_len(s, x, ci, cj);
+            if (rsize && s.proof_en) proofBytes += mergeProofBytes(s, x, ci, cj);
             if (rsize == 1) nElements++;
             else if (rsize) {
                 if (++nAddedCls > nClsBefore || (rlimit && rsize > rlimit)) return false;
@@ -505,6 +557,7 @@ bool countResolvents(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other,
             }
         }
     }
+    if (proofGuard(s, nElements, proofBytes)) return false;
     if (nAddedCls > ADDEDCLS_MAX || nAddedLits > ADDEDLITS_MAX) return false;
     if (s.o.ve_lbound_en) {
         u32 nLitsBefore = 0;
@@ -517,6 +570,7 @@ bool countResolvents(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other,
 // elimination.cuh:365-441 ; returns TRUE when substitution is NOT possible
 bool countSubstituted(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other, u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     const int rlimit = int(s.o.ve_clause_max);
+    u32 proofBytes = 0;
     for (u32 i : me) {
         const Clause& ci = s.cls[i];
         if (ci.learnt()) continue;
@@ -525,6 +579,7 @@ bool countSubstituted(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other
             const Clause& cj = s.cls[j];
             if (cj.original() && ci_m != bool(cj.molten)) {
                 const int rsize = merge_len(s, x, ci, cj);
+                if (rsize && s.proof_en) proofBytes += mergeProofBytes(s, x, ci, cj);
                 if (rsize == 1) nElements++;
                 else if (rsize) {
                     if (++nAddedCls > nClsBefore || (rlimit && rsize > rlimit)) return true;
@@ -533,6 +588,7 @@ bool countSubstituted(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other
             }
         }
     }
+    if (proofGuard(s, nElements, proofBytes)) return true;
     if (nAddedCls > ADDEDCLS_MAX || nAddedLits > ADDEDLITS_MAX) return true;
     if (s.o.ve_lbound_en) {
         u32 nLitsBefore = 0;
@@ -545,6 +601,7 @@ bool countSubstituted(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other
 // function.cuh:181-257 ; TRUE when not possible
 bool countCoreSubstituted(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& other, u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     const int rlimit = int(s.o.ve_clause_max);
+    u32 proofBytes = 0;
     for (u32 i : me) {
         const Clause& ci = s.cls[i];
         if (ci.learnt()) continue;
@@ -553,6 +610,7 @@ bool countCoreSubstituted(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& o
             const Clause& cj = s.cls[j];
             if (cj.original() && (!ci_m || !cj.molten)) {
                 const int rsize = merge_len(s, x, ci, cj);
+                if (rsize && s.proof_en) proofBytes += mergeProofBytes(s, x, ci, cj);
                 if (rsize == 1) nElements++;
                 else if (rsize) {
                     if (++nAddedCls > nClsBefore || (rlimit && rsize > rlimit)) return true;
@@ -561,6 +619,7 @@ bool countCoreSubstituted(S& s, u32 x, u32 nClsBefore, const OL& me, const OL& o
             }
         }
     }
+    if (proofGuard(s, nElements, proofBytes)) return true;
     if (nAddedCls > ADDEDCLS_MAX || nAddedLits > ADDEDLITS_MAX) return true;
     if (s.o.ve_lbound_en) {
         u32 nLitsBefore = 0;
@@ -636,6 +695,10 @@ void substitute_single(S& s, u32 p, u32 n, u32 def, const OL& poss, const OL& ne
     if (nPosUnits || nNegUnits) {
         if (nNegUnits) appendUnits(s, negs);
         if (nPosUnits) appendUnits(s, poss);
+    }
+    if (s.proof_en) {   // equivalence.cuh:100-109, addProof proofutils.cuh:172-180
+        for (u32 ci : negs) if (s.cls[ci].original()) saveProofClause(s, s.cls[ci], PROOF_ADDED);
+        for (u32 ci : poss) if (s.cls[ci].original()) saveProofClause(s, s.cls[ci], PROOF_ADDED);
     }
 }
 
@@ -967,7 +1030,12 @@ void emit_resolvents(S& s, u32 x, u32 elimType, u32 nAddedCls, u32 addedPos, u64
             out.resize(size_t(ci.sz) + cj.sz);
             const int rsize = merge_out(s, x, s.L(ci), ci.sz, s.L(cj), cj.sz, out.data());
             if (!rsize) continue;
-            if (rsize == 1) { s.units.push_back(out[0]); continue; }
+            if (rsize == 1) {   // bounded.cuh:76-81, 99-105: unit + saveProofUnit
+                s.units.push_back(out[0]);
+                if (s.proof_en) saveProofClause(s, out.data(), 1, PROOF_ADDED);
+                continue;
+            }
+            if (s.proof_en) saveProofClause(s, out.data(), rsize, PROOF_ADDED);   // bounded.cuh:91-92, 117-118
             // new SCLAUSE: ORIGINAL, added, sorted, sig (bounded.cuh:86-120)
             Clause a;
             a.st = ORIGINAL, a.molten = 0, a.added = 1, a.usage = 0, a.lbd = 0, a.sig = 0, a.sz = rsize;
@@ -1141,6 +1209,19 @@ void updateOL(S& s, OL& ol) {
     }
     ol.resize(j);
 }
+// saveProof (proofutils.cuh:182-200): the list filter of updateOL plus the proof lines - a strengthened
+// (molten) clause is ADDED in its new form, a subsumed one DELETED; a clause that is both gets both lines
+void saveProofSub(S& s, OL& ol) {
+    size_t j = 0;
+    for (size_t i = 0; i < ol.size(); i++) {
+        Clause& c = s.cls[ol[i]];
+        const bool deleted = c.deleted();
+        if (c.molten) { saveProofClause(s, c, PROOF_ADDED); c.molten = 0; }
+        else if (!deleted) ol[j++] = ol[i];
+        if (deleted) saveProofClause(s, c, PROOF_DELETED);
+    }
+    ol.resize(j);
+}
 // subsume.cuh:402-484
 void SUB(S& s) {
     for (u32 tid = 0; tid < s.numElected; tid++) {
@@ -1166,8 +1247,8 @@ void SUB(S& s) {
             if (nPosUnits) appendUnits(s, poss);
             if (nNegUnits) appendUnits(s, negs);
         }
-        updateOL(s, poss);
-        updateOL(s, negs);
+        if (s.proof_en) { saveProofSub(s, poss); saveProofSub(s, negs); }   // subsume.cuh:465-475
+        else { updateOL(s, poss); updateOL(s, negs); }
     }
 }
 
@@ -1186,7 +1267,11 @@ void BCE(S& s) {
                 if (cj.deleted() || cj.learnt()) continue;
                 if (!isTautology(s, x, ci, cj)) { allTautology = false; break; }
             }
-            if (allTautology) { saveClause(s, ci, n); ci.st = DELETED; }
+            if (allTautology) {
+                saveClause(s, ci, n);
+                if (s.proof_en) saveProofClause(s, ci, PROOF_DELETED);   // blocked.cuh:67-72
+                ci.st = DELETED;
+            }
         }
     }
 }
@@ -1209,6 +1294,7 @@ void forward_equ(S& s, const u32* m_c, int m_len, u32 type) {
             if (m_len == c.sz && (c.learnt() || c.st == type) && SUBSIG(m_sig, c.sig) && !c.deleted() &&
                 std::equal(m_c, m_c + m_len, s.L(c))) {
                 c.st = DELETED;
+                if (s.proof_en) saveProofClause(s, c, PROOF_DELETED);   // redundancy.cuh:122-129
                 break;
             }
         }
@@ -1275,6 +1361,11 @@ void simplifying(S& s) {
     s.data_cap = numCls * NBUCKETS + numLits;
     s.numClauses = C0, s.numLiterals = L0;
     prepCNF(s);
+    if (s.proof_en) {   // cuPROOF::count (proof.cu:101-121): bytes of every literal of the formula, x 1.5 (simplify.cu:128-132)
+        u64 bytes = 0;
+        for (const Clause& c : s.cls) for (int k = 0; k < c.sz; k++) bytes += proofLitBytes(s, s.L(c)[k]);
+        s.proofCap = u32(double(u32(bytes)) * 1.5);
+    }
     s.phase = s.multiplier = 0;
     i64 cdiff = INT64_MAX, ldiff = INT64_MAX;
     i64 clsbefore = i64(s.numClauses), litsbefore = i64(s.numLiterals);
@@ -1286,12 +1377,13 @@ void simplifying(S& s) {
         if (!s.numClauses) break;
         if (!LCVE(s)) break;
         sortOT(s);
-        if (stop(s, cdiff, ldiff)) { if (s.o.ere_en && s.numElected) ERE(s); break; }
+        if (stop(s, cdiff, ldiff)) { if (s.o.ere_en && s.numElected) { ERE(s); flushProof(s); } break; }   // elimination.cu:305-306
         const u64 clsBeforeVE = s.cls.size();
         const u32 electedNow = s.numElected;
         if (s.o.sub_en || s.o.ve_plus_en) SUB(s);
         if (s.o.ve_en) VE(s);
         if (s.o.bce_en && !s.elected.empty()) BCE(s);
+        flushProof(s);                     // cacheProof :174 ... writeProof :184
         u64 nc, nl;
         countAll(s, nc, nl);
         const u32 remained = u32(s.elected.size());
@@ -1440,6 +1532,14 @@ void oracle_copy_result(const oracle_ctx* s, uint32_t* bits, uint32_t* sig, uint
 }
 
 void oracle_keep_snapshots(oracle_ctx* s, int keep) { s->keep_snaps = keep != 0; }
+void oracle_enable_proof(oracle_ctx* s, int on) { s->proof_en = on != 0; }
+int oracle_proof_chunks(const oracle_ctx* s) { return int(s->proofChunks.size()); }
+uint64_t oracle_proof_chunk_size(const oracle_ctx* s, int i) { return s->proofChunks[size_t(i)].size(); }
+void oracle_copy_proof_chunk(const oracle_ctx* s, int i, uint8_t* out) {
+    const std::vector<uint8_t>& c = s->proofChunks[size_t(i)];
+    if (!c.empty()) memcpy(out, c.data(), c.size());
+}
+uint32_t oracle_proof_capacity(const oracle_ctx* s) { return s->proofCap; }
 // incremental solving: variables under assumption are never candidates (Solver::LCVE, lcve.cu:316-323, lcve_k :88)
 void oracle_set_assumed(oracle_ctx* s, const uint8_t* assumed) {
     if (assumed) s->assumed.assign(assumed, assumed + s->V + 1); else s->assumed.clear();

@@ -75,6 +75,15 @@ void oracle_copy_result(const oracle_ctx* c, uint32_t* bits, uint32_t* sig, uint
                         uint32_t* lits, uint8_t* eliminated, uint32_t* resolved, uint32_t* trail);
 /* snapshot of the live clauses after round r (only kept when keep_snapshots != 0) */
 void oracle_keep_snapshots(oracle_ctx* c, int keep);
+/* Device DRAT stream (-proof: src/gpu/proof.cu, proofutils.cuh): enable before oracle_run.  One chunk
+ * per cacheProof/writeProof pair (a SUB/BVE/BCE round, simplify.cu:174-184; the ERE round,
+ * elimination.cu:305-306), in binary DRAT: 'a'|'d', 7-bit varints of the ORIGINAL literals, 0.
+ * Also activates the proof guards of the BVE counting functions (resolve.cuh:66-70). */
+void oracle_enable_proof(oracle_ctx* c, int on);
+int  oracle_proof_chunks(const oracle_ctx* c);
+uint64_t oracle_proof_chunk_size(const oracle_ctx* c, int i);
+void oracle_copy_proof_chunk(const oracle_ctx* c, int i, uint8_t* out);
+uint32_t oracle_proof_capacity(const oracle_ctx* c);   /* 1.5 x proof bytes of the input literals (simplify.cu:128-132) */
 /* assumed[max_var+1]: variables under assumption (incremental mode) are never elected; NULL clears */
 void oracle_set_assumed(oracle_ctx* c, const uint8_t* assumed);
 uint64_t oracle_snapshot_clauses(const oracle_ctx* c, int round);

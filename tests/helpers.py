@@ -83,6 +83,11 @@ def oracle_lib():
         lib.oracle_num_elections.argtypes = [P]; lib.oracle_num_elections.restype = C.c_int
         lib.oracle_election_size.argtypes = [P, C.c_int]; lib.oracle_election_size.restype = C.c_uint64
         lib.oracle_copy_election.argtypes = [P, C.c_int, _u32p]
+        lib.oracle_enable_proof.argtypes = [P, C.c_int]
+        lib.oracle_proof_chunks.argtypes = [P]; lib.oracle_proof_chunks.restype = C.c_int
+        lib.oracle_proof_chunk_size.argtypes = [P, C.c_int]; lib.oracle_proof_chunk_size.restype = C.c_uint64
+        lib.oracle_copy_proof_chunk.argtypes = [P, C.c_int, _u8p]
+        lib.oracle_proof_capacity.argtypes = [P]; lib.oracle_proof_capacity.restype = C.c_uint32
         lib.oracle_prep.argtypes = [C.c_uint64, _u32p, _u64p, _u32p]
         lib.oracle_histogram.argtypes = [C.c_uint64, _u32p, C.c_uint32, _u32p]
         lib.oracle_extend_model.argtypes = [_u8p, C.c_uint32, _u32p, C.c_uint64]; lib.oracle_extend_model.restype = C.c_uint64
@@ -129,8 +134,9 @@ def make_oracle_opts(**over) -> OracleOpts:
     return o
 
 
-def run_oracle(max_var, lits, offs, meta=None, snapshots=False, vorg=None, vstate=None, assumed=None, **over):
-    """Run the CPU oracle -> (Dump, round_stats uint64[R,5], [snapshot Dumps])."""
+def run_oracle(max_var, lits, offs, meta=None, snapshots=False, vorg=None, vstate=None, assumed=None, proof=False, **over):
+    """Run the CPU oracle -> (Dump, round_stats uint64[R,5], [snapshot Dumps]).
+    proof=True: the device DRAT stream is on; Dump.extra["proof"] = list of chunks (bytes), extra["proof_cap"]."""
     lib = oracle_lib()
     o = make_oracle_opts(**over)
     h = C.c_void_p()
@@ -145,6 +151,7 @@ def run_oracle(max_var, lits, offs, meta=None, snapshots=False, vorg=None, vstat
     lib.oracle_create(C.byref(o), max_var, len(offs) - 1, lits, offs, meta_p, ptr[0], ptr[1], C.byref(h))
     try:
         lib.oracle_keep_snapshots(h, int(snapshots))
+        lib.oracle_enable_proof(h, int(proof))
         if keep[2] is not None:
             lib.oracle_set_assumed(h, ptr[2])
         state = lib.oracle_run(h)
@@ -175,6 +182,110 @@ def run_oracle(max_var, lits, offs, meta=None, snapshots=False, vorg=None, vstat
                 lib.oracle_copy_election(h, i, e)
                 elections.append(e)
             d.extra["elections"] = elections
+        if proof:
+            chunks = []
+            for i in range(lib.oracle_proof_chunks(h)):
+                b = np.empty(lib.oracle_proof_chunk_size(h, i), np.uint8)
+                if len(b):
+                    lib.oracle_copy_proof_chunk(h, i, b)
+                chunks.append(b.tobytes())
+            d.extra["proof"] = chunks
+            d.extra["proof_cap"] = lib.oracle_proof_capacity(h)
     finally:
         lib.oracle_destroy(h)
     return d, rs, snaps
+
+
+# ------------------------------------------------------------------ DRAT (binary) helpers for the proof-stream tests
+def drat_parse(chunk: bytes):
+    """binary DRAT -> [(b'a'|b'd', tuple of literals in the 2*var+sign encoding)]  (proof.cu:123-157 is the reader)"""
+    out = []
+    i, n = 0, len(chunk)
+    while i < n:
+        kind = chunk[i:i + 1]
+        assert kind in (b"a", b"d"), f"bad line prefix {kind!r} at byte {i}"
+        i += 1
+        lits = []
+        while True:
+            assert i < n, "truncated proof line"
+            if chunk[i] == 0:
+                i += 1
+                break
+            v, shift = 0, 0
+            while True:
+                b = chunk[i]; i += 1
+                v |= (b & 0x7F) << shift
+                shift += 7
+                if not (b & 0x80):
+                    break
+            lits.append(v)
+        assert lits, "empty proof clause"
+        out.append((kind, tuple(lits)))
+    return out
+
+
+def drat_canonical(chunk: bytes):
+    """order-free form of a chunk: sorted (kind, sorted literals) lines - the reference appends the lines of
+    different variables in whatever order their threads reserve space (cuVecB::jump)."""
+    return sorted((k, tuple(sorted(l))) for k, l in drat_parse(chunk))
+
+
+class RupChecker:
+    """Forward DRAT check, additions only by reverse unit propagation (every line the simplifier adds -
+    strengthened clauses, substituted clauses, resolvents - is RUP).  Small formulas only: naive propagation."""
+
+    def __init__(self, clauses):
+        self.db = {}
+        for c in clauses:
+            self._add(tuple(sorted(set(c))))
+
+    def _add(self, c):
+        self.db[c] = self.db.get(c, 0) + 1
+
+    def has(self, c):
+        return self.db.get(tuple(sorted(set(c))), 0) > 0
+
+    def delete(self, c):
+        c = tuple(sorted(set(c)))
+        if self.db.get(c, 0) <= 0:
+            return False
+        self.db[c] -= 1
+        if not self.db[c]:
+            del self.db[c]
+        return True
+
+    def rup(self, c):
+        """True iff unit propagation on the database refutes the negation of clause c."""
+        cs = set(c)
+        if any((l ^ 1) in cs for l in cs):
+            return True   # tautology
+        assign = {l >> 1: (l & 1) for l in cs}   # every literal of c false: var = sign bit (2v+1 = negative literal)
+
+        def val(l):
+            a = assign.get(l >> 1)
+            return None if a is None else (a == 1 - (l & 1))
+
+        changed = True
+        while changed:
+            changed = False
+            for cl in self.db:
+                unassigned, n_un, sat = None, 0, False
+                for l in cl:
+                    v = val(l)
+                    if v is True:
+                        sat = True
+                        break
+                    if v is None:
+                        n_un += 1
+                        unassigned = l
+                if sat:
+                    continue
+                if n_un == 0:
+                    return True   # conflict
+                if n_un == 1:
+                    assign[unassigned >> 1] = 1 - (unassigned & 1)
+                    changed = True
+        return False
+
+    def add(self, c):
+        self._add(tuple(sorted(set(c))))
