@@ -67,6 +67,7 @@ typedef struct sigma_opts {
     int32_t  final_gc;          /* compact before store (simplify(skip_transfer_to_host)) */
     int32_t  profile;           /* -profilegpu: per-stage CUDA-event times */
     int32_t  aggr_cnf_sort;     /* -aggresivesort (off): clauses leave in OLIST_CMP order (cnf.cu:232-233, key.cuh:67-83) */
+    int32_t  proof_en;          /* -proof (off): device DRAT stream (proof.cu, proofutils.cuh); set before sigma_load */
 } sigma_opts;
 
 /* Per-round report; replaces the LOG2 lines + inf.* updates of simplify.cu:163-186. */
@@ -159,6 +160,23 @@ int  sigma_store(sigma_ctx* c, uint32_t* bits, uint32_t* sig, uint64_t* offs, ui
                  uint8_t* eliminated, uint32_t* resolved, uint32_t* trail);
 /* the reference's own record stream {bits, sig, size, lits...} + uint64 refs, for newClause(SCLAUSE&) */
 int  sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t* refs);
+
+/* Device DRAT proof stream; replaces cuPROOF (src/gpu/proof.cuh:30-71, proof.cu) and the proof hooks of
+ * sub_k / ve_k_1 / ve_k_2 / bce_k / ere_k (proofutils.cuh).  With opts.proof_en the kernels append binary
+ * DRAT lines - 'a' | 'd', the ORIGINAL literals (vorg) as 7-bit varints, 0 - to a device buffer of the
+ * reference's capacity (1.5 x the proof bytes of the input literals, simplify.cu:128-132; exceeding it is
+ * SIGMA_OVERFLOW where the reference only asserts).  Lines: strengthened clauses added and subsumed ones
+ * deleted (SUB), substituted clauses and resolvents added (BVE), blocked (BCE) and redundant (ERE) clauses
+ * deleted.  Once per round - where the reference runs cacheProof + writeProof (simplify.cu:174-184,
+ * elimination.cu:305-306) - the stream is copied to pinned host memory as one chunk, handed to the sink
+ * (the shim forwards it byte by byte to PROOF::write, proof.cu:185-190) and kept until the next sigma_begin.
+ * The order of the lines of different variables inside a stage is unspecified, as in the reference
+ * (threads reserve space with cuVecB::jump). */
+typedef void (*sigma_proof_sink)(void* user, const uint8_t* bytes, uint64_t num_bytes);
+int  sigma_set_proof_sink(sigma_ctx* c, sigma_proof_sink sink, void* user);
+int  sigma_proof_chunks(const sigma_ctx* c, uint32_t* num_chunks, uint64_t* total_bytes, uint32_t* capacity);
+int  sigma_proof_chunk_size(const sigma_ctx* c, uint32_t chunk, uint64_t* num_bytes);
+int  sigma_proof_chunk_copy(const sigma_ctx* c, uint32_t chunk, uint8_t* out);
 
 /* parity / debugging */
 int  sigma_snapshot(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals);   /* sizes of the live CNF now */

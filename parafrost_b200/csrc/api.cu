@@ -152,6 +152,8 @@ extern "C" int sigma_destroy(sigma_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->arena) cudaFree(c->arena);
     if (c->hdc) cudaFreeHost(c->hdc);
+    if (c->proofHost) cudaFreeHost(c->proofHost);
+    free(c->proofAll); free(c->proofEnds);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evRun0) cudaEventDestroy(c->evRun0);
@@ -212,6 +214,8 @@ static size_t carve(Ctx* c, char* base) {
     c->flagA = a.take<u32>(nflag); c->flagB = a.take<u32>(nflag); c->flag64 = a.take<u64>(capC + 2);
     c->radixHist = a.take<u32>(256 * radixBlocks);
     c->qMed = a.take<u32>(ND);
+    if (c->proofCarved) { c->proofBuf = a.take<unsigned char>(c->proofPhys + 64); c->proofSnap = a.take<u32>(capC / 32 + 2); }
+    else { c->proofBuf = nullptr; c->proofSnap = nullptr; }
     c->dc = a.take<DevCounters>(1);
     return a.off + 256;
 }
@@ -222,7 +226,20 @@ __global__ void k_iota(u32* __restrict__ a, u32 n) {
 
 // ------------------------------------------------------------------ load
 // sizes the logical capacities and the arena for a formula of num_clauses clauses / L0 literals
-static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u64 orgC, u64 orgL) {
+static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u64 orgC, u64 orgL, const uint32_t* vorg) {
+    // device DRAT stream: the logical capacity is the reference's (1.5 x the proof bytes of the input literals, counted on
+    // the device at sigma_begin); the buffer is sized here from the widest literal, which bounds it
+    c->proofCarved = c->o.proof_en != 0;
+    if (c->proofCarved) {
+        u32 maxOrg = max_var;
+        if (vorg) { maxOrg = 1; for (size_t v = 1; v <= max_var; v++) if (vorg[v] > maxOrg) maxOrg = vorg[v]; }
+        if (maxOrg >= (1u << 30)) return SIGMA_BAD_ARGUMENT;
+        u32 widest = 2 * maxOrg + 1, b = 1;
+        while (widest & 0xFFFFFF80u) { b++; widest >>= 7; }
+        c->proofBMax = b;
+        c->proofPhys = (u64)(1.5 * (double)b * (double)L0) + 16;
+        if (c->proofPhys >= 0xFFFFFF00ull) return SIGMA_AWAKEN_FAIL;   // the reference's proof capacity is a uint32 (simplify.cu:130)
+    }
     // election words carry a 27-bit rank (lcve.cu); clause indices are 32-bit
     if (max_var >= (1u << 27) - 2 || num_clauses >= 0xFFFFFFF0ull) return SIGMA_BAD_ARGUMENT;
     c->V = max_var; c->ND = 2 * (max_var + 1);
@@ -264,6 +281,11 @@ static int finishLoad(Ctx* c, const uint32_t* vorg, const uint8_t* vstate, const
     else CUDA_TRY(cudaMemsetAsync(c->vstate0, 0, V1, c->stream));
     if (assumed) CUDA_TRY(cudaMemcpyAsync(c->assumed, assumed, V1, cudaMemcpyHostToDevice, c->stream));
     else c->assumed = nullptr;
+    if (c->proofCarved && c->proofHostCap < c->proofPhys) {   // pinned mirror of the device stream (cuPROOF::alloc, proof.cu:201-230)
+        if (c->proofHost) { cudaFreeHost(c->proofHost); c->proofHost = nullptr; c->proofHostCap = 0; }
+        CUDA_TRY(cudaMallocHost(&c->proofHost, c->proofPhys));
+        c->proofHostCap = c->proofPhys;
+    }
     i64 un = c->V;
     if (vstate) for (size_t v = 1; v < V1; v++) if (vstate[v]) un--;
     c->unassigned0 = un;
@@ -284,7 +306,7 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
         orgC = 0; orgL = 0;
         for (u64 i = 0; i < num_clauses; i++) if (!(meta[i] & CB_LEARNT)) { orgC++; orgL += offs[i + 1] - offs[i]; }
     }
-    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL);
+    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL, vorg);
     if (rc) return rc;
     // host -> device (extractCNF + reflectCNF, cnf.cu:166-184)
     CUDA_TRY(cudaMemcpyAsync(c->inLits, lits, L0 * 4, cudaMemcpyHostToDevice, c->stream));
@@ -325,7 +347,7 @@ extern "C" int sigma_load_sclauses(sigma_ctx* c, uint32_t max_var, uint64_t num_
         if (r + NBUCKETS > num_words) return SIGMA_BAD_ARGUMENT;
         if ((data_words[r] & CB_ST_MASK) == 0) { orgC++; orgL += data_words[r + 2]; }
     }
-    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL);
+    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL, vorg);
     if (rc) return rc;
     // the reference's own two copies (reflectCNF, cnf.cu:166-174): record stream and refs, staged in
     // the inactive clause buffer, then unpacked on the device
@@ -353,6 +375,7 @@ static KOpts makeK(Ctx* c) {
     k.sh_max_bve_out1 = c->o.sh_max_bve_out1; k.ere_clause_max = c->o.ere_clause_max;
     k.ve_fun_en = c->o.ve_fun_en && !c->varcoreDead; k.ve_lbound_en = c->o.ve_lbound_en; k.in_mode = c->o.sigma_calls > 1;
     k.refsCap = (u32)c->refsCap; k.dataCap = c->dataCap;
+    k.proof_en = c->o.proof_en && c->proofCarved;
     return k;
 }
 
@@ -384,6 +407,11 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     c->hdc->lastElimID = -1; c->hdc->misStopRank = NOVAR;
     for (int i = 0; i < 12; i++) c->hdc->froz12[i] = NOVAR;
     CUDA_TRY(cudaMemcpyAsync(c->dc, c->hdc, sizeof(DevCounters), cudaMemcpyHostToDevice, c->stream));
+    c->proofAllSize = 0; c->nProofChunks = 0;
+    if (c->o.proof_en) {
+        if (!c->proofCarved) { snprintf(c->err, sizeof c->err, "proof_en must be set before sigma_load (the stream buffer is carved with the arena)"); return SIGMA_BAD_ARGUMENT; }
+        launchProofCount(c);   // cuPROOF::count + the 1.5 x capacity (simplify.cu:128-132)
+    }
     CUDA_TRY(cudaMemcpyAsync(c->vstate, c->vstate0, V1, cudaMemcpyDeviceToDevice, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->eliminated, 0, V1, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->varcore, 0xFF, V1 * 4, c->stream));
@@ -397,6 +425,45 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     if (!c->C0) c->loopDone = true;
     // alldisabled (solver.hpp:722)
     if (!c->o.phases && !(c->o.all_en | c->o.ere_en)) c->loopDone = true;
+    return SIGMA_OK;
+}
+
+// cuPROOF::cacheProof + writeProof (proof.cu:160-199, 232-247): the round's device stream -> pinned host -> sink + chunk
+// store; c->hdc must be fresh (syncCounters).  Also the place where the proof-mode failures surface.
+static int flushProof(Ctx* c) {
+    if (!c->o.proof_en) return SIGMA_OK;
+    const u32 n = c->hdc->proofSize;
+    if ((c->hdc->flags & 32u) || n > c->hdc->proofCap) {
+        snprintf(c->err, sizeof c->err, "proof stream overflow: %u bytes in one round, capacity %u (the reference only asserts, vector.cu)", n, c->hdc->proofCap);
+        return SIGMA_OVERFLOW;
+    }
+    if (c->hdc->flags & 16u) {
+        snprintf(c->err, sizeof c->err, "a BVE candidate is large enough to trip the proof guard (ADDEDPROOF_MAX, resolve.cuh:66-70): not supported with proof_en");
+        return SIGMA_OVERFLOW;
+    }
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(c->proofHost, c->proofBuf, n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemsetAsync(&c->dc->proofSize, 0, 4, c->stream));   // header.clear() (proof.cu:239-240)
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->hdc->proofSize = 0;
+        if (c->proofAllSize + n > c->proofAllCap) {
+            u64 cap = c->proofAllCap ? c->proofAllCap * 2 : (1u << 16);
+            while (cap < c->proofAllSize + n) cap *= 2;
+            unsigned char* p = (unsigned char*)realloc(c->proofAll, cap);
+            if (!p) return SIGMA_AWAKEN_FAIL;
+            c->proofAll = p; c->proofAllCap = cap;
+        }
+        memcpy(c->proofAll + c->proofAllSize, c->proofHost, n);
+        c->proofAllSize += n;
+    }
+    if (c->nProofChunks == c->capProofChunks) {
+        const u32 cap = c->capProofChunks ? c->capProofChunks * 2 : 16;
+        u64* p = (u64*)realloc(c->proofEnds, cap * sizeof(u64));
+        if (!p) return SIGMA_AWAKEN_FAIL;
+        c->proofEnds = p; c->capProofChunks = cap;
+    }
+    c->proofEnds[c->nProofChunks++] = c->proofAllSize;
+    if (n && c->proofSink) c->proofSink(c->proofUser, c->proofHost, n);
     return SIGMA_OK;
 }
 
@@ -512,11 +579,13 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     if (!stop) { StageTimer t(c, ST_SOT); launchSortOT(c, 1); }
     if (stop) {
         r.kind = 1;
-        if (c->o.ere_en && c->numElected) { StageTimer t(c, ST_ERE); launchERE(c, k); }
+        const bool ereRan = c->o.ere_en && c->numElected;
+        if (ereRan) { StageTimer t(c, ST_ERE); launchERE(c, k); }
         c->loopDone = true;
         launchCount(c);
         if ((rc = syncCounters(c))) return rc;
         c->countsFresh = true;
+        if (ereRan && (rc = flushProof(c))) return rc;   // elimination.cu:305-306
         r.clauses = c->hdc->liveCls; r.literals = c->hdc->liveLits;
         r.ms = (float)(nowMs() - t0);
         pushRound(c, r); if (rep) *rep = r;
@@ -534,6 +603,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     if ((rc = syncCounters(c))) return rc;
     c->countsFresh = true;
     if (c->hdc->flags & 3u) { snprintf(c->err, sizeof c->err, "device vector overflow (flags %u)", c->hdc->flags); return SIGMA_OVERFLOW; }
+    if ((rc = flushProof(c))) return rc;   // cacheProof / writeProof, simplify.cu:174-184
     // updateNumPVs (simplify.cu:35-41)
     const u32 remained = c->o.ve_en ? c->hdc->numElected : c->numElected;
     r.eliminated = c->lastElectedCount - remained;
@@ -607,6 +677,31 @@ extern "C" int sigma_round_reports(const sigma_ctx* c, sigma_round_report* out, 
     if (!c || !out) return SIGMA_BAD_ARGUMENT;
     const u32 n = c->nRounds < max_rounds ? c->nRounds : max_rounds;
     memcpy(out, c->rounds, n * sizeof(sigma_round_report));
+    return SIGMA_OK;
+}
+
+// ------------------------------------------------------------------ proof stream (host side)
+extern "C" int sigma_set_proof_sink(sigma_ctx* c, sigma_proof_sink sink, void* user) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    c->proofSink = sink; c->proofUser = user;
+    return SIGMA_OK;
+}
+extern "C" int sigma_proof_chunks(const sigma_ctx* c, uint32_t* num_chunks, uint64_t* total_bytes, uint32_t* capacity) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    if (num_chunks) *num_chunks = c->nProofChunks;
+    if (total_bytes) *total_bytes = c->proofAllSize;
+    if (capacity) *capacity = c->hdc ? c->hdc->proofCap : 0;
+    return SIGMA_OK;
+}
+extern "C" int sigma_proof_chunk_size(const sigma_ctx* c, uint32_t chunk, uint64_t* num_bytes) {
+    if (!c || !num_bytes || chunk >= c->nProofChunks) return SIGMA_BAD_ARGUMENT;
+    *num_bytes = c->proofEnds[chunk] - (chunk ? c->proofEnds[chunk - 1] : 0);
+    return SIGMA_OK;
+}
+extern "C" int sigma_proof_chunk_copy(const sigma_ctx* c, uint32_t chunk, uint8_t* out) {
+    if (!c || !out || chunk >= c->nProofChunks) return SIGMA_BAD_ARGUMENT;
+    const u64 lo = chunk ? c->proofEnds[chunk - 1] : 0;
+    memcpy(out, c->proofAll + lo, c->proofEnds[chunk] - lo);
     return SIGMA_OK;
 }
 

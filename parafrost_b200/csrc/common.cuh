@@ -101,7 +101,8 @@ struct DevCounters {
     u32 wlNext;        // MIS worklist append cursor
     u32 wlCnt[3];      // rotating MIS worklist sizes (lcve.cu)
     u32 firstStop;     // rank of the first bound-violating candidate (lcve.cu)
-    u32 flags;         // bit0: resolved overflow, bit1: units overflow, bit2: hole after failed MEMORY_SAFE, bit3: a clause with >= 2^14 literals
+    u32 flags;         // bit0: resolved overflow, bit1: units overflow, bit2: hole after failed MEMORY_SAFE, bit3: a clause with >= 2^14 literals,
+                       // bit4: a BVE candidate could trip the proof guard (resolve.cuh:66-70), bit5: proof stream overflow
     u32 bcpCurr, bcpNext, bcpConfl, bcpLevel;
     u32 nFrozen;       // number of first-frozen variables mapped into varcore (<= 12 needed)
     u32 unassignedDec; // variables assigned by prop()
@@ -110,12 +111,16 @@ struct DevCounters {
     u32 bin[4];        // group-size class sizes of the elected variables (elim.cu) + redo queue
     u32 scratch[16];   // 0,1 scan totals; 2 MIS push count; 3,4 ERE queue count / overflow; 5 load check; 6 max score; 7 big-bucket units; 8 MIS_HALF count; 9 freezer count
     u32 froz12[12];    // variables currently holding a function-table index in varcore
+    // device DRAT stream (elim.cu, proof kernels): bytes appended this round, the reference's capacity, units mark
+    u32 proofSize, proofCap, proofUnits0, proofPad;
+    u64 proofLitBytes; // proof bytes of every literal of the loaded formula (cuPROOF::count, proof.cu:101-121)
 };
 
 struct KOpts {   // kernel-side options (replaces __constant__ kOpts, options.cuh:27-45)
     u32 ve_clause_max, xor_max_arity, sub_max_occurs, ere_max_occurs, bce_max_occurs, sh_max_bve_out1;
     int ere_clause_max;
     int ve_fun_en, ve_lbound_en, in_mode;
+    int proof_en;      // opts.proof_en: SUB leaves the molten marks for the proof pass
     u32 refsCap;       // logical refs capacity
     u64 dataCap;       // logical data capacity (words)
 };
@@ -176,6 +181,11 @@ struct Ctx {
     i64 unassigned0;   // unassigned variables of the loaded formula (inf.unassigned)
     // per-kernel CUDA-event timing (sigma_kernel_profile): event pairs recorded on the launch stream
     bool ktOn; cudaEvent_t* ktEv; int* ktId; u32 ktUsed;
+    // device DRAT stream: device buffer + deleted-flag snapshot (arena), pinned staging, host chunk store
+    unsigned char* proofBuf; u32* proofSnap; u64 proofPhys; u32 proofBMax; bool proofCarved;
+    unsigned char* proofHost; u64 proofHostCap;
+    unsigned char* proofAll; u64 proofAllSize, proofAllCap; u64* proofEnds; u32 nProofChunks, capProofChunks;
+    sigma_proof_sink proofSink; void* proofUser;
     float ktMs[KT_MAX_KERNELS]; u32 ktCount[KT_MAX_KERNELS];
 };
 
@@ -265,5 +275,6 @@ void launchSUB(Ctx* c, const KOpts& k);
 void launchVE(Ctx* c, const KOpts& k);
 void launchBCE(Ctx* c, const KOpts& k);
 void launchERE(Ctx* c, const KOpts& k);
+void launchProofCount(Ctx* c);   // cuPROOF::count: dc->proofLitBytes, dc->proofCap
 // api.cu
 int  syncCounters(Ctx* c);   // D2H of DevCounters into c->hdc, stream synchronised

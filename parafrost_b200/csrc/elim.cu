@@ -914,7 +914,7 @@ template <int GS> __device__ void updateOL(GT<GS>& g, u32 lit) {
         if (j < n) {
             ci = list[j];
             const u32 w = g.hdr[ci].w;
-            if (C_MOLTEN(w)) g.hdr[ci].w = w & ~CB_MOLTEN;
+            if (C_MOLTEN(w)) { if (!g.k.proof_en) g.hdr[ci].w = w & ~CB_MOLTEN; }   // proof mode: k_proof_stream prints, then freezes
             else if (!C_DELETED(w)) keep = true;
         }
         const u32 m = BALLOT(keep);
@@ -1339,6 +1339,154 @@ static void binElected(Ctx* c, const KOpts& k, bool countOnDevice, bool byShape 
         shapeSort(c, c->wlB, &c->dc->bin[1], c->numElected);
     }
 }
+
+// ------------------------------------------------------------------ device DRAT stream (proof.cu, proofutils.cuh)
+// The reference threads proof code through every elimination kernel (count the bytes, reserve with
+// cuVecB::jump, write).  Here the hot kernels stay as they are and the lines are produced by small passes
+// that run only with opts.proof_en, right after the stage whose effect they record:
+//   SUB   k_proof_stream(MOLTEN) : a strengthened clause still carries its molten mark (k_sub keeps it in proof
+//                                  mode) -> 'a' line with the new literals, mark cleared (saveProof, proofutils.cuh:182-200)
+//         k_proof_stream(NEWDEL) : clauses deleted since the k_proof_snap bitmap -> 'd' lines
+//   BVE   k_proof_equ            : clauses rewritten by an equivalence substitution -> 'a' (addProof, equivalence.cuh:100-109)
+//         k_proof_units, k_proof_stream(RANGE) : the resolvents of phase 3, units and clauses -> 'a' (bounded.cuh:76-120)
+//   BCE / ERE  k_proof_snap + k_proof_stream(NEWDEL) -> 'd' (blocked.cuh:67-72, redundancy.cuh:122-129)
+// All of them stream headers (16 B per clause) and touch literals only of the clauses they print.  A warp sizes its
+// 32 lines, reserves their bytes with ONE atomic on dc->proofSize and writes them in order.
+struct ProofOut { unsigned char* buf; };
+#define PROOF_MOLTEN 1u
+#define PROOF_NEWDEL 2u
+#define PROOF_RANGE 3u
+// bytes of the 7-bit varint of the ORIGINAL literal (BLUT / COUNTBYTES, proof.cu:31-41)
+__device__ __forceinline__ u32 proofOrgLit(const u32* __restrict__ vorg, u32 lit) { return (vorg[LABS(lit)] << 1) | LSIGN(lit); }
+__device__ __forceinline__ u32 proofLitBytes(const u32* __restrict__ vorg, u32 lit) { return (38u - (u32)__clz((int)proofOrgLit(vorg, lit))) / 7u; }
+__device__ __forceinline__ u32 proofClauseBytes(const u32* __restrict__ vorg, const u32* lits, u32 n) {
+    u32 b = 2;   // prefix + terminating 0 (countProofBytes, proofutils.cuh:34-60)
+    for (u32 k = 0; k < n; k++) b += proofLitBytes(vorg, lits[k]);
+    return b;
+}
+// saveProofClause (proofutils.cuh:123-170)
+__device__ __forceinline__ void proofWriteClause(unsigned char* out, const u32* __restrict__ vorg, const u32* lits, u32 n, unsigned char state) {
+    *out++ = state;
+    for (u32 k = 0; k < n; k++) {
+        u32 org = proofOrgLit(vorg, lits[k]);
+        while (org & 0xFFFFFF80u) { *out++ = (unsigned char)((org & 0x7Fu) | 0x80u); org >>= 7; }
+        *out++ = (unsigned char)org;
+    }
+    *out = 0;
+}
+// the 32 lanes of a warp append their lines (bytes == 0: none) in lane order; returns this lane's write pointer or null
+__device__ __forceinline__ unsigned char* proofReserve(const G& g, const ProofOut& po, u32 bytes) {
+    const u32 incl = warpIncl(bytes);
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) return nullptr;
+    u32 base = 0;
+    if (laneId() == 0) {
+        base = atomicAdd(&g.dc->proofSize, total);
+        if ((u64)base + total > g.dc->proofCap) atomicOr(&g.dc->flags, 32u);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!bytes || (u64)base + total > g.dc->proofCap) return nullptr;
+    return po.buf + base + (incl - bytes);
+}
+// snap bit i = clause i is deleted now
+__global__ void __launch_bounds__(256) k_proof_snap(const uint4* __restrict__ hdr, u32 n, u32* __restrict__ snap) {
+    const u32 nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5; base < n; base += nWarps << 5) {
+        const u32 i = base + laneId();
+        const u32 m = __ballot_sync(0xffffffffu, i < n && C_DELETED(hdr[i].w));
+        if (laneId() == 0) snap[base >> 5] = m;
+    }
+}
+__global__ void __launch_bounds__(256) k_proof_stream(G g, ProofOut po, const u32* __restrict__ snap, u32 lo, u32 hiHost, const u32* hiDev, u32 mode) {
+    const u32 hi = hiDev ? *hiDev : hiHost;
+    const u32 nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 base = lo + (((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5); base < hi; base += nWarps << 5) {
+        const u32 i = base + laneId();
+        uint4 h = make_uint4(0, 0, 0, 0);
+        bool emit = false;
+        if (i < hi) {
+            h = g.hdr[i];
+            if (mode == PROOF_MOLTEN) emit = C_MOLTEN(h.w) != 0;
+            else if (mode == PROOF_NEWDEL) emit = C_DELETED(h.w) && !((snap[i >> 5] >> (i & 31u)) & 1u);
+            else emit = !C_DELETED(h.w) && h.y > 0;
+        }
+        const u32 bytes = emit ? proofClauseBytes(g.vorg, g.pool + h.x, h.y) : 0u;
+        unsigned char* out = proofReserve(g, po, bytes);
+        if (out) proofWriteClause(out, g.vorg, g.pool + h.x, h.y, mode == PROOF_NEWDEL ? (unsigned char)'d' : (unsigned char)'a');
+        if (emit && mode == PROOF_MOLTEN) g.hdr[i].w = h.w & ~CB_MOLTEN;   // c.freeze() (proofutils.cuh:191)
+    }
+}
+// resolvent units of phase 3: units[dc->proofUnits0 .. dc->numUnits) (saveProofUnit, proofutils.cuh:123-128)
+__global__ void k_proof_mark_units(DevCounters* dc) { dc->proofUnits0 = dc->numUnits; }
+__global__ void __launch_bounds__(256) k_proof_units(G g, ProofOut po) {
+    const u32 lo = g.dc->proofUnits0, hi = min(g.dc->numUnits, g.unitsCap);
+    const u32 nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 base = lo + (((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5); base < hi; base += nWarps << 5) {
+        const u32 i = base + laneId();
+        u32 lit = 0;
+        if (i < hi) lit = g.units[i];
+        const u32 bytes = lit ? 2u + proofLitBytes(g.vorg, lit) : 0u;
+        unsigned char* out = proofReserve(g, po, bytes);
+        if (out) proofWriteClause(out, g.vorg, &lit, 1, (unsigned char)'a');
+    }
+}
+// Equivalence substitution: a variable eliminated in phase 1 without resolvents keeps its lists only if it was
+// substituted (toblivion clears them), and what is still ORIGINAL in them are the rewritten clauses - negative list
+// first (equivalence.cuh:107-108).  One warp per elected variable, before the survivors are compacted.
+__global__ void __launch_bounds__(256) k_proof_equ(G g, ProofOut po, u32 E) {
+    const u32 nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tid < E; tid += nWarps) {
+        const u32 x = g.elected[tid];
+        const u32 e = g.eliminated[x];
+        if (!(e & MELTING_MASK) || (e & ADDING_MASK)) continue;
+        for (int side = 1; side >= 0; side--) {
+            const u32 lit = V2L(x) | (u32)side;
+            const u32 cnt = g.otSize[lit];
+            const u32* list = g.occurs + g.otStart[lit];
+            for (u32 base = 0; base < cnt; base += 32) {
+                const u32 j = base + laneId();
+                uint4 h = make_uint4(0, 0, 0, 0);
+                bool emit = false;
+                if (j < cnt) { h = g.hdr[list[j]]; emit = C_ORIGINAL(h.w) && h.y > 0; }
+                const u32 bytes = emit ? proofClauseBytes(g.vorg, g.pool + h.x, h.y) : 0u;
+                unsigned char* out = proofReserve(g, po, bytes);
+                if (out) proofWriteClause(out, g.vorg, g.pool + h.x, h.y, (unsigned char)'a');
+            }
+        }
+    }
+}
+// The counting functions of the reference refuse a candidate whose resolvents need more than ADDEDPROOF_MAX proof bytes
+// or produce more than ADDEDCLS_MAX units (resolve.cuh:66-70, :152-154, elimination.cuh:445-447, function.cuh:232-235).
+// Phase 1 does not count proof bytes; a candidate that could reach the limit (bound from its literal count and the
+// widest literal) is reported instead of being decided differently - it takes tens of thousands of added literals.
+__global__ void __launch_bounds__(256) k_proof_guard(G g, u32 E, u32 bmax) {
+    for (u32 tid = blockIdx.x * blockDim.x + threadIdx.x; tid < E; tid += gridDim.x * blockDim.x) {
+        const u32 info = g.veType[tid];
+        if (!RECOVERTYPE(info)) continue;
+        const u64 cls = RECOVERADDEDCLS(info), lits = RECOVERADDEDLITS(info), units = g.veUcnt[tid];
+        if (units > ADDEDCLS_MAX || (u64)bmax * lits + 2 * cls + (u64)(bmax + 2) * units > 0x3FFFFull) atomicOr(&g.dc->flags, 16u);
+    }
+}
+// cuPROOF::count (proof.cu:65-121): proof bytes of every literal of the loaded formula
+__global__ void __launch_bounds__(256) k_proof_count(const u32* __restrict__ lits, u64 n, const u32* __restrict__ vorg, DevCounters* dc) {
+    u32 local = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) local += proofLitBytes(vorg, lits[i]);
+    local = warpSum(local);
+    if (laneId() == 0 && local) atomicAdd((unsigned long long*)&dc->proofLitBytes, (unsigned long long)local);
+}
+__global__ void k_proof_cap(DevCounters* dc) { dc->proofCap = (u32)((double)(u32)dc->proofLitBytes * 1.5); dc->proofSize = 0; }   // simplify.cu:130-131
+void launchProofCount(Ctx* c) {
+    LAUNCH(c, k_proof_count, gridFor(c->L0, 256, 8), 256, 0, c->inLits, c->L0, c->vorg, c->dc);
+    LAUNCH(c, k_proof_cap, 1, 1, 0, c->dc);
+}
+static void proofSnap(Ctx* c) {
+    const u32 n = c->hdc->numCls;
+    LAUNCH(c, k_proof_snap, gridFor(n, 256), 256, 0, c->hdr[c->cur], n, c->proofSnap);
+}
+static void proofStream(Ctx* c, const G& g, u32 lo, u32 hiHost, const u32* hiDev, u32 mode, u64 sizeHint) {
+    ProofOut po{c->proofBuf};
+    LAUNCH(c, k_proof_stream, gridFor(sizeHint, 256), 256, 0, g, po, c->proofSnap, lo, hiHost, hiDev, mode);
+}
 #define LAUNCH_CLASSES(c, kern, block, E, g, ...)                                                            \
     do {                                                                                                     \
         LAUNCH(c, kern<4>, groupGrid(E, 4, block), block, 0, asGroup<4>(g), ##__VA_ARGS__, c->wlA, &c->dc->bin[0]);   \
@@ -1350,7 +1498,13 @@ void launchSUB(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
     binElected(c, k, false, true);
+    if (k.proof_en) proofSnap(c);
     LAUNCH_CLASSES(c, k_sub, 128, c->numElected, g);
+    if (k.proof_en) {   // subsume.cuh:465-475: strengthened clauses added, then subsumed ones deleted
+        const u32 n = c->hdc->numCls;
+        proofStream(c, g, 0, n, nullptr, PROOF_MOLTEN, n);
+        proofStream(c, g, 0, n, nullptr, PROOF_NEWDEL, n);
+    }
 }
 
 // veAsync + postVE (elimination.cu:131-154, 235-266)
@@ -1366,6 +1520,10 @@ void launchVE(Ctx* c, const KOpts& k) {
     LAUNCH(c, k_ve_phase1<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
     LAUNCH(c, k_ve_phase1<32>, groupGrid(E, 32, 128), 128, 0, asGroup<32>(g), c->sortK, &c->dc->bin[2], redo, redoCount);
     LAUNCH(c, k_ve_phase1<32>, 148, 128, 0, asGroup<32>(g), redo, redoCount, redo, redoCount);   // variables handed over by the small groups
+    if (k.proof_en) {
+        LAUNCH(c, k_proof_guard, gridFor(E, 256), 256, 0, g, E, c->proofBMax);
+        LAUNCH(c, k_proof_mark_units, 1, 1, 0, c->dc);   // units before this mark come from substitutions (no unit lines)
+    }
     // phase 2: exclusive scans seeded with the current CNF sizes
     VEBase vb;
     vb.numCls0 = c->hdc->numCls; vb.poolUsed0 = c->hdc->poolUsed; vb.dataSize0 = c->hdc->dataSize;
@@ -1373,6 +1531,12 @@ void launchVE(Ctx* c, const KOpts& k) {
     scanExclusiveU64(c, c->veRref, c->veRref, E, vb.dataSize0);
     LAUNCH_CLASSES(c, k_ve_phase3, 128, E, g, vb, c->flagA);
     LAUNCH(c, k_ve_resize, 1, 1, 0, g, vb);
+    if (k.proof_en) {   // before elected[] is compacted: k_proof_equ walks the lists of the variables eliminated in phase 1
+        ProofOut po{c->proofBuf};
+        LAUNCH(c, k_proof_equ, gridFor((u64)E * 32, 256), 256, 0, g, po, E);
+        LAUNCH(c, k_proof_units, 148, 256, 0, g, po);
+        proofStream(c, g, vb.numCls0, 0, &c->dc->numCls, PROOF_RANGE, c->capC - vb.numCls0);
+    }
     // elected := survivors, order kept (cub::DeviceSelect::If in postVE)
     scanExclusiveU32(c, c->flagA, c->flagB, E, 0, &c->dc->numElected);
     {
@@ -1386,7 +1550,9 @@ void launchBCE(Ctx* c, const KOpts& k) {
     if (!c->numElected) return;
     G g = makeG(c, k);
     binElected(c, k, false);
+    if (k.proof_en) proofSnap(c);
     LAUNCH_CLASSES(c, k_bce, 128, c->numElected, g);
+    if (k.proof_en) proofStream(c, g, 0, c->hdc->numCls, nullptr, PROOF_NEWDEL, c->hdc->numCls);   // blocked.cuh:67-72
 }
 
 void launchERE(Ctx* c, const KOpts& k) {
@@ -1414,6 +1580,7 @@ void launchERE(Ctx* c, const KOpts& k) {
     Q.count = &c->dc->scratch[3]; Q.overflow = &c->dc->scratch[4]; Q.need = c->needSort;
     cudaMemsetAsync(Q.count, 0, 8, c->stream);
     cudaMemsetAsync(c->needSort, 0, c->ND, c->stream);
+    if (k.proof_en) proofSnap(c);   // the first pass only records: nothing is deleted before the snapshot is taken
     LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g, Q);
     if (syncCounters(c)) return;
     const u32 nq = c->hdc->scratch[3];
@@ -1425,4 +1592,5 @@ void launchERE(Ctx* c, const KOpts& k) {
         launchSortOT(c, 2);
         LAUNCH(c, k_ere_apply, gridFor(nq, 256), 256, 0, asGroup<32>(g), Q.items, Q.count);
     }
+    if (k.proof_en) proofStream(c, g, 0, n, nullptr, PROOF_NEWDEL, n);   // redundancy.cuh:122-129
 }

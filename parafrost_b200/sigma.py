@@ -29,6 +29,7 @@ class SigmaOpts(C.Structure):
         ("xor_max_arity", C.c_uint32), ("ere_clause_max", C.c_int32), ("ere_max_occurs", C.c_uint32),
         ("sub_max_occurs", C.c_uint32), ("bce_max_occurs", C.c_uint32), ("sh_max_bve_out1", C.c_uint32),
         ("sigma_calls", C.c_int32), ("final_gc", C.c_int32), ("profile", C.c_int32), ("aggr_cnf_sort", C.c_int32),
+        ("proof_en", C.c_int32),
     ]
 
 
@@ -74,6 +75,7 @@ SYMBOLS = [
     "sigma_default_opts", "sigma_normalize_opts", "sigma_create", "sigma_destroy", "sigma_set_opts", "sigma_set_stream", "sigma_load", "sigma_load_sclauses",
     "sigma_run", "sigma_begin", "sigma_round", "sigma_finish", "sigma_num_rounds", "sigma_round_reports",
     "sigma_result_sizes", "sigma_store", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
+    "sigma_set_proof_sink", "sigma_proof_chunks", "sigma_proof_chunk_size", "sigma_proof_chunk_copy",
     "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
 ]
 
@@ -107,6 +109,10 @@ def lib():
         L.sigma_snapshot.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.sigma_debug_elected.argtypes = [P, P, C.POINTER(C.c_uint32)]
         L.sigma_debug_hist.argtypes = [P, P]
+        L.sigma_set_proof_sink.argtypes = [P, P, P]
+        L.sigma_proof_chunks.argtypes = [P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.sigma_proof_chunk_size.argtypes = [P, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.sigma_proof_chunk_copy.argtypes = [P, C.c_uint32, P]
         L.sigma_kernel_profile.argtypes = [P, C.c_int]
         L.sigma_kernel_times.argtypes = [P, P, P, P, C.POINTER(C.c_uint32)]
         L.sigma_memory.argtypes = [P] + [C.POINTER(C.c_uint64)] * 3
@@ -122,6 +128,7 @@ FLAG_MAP = {  # the reference's CLI flags (src/gpu/options.cpp:24-43, options.cu
     "-no-ere": {"ere_en": 0}, "-ere": {"ere_en": 1}, "-no-vefunction": {"ve_fun_en": 0}, "-bce": {"bce_en": 1},
     "-all": {"all_en": 1}, "-no-sub": {"sub_en": 0}, "-no-veextend": {"ve_plus_en": 0}, "-no-ve": {"ve_en": 0},
     "-velitsbound": {"ve_lbound_en": 1}, "-profilegpu": {"profile": 1}, "-aggresivesort": {"aggr_cnf_sort": 1}, "-no-lcvefast": {}, "-quiet": {},
+    "-proof": {"proof_en": 1},
 }
 VALUE_FLAGS = {
     "--phases": "phases", "--mupos": "mu_pos", "--muneg": "mu_neg", "--electionsmin": "lcve_min_vars",
@@ -276,6 +283,32 @@ class Simplifier:
     def snapshot(self) -> dict:
         """Live clause list right now (per-round parity checks)."""
         return self.store()
+
+    # cuPROOF::cacheProof / writeProof (proof.cu:160-199, 232-247)
+    PROOF_SINK = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_uint8), C.c_uint64)
+
+    def set_proof_sink(self, fn):
+        """fn(bytes) is called with every round's chunk of the device DRAT stream (flag ``-proof``)."""
+        if fn is None:
+            self._sink = None
+            self._check(self._lib.sigma_set_proof_sink(self._h, None, None))
+            return
+        self._sink = self.PROOF_SINK(lambda _u, p, n: fn(C.string_at(p, n)))
+        self._check(self._lib.sigma_set_proof_sink(self._h, C.cast(self._sink, C.c_void_p), None))
+
+    def proof_chunks(self):
+        """-> ([one bytes object per cacheProof/writeProof point of the last run], capacity in bytes)"""
+        n, tot, cap = C.c_uint32(), C.c_uint64(), C.c_uint32()
+        self._check(self._lib.sigma_proof_chunks(self._h, C.byref(n), C.byref(tot), C.byref(cap)))
+        out = []
+        for i in range(n.value):
+            sz = C.c_uint64()
+            self._check(self._lib.sigma_proof_chunk_size(self._h, i, C.byref(sz)))
+            buf = np.empty(max(sz.value, 1), np.uint8)
+            if sz.value:
+                self._check(self._lib.sigma_proof_chunk_copy(self._h, i, _ptr(buf)))
+            out.append(buf[: sz.value].tobytes())
+        return out, cap.value
 
     def debug_elected(self):
         n = C.c_uint32(0)

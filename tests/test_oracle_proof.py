@@ -1,0 +1,109 @@
+"""CPU checks of the oracle's device-DRAT restatement (src/gpu/proof.cu, proofutils.cuh).
+
+The reference holds no golden proof for this path and its GPU binary cannot run here, so the stream is
+pinned semantically: every added line must follow from the formula by unit propagation (RUP), every
+deleted line must name a clause that exists, every clause of the simplified result must be in the
+checker's database at the end, and switching the proof on must not change the simplification."""
+import numpy as np
+import pytest
+
+import helpers
+import sgd
+
+CASES = {
+    "k3_r30": ("ksat", 12, [800, 2400, 3]),
+    "k3_r42": ("ksat", 11, [600, 2520, 3]),
+    "miter_a": ("miter", 22, [40, 700, 300, 200, 8]),
+    "mult6": ("mult", 31, [6]),
+    "mult10": ("mult", 32, [10]),
+    "parity": ("parity", 41, [300]),
+    "multpar": ("multpar", 51, [5, 120]),
+}
+FLAGSETS = {"def": [], "all": ["-all"], "p2_bce": ["--phases=2", "-bce"], "nofun": ["-no-vefunction"]}
+
+
+def clauses_of(lits, offs, vorg=None):
+    out = []
+    for i in range(len(offs) - 1):
+        c = [int(x) for x in lits[int(offs[i]):int(offs[i + 1])]]
+        if vorg is not None:
+            c = [(int(vorg[l >> 1]) << 1) | (l & 1) for l in c]
+        out.append(tuple(c))
+    return out
+
+
+def check_stream(chunks, original, result, defer_deletions=False):
+    """forward check of the chunks; returns (#added, #deleted)"""
+    ck = helpers.RupChecker(original)
+    na = nd = 0
+    for r, ch in enumerate(chunks):
+        pending = []
+        for kind, l in helpers.drat_parse(ch):
+            if kind == b"a":
+                assert ck.rup(l), f"chunk {r}: added clause {l} is not RUP"
+                ck.add(l)
+                na += 1
+            elif defer_deletions:
+                pending.append(l)
+            else:
+                assert ck.delete(l), f"chunk {r}: deleted clause {l} is not in the formula"
+                nd += 1
+        for l in pending:
+            assert ck.delete(l), f"chunk {r}: deleted clause {l} is not in the formula"
+            nd += 1
+    for c in result:
+        assert ck.has(c), f"result clause {c} is neither original nor derived in the proof"
+    return na, nd
+
+
+@pytest.mark.parametrize("fl", list(FLAGSETS))
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_proof_is_valid_drat(name, fl):
+    fam, seed, args = CASES[name]
+    flags = FLAGSETS[fl]
+    V, lits, offs = helpers.gen_cnf(fam, seed, args)
+    plain, rs0, _ = helpers.run_oracle(V, lits, offs, **helpers.opts_from_flags(flags))
+    d, rs, _ = helpers.run_oracle(V, lits, offs, proof=True, **helpers.opts_from_flags(flags))
+    assert not sgd.compare(d, plain) and (rs == rs0).all()      # the proof guards never fire at these sizes
+    chunks = d.extra["proof"]
+    assert all(len(c) <= d.extra["proof_cap"] for c in chunks)   # cuPROOF::alloc capacity (simplify.cu:128-132)
+    na, nd = check_stream(chunks, clauses_of(lits, offs), clauses_of(d.lits, d.offs))
+    if name != "parity" and len(rs):
+        assert na > 0
+
+
+def test_oracle_proof_uses_original_literals():
+    """vorg maps the working variables to sparse original numbers: multi-byte varints, ORIGINIZELIT."""
+    fam, seed, args = CASES["mult10"]
+    V, lits, offs = helpers.gen_cnf(fam, seed, args)
+    rng = np.random.default_rng(5)
+    vorg = np.zeros(V + 1, np.uint32)
+    vorg[1:] = np.sort(rng.choice(np.arange(1, 3_000_000, dtype=np.uint32), V, replace=False))   # up to 4-byte literals
+    d, rs, _ = helpers.run_oracle(V, lits, offs, vorg=vorg, proof=True)
+    ident, _, _ = helpers.run_oracle(V, lits, offs, proof=True)
+    # same lines, renamed
+    for a, b in zip(d.extra["proof"], ident.extra["proof"]):
+        la, lb = helpers.drat_parse(a), helpers.drat_parse(b)
+        assert [(k, tuple((int(vorg[x >> 1]) << 1) | (x & 1) for x in l)) for k, l in lb] == la
+    assert d.extra["proof_cap"] > ident.extra["proof_cap"]
+    check_stream(d.extra["proof"], clauses_of(lits, offs, vorg), clauses_of(d.lits, d.offs, vorg))
+
+
+def test_drat_varint_roundtrip():
+    lits = [2, 3, 127, 128, 255, 16383, 16384, 2_097_151, 2_097_152, 268_435_455, 268_435_456, 0x7FFFFFFF]
+    raw = bytearray(b"a")
+    for l in lits:
+        v = l
+        while v & ~0x7F:
+            raw.append((v & 0x7F) | 0x80)
+            v >>= 7
+        raw.append(v)
+    raw.append(0)
+    assert helpers.drat_parse(bytes(raw)) == [(b"a", tuple(lits))]
+
+
+def test_rup_checker_rejects_a_wrong_line():
+    ck = helpers.RupChecker([(2, 4), (3, 6)])     # (x1 v x2), (-x1 v x3)
+    assert ck.rup((4, 6))                          # resolvent
+    assert not ck.rup((4,))                        # x2 alone does not follow
+    assert not ck.delete((2, 6))
