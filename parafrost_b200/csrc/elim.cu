@@ -1406,7 +1406,9 @@ __global__ void __launch_bounds__(256) k_proof_stream(G g, ProofOut po, const u3
         bool emit = false;
         if (i < hi) {
             h = g.hdr[i];
-            if (mode == PROOF_MOLTEN) emit = C_MOLTEN(h.w) != 0;
+            // a clause deleted before the snapshot may still carry the molten mark of the gate search that preceded its
+            // elimination (deleteAll keeps it); only clauses alive when SUB started can have been strengthened by it
+            if (mode == PROOF_MOLTEN) emit = C_MOLTEN(h.w) && !((snap[i >> 5] >> (i & 31u)) & 1u);
             else if (mode == PROOF_NEWDEL) emit = C_DELETED(h.w) && !((snap[i >> 5] >> (i & 31u)) & 1u);
             else emit = !C_DELETED(h.w) && h.y > 0;
         }

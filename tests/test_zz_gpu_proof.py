@@ -118,3 +118,82 @@ def test_proof_off_leaves_no_stream_and_late_enable_is_refused():
         assert sum(len(c) for c in chunks) > 0
     finally:
         s.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# randomised: the proof stream under random formulas and option sets
+import os  # noqa: E402
+
+from test_gpu_parity import FUZZ_FLAGS, random_cnf  # noqa: E402
+
+
+def _compare_streams(V, lits, offs, flags, calls, ctx, meta=None, vorg=None, vstate=None, assumed=None):
+    try:
+        over = helpers.opts_from_flags(flags)
+    except KeyError:
+        pytest.skip("flag combination not expressible")
+    over["sigma_calls"] = calls
+    od, ors, _ = helpers.run_oracle(V, lits, offs, meta=meta, vorg=vorg, vstate=vstate, assumed=assumed, proof=True, **over)
+    s = sigma().Simplifier(0, flags=list(flags) + ["-proof"], sigma_calls=calls)
+    try:
+        s.load(V, lits, offs, meta=meta, vorg=vorg, vstate=vstate, assumed=assumed)
+        fin = s.simplify()
+        ed = to_dump(V, s.store(), fin["cnfstate"])
+        chunks, cap = s.proof_chunks()
+    finally:
+        s.close()
+    assert od.cnfstate == fin["cnfstate"], ctx
+    if od.cnfstate == 0:
+        return   # UNSAT by propagation: the answer is the result (the conflict surfaces on a schedule-dependent variable)
+    assert not sgd.compare(ed, od), ctx
+    assert cap == od.extra["proof_cap"], ctx
+    assert [len(c) for c in chunks] == [len(c) for c in od.extra["proof"]], ctx
+    for r, (a, b) in enumerate(zip(chunks, od.extra["proof"])):
+        assert helpers.drat_canonical(a) == helpers.drat_canonical(b), (ctx, r)
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("SIGMA_PROOF_FUZZ_SEEDS", "32")))))
+def test_proof_stream_fuzz_random(seed):
+    rng = np.random.default_rng(31000 + seed)
+    V = int(rng.integers(30, 400))
+    ratio = float(rng.choice([1.5, 2.5, 4.0, 6.0]))
+    kmin = int(rng.integers(2, 4)); kmax = int(rng.integers(kmin, 10))
+    lits, offs = random_cnf(rng, V, max(8, int(V * ratio)), kmin, kmax)
+    flags = list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    if rng.random() < 0.3:
+        flags += list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    calls = int(rng.integers(1, 4))
+    meta = vorg = vstate = assumed = None
+    if calls > 1 and rng.random() < 0.7:
+        meta = np.zeros(len(offs) - 1, np.uint32)
+        sz = np.diff(offs.astype(np.int64))
+        lrn = (rng.random(len(meta)) < 0.25) & (sz > 1)
+        meta[lrn] = 1 | (rng.integers(0, 3, int(lrn.sum())).astype(np.uint32) << 4) | (rng.integers(2, 9, int(lrn.sum())).astype(np.uint32) << 6)
+    if rng.random() < 0.3:
+        vstate = (rng.random(V + 1) < 0.04).astype(np.uint8) * 3; vstate[0] = 0
+    if rng.random() < 0.3:
+        assumed = (rng.random(V + 1) < 0.06).astype(np.uint8)
+    if rng.random() < 0.5:   # sparse original numbering: literals of 1 to 4 proof bytes
+        vorg = np.zeros(V + 1, np.uint32)
+        vorg[1:] = rng.permutation(V).astype(np.uint32) * int(rng.choice([1, 40, 3000])) + 1 + int(rng.integers(0, 5000))
+    _compare_streams(V, lits, offs, flags, calls, (seed, V, len(offs) - 1, kmin, kmax, flags, calls), meta, vorg, vstate, assumed)
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("SIGMA_PROOF_FUZZ2_SEEDS", "24")))))
+def test_proof_stream_fuzz_structured(seed):
+    rng = np.random.default_rng(32000 + seed)
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        fam, args = "miter", [int(rng.integers(8, 60)), int(rng.integers(60, 1500)), int(rng.integers(0, 1001)), int(rng.integers(0, 400)), int(rng.integers(1, 33))]
+    elif kind == 1:
+        fam, args = "mult", [int(rng.integers(3, 13))]
+    elif kind == 2:
+        fam, args = "parity", [int(rng.integers(10, 600))]
+    else:
+        fam, args = "multpar", [int(rng.integers(3, 9)), int(rng.integers(10, 300))]
+    V, lits, offs = helpers.gen_cnf(fam, 8000 + seed, args)
+    flags = list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    if rng.random() < 0.4:
+        flags += list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    calls = int(rng.integers(1, 3))
+    _compare_streams(V, lits, offs, flags, calls, (seed, fam, args, flags, calls))
