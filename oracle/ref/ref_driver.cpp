@@ -147,7 +147,7 @@ int main(int argc, char** argv)
 		RefDriver* drv = new RefDriver(std::string(argv[1]));
 		init_solver(drv);
 		const int rc = drv->run(argv[2]);
-		fflush(stdout);
+		fflush(NULL); // stdout and, with -proof, the reference's proof file (PROOF::write is buffered stdio)
 		_exit(rc); // skip the reference's teardown; the dump is on disk
 	}
 	catch (std::bad_alloc&) { fprintf(stderr, "ref_driver: bad_alloc\n"); return 3; }
