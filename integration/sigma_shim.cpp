@@ -241,10 +241,7 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 		stats.sigma.all.literals += iliterals - int64(inf.numLiterals);
 		stats.sigma.all.variables += int64(inf.maxMelted) - imelted;
 		last.shrink.removed = stats.shrunken;
-		forall_variables(v) {                                            // markEliminated, transfer.cu:42-60
-			if (eliminated[v] && !IS_FORCED(eliminated[v])) markEliminated(v);
-		}
-		if (!inf.unassigned || !inf.numClauses || rep.cnfstate == SIGMA_SAT) {
+		if (!inf.unassigned || !inf.numClauses || rep.cnfstate == SIGMA_SAT) {   // simplify.cu:198-209 (before markEliminated, as there)
 			const uint32 off = model.resolved.size();
 			model.resolved.resize(off + uint32(g_resolved.size()));
 			for (size_t i = 0; i < g_resolved.size(); i++) model.resolved[off + uint32(i)] = g_resolved[i];
@@ -254,6 +251,9 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 			cnfstate = SAT;
 			printStats(1, 's', CGREEN);
 			break;
+		}
+		forall_variables(v) {                                            // markEliminated, transfer.cu:42-60
+			if (eliminated[v] && !IS_FORCED(eliminated[v])) markEliminated(v);
 		}
 		if (skip_transfer_to_host) {                                     // the simplified CNF stays resident in the context
 			printStats(1, 's', CGREEN);

@@ -103,3 +103,33 @@ def test_no_gpu_means_loud_failure(lib):
     from parafrost_b200 import sigma
     with pytest.raises(sigma.SigmaError):
         sigma.Simplifier(0)
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """include/sigma.h is the FFI surface: it must be valid C99 by itself (no C++, no CUDA, no torch types) and a C
+    program must link against the library with nothing else on the link line."""
+    import parafrost_b200
+    hdr = os.path.join(ROOT, "include", "sigma.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "sigma.h"\n#include <stdio.h>\n'
+        "static void sink(void* u, const uint8_t* b, uint64_t n) { (void)u; (void)b; (void)n; }\n"
+        "int main(void) {\n"
+        "  sigma_opts o; sigma_ctx* c = 0; int rc;\n"
+        "  sigma_default_opts(&o); o.proof_en = 1; sigma_normalize_opts(&o);\n"
+        "  rc = sigma_create(0, &o, &c);\n"
+        '  printf("%d %d %d\\n", rc, (int)sizeof o, o.phases);\n'
+        "  if (!rc) { sigma_set_proof_sink(c, sink, 0); sigma_destroy(c); }\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(parafrost_b200.lib_path())
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                        "-L", libdir, "-lsigma_b200", "-Wl,-rpath," + libdir], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout.split()
+    from parafrost_b200 import sigma
+    assert int(out[1]) == C.sizeof(sigma.SigmaOpts)      # the ctypes mirror has the layout the C compiler sees
+    assert int(out[2]) == 5
