@@ -19,7 +19,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "parafrost_gpu")
 ANSI = re.compile(r"\x1b\[[0-9;]*m")
 
 
-def run(binary, cnf, *flags, timeout=120):
+def run(binary, cnf, *flags, timeout=40):
     r = subprocess.run([binary, cnf] + list(flags), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
     out = ANSI.sub("", r.stdout)
     ans = [l for l in out.splitlines() if l.startswith("s ")]
