@@ -51,8 +51,10 @@ def check_stream(chunks, original, result, defer_deletions=False):
         for l in pending:
             assert ck.delete(l), f"chunk {r}: deleted clause {l} is not in the formula"
             nd += 1
+    # a clause of the result is an original or added clause, or one of those shortened by root-level units in prop()
+    # (bcp_apply_k, elimbcp.cu:124-141, writes no proof line: the shortened clause follows by unit propagation)
     for c in result:
-        assert ck.has(c), f"result clause {c} is neither original nor derived in the proof"
+        assert ck.has(c) or ck.rup(c), f"result clause {c} does not follow from the formula and the proof"
     return na, nd
 
 
@@ -136,3 +138,42 @@ def test_oracle_proof_matches_reference_file(key):
     mine = b"".join(d.extra["proof"])
     assert len(mine) == len(raw)
     assert helpers.drat_canonical(mine) == helpers.drat_canonical(raw)
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("SIGMA_PROOF_CPU_SEEDS", "48")))))
+def test_oracle_proof_fuzz(seed):
+    """the generator of test_zz_gpu_proof.py::test_proof_stream_fuzz_random: random formulas with learnt clauses,
+    inactive / assumed variables, sparse original numbering and units, under random option sets"""
+    from test_gpu_parity import FUZZ_FLAGS, random_cnf
+    rng = np.random.default_rng(31000 + seed)
+    V = int(rng.integers(30, 400))
+    ratio = float(rng.choice([1.5, 2.5, 4.0, 6.0]))
+    kmin = int(rng.integers(2, 4)); kmax = int(rng.integers(kmin, 10))
+    lits, offs = random_cnf(rng, V, max(8, int(V * ratio)), kmin, kmax)
+    flags = list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    if rng.random() < 0.3:
+        flags += list(FUZZ_FLAGS[int(rng.integers(0, len(FUZZ_FLAGS)))])
+    calls = int(rng.integers(1, 4))
+    meta = vorg = vstate = assumed = None
+    if calls > 1 and rng.random() < 0.7:
+        meta = np.zeros(len(offs) - 1, np.uint32)
+        sz = np.diff(offs.astype(np.int64))
+        lrn = (rng.random(len(meta)) < 0.25) & (sz > 1)
+        meta[lrn] = 1 | (rng.integers(0, 3, int(lrn.sum())).astype(np.uint32) << 4) | (rng.integers(2, 9, int(lrn.sum())).astype(np.uint32) << 6)
+    if rng.random() < 0.3:
+        vstate = (rng.random(V + 1) < 0.04).astype(np.uint8) * 3; vstate[0] = 0
+    if rng.random() < 0.3:
+        assumed = (rng.random(V + 1) < 0.06).astype(np.uint8)
+    if rng.random() < 0.5:
+        vorg = np.zeros(V + 1, np.uint32)
+        vorg[1:] = rng.permutation(V).astype(np.uint32) * int(rng.choice([1, 40, 3000])) + 1 + int(rng.integers(0, 5000))
+    try:
+        over = helpers.opts_from_flags(flags)
+    except KeyError:
+        pytest.skip("flag combination not expressible")
+    over["sigma_calls"] = calls
+    d, _, _ = helpers.run_oracle(V, lits, offs, meta=meta, vorg=vorg, vstate=vstate, assumed=assumed, proof=True, **over)
+    if d.cnfstate == 0:
+        pytest.skip("UNSAT by propagation")
+    assert all(len(c) <= d.extra["proof_cap"] for c in d.extra["proof"])
+    check_stream(d.extra["proof"], clauses_of(lits, offs, vorg), clauses_of(d.lits, d.offs, vorg))
