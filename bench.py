@@ -362,6 +362,9 @@ def main():
     ap.add_argument("--impl", default="sigma-b200", choices=["sigma-b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--batch", type=int, default=64, help="cfg5: number of instances in the batch")
+    ap.add_argument("--pipeline", type=int, default=0,
+                    help="K >= 2: additionally report e2e_pipelined - the e2e steps dealt to K engine contexts on the GPU "
+                         "(parafrost_b200.replicas.Pipeline), so that copies and kernels of neighbouring steps overlap")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", default="", help="reference CLI flags for the engine, space separated (e.g. '--phases=5 -no-ere')")
@@ -457,6 +460,24 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     clk = clocks.stop()
+    # ---- optional: the same e2e steps through K contexts (every step still copies its input in and its result out)
+    piped = None
+    if a.pipeline > 1:
+        from parafrost_b200 import replicas as _rep
+        bufs = [{"bits": alloc(capC, np.uint32), "sig": alloc(capC, np.uint32), "offs": alloc(capC + 1, np.uint64),
+                 "lits": alloc(capL, np.uint32), "eliminated": np.zeros(V + 1, np.uint8), "resolved": alloc(C0 + L0 + 2, np.uint32),
+                 "trail": alloc(3 * (V + 1), np.uint32)} for _ in range(a.pipeline)]
+        with _rep.Pipeline(local, depth=a.pipeline, flags=flags) as pipe:
+            pipe.run([(V, lits, offs)] * a.pipeline, lambda *_: None, bufs)                  # warm-up: arenas, first launches
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            nsteps = max(a.steps, a.pipeline)
+            pipe.run([(V, lits, offs)] * nsteps, lambda *_: None, bufs)
+            torch.cuda.synchronize()
+            p1.record()
+            p1.synchronize()
+            piped = {"ms": p0.elapsed_time(p1), "steps": nsteps}
 
     lit_step = sum(r["literals_in"] for r in rounds)
     nrounds = max(1, len(rounds))
@@ -484,6 +505,11 @@ def main():
             "e2e": {"value": lit_all * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": int(lits.nbytes + offs.nbytes), "d2h_bytes_per_step": d2h // a.steps},
             "gpu_launches": int(launches), "clocks": clk,
+            **({"e2e_pipelined": {"value": lit_step * piped["steps"] / (piped["ms"] * 1e-3), "unit": UNIT, "contexts": a.pipeline,
+                                  "steps": piped["steps"], "ms_per_step": piped["ms"] / piped["steps"],
+                                  "note": "rank 0 only; every step copies its input from and its result to pinned host memory, "
+                                          "steps run on K contexts so that PCIe legs and kernels of neighbouring steps overlap"}}
+               if piped else {}),
             "result": {"clauses_out": reps[-1]["clauses"], "literals_out": reps[-1]["literals"], "eliminated_vars": reps[-1]["eliminated_vars"],
                        "cnfstate": reps[-1]["cnfstate"]},
             "roofline": roofline(ktimes, meanC, meanL, V, peaks, a.workload),

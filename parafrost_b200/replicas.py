@@ -73,3 +73,92 @@ def reduce_timing(dist, ms_local: float, units_local: float, device="cpu"):
 def rank_seed(seed: int, rank: int) -> int:
     """Replica r of a single-config bench simplifies its own formula of the same shape."""
     return seed + 1000 * rank
+
+
+class Pipeline:
+    """Several engine contexts on ONE device for a stream of independent instances (BASELINE.json config 5 on each
+    rank): every context has its own CUDA stream (sigma_create) and its own host thread, and each thread takes the
+    next instance off a shared queue and runs load -> simplify -> store on it.  With `depth` >= 3 the host->device
+    copy of instance i+1, the kernels of instance i and the device->host copy of instance i-1 are in flight at the
+    same time (two copy engines + the SMs), where a single context leaves the GPU idle during the PCIe legs - which
+    are most of an end-to-end step (24.5 of 30 ms on cfg2).  The reference has nothing like it (one
+    Solver per process, blocking copies); nothing crosses between the contexts, results are bit-identical to the
+    sequential run.  The C ABI calls release the GIL (ctypes), so plain threads are enough.
+
+    make() -> an object with load / simplify / rounds / store / close (sigma.Simplifier); injectable for CPU tests.
+    """
+
+    def __init__(self, device: int = 0, depth: int = 3, flags=(), make=None, **opts):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        if make is None:
+            from . import sigma
+
+            def make():
+                return sigma.Simplifier(device, flags=flags, **opts)
+        self._ctx = []
+        try:
+            for _ in range(depth):
+                self._ctx.append(make())
+        except Exception:
+            self.close()
+            raise
+
+    @property
+    def depth(self) -> int:
+        return len(self._ctx)
+
+    def run(self, jobs, consume, outbufs=None):
+        """jobs: sequence of (max_var, lits, offs) or (max_var, lits, offs, meta) in HOST memory (pinned for real
+        overlap).  consume(i, report, rounds, stored) is called on the worker thread that finished instance i;
+        `stored` are views into that worker's output buffers (outbufs[w], a dict for Simplifier.store(into=...), or
+        fresh arrays when outbufs is None) and are only valid during the call.  Instances are started in index
+        order; the first exception stops the queue and is re-raised here."""
+        import threading
+        jobs = list(jobs)
+        if outbufs is not None and len(outbufs) < len(self._ctx):
+            raise ValueError("one output buffer set per context is needed")
+        lock = threading.Lock()
+        state = {"next": 0, "error": None}
+
+        def worker(w):
+            s = self._ctx[w]
+            while True:
+                with lock:
+                    if state["error"] is not None or state["next"] >= len(jobs):
+                        return
+                    i = state["next"]
+                    state["next"] += 1
+                try:
+                    job = jobs[i]
+                    s.load(job[0], job[1], job[2], meta=job[3] if len(job) > 3 else None)
+                    rep = s.simplify()
+                    stored = s.store(into=outbufs[w]) if outbufs is not None else s.store()
+                    consume(i, rep, s.rounds(), stored)
+                except BaseException as e:   # noqa: BLE001 - handed to the caller
+                    with lock:
+                        if state["error"] is None:
+                            state["error"] = e
+                    return
+
+        threads = [threading.Thread(target=worker, args=(w,), daemon=True) for w in range(len(self._ctx))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if state["error"] is not None:
+            raise state["error"]
+
+    def close(self):
+        for s in self._ctx:
+            try:
+                s.close()
+            except Exception:
+                pass
+        self._ctx = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

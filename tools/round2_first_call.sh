@@ -11,4 +11,5 @@ GOLDEN_PROOF_JOBS=1 timeout 170 python tests/golden/make_golden_proofs.py > gpur
 timeout 120 python -m pytest tests/test_zzz_gpu_dropin.py -q --runxfail --timeout 60 > gpurun_out/r02_dropin.log 2>&1
 timeout 150 python -m pytest tests -q -m gpu -x --timeout 120 > gpurun_out/r02_pytest_gpu.log 2>&1
 timeout 90 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_cfg2.json 2> gpurun_out/r02_bench_cfg2.err
+timeout 120 python bench.py --steps 9 --warmup 3 --pipeline 3 --no-cpu-baseline > gpurun_out/r02_bench_cfg2_pipe3.json 2> gpurun_out/r02_bench_cfg2_pipe3.err
 tail -3 gpurun_out/r02_golden_proofs.log gpurun_out/r02_dropin.log gpurun_out/r02_pytest_gpu.log gpurun_out/r02_bench_cfg2.json
