@@ -133,3 +133,23 @@ def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
     from parafrost_b200 import sigma
     assert int(out[1]) == C.sizeof(sigma.SigmaOpts)      # the ctypes mirror has the layout the C compiler sees
     assert int(out[2]) == 5
+
+
+def test_cpp_example_builds_parses_and_fails_loudly_without_a_gpu(lib, tmp_path):
+    """examples/sigma_cli.cpp: the C ABI from a plain g++ program (no nvcc, no reference headers)."""
+    import parafrost_b200
+    libdir = os.path.dirname(parafrost_b200.lib_path())
+    exe = tmp_path / "sigma_cli"
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "sigma_cli.cpp"), "-L", libdir, "-lsigma_b200", "-Wl,-rpath," + libdir, "-o", str(exe)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    cnf = tmp_path / "t.cnf"
+    cnf.write_text("c tiny\np cnf 3 3\n1 -2 0\n2 3 0\n-1 -3 0\n")
+    r = subprocess.run([str(exe), str(cnf)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert "3 variables, 3 clauses, 6 literals" in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "no CPU path" in r.stdout      # loud failure, no fallback
+    else:
+        assert r.returncode == 0 and "\ns " in r.stdout
