@@ -177,3 +177,20 @@ def test_oracle_proof_fuzz(seed):
         pytest.skip("UNSAT by propagation")
     assert all(len(c) <= d.extra["proof_cap"] for c in d.extra["proof"])
     check_stream(d.extra["proof"], clauses_of(lits, offs, vorg), clauses_of(d.lits, d.offs, vorg))
+
+
+def test_binary_to_text_drat():
+    """tools/drat_text.py against the reference's own proof file of the parity instance and a hand-made stream"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(PROOF_DIR), "..", "..", "tools"))
+    import drat_text
+    assert drat_text.to_text(b"a\x04\x07\x00d\x80\x02\x00") == "2 -3 0\nd 128 0\n"
+    raw = gzip.open(os.path.join(PROOF_DIR, "k3_r42__nofun.drat.gz")).read()
+    txt = drat_text.to_text(raw).splitlines()
+    parsed = helpers.drat_parse(raw)
+    assert len(txt) == len(parsed) == 71
+    for line, (kind, lits) in zip(txt, parsed):
+        want = [(-(l >> 1) if l & 1 else l >> 1) for l in lits]
+        assert line == ("d " if kind == b"d" else "") + " ".join(map(str, want)) + " 0"
+    with pytest.raises(ValueError):
+        drat_text.to_text(b"x\x04\x00")
