@@ -158,6 +158,10 @@ int  sigma_result_sizes(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_liter
                         uint64_t* num_resolved, uint64_t* num_trail);
 int  sigma_store(sigma_ctx* c, uint32_t* bits, uint32_t* sig, uint64_t* offs, uint32_t* lits,
                  uint8_t* eliminated, uint32_t* resolved, uint32_t* trail);
+/* What writeBackCNF -> newClause(SCLAUSE&) reads (cnf.cu:186-198, sclause.cpp:22-55): word 0, size and literals of every
+ * clause in ref order - no signatures, no 64-bit offsets (8 + 4|c| bytes per clause over PCIe instead of 16 + 4|c|). */
+int  sigma_store_compact(sigma_ctx* c, uint32_t* bits, uint32_t* sizes, uint32_t* lits,
+                         uint8_t* eliminated, uint32_t* resolved, uint32_t* trail);
 /* the reference's own record stream {bits, sig, size, lits...} + uint64 refs, for newClause(SCLAUSE&) */
 int  sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t* refs);
 

@@ -132,8 +132,22 @@ extern "C" int sigma_create(int device, const sigma_opts* o, sigma_ctx** out) {
 
 extern "C" int sigma_set_opts(sigma_ctx* c, const sigma_opts* o) {
     if (!c || !o) return SIGMA_BAD_ARGUMENT;
+    const sigma_opts old = c->o;
     c->o = *o;
     sigma_normalize_opts(&c->o);
+    if (c->loaded) {
+        // the arena was carved for the options in force at sigma_load (prepareLoad): options that enlarge the logical
+        // capacities (ve_en, lits_mul, phases) or need the proof buffer are refused here instead of overrunning it later
+        u64 lc = 0, lw = 0;
+        const bool ok = logicalCaps(c, c->C0, c->L0, c->orgClauses, c->orgLiterals, &lc, &lw) && lc <= c->capC && lw <= c->capW &&
+                        (!c->o.proof_en || c->proofCarved);
+        if (!ok) {
+            c->o = old;
+            snprintf(c->err, sizeof c->err, "sigma_set_opts: these options need a larger arena than the loaded formula was given; set them before sigma_load");
+            return SIGMA_BAD_ARGUMENT;
+        }
+        c->logC = lc; c->logW = lw;
+    }
     return SIGMA_OK;
 }
 
@@ -225,6 +239,17 @@ __global__ void k_iota(u32* __restrict__ a, u32 n) {
 }
 
 // ------------------------------------------------------------------ load
+// the reference's logical capacities for a formula under the context's options (simplify.cu:84-98)
+static bool logicalCaps(const Ctx* c, u64 num_clauses, u64 L0, u64 orgC, u64 orgL, u64* logC, u64* logW) {
+    u64 numCls = num_clauses, numLits = L0;
+    if (c->o.phases) {
+        numCls += c->o.ve_en ? orgC : 0;
+        numLits += c->o.ve_en ? (u64)((double)orgL * c->o.lits_mul) : 0;
+    }
+    if (numCls >= 0xFFFFFFF0ull || numCls * NBUCKETS + numLits >= 0xFFFFFFF0ull) return false;
+    *logC = numCls; *logW = numCls * NBUCKETS + numLits;
+    return true;
+}
 // sizes the logical capacities and the arena for a formula of num_clauses clauses / L0 literals
 static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u64 orgC, u64 orgL, const uint32_t* vorg) {
     // device DRAT stream: the logical capacity is the reference's (1.5 x the proof bytes of the input literals, counted on
@@ -245,15 +270,18 @@ static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u
     c->V = max_var; c->ND = 2 * (max_var + 1);
     c->C0 = num_clauses; c->L0 = L0;
     c->orgClauses = orgC; c->orgLiterals = orgL;
-    // logical capacities of awaken (simplify.cu:84-98); the physical buffers are sized for them
-    u64 numCls = num_clauses, numLits = L0;
-    if (c->o.phases) {
-        numCls += c->o.ve_en ? orgC : 0;
-        numLits += c->o.ve_en ? (u64)((double)orgL * c->o.lits_mul) : 0;
-    }
-    if (numCls >= 0xFFFFFFF0ull || numCls * NBUCKETS + numLits >= 0xFFFFFFF0ull) return SIGMA_CNFALLOC_FAIL;
+    // logical capacities of awaken (simplify.cu:84-98)
+    if (!logicalCaps(c, num_clauses, L0, orgC, orgL, &c->logC, &c->logW)) return SIGMA_CNFALLOC_FAIL;
+    // Physical sizes: at least the logical ones.  reallocCNF(true) (cnf.cu:129-144) moves the logical capacities to
+    // 2 x the live clauses (+ literals) at every GC; the reference reallocates, this arena does not, so it is sized
+    // for that up front as far as the input tells (learnt clauses loaded: 2 C0 > C0 + originals).  A resolvent batch
+    // that fits the logical capacities but not the arena fails the round loudly (flags bit 6), never silently.
+    u64 numCls = c->logC;
+    if (c->o.phases && c->o.ve_en && 2 * num_clauses > numCls) numCls = 2 * num_clauses;
+    const u64 numWords = c->logW + (numCls - c->logC) * NBUCKETS;
+    if (numCls >= 0xFFFFFFF0ull || numWords >= 0xFFFFFFF0ull) return SIGMA_CNFALLOC_FAIL;
     c->capC = (u32)numCls;
-    c->capW = numCls * NBUCKETS + numLits;      // data cap in words: a pool this big can never overflow
+    c->capW = numWords;                         // data cap in words: a pool this big can never overflow below the logical caps
     const u64 rc = num_clauses + L0;            // savedLits (simplify.cu:85)
     c->resolvedCap = (u32)(rc > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : rc);
     const size_t need = carve(c, nullptr);
@@ -374,7 +402,8 @@ static KOpts makeK(Ctx* c) {
     k.sub_max_occurs = c->o.sub_max_occurs; k.ere_max_occurs = c->o.ere_max_occurs; k.bce_max_occurs = c->o.bce_max_occurs;
     k.sh_max_bve_out1 = c->o.sh_max_bve_out1; k.ere_clause_max = c->o.ere_clause_max;
     k.ve_fun_en = c->o.ve_fun_en && !c->varcoreDead; k.ve_lbound_en = c->o.ve_lbound_en; k.in_mode = c->o.sigma_calls > 1;
-    k.refsCap = (u32)c->refsCap; k.dataCap = c->dataCap;
+    k.refsCap = (u32)(c->refsCap > 0xFFFFFFFFull ? 0xFFFFFFFFull : c->refsCap); k.dataCap = c->dataCap;
+    k.physC = c->capC; k.physW = c->capW;
     k.proof_en = c->o.proof_en && c->proofCarved;
     return k;
 }
@@ -416,7 +445,7 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     CUDA_TRY(cudaMemsetAsync(c->eliminated, 0, V1, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->varcore, 0xFF, V1 * 4, c->stream));
     // logical capacities (simplify.cu:84-98)
-    c->refsCap = c->capC; c->dataCap = c->capW;
+    c->refsCap = c->logC; c->dataCap = c->logW;
     c->numClauses = c->C0; c->numLiterals = c->L0;
     c->cdiff = INT64_MAX; c->ldiff = INT64_MAX;
     c->clsbefore = (i64)c->numClauses; c->litsbefore = (i64)c->numLiterals;
@@ -603,6 +632,12 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     if ((rc = syncCounters(c))) return rc;
     c->countsFresh = true;
     if (c->hdc->flags & 3u) { snprintf(c->err, sizeof c->err, "device vector overflow (flags %u)", c->hdc->flags); return SIGMA_OVERFLOW; }
+    if (c->hdc->flags & 64u) {
+        snprintf(c->err, sizeof c->err, "resolvents fit the reference's logical capacities (%llu refs / %llu words after a GC) but not the arena "
+                 "(%u / %llu): the reference would have reallocated here", (unsigned long long)c->refsCap, (unsigned long long)c->dataCap, c->capC,
+                 (unsigned long long)c->capW);
+        return SIGMA_OVERFLOW;
+    }
     if ((rc = flushProof(c))) return rc;   // cacheProof / writeProof, simplify.cu:174-184
     // updateNumPVs (simplify.cu:35-41)
     const u32 remained = c->o.ve_en ? c->hdc->numElected : c->numElected;
@@ -634,6 +669,7 @@ extern "C" int sigma_finish(sigma_ctx* c, sigma_report* rep) {
     if (!c->countsFresh) {   // the last round ended with a count and nothing touched the clause store since
         launchCount(c);
         if ((rc = syncCounters(c))) return rc;
+        c->countsFresh = true;
     }
     c->numClauses = c->hdc->liveCls; c->numLiterals = c->hdc->liveLits;
     // simplify.cu:198-209
@@ -709,21 +745,29 @@ extern "C" int sigma_proof_chunk_copy(const sigma_ctx* c, uint32_t chunk, uint8_
 extern "C" int sigma_snapshot(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals) {
     if (!c || !c->begun) return SIGMA_NOT_LOADED;
     CUDA_TRY(cudaSetDevice(c->device));
+    launchCount(c);
     int rc = syncCounters(c);
     if (rc) return rc;
-    u64 nc, nl;
-    if ((rc = launchStore(c, &nc, &nl, false, false))) return rc;
-    if (num_clauses) *num_clauses = nc;
-    if (num_literals) *num_literals = nl;
+    if (num_clauses) *num_clauses = c->hdc->liveCls;
+    if (num_literals) *num_literals = c->hdc->liveLits;
     return SIGMA_OK;
 }
 
 extern "C" int sigma_result_sizes(sigma_ctx* c, uint64_t* num_clauses, uint64_t* num_literals, uint64_t* num_resolved,
                                   uint64_t* num_trail) {
     if (!c || !c->begun) return SIGMA_NOT_LOADED;
-    int rc = sigma_snapshot(c, num_clauses, num_literals);
-    if (rc) return rc;
-    if (c->cnfstate != SIGMA_UNSOLVED) { if (num_clauses) *num_clauses = 0; if (num_literals) *num_literals = 0; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    // sizes only: the live counts of the last k_count are still valid after sigma_finish (nothing touched the store);
+    // between rounds one counting pass is enough - the store kernels run once, in sigma_store* itself
+    int rc;
+    if (!(c->loopDone && c->countsFresh)) {
+        launchCount(c);
+        if ((rc = syncCounters(c))) return rc;
+        c->countsFresh = c->loopDone;
+    }
+    const bool live = c->cnfstate == SIGMA_UNSOLVED;
+    if (num_clauses) *num_clauses = live ? c->hdc->liveCls : 0;
+    if (num_literals) *num_literals = live ? c->hdc->liveLits : 0;
     if (num_resolved) *num_resolved = c->hdc->resolvedSize;
     if (num_trail) *num_trail = c->hdc->trailSize;
     return SIGMA_OK;
@@ -737,7 +781,7 @@ extern "C" int sigma_store(sigma_ctx* c, uint32_t* bits, uint32_t* sig, uint64_t
     if (rc) return rc;
     u64 nc = 0, nl = 0;
     // -aggresivesort orders the final write-back only (cacheCNF); a store between two sigma_round calls is a snapshot in ref order
-    if ((rc = launchStore(c, &nc, &nl, false, c->loopDone))) return rc;
+    if ((rc = launchStore(c, &nc, &nl, 0, c->loopDone))) return rc;
     const int dst = 1 - c->cur;
     const bool live = c->cnfstate == SIGMA_UNSOLVED;
     if (offs) {
@@ -759,13 +803,39 @@ extern "C" int sigma_store(sigma_ctx* c, uint32_t* bits, uint32_t* sig, uint64_t
     return SIGMA_OK;
 }
 
+// What Solver::writeBackCNF -> newClause(SCLAUSE&) actually reads (sclause.cpp:22-55): word 0, the size and the literals.
+// No signatures, no 64-bit offsets: 8 + 4 |c| bytes per clause over PCIe instead of 16 + 4 |c|.
+extern "C" int sigma_store_compact(sigma_ctx* c, uint32_t* bits, uint32_t* sizes, uint32_t* lits, uint8_t* eliminated,
+                                   uint32_t* resolved, uint32_t* trail) {
+    if (!c || !c->begun) return SIGMA_NOT_LOADED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = syncCounters(c);
+    if (rc) return rc;
+    u64 nc = 0, nl = 0;
+    if ((rc = launchStore(c, &nc, &nl, 2, c->loopDone))) return rc;
+    const int dst = 1 - c->cur;
+    if (c->cnfstate == SIGMA_UNSOLVED && nc) {
+        const u32* oBits = (const u32*)c->hdr[dst];
+        if (bits) CUDA_TRY(cudaMemcpyAsync(bits, oBits, nc * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (sizes) CUDA_TRY(cudaMemcpyAsync(sizes, oBits + c->capC, nc * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (lits && nl) CUDA_TRY(cudaMemcpyAsync(lits, c->pool[dst], nl * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (eliminated) CUDA_TRY(cudaMemcpyAsync(eliminated, c->eliminated, (size_t)c->V + 1, cudaMemcpyDeviceToHost, c->stream));
+    if (resolved && c->hdc->resolvedSize)
+        CUDA_TRY(cudaMemcpyAsync(resolved, c->resolved, (size_t)c->hdc->resolvedSize * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (trail && c->hdc->trailSize)
+        CUDA_TRY(cudaMemcpyAsync(trail, c->trail, (size_t)c->hdc->trailSize * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SIGMA_OK;
+}
+
 extern "C" int sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t* refs) {
     if (!c || !c->begun) return SIGMA_NOT_LOADED;
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = syncCounters(c);
     if (rc) return rc;
     u64 nc = 0, nl = 0;
-    if ((rc = launchStore(c, &nc, &nl, true, c->loopDone))) return rc;
+    if ((rc = launchStore(c, &nc, &nl, 1, c->loopDone))) return rc;
     if (c->cnfstate != SIGMA_UNSOLVED || !nc) return SIGMA_OK;
     const int dst = 1 - c->cur;
     if (data_words) CUDA_TRY(cudaMemcpyAsync(data_words, c->pool[dst], (nc * NBUCKETS + nl) * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -449,9 +449,11 @@ __global__ void k_store_arrays(const uint4* __restrict__ hdr, const u32* __restr
         const u32 j = pCls[i], off = pLits[i];
         const u32* s = pool + h.x;
         for (u32 k = 0; k < h.y; k++) oLits[off + k] = s[k];
-        oBits[j] = h.w; oSig[j] = h.z; oOffs[j] = off;
+        oBits[j] = h.w;
+        if (oOffs) { oSig[j] = h.z; oOffs[j] = off; }
+        else oSig[j] = h.y;   // compact form: the size takes the place of the signature, no offsets
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) oOffs[*totCls] = *totLits;
+    if (oOffs && blockIdx.x == 0 && threadIdx.x == 0) oOffs[*totCls] = *totLits;
 }
 
 // the reference's record stream: {bits, sig, size, lits...} at refs[j] (cnf.cuh:82-97)
@@ -516,7 +518,7 @@ static int aggressiveOrder(Ctx* c, u32 n) {
 }
 
 // Selects the live clauses into the staging buffers (the inactive CNF buffer); returns sizes.
-int launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm, bool writeBackOrder) {
+int launchStore(Ctx* c, u64* nCls, u64* nLits, int form, bool writeBackOrder) {   // form: 0 arrays, 1 SCLAUSE records, 2 compact arrays
     const u32 n = c->hdc->numCls;
     const int src = c->cur, dst = 1 - c->cur;
     u32* tot = c->dc->scratch;
@@ -529,13 +531,13 @@ int launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm, bool writeBackO
         const int rc = aggressiveOrder(c, n);
         if (rc) return rc;
     }
-    if (sclauseForm)
+    if (form == 1)
         LAUNCH(c, k_store_sclause, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, c->pool[dst], c->flag64);
     else {
         u32* oBits = (u32*)c->hdr[dst];
         u32* oSig = oBits + c->capC;
         LAUNCH(c, k_store_arrays, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, oBits, oSig,
-               c->flag64, c->pool[dst], tot, tot + 1);
+               form == 2 ? (u64*)nullptr : c->flag64, c->pool[dst], tot, tot + 1);
     }
     u32 t[2];
     cudaError_t e = cudaMemcpyAsync(t, tot, 8, cudaMemcpyDeviceToHost, c->stream);

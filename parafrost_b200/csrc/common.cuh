@@ -102,7 +102,8 @@ struct DevCounters {
     u32 wlCnt[3];      // rotating MIS worklist sizes (lcve.cu)
     u32 firstStop;     // rank of the first bound-violating candidate (lcve.cu)
     u32 flags;         // bit0: resolved overflow, bit1: units overflow, bit2: hole after failed MEMORY_SAFE, bit3: a clause with >= 2^14 literals,
-                       // bit4: a BVE candidate could trip the proof guard (resolve.cuh:66-70), bit5: proof stream overflow
+                       // bit4: a BVE candidate could trip the proof guard (resolve.cuh:66-70), bit5: proof stream overflow,
+                       // bit6: resolvents fit the logical capacities but not the arena, bit7: bad literal / offsets in the input
     u32 bcpCurr, bcpNext, bcpConfl, bcpLevel;
     u32 nFrozen;       // number of first-frozen variables mapped into varcore (<= 12 needed)
     u32 unassignedDec; // variables assigned by prop()
@@ -123,6 +124,8 @@ struct KOpts {   // kernel-side options (replaces __constant__ kOpts, options.cu
     int proof_en;      // opts.proof_en: SUB leaves the molten marks for the proof pass
     u32 refsCap;       // logical refs capacity
     u64 dataCap;       // logical data capacity (words)
+    u32 physC;         // clause slots the arena really holds (hdr[]) ...
+    u64 physW;         // ... and literal words (pool[]): the logical capacities may pass them after a GC (api.cu: buildOT)
 };
 
 #define KT_MAX_KERNELS 96
@@ -141,7 +144,8 @@ struct Ctx {
     // arena
     char* arena; size_t arenaBytes, arenaUsed, arenaPeak; u64 cudaMallocs;
     // sizes
-    u32 V, ND; u64 C0, L0; u32 capC; u64 capW; u32 resolvedCap;
+    u32 V, ND; u64 C0, L0; u32 capC; u64 capW; u32 resolvedCap;   // capC / capW: physical sizes of hdr[] / pool[]
+    u64 logC, logW;    // the reference's logical capacities of awaken (simplify.cu:84-98) for the loaded formula and options
     u64 orgClauses, orgLiterals;
     bool loaded, begun;
     // input (pristine)
@@ -261,7 +265,7 @@ void launchHistKey(Ctx* c);
 void launchScatter(Ctx* c);
 void launchCount(Ctx* c);
 void launchGC(Ctx* c);
-int  launchStore(Ctx* c, u64* nCls, u64* nLits, bool sclauseForm, bool writeBackOrder);   // writeBackOrder: apply -aggresivesort (cacheCNF only)
+int  launchStore(Ctx* c, u64* nCls, u64* nLits, int form, bool writeBackOrder);   // form: 0 arrays (bits, sig, offs), 1 SCLAUSE records, 2 compact (bits, sizes);   // writeBackOrder: apply -aggresivesort (cacheCNF only)
 // otsort.cu
 void launchSortOT(Ctx* c, int mode);   // 0 all lists, 1 elected variables, 2 lists flagged in needSort
 // lcve.cu

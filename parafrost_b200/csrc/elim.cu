@@ -701,8 +701,12 @@ __global__ void __launch_bounds__(128) k_ve_phase3(GT<GS> g, VEBase vb, u32* __r
             const u32 np = g.otSize[p], nn = g.otSize[n];
             const u32* P = g.occurs + g.otStart[p];
             const u32* N = g.occurs + g.otStart[n];
-            const bool safe = ((u64)addedPos + nAddedCls <= g.k.refsCap) &&
-                              (addedRef + nAddedLits + (u64)NBUCKETS * nAddedCls <= g.k.dataCap);
+            bool safe = ((u64)addedPos + nAddedCls <= g.k.refsCap) &&
+                        (addedRef + nAddedLits + (u64)NBUCKETS * nAddedCls <= g.k.dataCap);
+            if (safe) {   // the logical capacities can pass the arena after a GC (api.cu: prepareLoad): fail loudly, never write outside
+                const u64 poolEnd = (u64)vb.poolUsed0 + ((addedRef - vb.dataSize0) - (u64)NBUCKETS * (addedPos - vb.numCls0)) + nAddedLits;
+                if ((u64)addedPos + nAddedCls > g.k.physC || poolEnd > g.k.physW) { safe = false; if (LANE == 0) atomicOr(&g.dc->flags, 64u); }
+            }
             if (safe) {
                 // saveResolved(p, n, cnf, poss, negs) elimination.cuh:505-550 : side chosen by list sizes
                 u32 c1, l1;

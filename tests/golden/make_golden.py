@@ -63,6 +63,14 @@ VARIANTS = {
     "aggr_bce_p2": ["-aggresivesort", "-bce", "--phases=2", "-no-ere"],
 }
 MEDIUM_VARIANTS = ["p1", "p2", "def", "nofun"]
+# The reference's ERE launch is broken whenever numElected < 4 * 8 * #SMs (every small instance): ereAsync sizes the
+# dynamic shared memory for block.y = ereminthreads = 4 rows (elimination.cu:206), then LOOP_OVERSUB_Y raises block.y
+# to max(ereminthreads, warpSize) = 32 (grid.cuh:85-104 with minThreads = MAX(MINTHREADS, warp), grid.cuh:196) without
+# resizing it, and ere_k's rows 4..31 write their resolvents past the allocation (redundancy.cuh:160) -> illegal
+# shared-memory access, sticky context error, garbage dump.  With --ereminthreads=32 (an option of the unmodified
+# binary) the size is computed for 32 rows from the start and the tuner leaves the shape alone.  Confirmed with
+# compute-sanitizer on the B200 (profiles/r02_ref_ere_sanitizer.log).  The launch shape does not enter ERE's result.
+ERE_LAUNCH_FIX = ["--ereminthreads=32"]
 
 
 def sh(cmd, **kw):
@@ -72,6 +80,7 @@ def sh(cmd, **kw):
 def main():
     """`--only v1,v2` runs just those variants (small instances) and merges them into the summary."""
     only = None
+    ere_only = "--ere-only" in sys.argv     # re-run just the variants whose last round is ERE (with ERE_LAUNCH_FIX)
     for i, a in enumerate(sys.argv):
         if a == "--only":
             only = sys.argv[i + 1].split(",")
@@ -87,6 +96,10 @@ def main():
         summary = json.load(open(os.path.join(ROOT, "tests", "golden", "summary.json")))
     log = open(os.path.join(OUT, "runs.log"), "w")
     groups = ((SMALL, only, True),) if only else ((SMALL, list(VARIANTS), True), (MEDIUM, MEDIUM_VARIANTS, False))
+    if ere_only:
+        summary = json.load(open(os.path.join(ROOT, "tests", "golden", "summary.json")))
+        ere = [v for v, f in VARIANTS.items() if "-no-ere" not in f]
+        groups = ((SMALL, ere, True), (MEDIUM, [v for v in MEDIUM_VARIANTS if v in ere], False))
     for group, variants, keep in groups:
         for name, (fam, seed, args) in group.items():
             cnf = os.path.join(TMP, name + ".cnf")
@@ -98,6 +111,8 @@ def main():
                 if os.path.exists(dump):
                     os.remove(dump)
                 flags = BASE + VARIANTS[var]
+                if "-no-ere" not in flags:
+                    flags = flags + ERE_LAUNCH_FIX
                 t0 = time.time()
                 try:
                     r = sh([drv, cnf, dump] + flags, timeout=600)

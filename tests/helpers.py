@@ -117,7 +117,7 @@ def opts_from_flags(flags) -> dict:
             k, v = f.split("=", 1)
             if k in VALUE_FLAGS:
                 o[VALUE_FLAGS[k]] = float(v) if k == "--literalsmul" else int(v)
-            elif k != "--mapperc":
+            elif k not in ("--mapperc", "--ereminthreads"):   # host-side / launch-shape options: no effect on the result
                 raise ValueError(f"unknown flag {f}")
         else:
             o.update(FLAG_MAP[f])

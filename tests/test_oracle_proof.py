@@ -133,8 +133,11 @@ def test_oracle_proof_matches_reference_file(key):
     V, lits, offs = helpers.gen_cnf(e["family"], e["seed"], e["args"])
     flags = [f for f in e["flags"] if f != "-proof"]
     d, _, _ = helpers.run_oracle(V, lits, offs, proof=True, **helpers.opts_from_flags(flags))
-    # (the dump beside the proof is not compared: these runs include the reference's ERE kernel, which leaves a sticky
-    #  CUDA error on sm_100 and an unusable dump - tests/test_oracle_golden.py; the proof chunks were written before it)
+    # the simplified CNF of the same run (ERE runs carry --ereminthreads=32, see tests/golden/make_golden.py ERE_LAUNCH_FIX)
+    if "fingerprint" in e and ("-no-ere" in flags or "--ereminthreads=32" in flags):
+        fp, g = d.fingerprint(), e["fingerprint"]
+        keys = ["cnfstate", "clauses", "literals", "eliminated", "h_full_ordered", "h_eliminated", "h_resolved_groups", "h_trail_multiset"]
+        assert {k: (fp[k], g[k]) for k in keys if fp[k] != g[k]} == {}
     mine = b"".join(d.extra["proof"])
     assert len(mine) == len(raw)
     assert helpers.drat_canonical(mine) == helpers.drat_canonical(raw)
