@@ -130,6 +130,8 @@ extern "C" int sigma_create(int device, const sigma_opts* o, sigma_ctx** out) {
     return SIGMA_OK;
 }
 
+static bool logicalCaps(const Ctx* c, u64 num_clauses, u64 L0, u64 orgC, u64 orgL, u64* logC, u64* logW);
+
 extern "C" int sigma_set_opts(sigma_ctx* c, const sigma_opts* o) {
     if (!c || !o) return SIGMA_BAD_ARGUMENT;
     const sigma_opts old = c->o;

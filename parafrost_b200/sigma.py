@@ -74,7 +74,7 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "sigma_default_opts", "sigma_normalize_opts", "sigma_create", "sigma_destroy", "sigma_set_opts", "sigma_set_stream", "sigma_load", "sigma_load_sclauses",
     "sigma_run", "sigma_begin", "sigma_round", "sigma_finish", "sigma_num_rounds", "sigma_round_reports",
-    "sigma_result_sizes", "sigma_store", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
+    "sigma_result_sizes", "sigma_store", "sigma_store_compact", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
     "sigma_set_proof_sink", "sigma_proof_chunks", "sigma_proof_chunk_size", "sigma_proof_chunk_copy",
     "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
 ]
@@ -105,6 +105,7 @@ def lib():
         L.sigma_round_reports.argtypes = [P, C.POINTER(RoundReport), C.c_uint32]
         L.sigma_result_sizes.argtypes = [P] + [C.POINTER(C.c_uint64)] * 4
         L.sigma_store.argtypes = [P, P, P, P, P, P, P, P]
+        L.sigma_store_compact.argtypes = [P, P, P, P, P, P, P]
         L.sigma_store_sclauses.argtypes = [P, P, P]
         L.sigma_snapshot.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.sigma_debug_elected.argtypes = [P, P, C.POINTER(C.c_uint32)]
@@ -146,7 +147,7 @@ def opts_from_flags(flags) -> dict:
             k, v = f.split("=", 1)
             if k in VALUE_FLAGS:
                 o[VALUE_FLAGS[k]] = float(v) if k == "--literalsmul" else int(v)
-            elif k != "--mapperc":
+            elif k not in ("--mapperc", "--ereminthreads"):
                 raise ValueError(f"unknown flag {f}")
         else:
             o.update(FLAG_MAP[f])
@@ -271,6 +272,20 @@ class Simplifier:
         }
         self._check(self._lib.sigma_store(self._h, *[_ptr(out[k]) for k in ("bits", "sig", "offs", "lits", "eliminated", "resolved", "trail")]))
         return out
+
+    def store_compact(self, into: dict | None = None) -> dict:
+        """What writeBackCNF -> newClause(SCLAUSE&) reads (sclause.cpp:22-55): word 0, size and literals of every clause -
+        8 + 4|c| bytes per clause over PCIe instead of 16 + 4|c| (no signatures, no 64-bit offsets)."""
+        nc, nl, nr, nt = (C.c_uint64() for _ in range(4))
+        self._check(self._lib.sigma_result_sizes(self._h, C.byref(nc), C.byref(nl), C.byref(nr), C.byref(nt)))
+        need = {"bits": nc.value, "sizes": nc.value, "lits": nl.value, "eliminated": self.max_var + 1, "resolved": nr.value, "trail": nt.value}
+        if into is None:
+            into = {k: (np.zeros(n, np.uint8) if k == "eliminated" else np.empty(n, np.uint32)) for k, n in need.items()}
+        for k, n in need.items():
+            if len(into[k]) < n:
+                raise SigmaError(f"store_compact: buffer {k} holds {len(into[k])} < {n}")
+        self._check(self._lib.sigma_store_compact(self._h, *[_ptr(into[k]) for k in ("bits", "sizes", "lits", "eliminated", "resolved", "trail")]))
+        return {k: into[k][:n] for k, n in need.items()}
 
     def store_sclauses(self):
         nc, nl, nr, nt = (C.c_uint64() for _ in range(4))
