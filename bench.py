@@ -101,27 +101,8 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- roofline
-def algorithmic_bytes(kernel, C, L, V, E=0):
-    """Compulsory HBM bytes of ONE launch (DESIGN.md 'Kernels'): C clause slots, L live literals,
-    V variables; 16-byte clause headers, 4-byte literals and occurrence entries."""
-    ND = 2 * V + 2
-    f = {
-        "k_awaken": 8 * C + 4 * L + 16 * C + 4 * L + 16 * C + 4 * ND,   # prep + the fused first-round histogram and sort keys
-        "k_hist_key": 16 * C + 4 * L + 16 * C + 4 * ND,
-        "k_hist": 16 * C + 4 * L + 4 * ND,
-        "k_ot_part": 16 * C + 4 * L + 8 * L,
-        "k_ot_place": 8 * L + 4 * L + 12 * ND,
-        "k_sort_small": 4 * L + 16 * L + 4 * L + 8 * ND,
-        "k_sort_med": 4 * L + 16 * L + 4 * L,
-        "k_sort_lists": 4 * L + 16 * L + 4 * L + 8 * ND,
-        "k_count": 16 * C,
-        "k_gc_copy": 16 * C + 4 * L + 8 * C + 16 * C + 4 * L,
-        "k_gc_flags": 16 * C + 8 * C,
-        "k_store_arrays": 16 * C + 4 * L + 8 * C + 16 * C + 4 * L,
-    }
-    return f.get(kernel)
-
-
+# Algorithmic bytes per kernel come from the engine itself (sigma_kernel_stats, csrc/*.cu: KB(...) beside every launch;
+# formulas in DESIGN.md 3 / SURVEY.md 8d) - the bench no longer keeps a second copy of them.
 def ncu_traffic(workload):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of this workload's kernels
     from the newest committed `ncu --set full` capture (profiles/*_ncu_traffic_<workload>.json,
@@ -142,40 +123,6 @@ def ncu_traffic(workload):
 def kbase(name):
     """'(k_ot_part<3, 5>)' / 'void k_sub<4>' -> 'k_ot_part' / 'k_sub' (the LAUNCH macro stringifies its argument)."""
     return name.replace("void ", "").strip("() ").split("<")[0]
-
-
-def roofline(ktimes, C, L, V, peaks, workload="cfg2"):
-    """Roofline of the dominant kernel.  Streaming kernels have closed-form algorithmic bytes
-    (DESIGN.md 3); the per-variable kernels (MIS rounds, BVE, SUB, ERE) are latency / instruction
-    bound gather kernels whose bytes depend on the elected set - when one of those leads, the line
-    names it (`dominant`) and carries the roofline of the largest kernel that HAS a byte formula."""
-    if not ktimes:
-        return None
-    peak = peaks.get("hbm_gbs")
-    src = "measured (MEASURED_PEAKS.json)"
-    if not peak:
-        peak, src = 6650.0, "fallback (B200_PROFILING.md)"
-    total = sum(v[0] for v in ktimes.values())
-    order = sorted(ktimes.items(), key=lambda kv: -kv[1][0])
-    dom_name, (dom_ms, dom_cnt) = order[0]
-    name, (ms, cnt) = next(((k, v) for k, v in order if algorithmic_bytes(kbase(k), C, L, V)), order[0])
-    traffic = ncu_traffic(workload)
-    b = algorithmic_bytes(kbase(name), C, L, V)
-    out = {"bound": "hbm", "kernel": name, "launches": cnt, "ms_per_launch": ms / cnt, "share_of_kernel_time": ms / total if total else None,
-           "peak": peak, "peak_source": src, "unit": "GB/s", "traffic": traffic.get(kbase(name))}
-    if b:
-        ach = b / (ms / cnt * 1e-3) / 1e9
-        out.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": b})
-    else:
-        out.update({"achieved": None, "frac": None, "algorithmic_bytes_per_launch": None})
-    if dom_name != name:
-        out["dominant"] = {"kernel": dom_name, "ms_per_launch": dom_ms / dom_cnt, "launches": dom_cnt, "share_of_kernel_time": dom_ms / total,
-                           "traffic": traffic.get(kbase(dom_name)),
-                           "note": "per-variable gather kernel: latency/instruction bound, no closed-form bytes (DESIGN.md 3)"}
-    out["top_kernels"] = [{"kernel": k, "ms": round(v[0], 3), "launches": v[1], "share": round(v[0] / total, 3),
-                           "gbs": (lambda bb: round(bb / (v[0] / v[1] * 1e-3) / 1e9, 1) if bb else None)(algorithmic_bytes(kbase(k), C, L, V))}
-                          for k, v in order[:8]]
-    return out
 
 
 # ----------------------------------------------------------------------------- reference CPU arm
@@ -247,19 +194,93 @@ def reference_arm(a):
     finally:
         os.remove(path)
     ms = sum(r["ms"] for r in runs)
-    lit = sum(r["literals"] for r in runs)
+    lit = L * len(runs)            # literals of the input formula per simplify() call, as in the engine's arm
     value = lit / (ms * 1e-3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "ms_per_round": ms / max(1, sum(r["rounds"] for r in runs)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": a.workload, "sample": desc, "solver": "reference CPU v3.2.5 (src/cpu), -no-solve -profilesimp, default inprocessing"},
+        "literals_per_round_s": sum(r["literals"] for r in runs) / (ms * 1e-3),
+        "config": {"workload": a.workload, "sample": desc, "solver": "reference CPU v3.2.5 (src/cpu), -no-solve -profilesimp, default inprocessing",
+                   "unit_definition": "literals of the input formula per simplify() call (all rounds) / time"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": desc,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- reference GPU arm
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+# largest member of each family the UNMODIFIED reference GPU build gets through on a B200 (it aborts above: DESIGN.md 4)
+REF_GPU_SAMPLE = {"cfg1": 1.0, "cfg2": 2_000_000 / 21_000_000}
+
+
+def run_ref_gpu(cnf_path, flags, timeout=900, host_mode=True):
+    """One simplify() of the unmodified reference GPU solver (oracle/_ref/ref_driver = its objects + a dump main).
+    host_mode: with the write-back into the host clause database (newClause), i.e. its end-to-end call."""
+    env = dict(os.environ)
+    if host_mode:
+        env["REF_DRIVER_HOST"] = "1"
+    dump = cnf_path + ".sgd"
+    t0 = time.perf_counter()
+    r = subprocess.run([REF_GPU, cnf_path, dump, "-quiet", "-profilegpu", "--ereminthreads=32"] + flags, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=timeout, env=env)
+    wall = time.perf_counter() - t0
+    if os.path.exists(dump):
+        os.remove(dump)
+    out = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout)
+    res = {"rc": r.returncode, "wall_s": wall, "flags": flags}
+    m = re.search(r"simplify wall ([0-9.]+) ms, state (\d+), clauses (\d+)", out)
+    if m:
+        res.update({"simplify_ms": float(m.group(1)), "cnfstate": int(m.group(2)), "clauses": int(m.group(3))})
+    m = re.search(r"stage ms (.*)", out)
+    if m:
+        tok = m.group(1).split()
+        res["stage_ms"] = {tok[i]: float(tok[i + 1]) for i in range(0, len(tok) - 1, 2)}
+    if "simplify_ms" not in res:
+        res["tail"] = out[-400:]
+    return res
+
+
+def ref_gpu_sample(workload):
+    import cnfgen
+    scale = REF_GPU_SAMPLE.get(workload)
+    if scale is None:
+        return None
+    fam, seed, args = workload_spec(workload, 0, scale)
+    path = f"/tmp/sigma_bench_refgpu_{workload}_{os.getpid()}.cnf"
+    V, lits, offs = cnfgen.gen_cnf(fam, seed, args, dimacs_path=path)
+    desc = f"{fam}{tuple(args)} seed {seed}: V={V} C={len(offs) - 1} L={len(lits)} ({scale:.4g} of {workload})"
+    return path, V, lits, offs, desc
+
+
+def reference_gpu_arm(a):
+    """--impl reference-gpu: the reference's own GPU build on the largest member of the workload's family it survives."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    smp = ref_gpu_sample(a.workload) if os.path.exists(REF_GPU) else None
+    if smp is None:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/ref_driver not built, or no size of this family runs on the reference GPU build"}))
+        return 0
+    path, V, lits, offs, desc = smp
+    try:
+        runs = [run_ref_gpu(path, a.flags.split()) for _ in range(max(1, a.steps))]
+    finally:
+        os.remove(path)
+    ok = [r for r in runs if "simplify_ms" in r]
+    if not ok:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "reference GPU run failed: " + runs[-1].get("tail", "")[-200:]}))
+        return 0
+    ms = sum(r["simplify_ms"] for r in ok) / len(ok)
+    value = len(lits) / (ms * 1e-3)
+    print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": len(ok), "warmup": 0, "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                      "config": {"workload": a.workload, "sample": desc, "solver": "reference GPU v4.1.1 (src/gpu), its default election mode (-lcvefast) unless --flags says otherwise, "
+                                 "simplify(false): extract + H2D + rounds + write-back to the host clause database", "flags": a.flags.split()},
+                      "stage_ms": ok[-1].get("stage_ms"), "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}}))
     return 0
 
 
@@ -377,52 +398,77 @@ def batch_main(a, torch, dist, barrier, rank, world, local):
 
 
 # ----------------------------------------------------------------------------- our arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="sigma-b200", choices=["sigma-b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--batch", type=int, default=64, help="cfg5: number of instances in the batch")
-    ap.add_argument("--pipeline", type=int, default=0,
-                    help="K >= 2: additionally report e2e_pipelined - the e2e steps dealt to K engine contexts on the GPU "
-                         "(parafrost_b200.replicas.Pipeline), so that copies and kernels of neighbouring steps overlap")
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; the line says so)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--flags", default="", help="reference CLI flags for the engine, space separated (e.g. '--phases=5 -no-ere')")
-    a = ap.parse_args()
-    if a.impl == "reference":
-        return reference_arm(a)
+def _pci_path(torch, local):
+    p = torch.cuda.get_device_properties(local)
+    if hasattr(p, "pci_bus_id"):
+        return f"/sys/bus/pci/devices/{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{getattr(p, 'pci_device_id', 0):02x}.0"
+    r = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)], stdout=subprocess.PIPE, text=True, timeout=20)
+    bus = r.stdout.strip().lower()          # 00000000:1b:00.0 -> 0000:1b:00.0
+    return "/sys/bus/pci/devices/" + bus[-12:]
 
-    import torch
+
+def bind_numa(local):
+    """Pin this rank to the CPUs (and, by first touch, the memory) of the NUMA node its GPU hangs off, BEFORE any pinned
+    buffer is allocated: at N = 8 the e2e step is bound by pinned H2D/D2H through host memory."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        path = _pci_path(torch, local)
+        node = int(open(path + "/numa_node").read().strip())
+        cpulist = open(path + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001 - binding is best effort, the line says what happened
+        info["error"] = repr(e)[:120]
+    return info
+
+
+def kernel_table(kstats, peak, traffic, top=10):
+    """[{kernel, ms, launches, share, bytes_per_launch, gbs, frac, traffic}] sorted by time.  bytes = the engine's own
+    algorithmic-byte count per kernel name (sigma_kernel_stats; formulas in DESIGN.md 3)."""
+    total = sum(v[0] for v in kstats.values()) or 1.0
+    rows = []
+    for k, (ms, cnt, by) in sorted(kstats.items(), key=lambda kv: -kv[1][0])[:top]:
+        gbs = by / (ms * 1e-3) / 1e9 if by > 0 and ms > 0 else None
+        rows.append({"kernel": k, "ms": round(ms, 3), "launches": cnt, "share": round(ms / total, 3),
+                     "bytes_per_launch": round(by / cnt) if by > 0 else None, "gbs": round(gbs, 1) if gbs else None,
+                     "frac": round(gbs / peak, 3) if gbs else None, "traffic": traffic.get(kbase(k))})
+    return rows
+
+
+def roofline_block(kstats, peaks, workload):
+    """Roofline of the DOMINANT kernel (largest share of the kernel time of a profiled step)."""
+    if not kstats:
+        return None
+    peak = peaks.get("hbm_gbs")
+    src = "measured (MEASURED_PEAKS.json, burst copy bandwidth)"
+    if not peak:
+        peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = ncu_traffic(workload)
+    rows = kernel_table(kstats, peak, traffic)
+    d = rows[0]
+    return {"bound": "hbm", "kernel": d["kernel"], "launches": d["launches"], "ms_per_launch": d["ms"] / d["launches"],
+            "share_of_kernel_time": d["share"], "achieved": d["gbs"], "peak": peak, "peak_source": src, "unit": "GB/s",
+            "frac": d["frac"], "algorithmic_bytes_per_launch": d["bytes_per_launch"], "traffic": d["traffic"],
+            "bytes_source": "engine-counted algorithmic bytes (sigma_kernel_stats): closed forms for the streaming kernels, "
+                            "sum of (4 + 16 + 4|c|) over the clauses of the variables handed to the per-variable kernels",
+            "top_kernels": rows}
+
+
+def measure(a, torch, workload, rank, world, local, barrier, steps, warmup, pipeline, with_clocks=True):
+    """One workload on this rank: device-resident steps, e2e steps (serial and through K contexts), a profiled pass."""
     import cnfgen
-    import parafrost_b200
-    from parafrost_b200 import sigma
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    if not os.path.exists(parafrost_b200.lib_path()):
-        parafrost_b200.build()
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    if a.workload == "cfg5":
-        return batch_main(a, torch, dist, barrier, rank, world, local)
-
-    # ---- synthetic input of the named shape, in pinned host memory
-    fam, seed, args = workload_spec(a.workload, rank, a.scale)
+    from parafrost_b200 import replicas, sigma
+    fam, seed, args = workload_spec(workload, rank, a.scale)
     pinned = []
 
     def alloc(n, dt):
@@ -437,77 +483,145 @@ def main():
     s = sigma.Simplifier(local, flags=flags)
     s.set_stream(stream.cuda_stream)
     s.load(V, lits, offs)
-    # result buffers for the e2e leg (pinned, sized by the logical capacities of awaken)
+    # result buffers for the e2e legs (pinned, sized by the logical capacities of awaken): what newClause() reads
     capC, capL = 2 * C0 + 16, 2 * L0 + 16
-    outbuf = {"bits": alloc(capC, np.uint32), "sig": alloc(capC, np.uint32), "offs": alloc(capC + 1, np.uint64),
-              "lits": alloc(capL, np.uint32), "eliminated": np.zeros(V + 1, np.uint8), "resolved": alloc(C0 + L0 + 2, np.uint32),
-              "trail": alloc(3 * (V + 1), np.uint32)}
 
-    def step_resident():
-        return s.simplify()
+    def outbuf():
+        return {"bits": alloc(capC, np.uint32), "sizes": alloc(capC, np.uint32), "lits": alloc(capL, np.uint32),
+                "eliminated": np.zeros(V + 1, np.uint8), "resolved": alloc(C0 + L0 + 2, np.uint32), "trail": alloc(3 * (V + 1), np.uint32)}
+    out0 = outbuf()
 
     def step_e2e():
         s.load(V, lits, offs)
         rep = s.simplify()
-        st = s.store(into=outbuf)
-        return rep, st
+        return rep, s.store_compact(into=out0)
 
-    for _ in range(a.warmup):
-        step_resident()
-    # ---- value: inputs resident in HBM
-    clocks = ClockSampler(local)
+    for _ in range(warmup):
+        s.simplify()
+    # ---- value: inputs resident in HBM, no per-kernel events in the timed region
+    clocks = ClockSampler(local) if with_clocks else None
     barrier()
-    clocks.start()
-    s.kernel_profile(1)
+    if clocks:
+        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    reps = [step_resident() for _ in range(a.steps)]
+    reps = [s.simplify() for _ in range(steps)]
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    ktimes = s.kernel_times()
-    s.kernel_profile(0)
     rounds = s.rounds()
-    # ---- e2e: host buffers in, host buffers out
-    for _ in range(min(a.warmup, 2)):
+    # ---- e2e, one context: host buffers in, host buffers out, every step
+    for _ in range(min(warmup, 2)):
         step_e2e()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     d2h = 0
-    for _ in range(a.steps):
+    for _ in range(steps):
         rep, st = step_e2e()
         d2h += sum(int(v.nbytes) for v in st.values())
     e1.record(stream)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    clk = clocks.stop()
-    # ---- optional: the same e2e steps through K contexts (every step still copies its input in and its result out)
+    # ---- e2e through K contexts (every step still copies its input in and its result out; copies and kernels of
+    # neighbouring steps overlap).  All ranks run it together: the PCIe / host-memory contention is part of the number.
     piped = None
-    if a.pipeline > 1:
-        from parafrost_b200 import replicas as _rep
-        bufs = [{"bits": alloc(capC, np.uint32), "sig": alloc(capC, np.uint32), "offs": alloc(capC + 1, np.uint64),
-                 "lits": alloc(capL, np.uint32), "eliminated": np.zeros(V + 1, np.uint8), "resolved": alloc(C0 + L0 + 2, np.uint32),
-                 "trail": alloc(3 * (V + 1), np.uint32)} for _ in range(a.pipeline)]
-        with _rep.Pipeline(local, depth=a.pipeline, flags=flags) as pipe:
-            pipe.run([(V, lits, offs)] * a.pipeline, lambda *_: None, bufs)                  # warm-up: arenas, first launches
+    if pipeline > 1:
+        bufs = [outbuf() for _ in range(pipeline)]
+        with replicas.Pipeline(local, depth=pipeline, flags=flags, compact=True) as pipe:
+            pipe.run([(V, lits, offs)] * pipeline, lambda *_: None, bufs)                  # warm-up: arenas, first launches
             torch.cuda.synchronize()
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
-            nsteps = max(a.steps, a.pipeline)
+            barrier()
+            nsteps = max(steps, 2 * pipeline)
+            t0 = time.perf_counter()
             pipe.run([(V, lits, offs)] * nsteps, lambda *_: None, bufs)
             torch.cuda.synchronize()
-            p1.record()
-            p1.synchronize()
-            piped = {"ms": p0.elapsed_time(p1), "steps": nsteps}
+            t1 = time.perf_counter()
+            barrier()
+            piped = {"ms": (t1 - t0) * 1e3, "steps": nsteps}
+    clk = clocks.stop() if clocks else None
+    # ---- profiled pass (outside every timed region): CUDA-event pair around each launch + the engine's byte counts
+    s.kernel_profile(1)
+    psteps = min(steps, 3)
+    for _ in range(psteps):
+        s.simplify()
+    kstats = s.kernel_stats()
+    s.kernel_profile(0)
+    mem = s.memory()
+    s.close()
+    return {"fam": fam, "seed": seed, "args": args, "V": V, "C0": C0, "L0": L0, "flags": flags, "ms": ms, "steps": steps, "reps": reps,
+            "rounds": rounds, "ms_e2e": ms_e2e, "h2d": int(lits.nbytes + offs.nbytes), "d2h": d2h // steps, "piped": piped, "clocks": clk,
+            "kstats": kstats, "psteps": psteps, "memory": mem}
 
-    lit_step = sum(r["literals_in"] for r in rounds)
-    nrounds = max(1, len(rounds))
-    launches = sum(r["kernel_launches"] for r in reps)
+
+def cpu_baseline_for(workload):
+    try:
+        path, sV, sC, sL, desc = ref_sample(workload)
+        try:
+            r = run_ref_cpu(path, sL)
+        finally:
+            os.remove(path)
+        return {"value": sL / (r["ms"] * 1e-3), "unit": UNIT, "cores": 1, "kind": "reference", "sample": desc, "ms": r["ms"],
+                "rounds": r["rounds"], "literals_per_round_s": r["literals"] / (r["ms"] * 1e-3), "host_cores_available": os.cpu_count()}
+    except Exception as e:  # the baseline is reported, never required for the line
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e!r}"[:200]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sigma-b200", choices=["sigma-b200", "reference", "reference-gpu"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--batch", type=int, default=64, help="cfg5: number of instances in the batch")
+    ap.add_argument("--pipeline", type=int, default=3,
+                    help="K >= 2: e2e steps are also dealt to K engine contexts on the GPU (parafrost_b200.replicas.Pipeline), so that "
+                         "copies and kernels of neighbouring steps overlap; 0/1: one context only")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; the line says so)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 block of the default (cfg2) line")
+    ap.add_argument("--flags", default="", help="reference CLI flags for the engine, space separated (e.g. '--phases=5 -no-ere')")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return reference_arm(a)
+    if a.impl == "reference-gpu":
+        return reference_gpu_arm(a)
+
+    import torch
+    import parafrost_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    if not os.path.exists(parafrost_b200.lib_path()):
+        parafrost_b200.build()
+    torch.cuda.set_device(local)
+    numa = bind_numa(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    if a.workload == "cfg5":
+        return batch_main(a, torch, dist, barrier, rank, world, local)
+
     from parafrost_b200 import replicas
-    ms, lit_all = replicas.reduce_timing(dist, ms, float(lit_step), device="cuda")      # max over ranks, units summed
-    ms_e2e, _ = replicas.reduce_timing(dist, ms_e2e, 0.0, device="cuda")
+    m = measure(a, torch, a.workload, rank, world, local, barrier, a.steps, a.warmup, a.pipeline)
+    # units: literals of the input formula simplified (one simplify() call = one pass over the formula, however many rounds)
+    ms, lit_all = replicas.reduce_timing(dist, m["ms"], float(m["L0"]), device="cuda")      # max over ranks, units summed
+    ms_e2e, _ = replicas.reduce_timing(dist, m["ms_e2e"], 0.0, device="cuda")
+    ms_pipe = None
+    if m["piped"]:
+        ms_pipe, _ = replicas.reduce_timing(dist, m["piped"]["ms"] / m["piped"]["steps"], 0.0, device="cuda")   # per step, max over ranks
 
     if rank == 0:
         peaks = {}
@@ -515,43 +629,64 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
-        meanC = float(np.mean([r["clauses"] for r in rounds])) if rounds else C0
-        meanL = float(np.mean([r["literals_in"] for r in rounds])) if rounds else L0
+        rounds, reps, steps = m["rounds"], m["reps"], m["steps"]
+        nrounds = max(1, len(rounds))
+        lit_rounds = sum(r["literals_in"] for r in rounds)
+        e2e_serial = lit_all * steps / (ms_e2e * 1e-3)
+        e2e = {"value": e2e_serial, "unit": UNIT, "ms_per_step": ms_e2e / steps, "mode": "one context: load -> run -> store, nothing overlapped",
+               "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+               "api": "sigma_load (pinned host CSR) -> sigma_run -> sigma_store_compact (bits, sizes, literals, eliminated, witness stack, trail to pinned host)"}
+        if ms_pipe:
+            e2e_pipe = lit_all / (ms_pipe * 1e-3)
+            e2e["serial"] = {"value": e2e_serial, "ms_per_step": ms_e2e / steps}
+            e2e["pipelined"] = {"value": e2e_pipe, "ms_per_step": ms_pipe, "contexts_per_gpu": a.pipeline, "timer": "host clock around the batch of steps, "
+                                "device synchronised on both sides, max over ranks"}
+            if e2e_pipe > e2e_serial:
+                e2e.update({"value": e2e_pipe, "ms_per_step": ms_pipe,
+                            "mode": f"{a.pipeline} contexts per GPU (replicas.Pipeline): every step still copies its input from and its result to pinned "
+                                    "host memory; the PCIe legs and kernels of neighbouring steps overlap"})
         line = {
-            "metric": METRIC, "value": lit_all * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "ms_per_round": ms / a.steps / nrounds, "rounds_per_step": nrounds,
+            "metric": METRIC, "value": lit_all * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": a.warmup,
+            "ms_per_step": ms / steps, "ms_per_round": ms / steps / nrounds, "rounds_per_step": nrounds,
+            "literals_per_round_s": lit_rounds * world * steps / (ms * 1e-3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": a.workload + ("" if a.scale == 1.0 else f" x{a.scale}"), "family": fam, "args": args, "seed": seed,
-                       "vars": V, "clauses": C0, "literals": L0, "flags": flags or "reference defaults (fixed-order election)",
-                       "l2": "inputs exceed L2 (no flush needed)" if 4 * L0 > 2 * 126e6 else "inputs fit L2: cold misses only on the first pass of a step",
-                       "parallelism": f"replicas x{world} (one CNF per GPU, no collective)"},
-            "e2e": {"value": lit_all * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
-                    "h2d_bytes_per_step": int(lits.nbytes + offs.nbytes), "d2h_bytes_per_step": d2h // a.steps},
-            "gpu_launches": int(launches), "clocks": clk,
-            **({"e2e_pipelined": {"value": lit_step * piped["steps"] / (piped["ms"] * 1e-3), "unit": UNIT, "contexts": a.pipeline,
-                                  "steps": piped["steps"], "ms_per_step": piped["ms"] / piped["steps"],
-                                  "note": "rank 0 only; every step copies its input from and its result to pinned host memory, "
-                                          "steps run on K contexts so that PCIe legs and kernels of neighbouring steps overlap"}}
-               if piped else {}),
+            "config": {"workload": a.workload + ("" if a.scale == 1.0 else f" x{a.scale}"), "family": m["fam"], "args": m["args"], "seed": m["seed"],
+                       "vars": m["V"], "clauses": m["C0"], "literals": m["L0"], "flags": m["flags"] or "reference defaults (fixed-order election)",
+                       "unit_definition": "literals of the input formula per simplify() call (all rounds) / time",
+                       "l2": "inputs exceed L2 (no flush needed)" if 4 * m["L0"] > 2 * 126e6 else "inputs fit L2: cold misses only on the first pass of a step",
+                       "parallelism": f"replicas x{world} (one CNF per GPU, no collective)", "numa": numa},
+            "e2e": e2e,
+            "gpu_launches": int(sum(r["kernel_launches"] for r in reps)), "clocks": m["clocks"],
             "result": {"clauses_out": reps[-1]["clauses"], "literals_out": reps[-1]["literals"], "eliminated_vars": reps[-1]["eliminated_vars"],
-                       "cnfstate": reps[-1]["cnfstate"]},
-            "roofline": roofline(ktimes, meanC, meanL, V, peaks, a.workload),
+                       "cnfstate": reps[-1]["cnfstate"], "rounds": [{k: r[k] for k in ("kind", "elected", "eliminated", "resolvents", "clauses", "literals")} for r in rounds]},
+            "roofline": roofline_block(m["kstats"], peaks, a.workload),
+            "memory": m["memory"],
         }
         if world == 1 and not a.no_cpu_baseline and os.path.exists(REF_CPU):
-            try:
-                path, sV, sC, sL, desc = ref_sample(a.workload)
-                try:
-                    r = run_ref_cpu(path, sL)
-                finally:
-                    os.remove(path)
-                line["cpu_baseline"] = {"value": r["literals"] / (r["ms"] * 1e-3), "unit": UNIT, "cores": 1, "kind": "reference",
-                                        "sample": desc, "ms": r["ms"], "rounds": r["rounds"], "host_cores_available": os.cpu_count()}
-            except Exception as e:  # the baseline is reported, never required for the line
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e!r}"[:200]}
+            line["cpu_baseline"] = cpu_baseline_for(a.workload)
         elif world == 1:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "skipped"}
+        # ---- secondary: the workload on which BVE / SUB / GC really fire (cfg2 eliminates nothing: VERDICT r01)
+        if world == 1 and a.workload == "cfg2" and not a.no_secondary and a.scale == 1.0:
+            try:
+                m3 = measure(a, torch, "cfg3", rank, world, local, barrier, min(a.steps, 5), min(a.warmup, 3), a.pipeline, with_clocks=False)
+                st3 = m3["steps"]
+                sec = {"workload": "cfg3", "vars": m3["V"], "clauses": m3["C0"], "literals": m3["L0"],
+                       "value": m3["L0"] * st3 / (m3["ms"] * 1e-3), "unit": UNIT, "ms_per_step": m3["ms"] / st3, "rounds_per_step": len(m3["rounds"]),
+                       "ms_per_round": m3["ms"] / st3 / max(1, len(m3["rounds"])),
+                       "e2e": {"value": m3["L0"] * st3 / (m3["ms_e2e"] * 1e-3), "ms_per_step": m3["ms_e2e"] / st3, "h2d_bytes_per_step": m3["h2d"],
+                               "d2h_bytes_per_step": m3["d2h"],
+                               **({"pipelined_ms_per_step": m3["piped"]["ms"] / m3["piped"]["steps"]} if m3["piped"] else {})},
+                       "result": {"clauses_out": m3["reps"][-1]["clauses"], "literals_out": m3["reps"][-1]["literals"],
+                                  "eliminated_vars": m3["reps"][-1]["eliminated_vars"]},
+                       "gpu_launches_per_step": int(m3["reps"][-1]["kernel_launches"]),
+                       "roofline": roofline_block(m3["kstats"], peaks, "cfg3")}
+                if not a.no_cpu_baseline and os.path.exists(REF_CPU):
+                    sec["cpu_baseline"] = cpu_baseline_for("cfg3")
+                line["secondary"] = sec
+            except Exception as e:  # noqa: BLE001 - the secondary block never costs the headline line
+                line["secondary"] = {"workload": "cfg3", "error": repr(e)[:300]}
         print(json.dumps(line))
-    s.close()
     if dist is not None:
         dist.barrier(device_ids=[local])
         dist.destroy_process_group()

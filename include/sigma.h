@@ -193,6 +193,10 @@ int  sigma_debug_hist(sigma_ctx* c, uint32_t* out);                             
  * sigma_kernel_times: names is n*64 chars, *n = capacity in, entries out. */
 int  sigma_kernel_profile(sigma_ctx* c, int enable);
 int  sigma_kernel_times(sigma_ctx* c, char* names, float* ms, uint32_t* counts, uint32_t* n);
+/* the same plus the ALGORITHMIC bytes each kernel name had to move over its launches (16-byte clause
+ * headers, 4-byte literals and list entries; the per-variable kernels sum (4 + 16 + 4|c|) over the clauses of the
+ * variables they were given, counted on the device) - the numerator of the per-kernel roofline. */
+int  sigma_kernel_stats(sigma_ctx* c, char* names, float* ms, uint32_t* counts, double* bytes, uint32_t* n);
 
 /* arena statistics (replaces cuArena's gpu_peak_used, simplify.cu:219-220) */
 int  sigma_memory(const sigma_ctx* c, uint64_t* arena_bytes, uint64_t* peak_used, uint64_t* cuda_mallocs);

@@ -60,11 +60,16 @@ extern "C" int sigma_kernel_profile(sigma_ctx* c, int enable) {
         for (int i = 0; i < 2 * KT_POOL; i++) CUDA_TRY(cudaEventCreate(&c->ktEv[i]));
     }
     if (c->ktOn) ktFlush(c);
-    if (enable == 2 || !enable) { /* keep totals */ } else { memset(c->ktMs, 0, sizeof c->ktMs); memset(c->ktCount, 0, sizeof c->ktCount); }
+    if (enable == 2 || !enable) { /* keep totals */ } else { memset(c->ktMs, 0, sizeof c->ktMs); memset(c->ktCount, 0, sizeof c->ktCount); memset(c->ktBytes, 0, sizeof c->ktBytes); }
+    c->ktLastId = -1;
     c->ktOn = enable != 0;
     return SIGMA_OK;
 }
+extern "C" int sigma_kernel_stats(sigma_ctx* c, char* names, float* ms, uint32_t* counts, double* bytes, uint32_t* n);
 extern "C" int sigma_kernel_times(sigma_ctx* c, char* names, float* ms, uint32_t* counts, uint32_t* n) {
+    return sigma_kernel_stats(c, names, ms, counts, nullptr, n);
+}
+extern "C" int sigma_kernel_stats(sigma_ctx* c, char* names, float* ms, uint32_t* counts, double* bytes, uint32_t* n) {
     if (!c || !n) return SIGMA_BAD_ARGUMENT;
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->ktOn) ktFlush(c);
@@ -76,6 +81,7 @@ extern "C" int sigma_kernel_times(sigma_ctx* c, char* names, float* ms, uint32_t
         if (names) { strncpy(names + 64 * out, i < gKtN ? gKtNames[i] : "(other)", 63); names[64 * out + 63] = 0; }
         if (ms) ms[out] = c->ktMs[i];
         if (counts) counts[out] = c->ktCount[i];
+        if (bytes) bytes[out] = c->ktBytes[i];
         out++;
     }
     *n = out;

@@ -70,6 +70,7 @@ void launchAwaken(Ctx* c) {
     cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
     LAUNCH(c, k_awaken, gridFor(c->C0, 256), 256, 0, c->inLits, c->inOffs, c->inMeta, c->C0, c->hdr[c->cur], c->pool[c->cur], c->hist, c->key,
            &c->dc->flags);
+    KB(c, 8.0 * c->C0 + 4.0 * c->L0 + (c->inMeta ? 4.0 * c->C0 : 0.0) + 16.0 * c->C0 + 4.0 * c->L0 + 16.0 * c->C0 + 4.0 * c->ND);   // offsets + literals in, headers + literals + keys + histogram out
     c->histFresh = true;   // hist[] and key[] describe the store until a kernel changes it (api.cu: buildOT)
 }
 
@@ -97,7 +98,10 @@ __global__ void k_hist_key(const uint4* __restrict__ hdr, const u32* __restrict_
 void launchHistKey(Ctx* c) {
     cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
     const u32 n = c->hdc->numCls;
-    if (n) LAUNCH(c, k_hist_key, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->hist, c->key, &c->dc->flags);
+    if (n) {
+        LAUNCH(c, k_hist_key, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->hist, c->key, &c->dc->flags);
+        KB(c, 16.0 * n + 4.0 * c->numLiterals + 16.0 * c->numClauses + 4.0 * c->ND);
+    }
 }
 
 // ------------------------------------------------------------------ occurrence lists: partition + place
@@ -358,9 +362,11 @@ void launchScatter(Ctx* c) {
     else
         LAUNCH(c, (k_ot_part<3, 5>), divup(n, PART_THREADS * 3), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
                c->otStart, c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
+    KB(c, 16.0 * n + 4.0 * c->numLiterals + 8.0 * c->numLiterals);   // headers + literals in, (literal, clause) pairs out
     u32* nBig = &c->dc->scratch[7];
     cudaMemsetAsync(nBig, 0, 4, c->stream);
     LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
+    KB(c, 8.0 * c->numLiterals + 4.0 * c->numLiterals + 12.0 * c->ND);   // pairs in, list entries out, list bounds
     LAUNCH(c, k_ot_place_big, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs, c->otBig, nBig);
 }
 
@@ -391,6 +397,7 @@ __global__ void k_count(const uint4* __restrict__ hdr, DevCounters* dc) {
 void launchCount(Ctx* c) {
     LAUNCH(c, k_count_reset, 1, 1, 0, c->dc);
     LAUNCH(c, k_count, 148 * 4, 256, 0, c->hdr[c->cur], c->dc);
+    KB(c, 16.0 * c->hdc->numCls);
 }
 
 // ------------------------------------------------------------------ GC compaction
@@ -430,10 +437,12 @@ void launchGC(Ctx* c) {
     if (!n) return;
     const int src = c->cur, dst = 1 - c->cur;
     LAUNCH(c, k_gc_flags, gridFor(n, 256), 256, 0, c->hdr[src], n, c->flagA, c->flagB);
+    KB(c, 24.0 * n);
     u32* tot = c->dc->scratch;
     scanExclusiveU32(c, c->flagA, c->flagA, n, 0, tot);
     scanExclusiveU32(c, c->flagB, c->flagB, n, 0, tot + 1);
     LAUNCH(c, k_gc_copy, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, c->hdr[dst], c->pool[dst]);
+    KB(c, 24.0 * n + 16.0 * c->numClauses + 8.0 * c->numLiterals);   // headers + scan values in, live literals in and out, live headers out
     LAUNCH(c, k_gc_finish, 1, 1, 0, c->dc, tot, tot + 1);
     c->cur = dst;
 }

@@ -115,6 +115,7 @@ struct DevCounters {
     // device DRAT stream (elim.cu, proof kernels): bytes appended this round, the reference's capacity, units mark
     u32 proofSize, proofCap, proofUnits0, proofPad;
     u64 proofLitBytes; // proof bytes of every literal of the loaded formula (cuPROOF::count, proof.cu:101-121)
+    u64 profBytes;     // kernel profile mode: bytes walked by the per-variable kernels (sigma_kernel_stats)
 };
 
 struct KOpts {   // kernel-side options (replaces __constant__ kOpts, options.cuh:27-45)
@@ -191,6 +192,7 @@ struct Ctx {
     unsigned char* proofAll; u64 proofAllSize, proofAllCap; u64* proofEnds; u32 nProofChunks, capProofChunks;
     sigma_proof_sink proofSink; void* proofUser;
     float ktMs[KT_MAX_KERNELS]; u32 ktCount[KT_MAX_KERNELS];
+    double ktBytes[KT_MAX_KERNELS]; int ktLastId;   // algorithmic bytes per kernel name, fed by KB() / profGather()
 };
 
 enum Stage { ST_VO = 0, ST_SIG, ST_IO, ST_GC, ST_COT, ST_SOT, ST_ROT, ST_VE, ST_SUB, ST_BCE, ST_ERE, ST_PROP, ST_LCVE, ST_CNT };
@@ -207,11 +209,15 @@ enum Stage { ST_VO = 0, ST_SIG, ST_IO, ST_GC, ST_COT, ST_SOT, ST_ROT, ST_VE, ST_
 #define LAUNCH(c, kern, grid, block, smem, ...)                     \
     do {                                                            \
         static int _kid = -1;                                       \
-        if ((c)->ktOn) { if (_kid < 0) _kid = ktRegister(#kern); ktBegin((c), _kid); } \
+        if ((c)->ktOn) { if (_kid < 0) _kid = ktRegister(#kern); ktBegin((c), _kid); (c)->ktLastId = _kid; } \
         kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__); \
         if ((c)->ktOn) ktEnd(c);                                    \
         (c)->launches++;                                            \
     } while (0)
+
+// algorithmic bytes of the launch just made (kernel profile mode only): what the kernel must move at least -
+// 16-byte clause headers, 4-byte literals and list entries
+#define KB(c, expr) do { if ((c)->ktOn && (c)->ktLastId >= 0) (c)->ktBytes[(c)->ktLastId] += (double)(expr); } while (0)
 
 static inline u32 divup(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
 // grid-stride launches: enough CTAs to fill 148 SMs several times over, never more than the work
@@ -282,3 +288,6 @@ void launchERE(Ctx* c, const KOpts& k);
 void launchProofCount(Ctx* c);   // cuPROOF::count: dc->proofLitBytes, dc->proofCap
 // api.cu
 int  syncCounters(Ctx* c);   // D2H of DevCounters into c->hdc, stream synchronised
+// elim.cu, profile mode: sum over the variables wl[0 .. *count) (indices into elected[], or variables when `direct`) of
+// (4 + 16 + 4|c|) over the clauses of both occurrence lists -> *out (host), the SUB / BVE / ERE / MIS byte formula of SURVEY 8d
+double profGather(Ctx* c, const u32* wl, const u32* countDev, u32 upper, bool direct);

@@ -1248,6 +1248,54 @@ __global__ void k_bin_elected(const u32* __restrict__ elected, const u32* nDev, 
     }
 }
 
+// ------------------------------------------------------------------ kernel profile mode: algorithmic bytes of the per-variable kernels
+// SUB / BVE / BCE / ERE must read, for every variable they are given, every clause of its two occurrence
+// lists: list entry (4) + header (16) + literals (4|c|).  Summed on the device over a worklist; `filter` (BVE phase 3)
+// keeps the variables with a recorded elimination type.
+__global__ void __launch_bounds__(256) k_gather_bytes(const u32* __restrict__ wl, const u32* __restrict__ count, u32 upper, const u32* __restrict__ elected,
+                                                      const u32* __restrict__ otStart, const u32* __restrict__ otSize, const u32* __restrict__ occurs,
+                                                      const uint4* __restrict__ hdr, const u32* __restrict__ filter, unsigned long long* out) {
+    const u32 n = count ? *count : upper;
+    unsigned long long b = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 item = wl ? wl[i] : i;
+        if (filter && !RECOVERTYPE(filter[item])) continue;
+        const u32 x = elected ? elected[item] : (item & 0x7FFFFFFFu);
+        for (u32 side = 0; side < 2; side++) {
+            const u32 lit = V2L(x) | side;
+            const u32 m = otSize[lit];
+            const u32* list = occurs + otStart[lit];
+            for (u32 j = 0; j < m; j++) b += 20u + 4u * hdr[list[j]].y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if ((threadIdx.x & 31u) == 0 && b) atomicAdd(out, b);
+}
+static double gatherBytes(Ctx* c, const u32* wl, const u32* countDev, u32 upper, bool direct, const u32* filter) {
+    if (!c->ktOn || !upper) return 0.0;
+    unsigned long long* out = (unsigned long long*)&c->dc->profBytes;
+    unsigned long long b = 0;
+    cudaMemsetAsync(out, 0, 8, c->stream);
+    k_gather_bytes<<<gridFor(upper, 256), 256, 0, c->stream>>>(wl, countDev, upper, direct ? nullptr : c->elected, c->otStart, c->otSize, c->occurs,
+                                                             c->hdr[c->cur], filter, out);
+    cudaMemcpyAsync(&b, out, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemsetAsync(out, 0, 8, c->stream);
+    cudaStreamSynchronize(c->stream);
+    return (double)b;
+}
+double profGather(Ctx* c, const u32* wl, const u32* countDev, u32 upper, bool direct) { return gatherBytes(c, wl, countDev, upper, direct, nullptr); }
+// bytes of the three group-size classes (worklists of k_bin_elected), taken BEFORE the stage runs (it shrinks the lists)
+struct ClassBytes { double b[3]; };
+static ClassBytes classBytes(Ctx* c, const u32* filter = nullptr) {
+    ClassBytes cb = {{0, 0, 0}};
+    if (!c->ktOn) return cb;
+    cb.b[0] = gatherBytes(c, c->wlA, &c->dc->bin[0], c->numElected, false, filter);
+    cb.b[1] = gatherBytes(c, c->wlB, &c->dc->bin[1], c->numElected, false, filter);
+    cb.b[2] = gatherBytes(c, c->sortK, &c->dc->bin[2], c->numElected, false, filter);
+    return cb;
+}
+
 // ------------------------------------------------------------------ host launchers
 static G makeG(Ctx* c, const KOpts& k) {
     G g;
@@ -1493,11 +1541,14 @@ static void proofStream(Ctx* c, const G& g, u32 lo, u32 hiHost, const u32* hiDev
     ProofOut po{c->proofBuf};
     LAUNCH(c, k_proof_stream, gridFor(sizeHint, 256), 256, 0, g, po, c->proofSnap, lo, hiHost, hiDev, mode);
 }
-#define LAUNCH_CLASSES(c, kern, block, E, g, ...)                                                            \
+#define LAUNCH_CLASSES(c, kern, block, E, g, cb, ...)                                                        \
     do {                                                                                                     \
         LAUNCH(c, kern<4>, groupGrid(E, 4, block), block, 0, asGroup<4>(g), ##__VA_ARGS__, c->wlA, &c->dc->bin[0]);   \
+        KB(c, (cb).b[0]);                                                                                    \
         LAUNCH(c, kern<8>, groupGrid(E, 8, block), block, 0, asGroup<8>(g), ##__VA_ARGS__, c->wlB, &c->dc->bin[1]);   \
+        KB(c, (cb).b[1]);                                                                                    \
         LAUNCH(c, kern<32>, groupGrid(E, 32, block), block, 0, asGroup<32>(g), ##__VA_ARGS__, c->sortK, &c->dc->bin[2]); \
+        KB(c, (cb).b[2]);                                                                                    \
     } while (0)
 
 void launchSUB(Ctx* c, const KOpts& k) {
@@ -1505,7 +1556,8 @@ void launchSUB(Ctx* c, const KOpts& k) {
     G g = makeG(c, k);
     binElected(c, k, false, true);
     if (k.proof_en) proofSnap(c);
-    LAUNCH_CLASSES(c, k_sub, 128, c->numElected, g);
+    const ClassBytes cb = classBytes(c);
+    LAUNCH_CLASSES(c, k_sub, 128, c->numElected, g, cb);
     if (k.proof_en) {   // subsume.cuh:465-475: strengthened clauses added, then subsumed ones deleted
         const u32 n = c->hdc->numCls;
         proofStream(c, g, 0, n, nullptr, PROOF_MOLTEN, n);
@@ -1522,9 +1574,13 @@ void launchVE(Ctx* c, const KOpts& k) {
     binElected(c, k, false, true);   // SUB shrank the lists: classes by the current sizes
     u32* redo = c->rank;       // rank[] is dead after the election
     u32* redoCount = &c->dc->bin[3];
+    const ClassBytes cb1 = classBytes(c);   // + 20 bytes per variable: type, ucnt, rpos, rref (SURVEY 8d "BVE count")
     LAUNCH(c, k_ve_phase1<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
+    KB(c, cb1.b[0]);
     LAUNCH(c, k_ve_phase1<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
+    KB(c, cb1.b[1]);
     LAUNCH(c, k_ve_phase1<32>, groupGrid(E, 32, 128), 128, 0, asGroup<32>(g), c->sortK, &c->dc->bin[2], redo, redoCount);
+    KB(c, cb1.b[2] + 20.0 * E);
     LAUNCH(c, k_ve_phase1<32>, 148, 128, 0, asGroup<32>(g), redo, redoCount, redo, redoCount);   // variables handed over by the small groups
     if (k.proof_en) {
         LAUNCH(c, k_proof_guard, gridFor(E, 256), 256, 0, g, E, c->proofBMax);
@@ -1535,8 +1591,24 @@ void launchVE(Ctx* c, const KOpts& k) {
     vb.numCls0 = c->hdc->numCls; vb.poolUsed0 = c->hdc->poolUsed; vb.dataSize0 = c->hdc->dataSize;
     scanExclusiveU32(c, c->veRpos, c->veRpos, E, vb.numCls0, nullptr);
     scanExclusiveU64(c, c->veRref, c->veRref, E, vb.dataSize0);
-    LAUNCH_CLASSES(c, k_ve_phase3, 128, E, g, vb, c->flagA);
+    // BVE emit: the lists of the variables that resolve + (kernel profile mode, after the fact) the resolvents written
+    const ClassBytes cb3 = classBytes(c, c->veType);
+    int kid3[3] = {-1, -1, -1};
+    LAUNCH(c, k_ve_phase3<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), vb, c->flagA, c->wlA, &c->dc->bin[0]);
+    KB(c, cb3.b[0]); kid3[0] = c->ktLastId;
+    LAUNCH(c, k_ve_phase3<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), vb, c->flagA, c->wlB, &c->dc->bin[1]);
+    KB(c, cb3.b[1]); kid3[1] = c->ktLastId;
+    LAUNCH(c, k_ve_phase3<32>, groupGrid(E, 32, 128), 128, 0, asGroup<32>(g), vb, c->flagA, c->sortK, &c->dc->bin[2]);
+    KB(c, cb3.b[2]); kid3[2] = c->ktLastId;
     LAUNCH(c, k_ve_resize, 1, 1, 0, g, vb);
+    if (c->ktOn && kid3[0] >= 0) {   // resolvents written: 16 bytes of header + 4 per literal; shared out by the classes' read bytes
+        DevCounters t;
+        cudaMemcpyAsync(&t, c->dc, sizeof t, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        const double wr = 16.0 * (t.numCls - vb.numCls0) + 4.0 * (t.poolUsed - vb.poolUsed0);
+        const double tot = cb3.b[0] + cb3.b[1] + cb3.b[2];
+        for (int q = 0; q < 3; q++) if (tot > 0) c->ktBytes[kid3[q]] += wr * cb3.b[q] / tot;
+    }
     if (k.proof_en) {   // before elected[] is compacted: k_proof_equ walks the lists of the variables eliminated in phase 1
         ProofOut po{c->proofBuf};
         LAUNCH(c, k_proof_equ, gridFor((u64)E * 32, 256), 256, 0, g, po, E);
@@ -1557,7 +1629,8 @@ void launchBCE(Ctx* c, const KOpts& k) {
     G g = makeG(c, k);
     binElected(c, k, false);
     if (k.proof_en) proofSnap(c);
-    LAUNCH_CLASSES(c, k_bce, 128, c->numElected, g);
+    const ClassBytes cb = classBytes(c);
+    LAUNCH_CLASSES(c, k_bce, 128, c->numElected, g, cb);
     if (k.proof_en) proofStream(c, g, 0, c->hdc->numCls, nullptr, PROOF_NEWDEL, c->hdc->numCls);   // blocked.cuh:67-72
 }
 
@@ -1573,6 +1646,7 @@ void launchERE(Ctx* c, const KOpts& k) {
     u32* bloom = (u32*)c->otPairs;
     cudaMemsetAsync(bloom, 0, bits / 8 + 32, c->stream);   // + the 256-bit clause-size mask
     LAUNCH(c, k_ere_bloom, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->key, n, bloom, (u32)(bits - 1));
+    KB(c, 32.0 * n);   // header word + key per clause (the filter bits stay in L2)
     g.bloom = bloom; g.bloomMask = (u32)(bits - 1);
     binElected(c, k, false);
     // Phase A records the resolvents that pass the filters; only the lists they will be searched in
@@ -1587,16 +1661,18 @@ void launchERE(Ctx* c, const KOpts& k) {
     cudaMemsetAsync(Q.count, 0, 8, c->stream);
     cudaMemsetAsync(c->needSort, 0, c->ND, c->stream);
     if (k.proof_en) proofSnap(c);   // the first pass only records: nothing is deleted before the snapshot is taken
-    LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g, Q);
+    const ClassBytes cb = classBytes(c);
+    LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g, cb, Q);
     if (syncCounters(c)) return;
     const u32 nq = c->hdc->scratch[3];
     if (c->hdc->scratch[4]) {   // more survivors than the queue holds: sort everything, search in place (nothing was deleted yet)
         launchSortOT(c, 0);
         Q.items = nullptr;
-        LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g, Q);
+        LAUNCH_CLASSES(c, k_ere_pairs, 256, c->numElected, g, cb, Q);
     } else if (nq) {
         launchSortOT(c, 2);
         LAUNCH(c, k_ere_apply, gridFor(nq, 256), 256, 0, asGroup<32>(g), Q.items, Q.count);
+        KB(c, 12.0 * nq + 2.0 * 36.0 * nq + 10.0 * 20.0 * nq);   // queue entry, the two parents, ~10 key probes of the binary search
     }
     if (k.proof_en) proofStream(c, g, 0, n, nullptr, PROOF_NEWDEL, n);   // redundancy.cuh:122-129
 }

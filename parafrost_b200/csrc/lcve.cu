@@ -117,8 +117,10 @@ void radixSortPairs(Ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, u32 n,
     if (passes > 4) passes = 4;
     for (u32 shift = 0; shift < 8 * passes; shift += 8) {
         LAUNCH(c, k_radix_hist, nblocks, RS_THREADS, 0, ki, n, shift, c->radixHist, nblocks);
+        KB(c, 4.0 * n);
         scanExclusiveU32(c, c->radixHist, c->radixHist, (u64)256 * nblocks, 0, nullptr);
         LAUNCH(c, k_radix_scatter, nblocks, RS_THREADS, 0, ki, vi, ko, vo, n, shift, c->radixHist, nblocks);
+        KB(c, 16.0 * n);
         u32* t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;
     }
@@ -167,6 +169,7 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
             const uint4 h_ = hdr[list_[j_]];                                                           \
             if (C_DELETED(h_.w)) continue;                                                             \
             const u32 csize = h_.y; (void)csize;                                                       \
+            pb_ += 20u + 8u * csize;   /* profile: list entry + header + literals + election words */  \
             const u32* l_ = pool + h_.x;                                                               \
             for (u32 k_ = 0; k_ < h_.y; k_++) { const u32 ul_ = l_[k_]; const u32 u = LABS(ul_); if (u != (V_)) { const bool upos = !LSIGN(ul_); (void)upos; const u32 wu = vinfo[u]; APPLY_ } } \
         }                                                                                              \
@@ -196,6 +199,7 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
             _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) {                                         \
                 if (C_DELETED(h_[u_].w)) continue;                                                     \
                 const u32 csize = h_[u_].y; (void)csize;                                               \
+                pb_ += 20u + 8u * csize;                                                               \
                 const u32* l_ = pool + h_[u_].x;                                                       \
                 u32 lv_[8], wv_[8];                                                                    \
                 _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) lv_[k_] = (u32)k_ < h_[u_].y ? l_[k_] : V2L(V_); /* literals */ \
@@ -211,11 +215,20 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
 // neighbour's state word agrees on FROZEN (a neighbour of a just-elected variable can neither be
 // elected nor become the live stopper in the same launch: it sees this variable undecided or elected).
 template <int GS>
-__device__ __forceinline__ void pushFreeze(u32 v, u32 r, u32 lane, const uint4* __restrict__ hdr, const u32* __restrict__ pool,
-                                           const u32* __restrict__ otStart, const u32* __restrict__ otSize,
-                                           const u32* __restrict__ occurs, u32* vinfo, u32 nsides) {
+__device__ __forceinline__ u32 pushFreeze(u32 v, u32 r, u32 lane, const uint4* __restrict__ hdr, const u32* __restrict__ pool,
+                                          const u32* __restrict__ otStart, const u32* __restrict__ otSize,
+                                          const u32* __restrict__ occurs, u32* vinfo, u32 nsides) {
     // nsides = 1 for a MIS_HALF variable: only the clauses of its positive list freeze their variables
+    u32 pb_ = 0;   // bytes this lane walked (kernel profile mode)
     MIS_WALK_ANY(GS, v, lane, nsides, { if (VI_STATE(wu) == MIS_UNDECIDED && VI_RANK(wu) > r) vinfo[u] = (wu & ~7u) | MIS_FROZEN; })
+    return pb_;
+}
+// profile mode: the bytes walked by this thread -> *prof (one atomic per warp)
+__device__ __forceinline__ void profAdd(unsigned long long* prof, unsigned long long pb) {
+    if (!prof) return;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) pb += __shfl_xor_sync(0xffffffffu, pb, o);
+    if ((threadIdx.x & 31u) == 0 && pb) atomicAdd(prof, pb);
 }
 
 // push for the variables elected by k_mis_first (thread-per-variable there: no group to walk the lists)
@@ -223,22 +236,26 @@ template <int GS>
 __global__ void __launch_bounds__(256) k_mis_push(const u32* __restrict__ list, const u32* __restrict__ count,
                                                   const uint4* __restrict__ hdr, const u32* __restrict__ pool,
                                                   const u32* __restrict__ otStart, const u32* __restrict__ otSize,
-                                                  const u32* __restrict__ occurs, u32* vinfo) {
+                                                  const u32* __restrict__ occurs, u32* vinfo, unsigned long long* prof) {
     const u32 n = *count;
     const u32 lane = threadIdx.x & (u32)(GS - 1);
     const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    unsigned long long pb = 0;
     for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) / GS; it < n; it += groupsPerGrid) {
         const u32 e = list[it];
         const u32 v = e & 0x7FFFFFFFu;   // bit 31: MIS_HALF
-        pushFreeze<GS>(v, VI_RANK(vinfo[v]), lane, hdr, pool, otStart, otSize, occurs, vinfo, (e >> 31) ? 1u : 2u);
+        pb += pushFreeze<GS>(v, VI_RANK(vinfo[v]), lane, hdr, pool, otStart, otSize, occurs, vinfo, (e >> 31) ? 1u : 2u);
     }
+    profAdd(prof, pb);
 }
 
 template <int GS>
 __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* __restrict__ wl1, u32 round, DevCounters* dc,
                                                    const uint4* __restrict__ hdr, const u32* __restrict__ pool,
                                                    const u32* __restrict__ otStart, const u32* __restrict__ otSize,
-                                                   const u32* __restrict__ occurs, u32* vinfo, u32* __restrict__ blocker, int maxcsize) {
+                                                   const u32* __restrict__ occurs, u32* vinfo, u32* __restrict__ blocker, int maxcsize,
+                                                   unsigned long long* prof) {
+    unsigned long long pb = 0;
     const u32* wlIn = (round & 1u) ? wl1 : wl0;
     u32* wlOut = (round & 1u) ? wl0 : wl1;
     const u32 nIn = dc->wlCnt[round % 3u];
@@ -252,6 +269,7 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
         const u32 v = wlIn[it];
         const u32 wv = vinfo[v];
         const u32 r = VI_RANK(wv);
+        if (lane == 0) pb += 16;   // worklist entry, election word, blocker and its word
         if (VI_STATE(wv) != MIS_UNDECIDED) continue;   // frozen by an elected neighbour's push
         if (r > dc->misStopRank) continue;  // beyond the cut: never looked at by the serial walk
         const u32 b = blocker[v];
@@ -262,6 +280,7 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
         }
         bool frozen = false, overP = false, overN = false;
         u32 bRank = NOVAR, bVar = 0;
+        u32 pb_ = 0;
         MIS_WALK_ANY(GS, v, lane, 2u, {
             if ((int)csize > maxcsize) { if (side_ == 0) overP = true; else overN = true; }
             if (VI_RANK(wu) < r) {
@@ -271,6 +290,7 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
                 else if (m == MIS_UNDECIDED && VI_CLASS(wu) == CS_CAND && VI_RANK(wu) < bRank) { bRank = VI_RANK(wu); bVar = u; }
             }
         })
+        pb += pb_;
         frozen = __any_sync(gmask, frozen);
         overP = __any_sync(gmask, overP);
         overN = __any_sync(gmask, overN);
@@ -293,8 +313,9 @@ __global__ void __launch_bounds__(256) k_mis_round(u32* __restrict__ wl0, u32* _
             else wlOut[atomicAdd(outCnt, 1u)] = v;
         }
         if (!frozen && !blocked && !overP && VI_CLASS(wv) == CS_CAND)   // just elected or MIS_HALF (uniform over the group)
-            pushFreeze<GS>(v, r, lane, hdr, pool, otStart, otSize, occurs, vinfo, overN ? 1u : 2u);
+            pb += pushFreeze<GS>(v, r, lane, hdr, pool, otStart, otSize, occurs, vinfo, overN ? 1u : 2u);
     }
+    profAdd(prof, pb);
 }
 
 // ------------------------------------------------------------------ first MIS round, clause-centric
@@ -451,8 +472,20 @@ __global__ void __launch_bounds__(128) k_frozen12(const u32* __restrict__ electe
 // ------------------------------------------------------------------ host driver
 #define MIS_BATCH 6   // MIS rounds queued per host round-trip (an empty round costs ~4 us, a round trip ~40 us)
 
+// kernel profile mode: fetch and clear the device byte counter, attribute it to the kernel launched last
+static void profCollect(Ctx* c, int kid) {
+    if (!c->ktOn || kid < 0) return;
+    unsigned long long b = 0;
+    cudaMemcpyAsync(&b, &c->dc->profBytes, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemsetAsync(&c->dc->profBytes, 0, 8, c->stream);
+    cudaStreamSynchronize(c->stream);
+    c->ktBytes[kid] += (double)b;
+}
+
 int runLCVE(Ctx* c) {
     const u32 V = c->V;
+    unsigned long long* prof = c->ktOn ? (unsigned long long*)&c->dc->profBytes : nullptr;
+    if (prof) cudaMemsetAsync(prof, 0, 8, c->stream);
     const u32 pmax = c->o.mu_pos << c->multiplier, nmax = c->o.mu_neg << c->multiplier;
     u32* vinfo = c->rank;
     u32* blocker = c->sortV;   // free once the radix sort is done
@@ -462,6 +495,7 @@ int runLCVE(Ctx* c) {
     CUDA_TRY(cudaMemsetAsync(&c->dc->scratch[8], 0, 4, c->stream));   // number of MIS_HALF decisions
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
            c->scores, c->eligible, c->cstat, c->dc);
+    KB(c, 18.0 * V);
     int rc = syncCounters(c);   // the largest score decides how many radix passes the sort needs (usually 2 of 4)
     if (rc) return rc;
     u32 bits = 0;
@@ -472,6 +506,7 @@ int runLCVE(Ctx* c) {
     CUDA_TRY(cudaMemsetAsync(nbr, 0xFF, (size_t)(V + 1) * 4, c->stream));
     CUDA_TRY(cudaMemsetAsync(ovs, 0, (size_t)V + 1, c->stream));
     LAUNCH(c, k_rank, gridFor(V, 256), 256, 0, c->eligible, c->cstat, V, vinfo, c->dc);
+    KB(c, 9.0 * V);
     rc = syncCounters(c);
     if (rc) return rc;
     const u32 firstStop = c->hdc->firstStop < V ? c->hdc->firstStop : V;   // everything ranked before it is walked for sure
@@ -499,6 +534,7 @@ int runLCVE(Ctx* c) {
         bool clausePass = (u64)n * avgOcc * 2 > nCls;
         if (dense && hPrev) {   // most of the chunk is frozen already: count what is left before choosing
             LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, vinfo, hPrev, H, wlIn, c->dc, round % 3u);
+            KB(c, 12.0 * (H - hPrev));
             if ((rc = syncCounters(c))) return rc;
             n = c->hdc->wlCnt[round % 3u];
             clausePass = (u64)n * avgOcc * 2 > nCls;
@@ -506,19 +542,23 @@ int runLCVE(Ctx* c) {
         }
         if (clausePass) {
             LAUNCH(c, k_mis_clauses, gridFor(nCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], nCls, vinfo, nbr, ovs, H, c->o.lcve_clause_max);
+            KB(c, 16.0 * nCls + 8.0 * c->numLiterals);   // headers, literals, election words
             u32* pushCount = &c->dc->scratch[2];
             CUDA_TRY(cudaMemsetAsync(pushCount, 0, 4, c->stream));
             LAUNCH(c, k_mis_first, gridFor(H - hPrev, 256), 256, 0, c->eligible, hPrev, H, vinfo, nbr, ovs, blocker, wlIn, c->dc, round % 3u,
                    c->flagA, pushCount);
+            KB(c, 21.0 * (H - hPrev));
             if (smallGroups)
                 LAUNCH(c, k_mis_push<8>, gridFor((u64)(H - hPrev) * 8, 256), 256, 0, c->flagA, pushCount, c->hdr[c->cur], c->pool[c->cur],
-                       c->otStart, c->otSize, c->occurs, vinfo);
+                       c->otStart, c->otSize, c->occurs, vinfo, prof);
             else
                 LAUNCH(c, k_mis_push<32>, gridFor((u64)(H - hPrev) * 32, 256), 256, 0, c->flagA, pushCount, c->hdr[c->cur], c->pool[c->cur],
-                       c->otStart, c->otSize, c->occurs, vinfo);
+                       c->otStart, c->otSize, c->occurs, vinfo, prof);
+            profCollect(c, c->ktLastId);
             n = H - hPrev;
         } else if (!(dense && hPrev))
             LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, vinfo, hPrev, H, wlIn, c->dc, round % 3u);
+            KB(c, 12.0 * (H - hPrev));
         u32 guard = 0;
         while (n) {
             if (++guard > 100000u) { snprintf(c->err, sizeof c->err, "MIS did not converge"); return SIGMA_AWAKEN_FAIL; }
@@ -528,11 +568,12 @@ int runLCVE(Ctx* c) {
             for (int b = 0; b < MIS_BATCH; b++, round++) {
                 if (smallGroups)
                     LAUNCH(c, k_mis_round<8>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
-                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max);
+                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max, prof);
                 else
                     LAUNCH(c, k_mis_round<32>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
-                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max);
+                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max, prof);
             }
+            profCollect(c, c->ktLastId);
             CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             n = c->hdc->wlCnt[round % 3u];

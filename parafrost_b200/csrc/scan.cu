@@ -107,11 +107,13 @@ __global__ void __launch_bounds__(1024) k_scan_small(const T* in, T* out, u32 n,
 template <typename T>
 static void scanImpl(Ctx* c, const T* in, T* out, u64 n, T init, T* tmp, T* totalOut) {
     if (!n) return;  // callers never scan empty ranges with a total
-    if (n <= SCAN_SMALL_MAX) { LAUNCH(c, k_scan_small<T>, 1, 1024, 0, in, out, (u32)n, init, totalOut); return; }
+    if (n <= SCAN_SMALL_MAX) { LAUNCH(c, k_scan_small<T>, 1, 1024, 0, in, out, (u32)n, init, totalOut); KB(c, 2.0 * sizeof(T) * n); return; }
     const u32 ntiles = divup(n, SCAN_TILE);
     LAUNCH(c, k_scan_reduce<T>, ntiles, SCAN_THREADS, 0, in, n, tmp);
+    KB(c, (double)sizeof(T) * n);
     LAUNCH(c, k_scan_tiles<T>, 1, 1024, 0, tmp, ntiles, init, totalOut);
     LAUNCH(c, k_scan_down<T>, ntiles, SCAN_THREADS, 0, in, out, n, tmp);
+    KB(c, 2.0 * sizeof(T) * n);
 }
 
 void scanExclusiveU32(Ctx* c, const u32* in, u32* out, u64 n, u32 init, u32* totalOut) {

@@ -88,9 +88,10 @@ class Pipeline:
     make() -> an object with load / simplify / rounds / store / close (sigma.Simplifier); injectable for CPU tests.
     """
 
-    def __init__(self, device: int = 0, depth: int = 3, flags=(), make=None, **opts):
+    def __init__(self, device: int = 0, depth: int = 3, flags=(), make=None, compact: bool = False, **opts):
         if depth < 1:
             raise ValueError("depth must be >= 1")
+        self._compact = compact   # results leave through sigma_store_compact (bits, sizes, literals): what newClause() reads
         if make is None:
             from . import sigma
 
@@ -133,7 +134,8 @@ class Pipeline:
                     job = jobs[i]
                     s.load(job[0], job[1], job[2], meta=job[3] if len(job) > 3 else None)
                     rep = s.simplify()
-                    stored = s.store(into=outbufs[w]) if outbufs is not None else s.store()
+                    store = s.store_compact if self._compact else s.store
+                    stored = store(into=outbufs[w]) if outbufs is not None else store()
                     consume(i, rep, s.rounds(), stored)
                 except BaseException as e:   # noqa: BLE001 - handed to the caller
                     with lock:

@@ -76,7 +76,7 @@ SYMBOLS = [
     "sigma_run", "sigma_begin", "sigma_round", "sigma_finish", "sigma_num_rounds", "sigma_round_reports",
     "sigma_result_sizes", "sigma_store", "sigma_store_compact", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
     "sigma_set_proof_sink", "sigma_proof_chunks", "sigma_proof_chunk_size", "sigma_proof_chunk_copy",
-    "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
+    "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_kernel_stats", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
 ]
 
 
@@ -116,6 +116,7 @@ def lib():
         L.sigma_proof_chunk_copy.argtypes = [P, C.c_uint32, P]
         L.sigma_kernel_profile.argtypes = [P, C.c_int]
         L.sigma_kernel_times.argtypes = [P, P, P, P, C.POINTER(C.c_uint32)]
+        L.sigma_kernel_stats.argtypes = [P, P, P, P, P, C.POINTER(C.c_uint32)]
         L.sigma_memory.argtypes = [P] + [C.POINTER(C.c_uint64)] * 3
         L.sigma_last_error.argtypes = [P]; L.sigma_last_error.restype = C.c_char_p
         L.sigma_version.restype = C.c_char_p
@@ -349,6 +350,17 @@ class Simplifier:
         n = C.c_uint32(cap)
         self._check(self._lib.sigma_kernel_times(self._h, names, ms, cnt, C.byref(n)))
         return {names.raw[64 * i:64 * (i + 1)].split(b"\0", 1)[0].decode(): (float(ms[i]), int(cnt[i])) for i in range(n.value)}
+
+    def kernel_stats(self) -> dict:
+        """-> {kernel name: (total ms, launches, algorithmic bytes)} since kernel_profile(1)."""
+        cap = 128
+        names = C.create_string_buffer(64 * cap)
+        ms = (C.c_float * cap)()
+        cnt = (C.c_uint32 * cap)()
+        by = (C.c_double * cap)()
+        n = C.c_uint32(cap)
+        self._check(self._lib.sigma_kernel_stats(self._h, names, ms, cnt, by, C.byref(n)))
+        return {names.raw[64 * i:64 * (i + 1)].split(b"\0", 1)[0].decode(): (float(ms[i]), int(cnt[i]), float(by[i])) for i in range(n.value)}
 
     def memory(self) -> dict:
         a, p, m = C.c_uint64(), C.c_uint64(), C.c_uint64()

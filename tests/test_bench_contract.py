@@ -35,17 +35,19 @@ def test_reference_arm_prints_one_json_line():
     assert d["config"]["workload"] == "cfg1"
 
 
-def test_roofline_picks_a_kernel_with_a_byte_formula():
+def test_roofline_is_the_dominant_kernel_with_engine_counted_bytes():
     b = load_bench()
     assert b.kbase("(k_ot_part<3, 5>)") == "k_ot_part" and b.kbase("void k_sub<4>") == "k_sub" and b.kbase("k_count") == "k_count"
-    C, L, V = 21e6, 105e6, 1_000_000
-    kt = {"k_mis_round<32>": (9.0, 100), "(k_ot_part<3, 5>)": (5.0, 5), "k_awaken": (4.0, 5), "k_ere_pairs<32>": (2.5, 5)}
-    r = b.roofline(kt, C, L, V, {"hbm_gbs": 6551.4})
-    assert r["kernel"] == "(k_ot_part<3, 5>)" and r["dominant"]["kernel"] == "k_mis_round<32>"
-    assert r["algorithmic_bytes_per_launch"] == 16 * C + 4 * L + 8 * L
-    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / 1e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / 6551.4) < 1e-12
-    r2 = b.roofline({"k_awaken": (4.0, 5)}, C, L, V, {})
-    assert r2["peak"] == 6650.0 and "fallback" in r2["peak_source"] and "dominant" not in r2
+    # {kernel: (ms, launches, algorithmic bytes)} as sigma_kernel_stats returns it
+    ks = {"k_mis_round<32>": (9.0, 100, 9.0e9), "(k_ot_part<3, 5>)": (5.0, 5, 5 * 1.596e9), "k_awaken": (4.0, 5, 0.0)}
+    r = b.roofline_block(ks, {"hbm_gbs": 6551.4}, "cfg2")
+    assert r["kernel"] == "k_mis_round<32>" and r["launches"] == 100 and abs(r["ms_per_launch"] - 0.09) < 1e-9
+    assert abs(r["achieved"] - 1000.0) < 0.1 and abs(r["frac"] - 1000.0 / 6551.4) < 1e-3
+    assert r["algorithmic_bytes_per_launch"] == 9.0e7
+    rows = {x["kernel"]: x for x in r["top_kernels"]}
+    assert abs(rows["(k_ot_part<3, 5>)"]["gbs"] - 1596.0) < 0.1 and rows["k_awaken"]["gbs"] is None
+    r2 = b.roofline_block({"k_awaken": (4.0, 5, 4e9)}, {}, "cfg2")
+    assert r2["peak"] == 6650.0 and "fallback" in r2["peak_source"]
 
 
 def test_batch_specs_cover_the_config5_range():
