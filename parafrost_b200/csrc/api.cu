@@ -143,18 +143,16 @@ extern "C" int sigma_set_opts(sigma_ctx* c, const sigma_opts* o) {
     const sigma_opts old = c->o;
     c->o = *o;
     sigma_normalize_opts(&c->o);
+    (void)old;
     if (c->loaded) {
         // the arena was carved for the options in force at sigma_load (prepareLoad): options that enlarge the logical
-        // capacities (ve_en, lits_mul, phases) or need the proof buffer are refused here instead of overrunning it later
+        // capacities (ve_en, lits_mul, phases) or need the proof buffer take effect with the next sigma_load; until then
+        // sigma_begin refuses to run instead of overrunning the arena
         u64 lc = 0, lw = 0;
         const bool ok = logicalCaps(c, c->C0, c->L0, c->orgClauses, c->orgLiterals, &lc, &lw) && lc <= c->capC && lw <= c->capW &&
                         (!c->o.proof_en || c->proofCarved);
-        if (!ok) {
-            c->o = old;
-            snprintf(c->err, sizeof c->err, "sigma_set_opts: these options need a larger arena than the loaded formula was given; set them before sigma_load");
-            return SIGMA_BAD_ARGUMENT;
-        }
-        c->logC = lc; c->logW = lw;
+        c->needReload = !ok;
+        if (ok) { c->logC = lc; c->logW = lw; }
     }
     return SIGMA_OK;
 }
@@ -277,6 +275,7 @@ static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u
     if (max_var >= (1u << 27) - 2 || num_clauses >= 0xFFFFFFF0ull) return SIGMA_BAD_ARGUMENT;
     c->V = max_var; c->ND = 2 * (max_var + 1);
     c->C0 = num_clauses; c->L0 = L0;
+    c->needReload = false;
     c->orgClauses = orgC; c->orgLiterals = orgL;
     // logical capacities of awaken (simplify.cu:84-98)
     if (!logicalCaps(c, num_clauses, L0, orgC, orgL, &c->logC, &c->logW)) return SIGMA_CNFALLOC_FAIL;
@@ -432,6 +431,11 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     if (!c) return SIGMA_BAD_ARGUMENT;
     if (!c->loaded) return SIGMA_NOT_LOADED;
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->needReload) {
+        snprintf(c->err, sizeof c->err, "the options set after sigma_load need a larger arena (or the proof buffer: proof_en must be set before "
+                 "sigma_load, the stream buffer is carved with the arena): load the formula again");
+        return SIGMA_BAD_ARGUMENT;
+    }
     const size_t V1 = (size_t)c->V + 1;
     c->cur = 0;
     c->phase = c->multiplier = 0; c->simpstate = SIGMA_OK; c->cnfstate = SIGMA_UNSOLVED; c->compacted = false;

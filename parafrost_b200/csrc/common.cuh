@@ -148,7 +148,7 @@ struct Ctx {
     u32 V, ND; u64 C0, L0; u32 capC; u64 capW; u32 resolvedCap;   // capC / capW: physical sizes of hdr[] / pool[]
     u64 logC, logW;    // the reference's logical capacities of awaken (simplify.cu:84-98) for the loaded formula and options
     u64 orgClauses, orgLiterals;
-    bool loaded, begun;
+    bool loaded, begun, needReload;   // needReload: options set after sigma_load do not fit the carved arena (sigma_set_opts)
     // input (pristine)
     u32* inLits; u64* inOffs; u32* inMeta;
     // CNF double buffer

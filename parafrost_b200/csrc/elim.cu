@@ -411,8 +411,29 @@ template <int GS> __device__ u32 fastEqualityCheck(GT<GS>& g, u32 x, u32 y, u32 
     for (int o = GS / 2; o; o >>= 1) found = min(found, __shfl_xor_sync(FULL, found, o, GS));
     return found;
 }
+// The same search when the variable's clauses sit in a local (shared-memory) copy: a clause {fx, y, z} contains fx, so it
+// is in F - the list of fx itself - whichever of the three lists the reference walks; copies of one clause share the
+// sort key and follow each other in index order, so the first match in F is the clause the reference finds.
+template <int GS> __device__ u32 fastEqualityLocal(GT<GS>& g, const u32* F, u32 nf, u32 x, u32 y, u32 z) {
+    u32 t;
+    if (y > z) { t = y; y = z; z = t; }
+    if (x > z) { t = x; x = z; z = t; }
+    if (x > y) { t = x; x = y; y = t; }
+    u32 found = NOVAR;
+    for (u32 j = LANE; j < nf; j += GS) {
+        const u32 ci = F[j];
+        const uint4 h = g.hdr[ci];
+        if (!C_MOLTEN(h.w) && C_ORIGINAL(h.w) && h.y == 3) {
+            const u32* l = g.pool + h.x;
+            if (l[0] == x && l[1] == y && l[2] == z) found = min(found, ci);
+        }
+    }
+#pragma unroll
+    for (int o = GS / 2; o; o >>= 1) found = min(found, __shfl_xor_sync(FULL, found, o, GS));
+    return found;
+}
 // ifthenelse.cuh:52-125
-template <int GS> __device__ bool findITEGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls,
+template <int GS, bool LOCAL = false> __device__ bool findITEGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls,
                             u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     if (g.hdr[D[nd - 1]].y == 2) return false;
     const u32 v = LABS(dx);
@@ -431,9 +452,9 @@ template <int GS> __device__ bool findITEGate(GT<GS>& g, u32 dx, const u32* D, u
             if (LABS(yi) == LABS(zj)) { t = yj; yj = zj; zj = t; }
             if (LABS(zi) == LABS(zj)) continue;
             if (yi != LFLIP(yj)) continue;
-            const u32 r1 = fastEqualityCheck(g, fx, yi, LFLIP(zi));
+            const u32 r1 = LOCAL ? fastEqualityLocal(g, F, nf, fx, yi, LFLIP(zi)) : fastEqualityCheck(g, fx, yi, LFLIP(zi));
             if (r1 == NOVAR) continue;
-            const u32 r2 = fastEqualityCheck(g, fx, yj, LFLIP(zj));
+            const u32 r2 = LOCAL ? fastEqualityLocal(g, F, nf, fx, yj, LFLIP(zj)) : fastEqualityCheck(g, fx, yj, LFLIP(zj));
             if (r2 == NOVAR) continue;
             melt(g, cii); melt(g, cjj); melt(g, r1); melt(g, r2);
             nElements = 0; nAddedCls = 0; nAddedLits = 0;
@@ -479,8 +500,40 @@ template <int GS> __device__ bool makeArity(GT<GS>& g, u32& parity, u32* literal
     if (found != NOVAR) { melt(g, found); return true; }
     return false;
 }
+// makeArity on the local copy: the flipped clause still holds dx or fx (an even number of literals is flipped), so it is
+// looked up in D or in F instead of the shortest list among its literals; same clause found (see fastEqualityLocal).
+template <int GS> __device__ bool makeArityLocal(GT<GS>& g, u32& parity, u32* literals, int size, u32 dx, const u32* D, u32 nd, const u32* F, u32 nf) {
+    const u32 oldparity = parity;
+    while (__popc(++parity) & 1) {}
+    if (LANE == 0)
+        for (int k = 0; k < size; k++) { const u32 bit = k < 32 ? 1u << k : 0u; if ((parity & bit) != (oldparity & bit)) literals[k] = LFLIP(literals[k]); }
+    GSYNC();
+    bool hasDx = false;
+    for (int k = 0; k < size; k++) hasDx |= literals[k] == dx;
+    const u32* list = hasDx ? D : F;
+    const u32 n = hasDx ? nd : nf;
+    u32 found = NOVAR;
+    for (u32 j = LANE; j < n; j += GS) {
+        const u32 ci = list[j];
+        const uint4 h = g.hdr[ci];
+        if (C_ORIGINAL(h.w) && (int)h.y == size) {
+            bool ok = true;
+            const u32* l = g.pool + h.x;
+            for (int a = 0; a < size && ok; a++) {
+                bool f = false;
+                for (int b = 0; b < size; b++) if (l[a] == literals[b]) { f = true; break; }
+                ok = f;
+            }
+            if (ok) found = min(found, ci);
+        }
+    }
+#pragma unroll
+    for (int o = GS / 2; o; o >>= 1) found = min(found, __shfl_xor_sync(FULL, found, o, GS));
+    if (found != NOVAR) { melt(g, found); return true; }
+    return false;
+}
 // xor.cuh:111-185
-template <int GS> __device__ bool findXORGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
+template <int GS, bool LOCAL = false> __device__ bool findXORGate(GT<GS>& g, u32 dx, const u32* D, u32 nd, u32 fx, const u32* F, u32 nf, u32 nOrgCls, u32* out_c,
                             u32& nElements, u32& nAddedCls, u32& nAddedLits) {
     if (g.hdr[D[nd - 1]].y == 2 || g.hdr[F[nf - 1]].y == 2) return false;
     const int maxarity = (int)g.k.xor_max_arity;
@@ -496,7 +549,7 @@ template <int GS> __device__ bool findXORGate(GT<GS>& g, u32 dx, const u32* D, u
         GSYNC();
         u32 parity = 0;
         int itargets = arity >= 32 ? 0 : (int)(1u << arity);   // what `1 << arity` yields on the device (shl clamps); explicit, no UB
-        while (--itargets && makeArity(g, parity, out_c, size)) {}
+        while (--itargets && (LOCAL ? makeArityLocal(g, parity, out_c, size, dx, D, nd, F, nf) : makeArity(g, parity, out_c, size))) {}
         if (itargets) freezeArities(g, D, nd, F, nf);
         else {
             melt(g, ci);
@@ -668,6 +721,139 @@ __global__ void __launch_bounds__(128) k_ve_phase1(GT<GS> g, const u32* __restri
                 if (!nAddedCls) { toblivionSave(g, p, n, pOrgs, nOrgs, P, np, N, nn); eliminatedNow = true; }
                 else if (elimType) record = true;
             }
+        }
+        if (LANE == 0) {
+            if (record) {
+                g.veType[tid] = ENCODEVARINFO(elimType, nAddedCls, nAddedLits);
+                g.veUcnt[tid] = nElements; g.veRpos[tid] = nAddedCls; g.veRref[tid] = (u64)nAddedLits + (u64)NBUCKETS * nAddedCls;
+            } else { g.veType[tid] = 0; g.veUcnt[tid] = 0; g.veRpos[tid] = 0; g.veRref[tid] = 0; }
+            if (eliminatedNow) g.eliminated[x] |= MELTING_MASK;
+        }
+        GSYNC();
+    }
+}
+
+// ------------------------------------------------------------------ BVE phase 1 on a local copy (4- and 8-lane classes)
+// The decision tree of bounded.cuh:282-394 walks the same few clauses again and again: every gate search re-reads
+// headers and literals through list entry -> header -> literals, three dependent loads per step, and the ITE / XOR
+// searches walk FOREIGN lists on top.  A variable of these classes has at most BIN_T8 clauses: they are gathered ONCE
+// (all lanes in parallel, the three loads of different clauses in flight together) into a shared-memory copy, the whole
+// tree - marks included - runs on the copy, and only the outcome goes back: changed molten marks (phase 3 reads them),
+// then the terminal action (witness + deletion, equivalence substitution) on the global clauses.
+// A variable with a clause longer than VE_LOCAL_K literals is handed to the 32-lane kernel (`redo`), like the
+// function-table candidates.
+#define VE_LOCAL_K 8
+template <int GS>
+__global__ void __launch_bounds__(128) k_ve_phase1_local(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount,
+                                                         u32* __restrict__ redo, u32* redoCount) {
+    constexpr int MAXC = GS == 4 ? (int)BIN_T4 : (int)BIN_T8;
+    constexpr int NG = 128 / GS;
+    constexpr int CNT = MAXC / GS;
+    __shared__ uint4 s_h[NG][MAXC];
+    __shared__ u32 s_l[NG][MAXC * VE_LOCAL_K];
+    __shared__ u32 s_w0[NG][MAXC];
+    __shared__ u32 s_out[NG][VE_SLICE_SMALL];
+    __shared__ u32 s_iota[MAXC];
+    if (threadIdx.x < MAXC) s_iota[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    const u32 gidx = threadIdx.x / GS;
+    uint4* lh = s_h[gidx]; u32* ll = s_l[gidx]; u32* w0 = s_w0[gidx]; u32* out_c = s_out[gidx];
+    GT<GS> lg = g;                 // the same engine state, clause store = the local copy, clause "index" = slot
+    lg.hdr = lh; lg.pool = ll;
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 count = *wlCount;
+    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
+        const u32 tid = wl[wi];
+        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
+        const u32 np = g.otSize[p], nn = g.otSize[n], tot = np + nn;
+        const u32* Pg = g.occurs + g.otStart[p];
+        const u32* Ng = g.occurs + g.otStart[n];
+        // ---- gather: entries, then headers, then literals, each as one batch of independent loads
+        u32 ci[CNT]; uint4 h[CNT];
+        bool big = tot > (u32)MAXC;
+#pragma unroll
+        for (int q = 0; q < CNT; q++) { const u32 j = LANE + q * GS; ci[q] = j < tot && !big ? (j < np ? Pg[j] : Ng[j - np]) : NOVAR; }
+#pragma unroll
+        for (int q = 0; q < CNT; q++) { h[q] = ci[q] != NOVAR ? g.hdr[ci[q]] : make_uint4(0, 0, 0, 0); big |= h[q].y > VE_LOCAL_K; }
+        if (__any_sync(FULL, big)) {
+            if (LANE == 0) redo[atomicAdd(redoCount, 1u)] = tid;
+            GSYNC();
+            continue;
+        }
+        GSYNC();   // the previous variable's readers of this slice are done
+#pragma unroll
+        for (int q = 0; q < CNT; q++) {
+            const u32 j = LANE + q * GS;
+            if (ci[q] != NOVAR) {
+                const u32* src = g.pool + h[q].x;
+                u32 lv[VE_LOCAL_K];
+#pragma unroll
+                for (int k = 0; k < VE_LOCAL_K; k++) lv[k] = (u32)k < h[q].y ? src[k] : 0u;
+#pragma unroll
+                for (int k = 0; k < VE_LOCAL_K; k++) ll[j * VE_LOCAL_K + k] = lv[k];
+                lh[j] = make_uint4(j * VE_LOCAL_K, h[q].y, h[q].z, h[q].w);
+                w0[j] = h[q].w;
+            }
+        }
+        GSYNC();
+        const u32* P = s_iota; const u32* N = s_iota + np;
+        // ---- the decision tree on the copy (same order and guards as k_ve_phase1)
+        u32 pOrgs, nOrgs;
+        if (g.k.in_mode) { u32 d; countOrgsLits(lg, P, np, pOrgs, d); countOrgsLits(lg, N, nn, nOrgs, d); }
+        else { pOrgs = np; nOrgs = nn; }
+        u32 elimType = 0, nElements = 0, nAddedCls = 0, nAddedLits = 0, def = 0;
+        bool oblivion = false, record = false, handOver = false;
+        if (!pOrgs || !nOrgs) oblivion = true;
+        else {
+            def = findEquGate(lg, p, n, P, np, N, nn);
+            if (def) {}
+            else if ((pOrgs == 1 || nOrgs == 1) && !countPairs(lg, 0, x, P, np, N, nn, 0, nElements, nAddedCls, nAddedLits)) {
+                if (nAddedCls) { elimType = RES_MASK; record = true; }
+                else oblivion = true;
+            }
+            else {
+                const u32 nClsBefore = pOrgs + nOrgs;
+                elimType = 0; nElements = 0; nAddedCls = 0; nAddedLits = 0;
+                if (nClsBefore > 2) {
+                    if (nOrgs < g.k.sh_max_bve_out1 && findAOGate(lg, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits))
+                        elimType = AOIX_MASK;
+                    else if (!nAddedCls && pOrgs < g.k.sh_max_bve_out1 && findAOGate(lg, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits))
+                        elimType = AOIX_MASK;
+                }
+                if (!elimType && nClsBefore > 3) {
+                    if (findITEGate<GS, true>(lg, p, P, np, n, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    else if (!nAddedCls && findITEGate<GS, true>(lg, n, N, nn, p, P, np, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    else if (findXORGate<GS, true>(lg, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    else if (!nAddedCls && findXORGate<GS, true>(lg, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                }
+                if (g.k.ve_fun_en && !elimType && nClsBefore > 2 && funPossible(lg, p, P, np) && funPossible(lg, n, N, nn)) handOver = true;
+                if (!handOver) {
+                    if (!elimType && !nAddedCls && !countPairs(lg, 1, x, P, np, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits))
+                        elimType = RES_MASK;
+                    if (!nAddedCls) oblivion = true;
+                    else if (elimType) record = true;
+                }
+            }
+        }
+        if (handOver) {   // no side effect outside the copy yet: failed gate attempts restored their marks
+            if (LANE == 0) redo[atomicAdd(redoCount, 1u)] = tid;
+            GSYNC();
+            continue;
+        }
+        // ---- outcome: marks that changed, then the terminal action on the global clauses
+        GSYNC();
+#pragma unroll
+        for (int q = 0; q < CNT; q++) {
+            const u32 j = LANE + q * GS;
+            if (ci[q] != NOVAR) { const u32 w = lh[j].w; if (w != w0[j]) g.hdr[ci[q]].w = w; }
+        }
+        GSYNC();
+        bool eliminatedNow = false;
+        if (oblivion) { toblivionSave(g, p, n, pOrgs, nOrgs, Pg, np, Ng, nn); eliminatedNow = true; }
+        else if (def) {
+            if (pOrgs > nOrgs) saveSide(g, Ng, nn, n, p, nOrgs); else saveSide(g, Pg, np, p, n, pOrgs);
+            substituteSingle(g, p, n, def, Pg, np, Ng, nn);
+            eliminatedNow = true;
         }
         if (LANE == 0) {
             if (record) {
@@ -954,6 +1140,85 @@ __global__ void __launch_bounds__(128) k_sub(GT<GS> g, const u32* __restrict__ w
     }
 }
 
+// SUB on a local copy (4- and 8-lane classes): same idea as k_ve_phase1_local - gather the variable's clauses once, run
+// strengthening and subsumption of both sides on the shared-memory copy, write back only the clauses that changed
+// (header; literals when one was removed), then units and updateOL on the global lists.  A variable with a clause longer
+// than VE_LOCAL_K literals goes to `redo`, processed by k_sub<32>.
+template <int GS>
+__global__ void __launch_bounds__(128) k_sub_local(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount,
+                                                   u32* __restrict__ redo, u32* redoCount) {
+    constexpr int MAXC = GS == 4 ? (int)BIN_T4 : (int)BIN_T8;
+    constexpr int NG = 128 / GS;
+    constexpr int CNT = MAXC / GS;
+    __shared__ uint4 s_h[NG][MAXC];
+    __shared__ u32 s_l[NG][MAXC * VE_LOCAL_K];
+    __shared__ u32 s_iota[MAXC];
+    if (threadIdx.x < MAXC) s_iota[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    const u32 gidx = threadIdx.x / GS;
+    uint4* lh = s_h[gidx]; u32* ll = s_l[gidx];
+    GT<GS> lg = g;
+    lg.hdr = lh; lg.pool = ll;
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    const u32 count = *wlCount;
+    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
+        const u32 tid = wl[wi];
+        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
+        const u32 np = g.otSize[p], nn = g.otSize[n], tot = np + nn;
+        if (np > g.k.sub_max_occurs || nn > g.k.sub_max_occurs) continue;
+        const u32* Pg = g.occurs + g.otStart[p];
+        const u32* Ng = g.occurs + g.otStart[n];
+        u32 ci[CNT]; uint4 h[CNT];
+        bool big = tot > (u32)MAXC;
+#pragma unroll
+        for (int q = 0; q < CNT; q++) { const u32 j = LANE + q * GS; ci[q] = j < tot && !big ? (j < np ? Pg[j] : Ng[j - np]) : NOVAR; }
+#pragma unroll
+        for (int q = 0; q < CNT; q++) { h[q] = ci[q] != NOVAR ? g.hdr[ci[q]] : make_uint4(0, 0, 0, 0); big |= h[q].y > VE_LOCAL_K; }
+        if (__any_sync(FULL, big)) {
+            if (LANE == 0) redo[atomicAdd(redoCount, 1u)] = tid;
+            GSYNC();
+            continue;
+        }
+        GSYNC();
+#pragma unroll
+        for (int q = 0; q < CNT; q++) {
+            const u32 j = LANE + q * GS;
+            if (ci[q] != NOVAR) {
+                const u32* src = g.pool + h[q].x;
+                u32 lv[VE_LOCAL_K];
+#pragma unroll
+                for (int k = 0; k < VE_LOCAL_K; k++) lv[k] = (u32)k < h[q].y ? src[k] : 0u;
+#pragma unroll
+                for (int k = 0; k < VE_LOCAL_K; k++) ll[j * VE_LOCAL_K + k] = lv[k];
+                lh[j] = make_uint4(j * VE_LOCAL_K, h[q].y, h[q].z, h[q].w);
+            }
+        }
+        GSYNC();
+        const u32* P = s_iota; const u32* N = s_iota + np;
+        const u32 nPosUnits = subSide(lg, P, np, N, nn, p, n);
+        const u32 nNegUnits = subSide(lg, N, nn, P, np, n, p);
+        GSYNC();
+        // write back what changed: a strengthened clause lost one literal (new size, signature, marks), a subsumed one is deleted
+#pragma unroll
+        for (int q = 0; q < CNT; q++) {
+            const u32 j = LANE + q * GS;
+            if (ci[q] != NOVAR) {
+                const uint4 nh = lh[j];
+                if (nh.y != h[q].y) { u32* dst = g.pool + h[q].x; for (u32 k = 0; k < nh.y; k++) dst[k] = ll[j * VE_LOCAL_K + k]; }
+                if (nh.y != h[q].y || nh.z != h[q].z || nh.w != h[q].w) g.hdr[ci[q]] = make_uint4(h[q].x, nh.y, nh.z, nh.w);
+            }
+        }
+        GSYNC();
+        if (nPosUnits || nNegUnits) {
+            u32 cursor = reserveUnits(g, nPosUnits + nNegUnits);
+            if (nPosUnits) appendUnits(g, Pg, np, cursor);
+            if (nNegUnits) appendUnits(g, Ng, nn, cursor);
+        }
+        updateOL(g, p);
+        updateOL(g, n);
+    }
+}
+// the variables handed over by k_sub_local
 // ------------------------------------------------------------------ BCE (blocked.cuh:26-97)
 template <int GS>
 __global__ void __launch_bounds__(128) k_bce(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount) {
@@ -1557,7 +1822,20 @@ void launchSUB(Ctx* c, const KOpts& k) {
     binElected(c, k, false, true);
     if (k.proof_en) proofSnap(c);
     const ClassBytes cb = classBytes(c);
-    LAUNCH_CLASSES(c, k_sub, 128, c->numElected, g, cb);
+    static const int subLocal = getenv("SIGMA_SUB_LOCAL") ? atoi(getenv("SIGMA_SUB_LOCAL")) : 1;   // 0: the gather-as-you-go kernels (A/B measurements)
+    if (subLocal) {
+        const u32 E = c->numElected;
+        u32* redo = c->rank;       // rank[] is dead after the election
+        u32* redoCount = &c->dc->bin[3];
+        LAUNCH(c, k_sub_local<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
+        KB(c, cb.b[0]);
+        LAUNCH(c, k_sub_local<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
+        KB(c, cb.b[1]);
+        LAUNCH(c, k_sub<32>, groupGrid(E, 32, 128), 128, 0, asGroup<32>(g), c->sortK, &c->dc->bin[2]);
+        KB(c, cb.b[2]);
+        LAUNCH(c, k_sub<32>, 148, 128, 0, asGroup<32>(g), redo, redoCount);   // variables with a long clause, handed over by the small groups
+    } else
+        LAUNCH_CLASSES(c, k_sub, 128, c->numElected, g, cb);
     if (k.proof_en) {   // subsume.cuh:465-475: strengthened clauses added, then subsumed ones deleted
         const u32 n = c->hdc->numCls;
         proofStream(c, g, 0, n, nullptr, PROOF_MOLTEN, n);
@@ -1575,10 +1853,18 @@ void launchVE(Ctx* c, const KOpts& k) {
     u32* redo = c->rank;       // rank[] is dead after the election
     u32* redoCount = &c->dc->bin[3];
     const ClassBytes cb1 = classBytes(c);   // + 20 bytes per variable: type, ucnt, rpos, rref (SURVEY 8d "BVE count")
-    LAUNCH(c, k_ve_phase1<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
-    KB(c, cb1.b[0]);
-    LAUNCH(c, k_ve_phase1<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
-    KB(c, cb1.b[1]);
+    static const int veLocal = getenv("SIGMA_VE_LOCAL") ? atoi(getenv("SIGMA_VE_LOCAL")) : 1;   // 0: the gather-as-you-go kernels (A/B measurements)
+    if (veLocal) {
+        LAUNCH(c, k_ve_phase1_local<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
+        KB(c, cb1.b[0]);
+        LAUNCH(c, k_ve_phase1_local<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
+        KB(c, cb1.b[1]);
+    } else {
+        LAUNCH(c, k_ve_phase1<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
+        KB(c, cb1.b[0]);
+        LAUNCH(c, k_ve_phase1<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
+        KB(c, cb1.b[1]);
+    }
     LAUNCH(c, k_ve_phase1<32>, groupGrid(E, 32, 128), 128, 0, asGroup<32>(g), c->sortK, &c->dc->bin[2], redo, redoCount);
     KB(c, cb1.b[2] + 20.0 * E);
     LAUNCH(c, k_ve_phase1<32>, 148, 128, 0, asGroup<32>(g), redo, redoCount, redo, redoCount);   // variables handed over by the small groups
