@@ -68,6 +68,11 @@ typedef struct sigma_opts {
     int32_t  profile;           /* -profilegpu: per-stage CUDA-event times */
     int32_t  aggr_cnf_sort;     /* -aggresivesort (off): clauses leave in OLIST_CMP order (cnf.cu:232-233, key.cuh:67-83) */
     int32_t  proof_en;          /* -proof (off): device DRAT stream (proof.cu, proofutils.cuh); set before sigma_load */
+    int32_t  lcve_fast;         /* -lcvefast: the reference CLI's default election (options.cpp:32, lcve.cu:150-217,338-366) - a maximal
+                                   independent set over the FILTERED candidates (the stop conditions of the serial walk become
+                                   filters, so more variables are elected).  sigma_default_opts leaves it 0 = -no-lcvefast, the
+                                   deterministic mode every parity run uses; the shim forwards the CLI's value.  The elected SET
+                                   equals the reference's; its order there comes from atomics, here it is the rank order. */
 } sigma_opts;
 
 /* Per-round report; replaces the LOG2 lines + inf.* updates of simplify.cu:163-186. */
@@ -84,7 +89,7 @@ typedef struct sigma_round_report {
     uint64_t literals;          /* inf.numLiterals after the round */
     uint64_t literals_in;       /* live literals when the round started */
     float    ms;                /* wall ms of the round (host clock, stream synchronised) */
-    float    pad;
+    uint32_t trail_added;       /* trail entries appended by this round's prop(): the first `propagated` are the BVE/SUB units */
 } sigma_round_report;
 
 /* Whole-call report; replaces stats.sigma.* (statistics.hpp:33-35). */
@@ -164,6 +169,59 @@ int  sigma_store_compact(sigma_ctx* c, uint32_t* bits, uint32_t* sizes, uint32_t
                          uint8_t* eliminated, uint32_t* resolved, uint32_t* trail);
 /* the reference's own record stream {bits, sig, size, lits...} + uint64 refs, for newClause(SCLAUSE&) */
 int  sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t* refs);
+
+/* Units assigned by the device prop() calls (elimbcp.cu:144-215), in the order the reference's host loop enqueues them
+ * (elimbcp.cu:185-200): per prop() first the units SUB/BVE produced (enqueueDevUnit), then the derived ones (enqueueUnit).
+ * sigma_trail_info: size of the whole trail and the range / seed count of the LAST prop(); valid between sigma_round calls
+ * and inside the proof sink, so a host can enqueue a round's units before that round's proof chunk, as the reference does. */
+int  sigma_trail_info(const sigma_ctx* c, uint64_t* total, uint32_t* last_from, uint32_t* last_count, uint32_t* last_seeds);
+int  sigma_copy_trail(sigma_ctx* c, uint64_t from, uint64_t count, uint32_t* out);
+
+/* Pinned (page-locked) host memory for the callers' edges: extractCNF / writeBackCNF buffers (cnf.cu:176-198) reach PCIe
+ * speed only from pinned pages; replaces cuMM::createMirror's pinned mirror (memory.cu). */
+void* sigma_pinned_alloc(size_t bytes);
+void  sigma_pinned_free(void* p);
+
+/* Device-resident result (simplify(skip_transfer_to_host), simplify.cu:221-229): views of what stays in the context's
+ * arena after sigma_run - replaces Solver::getDeviceCNF / getDeviceOT / getVars (solver.hpp:694-705) for integrations
+ * that keep working on the GPU (gpu4bmc).  Pointers are DEVICE pointers, valid until the next sigma_load / sigma_begin /
+ * sigma_destroy; clause i = headers[i] {x: offset into literals, y: size, z: signature, w: SCLAUSE word 0 (bit 1 =
+ * deleted)}, i < clause_slots. */
+typedef struct sigma_device_cnf {
+    int32_t  device;
+    void*    stream;            /* cudaStream_t all work of the context is ordered on */
+    uint32_t max_var;
+    uint32_t clause_slots;      /* cnf->size(): live and deleted slots */
+    uint64_t pool_words;
+    uint64_t live_clauses, live_literals;
+    const void*     headers;    /* uint4[clause_slots] */
+    const uint32_t* literals;
+    const uint32_t* ot_start;   /* [2V+3] occurrence lists: entries ot_entries[ot_start[lit] .. + ot_size[lit]) */
+    const uint32_t* ot_size;
+    const uint32_t* ot_entries;
+    const uint8_t*  eliminated; /* [V+1] MELTING 1 | ADDING 2 | FORCED 4 (constants.cuh:33-36) */
+    const uint8_t*  vstate;     /* [V+1] */
+    const uint32_t* vorg;       /* [V+1] */
+    const uint32_t* elected;    /* survivors of the last election */
+    uint32_t num_elected;
+    const uint32_t* units;
+    const uint32_t* resolved;   /* witness stack of this call */
+    uint64_t resolved_words;
+    const uint32_t* trail;
+    uint64_t trail_units;
+} sigma_device_cnf;
+int  sigma_device_view(sigma_ctx* c, sigma_device_cnf* out);
+
+/* The next inprocessing call ON the resident result: the live clauses of the finished call become the input of the next
+ * one without crossing PCIe (device-side copy into the input arrays, order kept, learnt flags / lbd / usage kept);
+ * only the clauses the host added since (num_new: learnt clauses, ...) and - optionally - the per-variable state travel.
+ *   vstate  NULL: derived on the device (inactive = inactive before, eliminated or assigned by the finished call)
+ *   assumed NULL: no assumptions
+ * opts.sigma_calls is advanced by one (later calls count original clauses only, bounded.cuh:428-430).  Fetch the witness
+ * stack / eliminated / trail of the finished call first (sigma_store_compact with NULL clause buffers): they restart.
+ * Then sigma_run / sigma_begin as usual.  SIGMA_CNFALLOC_FAIL if the continued formula outgrew what sigma_load carved. */
+int  sigma_continue(sigma_ctx* c, uint64_t num_new, const uint32_t* new_lits, const uint64_t* new_offs, const uint32_t* new_meta,
+                    const uint8_t* vstate, const uint8_t* assumed);
 
 /* Device DRAT proof stream; replaces cuPROOF (src/gpu/proof.cuh:30-71, proof.cu) and the proof hooks of
  * sub_k / ve_k_1 / ve_k_2 / bce_k / ere_k (proofutils.cuh).  With opts.proof_en the kernels append binary

@@ -19,6 +19,9 @@
 #include "options.cuh"
 #include "memory.cuh"
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "sigma.h"
@@ -78,8 +81,7 @@ void CACHER::destroy() {}                                        // cache.cu
 // ---- state of the binding (the reference is one Solver per process)
 namespace {
 	sigma_ctx*             g_ctx = nullptr;
-	std::vector<uint32_t>  g_data;         // the simplified CNF as the reference's SCLAUSE record stream (sigma_store_sclauses)
-	std::vector<uint64_t>  g_refs;
+	size_t                 g_nData = 0, g_nRefs = 0;   // the simplified CNF as the reference's SCLAUSE record stream, in the pinned buffers below
 	std::vector<uint32_t>  g_resolved;     // witness stack produced by this call (cacheResolved, transfer.cu:83-96)
 
 	void fillOpts(sigma_opts& o, const OPTION& opts, const GOPTION& g, const int calls)
@@ -100,14 +102,73 @@ namespace {
 		o.profile = g.profile_gpu;
 		o.aggr_cnf_sort = opts.aggr_cnf_sort;
 		o.proof_en = g.hostKOpts.proof_en;
+		o.lcve_fast = opts.lcve_fast;                 // -lcvefast, the CLI's default (options.cpp:32): filtered-candidate MIS
 		sigma_normalize_opts(&o);
 	}
 
-	// cuPROOF::writeProof (proof.cu:160-199): the round's binary DRAT bytes go to the reference's proof file
+	// pinned host buffers of the two edges (cuMM::createMirror keeps the reference's mirror pinned as well, memory.cu)
+	struct Pinned {
+		void* p = nullptr; size_t cap = 0;
+		void* get(size_t bytes) {
+			if (bytes > cap) { sigma_pinned_free(p); cap = bytes + bytes / 8 + 4096; p = sigma_pinned_alloc(cap); if (!p) cap = 0; }
+			return p;
+		}
+		void release() { sigma_pinned_free(p); p = nullptr; cap = 0; }
+	};
+	Pinned g_pinData, g_pinRefs;
+
+	// runs fn(begin, end, worker) over [0, n) on the host cores (extractCNF / markEliminated are per-item independent)
+	template <class F> void parallelFor(size_t n, F fn)
+	{
+		unsigned hw = std::thread::hardware_concurrency();
+		size_t T = hw ? hw : 4;
+		if (T > 32) T = 32;
+		if (n < 65536 || T == 1) { fn(size_t(0), n, 0u); return; }
+		std::vector<std::thread> th;
+		const size_t per = (n + T - 1) / T;
+		for (size_t t = 0; t < T; t++) {
+			const size_t b = t * per, e = std::min(n, b + per);
+			if (b >= e) break;
+			th.emplace_back([=] { fn(b, e, unsigned(t)); });
+		}
+		for (auto& x : th) x.join();
+	}
+
+	// units of one device prop() in the reference's host order (elimbcp.cu:185-200): the first `seeds` came from SUB/BVE
+	// (enqueueDevUnit: frozen, no proof line), the rest were derived (enqueueUnit: learnt, proof line).  A literal that is
+	// on the trail already (two variables can emit the same unit) is skipped instead of being pushed twice.
+	struct UnitReplay { Solver* solver; uint64_t seen; };
+	UnitReplay g_replay = { nullptr, 0 };
+
+}
+
+// a member of Solver so that it can reach enqueueDevUnit / enqueueUnit: replays the units of the last device prop()
+void Solver::cacheUnits(const cudaStream_t&)
+{
+	uint64_t total = 0; uint32_t from = 0, count = 0, seeds = 0;
+	if (sigma_trail_info(g_ctx, &total, &from, &count, &seeds) != SIGMA_OK) return;
+	if (uint64_t(from) + count <= g_replay.seen || !count) return;       // this prop() was replayed already
+	std::vector<uint32_t> units(count);
+	if (sigma_copy_trail(g_ctx, from, count, units.data()) != SIGMA_OK) return;
+	for (uint32_t i = 0; i < count; i++) {
+		const uint32 unit = units[i];
+		if (!active(unit)) continue;
+		if (i < seeds) enqueueDevUnit(unit);
+		else enqueueUnit(unit);
+	}
+	sp->propagated = trail.size();
+	stats.units.forced += count;
+	g_replay.seen = uint64_t(from) + count;
+}
+
+namespace {
+	// cuPROOF::writeProof (proof.cu:160-199): the round's binary DRAT bytes go to the reference's proof file - after the
+	// units of the round's prop(), whose lines the reference writes at the top of the round
 	void proofSink(void* user, const uint8_t* bytes, uint64_t n)
 	{
-		PROOF* proof = static_cast<PROOF*>(user);
-		for (uint64_t i = 0; i < n; i++) proof->write(Byte(bytes[i]));
+		Solver* solver = static_cast<Solver*>(user);
+		solver->cacheUnits(0);
+		for (uint64_t i = 0; i < n; i++) solver->proof.write(Byte(bytes[i]));
 	}
 }
 
@@ -121,14 +182,15 @@ void Solver::optSimp()
 		LOGERRORN("cannot create the simplifier context on device 0");
 		killSolver();
 	}
-	if (o.proof_en) sigma_set_proof_sink(g_ctx, proofSink, &proof);
+	if (o.proof_en) sigma_set_proof_sink(g_ctx, proofSink, this);
 }
 
 // Solver::freeSimp (simplify.cu:254-266)
 void Solver::freeSimp()
 {
 	if (g_ctx != nullptr) sigma_destroy(g_ctx), g_ctx = nullptr;
-	g_data.clear(), g_refs.clear(), g_resolved.clear();
+	g_pinData.release(), g_pinRefs.release();
+	g_nData = g_nRefs = 0, g_resolved.clear();
 	vars = NULL, cnf = NULL, ot = NULL, hcnf = NULL;
 }
 
@@ -139,7 +201,7 @@ void Solver::newBeginning()
 	assert(wt.empty());
 	assert(orgs.empty());
 	assert(learnts.empty());
-	cm.init(g_data.size());
+	cm.init(g_nData);
 	// cacheResolved (transfer.cu:83-96)
 	if (!g_resolved.empty()) {
 		const uint32 off = model.resolved.size();
@@ -150,14 +212,16 @@ void Solver::newBeginning()
 	}
 	// writeBackCNF (cnf.cu:186-198): the records are the reference's own SCLAUSE layout (sclause.cuh:37-42)
 	stats.literals.original = stats.literals.learnt = 0;
-	for (size_t i = 0; i < g_refs.size(); i++) {
-		SCLAUSE& s = *reinterpret_cast<SCLAUSE*>(g_data.data() + g_refs[i]);
+	uint32_t* data = static_cast<uint32_t*>(g_pinData.p);
+	const uint64_t* refs = static_cast<const uint64_t*>(g_pinRefs.p);
+	for (size_t i = 0; i < g_nRefs; i++) {      // serial: newClause allocates in the reference's clause arena `cm`
+		SCLAUSE& s = *reinterpret_cast<SCLAUSE*>(data + refs[i]);
 		if (s.deleted()) continue;
 		newClause(s);
 	}
 	stats.clauses.original = orgs.size();
 	stats.clauses.learnt = learnts.size();
-	g_data.clear(), g_refs.clear();
+	g_nData = g_nRefs = 0;
 }
 
 // Solver::simplify + Solver::simplifying (simplify.cu:57-75, 136-241)
@@ -175,22 +239,42 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 		timer.stop();
 		stats.time.solve += timer.cpuTime();
 		timer.start();
-		// ---- awaken (simplify.cu:77-134): the host clause database as CSR buffers (extractCNF, cnf.cu:176-184)
+		// ---- awaken (simplify.cu:77-134).  extractCNF (cnf.cu:176-184) in two parallel passes: sizes, prefix sum, then every
+		// worker writes its clauses as the reference's own SCLAUSE records {word 0, sig, size, literals} straight into pinned
+		// memory - the mirror `hcnf` that reflectCNF ships (cnf.cu:166-174), taken by sigma_load_sclauses as it is.
 		simpstate = AWAKEN_SUCC;
-		std::vector<uint32_t> lits, meta;
-		std::vector<uint64_t> offs(1, 0);
-		lits.reserve(size_t(maxLiterals()));
-		BCNF* sets[2] = { &orgs, &learnts };
-		for (int k = 0; k < 2; k++) {
-			BCNF& src = *sets[k];
-			for (uint32 i = 0; i < src.size(); i++) {
-				CLAUSE& c = cm[src[i]];
-				if (c.deleted()) continue;
-				for (int j = 0; j < c.size(); j++) lits.push_back(c[j]);
-				meta.push_back(c.learnt() ? (1u | (uint32_t(c.usage()) << 4) | (uint32_t(c.lbd()) << 6)) : 0u);
-				offs.push_back(lits.size());
+		const size_t nOrg = orgs.size(), nAll = nOrg + learnts.size();
+		std::vector<uint64_t> pos(nAll + 1);                      // word offset of clause i's record, then compacted to refs
+		parallelFor(nAll, [&](size_t b, size_t e, unsigned) {
+			for (size_t i = b; i < e; i++) {
+				CLAUSE& c = cm[i < nOrg ? orgs[uint32(i)] : learnts[uint32(i - nOrg)]];
+				pos[i] = c.deleted() ? 0 : uint64_t(c.size()) + 3;
 			}
-		}
+		});
+		uint64_t words = 0, nCls = 0;
+		for (size_t i = 0; i < nAll; i++) { const uint64_t w = pos[i]; pos[i] = words; words += w; nCls += w != 0; }
+		pos[nAll] = words;
+		uint32_t* hdata = static_cast<uint32_t*>(g_pinData.get((words + 4) * sizeof(uint32_t)));
+		uint64_t* hrefs = static_cast<uint64_t*>(g_pinRefs.get((nAll + 2) * sizeof(uint64_t)));
+		if (!hdata || !hrefs) { simpstate = AWAKEN_FAIL; recycle(); break; }
+		std::vector<uint64_t> rank(nAll + 1);                     // index of clause i among the live ones
+		{ uint64_t r = 0; for (size_t i = 0; i < nAll; i++) { rank[i] = r; r += pos[i + 1] != pos[i]; } rank[nAll] = r; }
+		std::atomic<uint64_t> nLits(0);
+		parallelFor(nAll, [&](size_t b, size_t e, unsigned) {
+			uint64_t lits = 0;
+			for (size_t i = b; i < e; i++) {
+				if (pos[i + 1] == pos[i]) continue;
+				CLAUSE& c = cm[i < nOrg ? orgs[uint32(i)] : learnts[uint32(i - nOrg)]];
+				uint32_t* rec = hdata + pos[i];
+				rec[0] = c.learnt() ? (1u | (uint32_t(c.usage()) << 4) | (uint32_t(c.lbd()) << 6)) : 0u;
+				rec[1] = 0;
+				rec[2] = uint32_t(c.size());
+				for (int j = 0; j < c.size(); j++) rec[3 + j] = c[j];
+				hrefs[rank[i]] = pos[i];
+				lits += uint64_t(c.size());
+			}
+			nLits += lits;
+		});
 		std::vector<uint8_t> vstate(inf.maxVar + 1, 0), assumedMask(inf.maxVar + 1, 0);
 		forall_variables(v) {
 			vstate[v] = uint8_t(sp->vstate[v].state);
@@ -199,8 +283,8 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 		sigma_opts o;
 		fillOpts(o, opts, gopts, int(stats.sigma.calls));
 		int rc = sigma_set_opts(g_ctx, &o);
-		if (!rc) rc = sigma_load(g_ctx, inf.maxVar, offs.size() - 1, lits.data(), offs.data(), meta.data(), vorg.data(), vstate.data(),
-		                         incremental ? assumedMask.data() : nullptr);
+		if (!rc) rc = sigma_load_sclauses(g_ctx, inf.maxVar, nCls, hdata, words, hrefs, vorg.data(), vstate.data(),
+		                                  incremental ? assumedMask.data() : nullptr);
 		if (rc) {                                                   // simplify.cu:152-155
 			LOGWARNING("simplifier could not load the formula (%d: %s)", rc, sigma_last_error(g_ctx));
 			simpstate = (rc == SIGMA_AWAKEN_FAIL) ? AWAKEN_FAIL : CNFALLOC_FAIL;
@@ -210,10 +294,18 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 		printStats(1, '-', CGREEN0);
 		wt.clear(true), orgs.clear(true), learnts.clear(true);
 		cm.destroy();
-		// ---- reduction phases (simplify.cu:156-186) on the device
-		const int64 imelted = inf.maxMelted, iclauses = int64(offs.size() - 1), iliterals = int64(lits.size());
+		// ---- reduction phases (simplify.cu:156-186) on the device, one loop iteration per call: the units of a round's
+		// prop() reach the host (and the proof file) before that round's proof chunk and before the next round
+		const int64 imelted = inf.maxMelted, iclauses = int64(nCls), iliterals = int64(nLits.load());
+		g_replay.solver = this, g_replay.seen = 0;
+		rc = sigma_begin(g_ctx);
+		int done = 0;
+		while (!rc && !done) {
+			rc = sigma_round(g_ctx, nullptr, &done);
+			if (!rc) cacheUnits(0);                                 // elimbcp.cu:185-200 (no-op when the proof sink did it already)
+		}
 		sigma_report rep;
-		rc = sigma_run(g_ctx, &rep);
+		if (!rc) rc = sigma_finish(g_ctx, &rep);
 		if (rc) {
 			LOGERRORN("simplifier failed (%d: %s)", rc, sigma_last_error(g_ctx));
 			killSolver();
@@ -221,17 +313,8 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 		uint64_t nC = 0, nL = 0, nR = 0, nT = 0;
 		sigma_result_sizes(g_ctx, &nC, &nL, &nR, &nT);
 		std::vector<uint8_t> eliminated(inf.maxVar + 1, 0);
-		std::vector<uint32_t> units(nT);
 		g_resolved.resize(nR);
-		sigma_store(g_ctx, nullptr, nullptr, nullptr, nullptr, eliminated.data(), g_resolved.data(), units.data());
-		// units forced on the device (prop(), elimbcp.cu:185-200); with a proof every one of them is (re)stated by the host
-		for (uint64_t i = 0; i < nT; i++) {
-			const uint32 unit = units[i];
-			if (opts.proof_en) enqueueUnit(unit);
-			else enqueueDevUnit(unit);
-		}
-		sp->propagated = trail.size();
-		stats.units.forced += nT;
+		sigma_store_compact(g_ctx, nullptr, nullptr, nullptr, eliminated.data(), g_resolved.data(), nullptr);
 		if (rep.cnfstate == SIGMA_UNSAT) { learnEmpty(); killSolver(); }   // elimbcp.cu:178, simplify.cu:168
 		inf.numClauses = uint32(rep.clauses), inf.numLiterals = uint32(rep.literals);
 		// ---- write back (simplify.cu:187-240)
@@ -252,15 +335,26 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 			printStats(1, 's', CGREEN);
 			break;
 		}
-		forall_variables(v) {                                            // markEliminated, transfer.cu:42-60
-			if (eliminated[v] && !IS_FORCED(eliminated[v])) markEliminated(v);
+		{                                                                // markEliminated (transfer.cu:42-60, solver.hpp:521-527) over the host cores
+			std::atomic<uint32_t> melted(0);
+			VSTATE* vs = sp->vstate;
+			parallelFor(size_t(inf.maxVar), [&](size_t b, size_t e, unsigned) {
+				uint32_t m = 0;
+				for (size_t v = b + 1; v <= e; v++)
+					if (eliminated[v] && !IS_FORCED(eliminated[v])) { vs[v].state = MELTED_M; m++; }
+				melted += m;
+			});
+			inf.unassigned -= melted.load();
 		}
-		if (skip_transfer_to_host) {                                     // the simplified CNF stays resident in the context
+		if (skip_transfer_to_host) {                                     // the simplified CNF stays resident in the context (sigma_device_view, sigma_continue)
 			printStats(1, 's', CGREEN);
 			break;
 		}
-		g_data.resize(size_t(3) * nC + nL), g_refs.resize(nC);
-		sigma_store_sclauses(g_ctx, g_data.data(), g_refs.data());       // cacheCNF, cnf.cu:200-237
+		g_nData = size_t(3) * nC + nL, g_nRefs = nC;
+		uint32_t* odata = static_cast<uint32_t*>(g_pinData.get((g_nData + 4) * sizeof(uint32_t)));
+		uint64_t* orefs = static_cast<uint64_t*>(g_pinRefs.get((g_nRefs + 2) * sizeof(uint64_t)));
+		if (!odata || !orefs) { LOGERRORN("no pinned memory for the write-back"); killSolver(); }
+		sigma_store_sclauses(g_ctx, odata, orefs);                       // cacheCNF, cnf.cu:200-237
 		if (canMap()) map(true);
 		else newBeginning();
 		rebuildWT(opts.sigma_priorbins);

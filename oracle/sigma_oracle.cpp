@@ -265,7 +265,10 @@ bool prop(S& s) {
         else { c.sig = sig; c.sz = newsz; }
     }
     // host enqueue :186-201 (duplicates included)
-    for (u32 u : s.units) { s.trail.push_back(u); s.vstate[ABS(u)] = 2; s.unassigned--; }
+    // every entry goes on the trail (the reference's host loop, elimbcp.cu:186-201, duplicates included: SURVEY B.11); the
+    // count of unassigned variables only moves for a variable assigned here for the first time (the reference decrements
+    // per entry in release builds - a latent double count that could only ever produce a spurious SAT; deliberate deviation)
+    for (u32 u : s.units) { s.trail.push_back(u); if (s.vstate[ABS(u)] != 2) s.unassigned--; s.vstate[ABS(u)] = 2; }
     countAll(s, s.numClauses, s.numLiterals);
     if (s.numLiterals) histSimp(s);
     createOT(s);
@@ -311,6 +314,44 @@ bool LCVE(S& s) {
     const u32 maxoccurs = s.o.lcve_max_occurs;
     s.elected.clear();
     s.frozenList.clear();
+    if (s.o.lcve_fast) {
+        // -lcvefast: mis_init_k / mis_round_k / mis_freeze_k (lcve.cu:150-217, 338-366).  The two stop conditions and the
+        // clause-size limit are FILTERS of the candidate set; rounds of "a candidate wins when no undecided candidate of
+        // lower rank shares a clause with it, winners freeze every neighbour" end in the greedy maximal independent set of
+        // the rank order.  The set is deterministic; the reference appends winners and frozen variables through atomics
+        // (insertAggr, mis_collect_k), so its ORDER is not - here: elected in rank order, frozen list in variable order.
+        std::vector<uint8_t> state(s.V + 1, 0);   // 0 none, 1 undecided, 2 elected, 3 frozen
+        auto oversize = [&](const OL& ol) {
+            for (u32 ci : ol) { const Clause& c = s.cls[ci]; if (!c.deleted() && c.sz > s.o.lcve_clause_max) return true; }
+            return false;
+        };
+        for (u32 v = 1; v <= s.V; v++) {
+            if (s.vstate[v] || (!s.assumed.empty() && s.assumed[v])) continue;
+            const u32 p = V2L(v), n = NEG(p), ps = s.hist[p], ns = s.hist[n];
+            if ((ps || ns) && ps <= maxoccurs && ns <= maxoccurs && !(ps >= pmax && ns >= nmax) && !oversize(s.ot[p]) && !oversize(s.ot[n]))
+                state[v] = 1;
+        }
+        for (u32 ei = 0; ei < s.V; ei++) {
+            const u32 cand = s.eligible[ei];
+            if (state[cand] != 1) continue;
+            state[cand] = 2;
+            s.elected.push_back(cand);
+            for (int side = 0; side < 2; side++)
+                for (u32 ci : s.ot[V2L(cand) | (u32)side]) {
+                    const Clause& c = s.cls[ci];
+                    if (c.deleted()) continue;
+                    const u32* l = s.L(c);
+                    for (int k = 0; k < c.sz; k++) {
+                        const u32 u = ABS(l[k]);
+                        if (u == cand) continue;
+                        s.frozen[u] = 1;
+                        if (state[u] == 1) state[u] = 3;
+                    }
+                }
+        }
+        for (u32 v = 1; v <= s.V; v++) if (s.frozen[v]) s.frozenList.push_back(v);
+    }
+    else
     // lcve_k :64-101
     for (u32 ei = 0; ei < s.V; ei++) {
         const u32 cand = s.eligible[ei];
@@ -1422,7 +1463,7 @@ void oracle_default_opts(oracle_opts* o) {
     o->phase_lits_min = 500; o->shrink_rate = 2; o->lits_mul = 1.0;
     o->ve_fun_en = 1; o->ve_lbound_en = 0; o->ve_clause_max = 100; o->xor_max_arity = 10;
     o->ere_clause_max = 250; o->ere_max_occurs = 3000; o->sub_max_occurs = 3000; o->bce_max_occurs = 3000;
-    o->sh_max_bve_out1 = 250; o->sigma_calls = 1; o->final_gc = 1; o->aggr_cnf_sort = 0;
+    o->sh_max_bve_out1 = 250; o->sigma_calls = 1; o->final_gc = 1; o->aggr_cnf_sort = 0; o->lcve_fast = 0;
 }
 
 void oracle_normalize_opts(oracle_opts* o) {  // options.cpp:291-296
@@ -1669,6 +1710,7 @@ int main(int argc, char** argv) {
         else if (a == "-no-veextend") o.ve_plus_en = 0;
         else if (a == "-no-ve") o.ve_en = 0;
         else if (a == "-no-lcvefast" || a == "-quiet") {}
+        else if (a == "-lcvefast") o.lcve_fast = 1;
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
     oracle_normalize_opts(&o);

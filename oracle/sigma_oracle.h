@@ -46,6 +46,8 @@ typedef struct oracle_opts {
     int32_t  sigma_calls;       /* stats.sigma.calls: 1 = preprocessing call */
     int32_t  final_gc;          /* 1: compact at the end like simplify(skip_transfer_to_host) */
     int32_t  aggr_cnf_sort;     /* -aggresivesort: refs stable-sorted by OLIST_CMP before the write-back (cnf.cu:232-233) */
+    int32_t  lcve_fast;         /* -lcvefast (the reference CLI's default; 0 here = the deterministic parity mode): election as a
+                                   maximal independent set over the FILTERED candidates (lcve.cu:150-217, 338-366) */
 } oracle_opts;
 
 void oracle_default_opts(oracle_opts* o);

@@ -97,6 +97,7 @@ extern "C" void sigma_default_opts(sigma_opts* o) {
     o->ve_fun_en = 1; o->ve_lbound_en = 0; o->ve_clause_max = 100; o->xor_max_arity = 10;
     o->ere_clause_max = 250; o->ere_max_occurs = 3000; o->sub_max_occurs = 3000; o->bce_max_occurs = 3000;
     o->sh_max_bve_out1 = 250; o->sigma_calls = 1; o->final_gc = 1; o->profile = 0;
+    o->lcve_fast = 0;   // the reference CLI's default is 1; parity needs the deterministic walk (sigma.h)
 }
 extern "C" void sigma_normalize_opts(sigma_opts* o) {  // options.cpp:291-296
     o->ve_en = o->ve_en || o->ve_plus_en;
@@ -207,9 +208,10 @@ static size_t carve(Ctx* c, char* base) {
     Carver a{base, 0};
     const size_t V1 = (size_t)c->V + 1, ND = c->ND, capC = c->capC, capW = c->capW;
     const size_t nflag = (capC > V1 ? capC : V1) + 2;
-    c->inLits = a.take<u32>(c->L0 + 1);
-    c->inOffs = a.take<u64>(c->C0 + 1);
-    c->inMeta = a.take<u32>(c->C0 + 1);
+    c->inLits = a.take<u32>(c->inCapL + 1);
+    c->inOffs = a.take<u64>(c->inCapC + 1);
+    c->inMetaBuf = a.take<u32>(c->inCapC + 1);
+    c->inMeta = c->inMetaBuf;
     for (int b = 0; b < 2; b++) { c->hdr[b] = a.take<uint4>(capC + 1); c->pool[b] = a.take<u32>(capW + 4); }
     c->key = a.take<uint4>(capC + 1);
     c->hist = a.take<u32>(ND + 2); c->otStart = a.take<u32>(ND + 2); c->otSize = a.take<u32>(ND + 2);
@@ -223,7 +225,7 @@ static size_t carve(Ctx* c, char* base) {
     c->vorg = a.take<u32>(V1); c->varcore = a.take<u32>(V1);
     c->mis = a.take<unsigned char>(V1); c->cstat = a.take<unsigned char>(V1);
     c->vstate = a.take<unsigned char>(V1); c->vstate0 = a.take<unsigned char>(V1);
-    c->assumed = a.take<unsigned char>(V1); c->eliminated = a.take<unsigned char>(V1);
+    c->assumedBuf = a.take<unsigned char>(V1); c->assumed = c->assumedBuf; c->eliminated = a.take<unsigned char>(V1);
     c->needSort = a.take<unsigned char>(ND + 4);
     c->wlA = a.take<u32>(V1); c->wlB = a.take<u32>(V1);
     c->veType = a.take<u32>(V1); c->veUcnt = a.take<u32>(V1); c->veRpos = a.take<u32>(V1); c->veRref = a.take<u64>(V1);
@@ -275,6 +277,7 @@ static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u
     if (max_var >= (1u << 27) - 2 || num_clauses >= 0xFFFFFFF0ull) return SIGMA_BAD_ARGUMENT;
     c->V = max_var; c->ND = 2 * (max_var + 1);
     c->C0 = num_clauses; c->L0 = L0;
+    c->inCapC = num_clauses + num_clauses / 8 + 1024; c->inCapL = L0 + L0 / 8 + 4096;   // input arrays: room for the clauses a sigma_continue appends
     c->needReload = false;
     c->orgClauses = orgC; c->orgLiterals = orgL;
     // logical capacities of awaken (simplify.cu:84-98)
@@ -291,6 +294,7 @@ static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u
     c->capW = numWords;                         // data cap in words: a pool this big can never overflow below the logical caps
     const u64 rc = num_clauses + L0;            // savedLits (simplify.cu:85)
     c->resolvedCap = (u32)(rc > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : rc);
+    c->resolvedCapPhys = c->resolvedCap;
     const size_t need = carve(c, nullptr);
     if (need > c->arenaBytes) {
         if (c->arena) { CUDA_TRY(cudaFree(c->arena)); c->arena = nullptr; c->arenaBytes = 0; }
@@ -353,7 +357,8 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
 
 // SCLAUSE records {word 0, sig, size, literals...} at refs[i] -> the engine's input arrays
 __global__ void k_unpack_sclauses(const u32* __restrict__ data, const u64* __restrict__ refs, u64 C, u64 numWords,
-                                  u32* __restrict__ inLits, u64* __restrict__ inOffs, u32* __restrict__ inMeta, u32* bad) {
+                                  u32* __restrict__ inLits, u64* __restrict__ inOffs, u32* __restrict__ inMeta, u32* bad,
+                                  unsigned long long* orgCL) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (u64)gridDim.x * blockDim.x) {
         const u64 r = refs[i];
         // records are appended in ref order without gaps (cnf.cuh:82-97): literal offset = ref - 3 i
@@ -367,6 +372,7 @@ __global__ void k_unpack_sclauses(const u32* __restrict__ data, const u64* __res
         if (i + 1 == C) inOffs[C] = o + sz;
         inMeta[i] = data[r] & ~(CB_DELETED | CB_MOLTEN | CB_ADDED);
         for (u32 k = 0; k < sz; k++) inLits[o + k] = data[r + NBUCKETS + k];
+        if ((data[r] & CB_ST_MASK) == 0) { atomicAdd(&orgCL[0], 1ull); atomicAdd(&orgCL[1], (unsigned long long)sz); }
     }
 }
 
@@ -376,13 +382,9 @@ extern "C" int sigma_load_sclauses(sigma_ctx* c, uint32_t max_var, uint64_t num_
     if (!c || !data_words || !refs || !max_var || num_words < NBUCKETS * num_clauses) return SIGMA_BAD_ARGUMENT;
     CUDA_TRY(cudaSetDevice(c->device));
     const u64 L0 = num_words - NBUCKETS * num_clauses;
-    u64 orgC = 0, orgL = 0;
-    for (u64 i = 0; i < num_clauses; i++) {
-        const u64 r = refs[i];
-        if (r + NBUCKETS > num_words) return SIGMA_BAD_ARGUMENT;
-        if ((data_words[r] & CB_ST_MASK) == 0) { orgC++; orgL += data_words[r + 2]; }
-    }
-    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL, vorg);
+    // originals (stats.clauses.original / literals.original) are counted by the unpack kernel; the arena is sized for the
+    // upper bound "every clause is original" first, the exact logical capacities follow below
+    int rc = prepareLoad(c, max_var, num_clauses, L0, num_clauses, L0, vorg);
     if (rc) return rc;
     // the reference's own two copies (reflectCNF, cnf.cu:166-174): record stream and refs, staged in
     // the inactive clause buffer, then unpacked on the device
@@ -392,12 +394,18 @@ extern "C" int sigma_load_sclauses(sigma_ctx* c, uint32_t max_var, uint64_t num_
     CUDA_TRY(cudaMemcpyAsync(dData, data_words, num_words * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(dRefs, refs, num_clauses * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemsetAsync(bad, 0, 4, c->stream));
+    unsigned long long* orgCL = (unsigned long long*)&c->dc->scratch[10];
+    CUDA_TRY(cudaMemsetAsync(orgCL, 0, 16, c->stream));
     if (num_clauses)
-        LAUNCH(c, k_unpack_sclauses, gridFor(num_clauses, 256), 256, 0, dData, dRefs, num_clauses, num_words, c->inLits, c->inOffs, c->inMeta, bad);
+        LAUNCH(c, k_unpack_sclauses, gridFor(num_clauses, 256), 256, 0, dData, dRefs, num_clauses, num_words, c->inLits, c->inOffs, c->inMeta, bad, orgCL);
     else CUDA_TRY(cudaMemsetAsync(c->inOffs, 0, 8, c->stream));
     u32 hbad = 0;
+    unsigned long long horg[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(horg, orgCL, 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->orgClauses = horg[0]; c->orgLiterals = horg[1];
+    if (!logicalCaps(c, num_clauses, L0, c->orgClauses, c->orgLiterals, &c->logC, &c->logW)) return SIGMA_CNFALLOC_FAIL;
     if (hbad) { snprintf(c->err, sizeof c->err, "SCLAUSE stream is not a gap-free sequence of records in ref order"); return SIGMA_BAD_ARGUMENT; }
     return finishLoad(c, vorg, vstate, assumed);
 }
@@ -440,6 +448,7 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     c->cur = 0;
     c->phase = c->multiplier = 0; c->simpstate = SIGMA_OK; c->cnfstate = SIGMA_UNSOLVED; c->compacted = false;
     c->nUnits = 0; c->numElected = 0; c->currMelted = 0; c->varcoreDead = false;
+    c->lastPropSeeds = c->lastPropTrail0 = c->lastPropTotal = 0;
     c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0; c->otValid = false; c->countsFresh = false; c->histFresh = false;
     memset(c->stageMs, 0, sizeof c->stageMs);
     c->unassigned = c->unassigned0;
@@ -581,6 +590,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
         StageTimer t(c, ST_PROP);
         bool conflict = false;
         r.propagated = c->nUnits;
+        c->lastPropSeeds = c->nUnits; c->lastPropTrail0 = c->hdc->trailSize; c->lastPropTotal = 0;
         if ((rc = runProp(c, &conflict))) return rc;
         if (conflict) {
             c->cnfstate = SIGMA_UNSAT; c->loopDone = true;
@@ -591,6 +601,8 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
         if ((rc = syncCounters(c))) return rc;
         c->numClauses = c->hdc->liveCls; c->numLiterals = c->hdc->liveLits;
         c->unassigned -= (i64)c->hdc->unassignedDec;
+        c->lastPropTotal = c->hdc->trailSize - c->lastPropTrail0;
+        r.trail_added = c->lastPropTotal;
         CUDA_TRY(cudaMemsetAsync(&c->dc->unassignedDec, 0, 4, c->stream));
         c->nUnits = 0;
         if (c->numLiterals) buildOT(c, false, nullptr);
@@ -601,6 +613,10 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     {
         StageTimer t(c, ST_LCVE);
         if ((rc = runLCVE(c))) return rc;
+    }
+    if (c->hdc->flags & 128u) {
+        snprintf(c->err, sizeof c->err, "the loaded formula holds a literal outside [2, 2 max_var + 2) or non-monotone clause offsets");
+        return SIGMA_BAD_ARGUMENT;
     }
     c->numElected = c->hdc->numElected;
     r.elected = c->numElected;
@@ -856,6 +872,169 @@ extern "C" int sigma_store_sclauses(sigma_ctx* c, uint32_t* data_words, uint64_t
     return SIGMA_OK;
 }
 
+// ------------------------------------------------------------------ trail of the device prop() calls
+extern "C" int sigma_trail_info(const sigma_ctx* c, uint64_t* total, uint32_t* last_from, uint32_t* last_count, uint32_t* last_seeds) {
+    if (!c || !c->begun) return SIGMA_NOT_LOADED;
+    if (total) *total = c->hdc->trailSize;
+    if (last_from) *last_from = c->lastPropTrail0;
+    if (last_count) *last_count = c->lastPropTotal;
+    if (last_seeds) *last_seeds = c->lastPropSeeds < c->lastPropTotal ? c->lastPropSeeds : c->lastPropTotal;
+    return SIGMA_OK;
+}
+extern "C" int sigma_copy_trail(sigma_ctx* c, uint64_t from, uint64_t count, uint32_t* out) {
+    if (!c || !c->begun) return SIGMA_NOT_LOADED;
+    if (!count) return SIGMA_OK;
+    if (!out || from + count > c->hdc->trailSize) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(out, c->trail + from, count * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SIGMA_OK;
+}
+
+// ------------------------------------------------------------------ pinned host buffers for the callers' edges
+extern "C" void* sigma_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void sigma_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ device-resident result: views and continuation
+extern "C" int sigma_device_view(sigma_ctx* c, sigma_device_cnf* v) {
+    if (!c || !v) return SIGMA_BAD_ARGUMENT;
+    if (!c->begun) return SIGMA_NOT_LOADED;
+    memset(v, 0, sizeof *v);
+    v->device = c->device; v->stream = (void*)c->stream;
+    v->max_var = c->V; v->clause_slots = c->hdc->numCls; v->pool_words = c->hdc->poolUsed;
+    v->live_clauses = c->numClauses; v->live_literals = c->numLiterals;
+    v->headers = c->hdr[c->cur]; v->literals = c->pool[c->cur];
+    v->ot_start = c->otStart; v->ot_size = c->otSize; v->ot_entries = c->occurs;
+    v->eliminated = c->eliminated; v->vstate = c->vstate; v->vorg = c->vorg;
+    v->elected = c->elected; v->num_elected = c->numElected;
+    v->units = c->units; v->resolved = c->resolved; v->resolved_words = c->hdc->resolvedSize;
+    v->trail = c->trail; v->trail_units = c->hdc->trailSize;
+    return SIGMA_OK;
+}
+
+// live clauses of the finished call -> the input arrays of the next one (order kept), originals counted
+__global__ void k_rebase(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n, const u32* __restrict__ pCls, const u32* __restrict__ pLits,
+                         u32* __restrict__ inLits, u64* __restrict__ inOffs, u32* __restrict__ inMeta, const u32* totCls, const u32* totLits,
+                         unsigned long long* orgCL) {
+    u32 oc = 0, ol = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w)) continue;
+        const u32 j = pCls[i], off = pLits[i];
+        const u32* s = pool + h.x;
+        for (u32 k = 0; k < h.y; k++) inLits[off + k] = s[k];
+        inOffs[j] = off;
+        inMeta[j] = C_LEARNT(h.w) ? (h.w & ~(CB_DELETED | CB_MOLTEN | CB_ADDED)) : 0u;
+        if (!C_LEARNT(h.w)) { oc++; ol += h.y; }
+    }
+    oc = warpSum(oc); ol = warpSum(ol);
+    if ((threadIdx.x & 31u) == 0 && oc) { atomicAdd(&orgCL[0], (unsigned long long)oc); atomicAdd(&orgCL[1], (unsigned long long)ol); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) inOffs[*totCls] = *totLits;
+}
+// variables eliminated (not forced) or assigned by the finished call are inactive in the next one; counts the active ones
+__global__ void k_vstate_next(const unsigned char* __restrict__ vstate, const unsigned char* __restrict__ eliminated, u32 V,
+                              unsigned char* __restrict__ vstate0, u32* active) {
+    u32 a = 0;
+    for (u32 v = 1 + blockIdx.x * blockDim.x + threadIdx.x; v <= V; v += gridDim.x * blockDim.x) {
+        unsigned char s = vstate[v];
+        const unsigned char e = eliminated[v];
+        if (!s && e && !(e & FORCED_MASK)) s = 3;   // MELTED_M (markEliminated, transfer.cu:42-60)
+        vstate0[v] = s;
+        a += !s;
+    }
+    a = warpSum(a);
+    if ((threadIdx.x & 31u) == 0 && a) atomicAdd(active, a);
+}
+
+extern "C" int sigma_continue(sigma_ctx* c, uint64_t num_new, const uint32_t* new_lits, const uint64_t* new_offs, const uint32_t* new_meta,
+                              const uint8_t* vstate, const uint8_t* assumed) {
+    if (!c) return SIGMA_BAD_ARGUMENT;
+    if (!c->begun || !c->loopDone) return SIGMA_NOT_LOADED;
+    if (c->cnfstate != SIGMA_UNSOLVED) { snprintf(c->err, sizeof c->err, "sigma_continue: the formula is already decided"); return SIGMA_BAD_ARGUMENT; }
+    if (num_new && (!new_lits || !new_offs)) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = syncCounters(c);
+    if (rc) return rc;
+    const u32 n = c->hdc->numCls;
+    const u64 newL = num_new ? new_offs[num_new] - new_offs[0] : 0;
+    u32* tot = c->dc->scratch;
+    unsigned long long* orgCL = (unsigned long long*)&c->dc->scratch[10];   // scratch[10..13], 8-byte aligned
+    CUDA_TRY(cudaMemsetAsync(orgCL, 0, 16, c->stream));
+    CUDA_TRY(cudaMemsetAsync(tot, 0, 8, c->stream));
+    u64 nc = 0, nl = 0;
+    if (n) {
+        // same selection as the store: flags, two scans; then the copy goes into the input arrays instead of the staging buffers
+        if ((rc = launchStore(c, &nc, &nl, 3, false))) return rc;
+        if (nc + num_new > c->inCapC || nl + newL > c->inCapL) {
+            snprintf(c->err, sizeof c->err, "sigma_continue: %llu clauses / %llu literals do not fit the input arrays carved at sigma_load (%llu / %llu): load again",
+                     (unsigned long long)(nc + num_new), (unsigned long long)(nl + newL), (unsigned long long)c->inCapC, (unsigned long long)c->inCapL);
+            return SIGMA_CNFALLOC_FAIL;
+        }
+        LAUNCH(c, k_rebase, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->flagA, c->flagB, c->inLits, c->inOffs, c->inMetaBuf, tot, tot + 1, orgCL);
+    } else CUDA_TRY(cudaMemsetAsync(c->inOffs, 0, 8, c->stream));
+    unsigned long long horg[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(horg, orgCL, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    u64 orgC = horg[0], orgL = horg[1];
+    // the clauses the host learnt since (or any other delta), appended in the order given
+    if (num_new) {
+        u64* shifted = (u64*)malloc((num_new + 1) * sizeof(u64));
+        if (!shifted) return SIGMA_AWAKEN_FAIL;
+        for (u64 i = 0; i <= num_new; i++) shifted[i] = nl + (new_offs[i] - new_offs[0]);
+        for (u64 i = 0; i < num_new; i++) if (!new_meta || !(new_meta[i] & CB_LEARNT)) { orgC++; orgL += new_offs[i + 1] - new_offs[i]; }
+        cudaError_t e = cudaMemcpyAsync(c->inOffs + nc, shifted, (num_new + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->inLits + nl, new_lits + new_offs[0], newL * 4, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = new_meta ? cudaMemcpyAsync(c->inMetaBuf + nc, new_meta, num_new * 4, cudaMemcpyHostToDevice, c->stream)
+                                           : cudaMemsetAsync(c->inMetaBuf + nc, 0, num_new * 4, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        free(shifted);
+        if (e != cudaSuccess) { snprintf(c->err, sizeof c->err, "sigma_continue: %s", cudaGetErrorString(e)); return -(int)e; }
+    }
+    // per-variable state of the next call
+    const size_t V1 = (size_t)c->V + 1;
+    if (vstate) {
+        CUDA_TRY(cudaMemcpyAsync(c->vstate0, vstate, V1, cudaMemcpyHostToDevice, c->stream));
+        i64 un = c->V;
+        for (size_t v = 1; v < V1; v++) if (vstate[v]) un--;
+        c->unassigned0 = un;
+    } else {
+        u32* active = &c->dc->scratch[14];
+        CUDA_TRY(cudaMemsetAsync(active, 0, 4, c->stream));
+        LAUNCH(c, k_vstate_next, gridFor(c->V, 256), 256, 0, c->vstate, c->eliminated, c->V, c->vstate0, active);
+        u32 ha = 0;
+        CUDA_TRY(cudaMemcpyAsync(&ha, active, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->unassigned0 = ha;
+    }
+    if (assumed) {
+        if (!c->assumedBuf) { snprintf(c->err, sizeof c->err, "sigma_continue: no assumption buffer"); return SIGMA_BAD_ARGUMENT; }
+        c->assumed = c->assumedBuf;
+        CUDA_TRY(cudaMemcpyAsync(c->assumed, assumed, V1, cudaMemcpyHostToDevice, c->stream));
+    } else c->assumed = nullptr;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // the formula of the next call; a later inprocessing call (stats.sigma.calls > 1: counts originals only, bounded.cuh:428-430)
+    c->C0 = nc + num_new; c->L0 = nl + newL;
+    c->orgClauses = orgC; c->orgLiterals = orgL;
+    c->inMeta = c->inMetaBuf;
+    c->o.sigma_calls++;
+    u64 lc = 0, lw = 0;
+    if (!logicalCaps(c, c->C0, c->L0, orgC, orgL, &lc, &lw) || lc > c->capC || lw > c->capW) {
+        snprintf(c->err, sizeof c->err, "sigma_continue: the logical capacities of the continued formula exceed the arena: load again");
+        c->needReload = true;
+        return SIGMA_CNFALLOC_FAIL;
+    }
+    c->logC = lc; c->logW = lw;
+    const u64 rcap = c->C0 + c->L0;
+    if (rcap > c->resolvedCapPhys) { snprintf(c->err, sizeof c->err, "sigma_continue: witness stack capacity"); c->needReload = true; return SIGMA_CNFALLOC_FAIL; }
+    c->resolvedCap = (u32)rcap;
+    c->begun = false;
+    return SIGMA_OK;
+}
+
 // ------------------------------------------------------------------ debugging / stats
 extern "C" int sigma_debug_elected(sigma_ctx* c, uint32_t* out, uint32_t* n) {
     if (!c || !c->begun || !n) return SIGMA_NOT_LOADED;
@@ -905,8 +1084,11 @@ extern "C" int sigma_stage_prep(int device, uint64_t num_clauses, uint32_t* lits
     return rc;
 }
 
-__global__ void k_stage_hist(const u32* __restrict__ lits, u64 n, u32* __restrict__ hist) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) atomicAdd(&hist[lits[i]], 1u);
+__global__ void k_stage_hist(const u32* __restrict__ lits, u64 n, u32* __restrict__ hist, u32 nbins, u32* bad) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u32 l = lits[i];
+        if (l < nbins) atomicAdd(&hist[l], 1u); else *bad = 1u;
+    }
 }
 extern "C" int sigma_stage_histogram(int device, uint64_t num_lits, const uint32_t* lits, uint32_t nbins, uint32_t* hist) {
     if (!lits || !hist) return SIGMA_BAD_ARGUMENT;
@@ -914,11 +1096,14 @@ extern "C" int sigma_stage_histogram(int device, uint64_t num_lits, const uint32
     if (e != cudaSuccess) return -(int)e;
     u32 *dl = nullptr, *dh = nullptr;
     if ((e = cudaMalloc(&dl, num_lits * 4 + 4)) != cudaSuccess) return -(int)e;
-    if ((e = cudaMalloc(&dh, (size_t)nbins * 4 + 4)) != cudaSuccess) { cudaFree(dl); return -(int)e; }
+    if ((e = cudaMalloc(&dh, (size_t)nbins * 4 + 8)) != cudaSuccess) { cudaFree(dl); return -(int)e; }
     cudaMemcpy(dl, lits, num_lits * 4, cudaMemcpyHostToDevice);
-    cudaMemset(dh, 0, (size_t)nbins * 4);
-    if (num_lits) k_stage_hist<<<gridFor(num_lits, 256), 256>>>(dl, num_lits, dh);
+    cudaMemset(dh, 0, (size_t)nbins * 4 + 8);
+    if (num_lits) k_stage_hist<<<gridFor(num_lits, 256), 256>>>(dl, num_lits, dh, nbins, dh + nbins);
     e = cudaMemcpy(hist, dh, (size_t)nbins * 4, cudaMemcpyDeviceToHost);
+    u32 bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&bad, dh + nbins, 4, cudaMemcpyDeviceToHost);
     cudaFree(dl); cudaFree(dh);
-    return e == cudaSuccess ? SIGMA_OK : -(int)e;
+    if (e != cudaSuccess) return -(int)e;
+    return bad ? SIGMA_BAD_ARGUMENT : SIGMA_OK;   // a literal >= nbins
 }

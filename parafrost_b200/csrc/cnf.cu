@@ -20,16 +20,25 @@
 // With hist != NULL the first round's histogram + sort-key pass (k_hist_key) is fused in: the sorted
 // literals are in registers anyway, so the clause store is not read again before the partition.
 __global__ void k_awaken(const u32* __restrict__ inLits, const u64* __restrict__ inOffs, const u32* __restrict__ inMeta,
-                         u64 C, uint4* __restrict__ hdr, u32* __restrict__ pool, u32* __restrict__ hist, uint4* __restrict__ key, u32* flags) {
+                         u64 C, uint4* __restrict__ hdr, u32* __restrict__ pool, u32* __restrict__ hist, uint4* __restrict__ key, u32* flags,
+                         u32 ND, u64 L0) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (u64)gridDim.x * blockDim.x) {
-        const u64 b = inOffs[i], e = inOffs[i + 1];
+        const u64 b = inOffs[i];
+        u64 e = inOffs[i + 1];
+        // input validation (the C ABI takes raw buffers): offsets must be monotone and inside the literal array, literals
+        // inside [2, 2V+2).  A bad entry is neutralised (empty clause / literal 2) and flagged: the call fails with
+        // SIGMA_BAD_ARGUMENT at its first read-back instead of indexing outside the tables.
+        if (e < b || e > L0 || e - b >= (1ull << 31)) { atomicOr(flags, 128u); e = b; }
         const int sz = (int)(e - b);
         u32* dst = pool + b;
         u32 sig = 0;
         if (sz <= 8) {
             u32 r[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) r[k] = (k < sz) ? inLits[b + k] : 0xFFFFFFFFu;
+            for (int k = 0; k < 8; k++) {
+                r[k] = (k < sz) ? inLits[b + k] : 0xFFFFFFFFu;
+                if (k < sz && (r[k] < 2u || r[k] >= ND)) { atomicOr(flags, 128u); r[k] = 2u; }
+            }
             // odd-even transposition network on 8 registers (padding sorts to the end)
 #pragma unroll
             for (int pass = 0; pass < 8; pass++) {
@@ -43,7 +52,8 @@ __global__ void k_awaken(const u32* __restrict__ inLits, const u64* __restrict__
             for (int k = 0; k < 8; k++) if (k < sz) { dst[k] = r[k]; sig |= MAPHASH(r[k]); }
         } else {
             for (int k = 0; k < sz; k++) {
-                const u32 t = inLits[b + k];
+                u32 t = inLits[b + k];
+                if (t < 2u || t >= ND) { atomicOr(flags, 128u); t = 2u; }
                 int j = k;
                 for (; j > 0 && t < dst[j - 1]; j--) dst[j] = dst[j - 1];
                 dst[j] = t;
@@ -69,7 +79,7 @@ void launchAwaken(Ctx* c) {
     if (!c->C0) return;
     cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
     LAUNCH(c, k_awaken, gridFor(c->C0, 256), 256, 0, c->inLits, c->inOffs, c->inMeta, c->C0, c->hdr[c->cur], c->pool[c->cur], c->hist, c->key,
-           &c->dc->flags);
+           &c->dc->flags, c->ND, c->L0);
     KB(c, 8.0 * c->C0 + 4.0 * c->L0 + (c->inMeta ? 4.0 * c->C0 : 0.0) + 16.0 * c->C0 + 4.0 * c->L0 + 16.0 * c->C0 + 4.0 * c->ND);   // offsets + literals in, headers + literals + keys + histogram out
     c->histFresh = true;   // hist[] and key[] describe the store until a kernel changes it (api.cu: buildOT)
 }
@@ -540,7 +550,8 @@ int launchStore(Ctx* c, u64* nCls, u64* nLits, int form, bool writeBackOrder) { 
         const int rc = aggressiveOrder(c, n);
         if (rc) return rc;
     }
-    if (form == 1)
+    if (form == 3) {}   // selection only (flagA / flagB hold the output positions): sigma_continue copies into the input arrays
+    else if (form == 1)
         LAUNCH(c, k_store_sclause, gridFor(n, 256), 256, 0, c->hdr[src], c->pool[src], n, c->flagA, c->flagB, c->pool[dst], c->flag64);
     else {
         u32* oBits = (u32*)c->hdr[dst];

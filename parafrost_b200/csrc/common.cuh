@@ -150,7 +150,7 @@ struct Ctx {
     u64 orgClauses, orgLiterals;
     bool loaded, begun, needReload;   // needReload: options set after sigma_load do not fit the carved arena (sigma_set_opts)
     // input (pristine)
-    u32* inLits; u64* inOffs; u32* inMeta;
+    u32* inLits; u64* inOffs; u32* inMeta; u32* inMetaBuf; u64 inCapC, inCapL;   // inCap*: carved sizes (slack for sigma_continue)
     // CNF double buffer
     uint4* hdr[2]; u32* pool[2]; int cur;
     uint4* key;
@@ -159,7 +159,8 @@ struct Ctx {
     uint2* otPairs; u32* otCur; u32* otBig; u32 otShift, otNB;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
     // vars
     u32 *scores, *eligible, *rank, *sortK, *sortV, *elected, *units, *resolved, *trail, *vorg, *varcore;
-    unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *eliminated, *needSort;
+    unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *assumedBuf, *eliminated, *needSort;
+    u64 resolvedCapPhys;
     u32 *wlA, *wlB;
     // BVE arrays
     u32 *veType, *veUcnt, *veRpos, *veRes, *veUoff, *veResOff; u64* veRref;
@@ -179,6 +180,7 @@ struct Ctx {
     cudaEvent_t ev0, ev1, evRun0, evRun1; bool ownStream;
     double msTotal;
     u32 lastElectedCount;
+    u32 lastPropSeeds, lastPropTrail0, lastPropTotal;   // the last prop(): BVE-origin units, trail size before it, entries it appended
     bool varcoreDead, attrSort, attrElim, attrOT;
     bool histFresh;    // hist[] / key[] were produced by k_awaken and the store is untouched since
     bool countsFresh;  // hdc->liveCls / liveLits describe the clause store as it is now

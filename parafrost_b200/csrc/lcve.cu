@@ -29,9 +29,12 @@
 #define VI_CLASS(w) (((w) >> 3) & 3u)
 #define VI_RANK(w) ((w) >> 5)
 
+// fast != 0 (-lcvefast, mis_init_k lcve.cu:150-173): the bound violators and the variables with an oversized clause
+// (ovsFast, k_mark_oversize) are no candidates at all instead of cutting the walk
 __global__ void k_scores(const u32* __restrict__ hist, const unsigned char* __restrict__ vstate,
                          const unsigned char* __restrict__ assumed, u32 V, u32 pmax, u32 nmax, u32 maxoccurs,
-                         u32* __restrict__ keys, u32* __restrict__ vals, unsigned char* __restrict__ cstat, DevCounters* dc) {
+                         u32* __restrict__ keys, u32* __restrict__ vals, unsigned char* __restrict__ cstat, DevCounters* dc,
+                         int fast, const unsigned char* __restrict__ ovsFast) {
     u32 kmax = 0;   // largest score: tells the host how many radix digits the sort needs
     for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < V; t += gridDim.x * blockDim.x) {
         const u32 v = t + 1;
@@ -40,8 +43,11 @@ __global__ void k_scores(const u32* __restrict__ hist, const unsigned char* __re
         kmax = max(kmax, ps * ns);
         vals[t] = v;
         unsigned char cs = CS_NONE;
-        if (!vstate[v] && !(assumed && assumed[v]) && (ps || ns))
-            cs = (ps > maxoccurs || ns > maxoccurs || (ps >= pmax && ns >= nmax)) ? CS_STOP : CS_CAND;
+        if (!vstate[v] && !(assumed && assumed[v]) && (ps || ns)) {
+            const bool stop = ps > maxoccurs || ns > maxoccurs || (ps >= pmax && ns >= nmax);
+            if (!fast) cs = stop ? CS_STOP : CS_CAND;
+            else cs = (stop || (ovsFast && ovsFast[v])) ? CS_NONE : CS_CAND;
+        }
         cstat[v] = cs;
     }
     kmax = warpMax(kmax);
@@ -469,6 +475,70 @@ __global__ void __launch_bounds__(128) k_frozen12(const u32* __restrict__ electe
     if (threadIdx.x == 0) dc->nFrozen = nf;
 }
 
+// ------------------------------------------------------------------ -lcvefast helpers
+// mis_oversize (lcve.cu:108-116) for every variable at once: one pass over the clause headers, literals read only of the
+// (rare) clauses longer than lcveclausemax
+__global__ void k_mark_oversize(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n, int maxcsize, unsigned char* __restrict__ ovs) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hdr[i];
+        if (C_DELETED(h.w) || (int)h.y <= maxcsize) continue;
+        for (u32 k = 0; k < h.y; k++) ovs[LABS(pool[h.x + k])] = 1;
+    }
+}
+// mis_freeze (lcve.cu:133-148): every variable sharing a clause with an elected one is frozen
+template <int GS>
+__global__ void __launch_bounds__(256) k_mark_frozen(const u32* __restrict__ elected, const u32* __restrict__ count, const uint4* __restrict__ hdr,
+                                                     const u32* __restrict__ pool, const u32* __restrict__ otStart, const u32* __restrict__ otSize,
+                                                     const u32* __restrict__ occurs, unsigned char* __restrict__ frozen) {
+    const u32 n = *count;
+    const u32 lane = threadIdx.x & (u32)(GS - 1);
+    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
+    for (u32 it = (blockIdx.x * blockDim.x + threadIdx.x) / GS; it < n; it += groupsPerGrid) {
+        const u32 v = elected[it];
+        for (u32 side = 0; side < 2; side++) {
+            const u32 lit = V2L(v) | side;
+            const u32 m = otSize[lit];
+            const u32* list = occurs + otStart[lit];
+            for (u32 j = lane; j < m; j += GS) {
+                const uint4 h = hdr[list[j]];
+                if (C_DELETED(h.w)) continue;
+                for (u32 k = 0; k < h.y; k++) { const u32 u = LABS(pool[h.x + k]); if (u != v) frozen[u] = 1; }
+            }
+        }
+    }
+}
+// mis_collect_k + mapfrozen_k (lcve.cu:205-215, 253-260): only indices < 12 are observable (function.cuh:35,143); the
+// reference hands them out through an atomic counter, here the frozen variables are taken in variable order.  One CTA.
+__global__ void __launch_bounds__(1024) k_first12_fast(const unsigned char* __restrict__ frozen, u32 V, DevCounters* dc, u32* __restrict__ varcore,
+                                                       u32* __restrict__ prev12) {
+    __shared__ u32 fv[MAXFUNVAR];
+    __shared__ u32 nf, wcnt[32];
+    if (threadIdx.x < MAXFUNVAR) { const u32 old = prev12[threadIdx.x]; if (old != NOVAR) varcore[old] = NOVAR; }
+    if (threadIdx.x == 0) nf = 0;
+    __syncthreads();
+    for (u32 base = 1; base <= V && nf < MAXFUNVAR; base += 1024) {
+        const u32 v = base + threadIdx.x;
+        const bool f = v <= V && frozen[v];
+        const u32 m = __ballot_sync(0xffffffffu, f);
+        if ((threadIdx.x & 31u) == 0) wcnt[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        u32 before = nf;
+        for (u32 w = 0; w < (threadIdx.x >> 5); w++) before += wcnt[w];
+        const u32 slot = before + __popc(m & lanemaskLt());
+        if (f && slot < MAXFUNVAR) fv[slot] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) { u32 t = nf; for (int w = 0; w < 32; w++) t += wcnt[w]; nf = t; }
+        __syncthreads();
+    }
+    const u32 cnt = nf < MAXFUNVAR ? nf : MAXFUNVAR;
+    if (threadIdx.x < MAXFUNVAR) {
+        const bool on = threadIdx.x < cnt;
+        prev12[threadIdx.x] = on ? fv[threadIdx.x] : NOVAR;
+        if (on) varcore[fv[threadIdx.x]] = threadIdx.x;
+    }
+    if (threadIdx.x == 0) dc->nFrozen = cnt;
+}
+
 // ------------------------------------------------------------------ host driver
 #define MIS_BATCH 6   // MIS rounds queued per host round-trip (an empty round costs ~4 us, a round trip ~40 us)
 
@@ -493,8 +563,17 @@ int runLCVE(Ctx* c) {
     unsigned char* ovs = c->mis;
     CUDA_TRY(cudaMemsetAsync(&c->dc->scratch[6], 0, 4, c->stream));
     CUDA_TRY(cudaMemsetAsync(&c->dc->scratch[8], 0, 4, c->stream));   // number of MIS_HALF decisions
+    const int fast = c->o.lcve_fast != 0;
+    if (fast) { const int rc0 = syncCounters(c); if (rc0) return rc0; }   // flags bit 3 (a clause with >= 2^14 literals) must be current
+    const int maxcsize = fast ? 0x7FFFFFFF : c->o.lcve_clause_max;   // -lcvefast: oversized clauses are filtered up front, never seen by the rounds
+    const unsigned char* ovsFast = nullptr;
+    if (fast && (c->o.lcve_clause_max < (1 << 14) || (c->hdc->flags & 8u))) {   // flags bit 3: some clause has >= 2^14 literals (k_hist_key)
+        CUDA_TRY(cudaMemsetAsync(c->needSort, 0, (size_t)V + 1, c->stream));
+        LAUNCH(c, k_mark_oversize, gridFor(c->hdc->numCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], c->hdc->numCls, c->o.lcve_clause_max, c->needSort);
+        ovsFast = c->needSort;
+    }
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
-           c->scores, c->eligible, c->cstat, c->dc);
+           c->scores, c->eligible, c->cstat, c->dc, fast, ovsFast);
     KB(c, 18.0 * V);
     int rc = syncCounters(c);   // the largest score decides how many radix passes the sort needs (usually 2 of 4)
     if (rc) return rc;
@@ -541,7 +620,7 @@ int runLCVE(Ctx* c) {
             if (clausePass) CUDA_TRY(cudaMemsetAsync(&c->dc->wlCnt[round % 3u], 0, 4, c->stream));   // k_mis_first refills the slot
         }
         if (clausePass) {
-            LAUNCH(c, k_mis_clauses, gridFor(nCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], nCls, vinfo, nbr, ovs, H, c->o.lcve_clause_max);
+            LAUNCH(c, k_mis_clauses, gridFor(nCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], nCls, vinfo, nbr, ovs, H, maxcsize);
             KB(c, 16.0 * nCls + 8.0 * c->numLiterals);   // headers, literals, election words
             u32* pushCount = &c->dc->scratch[2];
             CUDA_TRY(cudaMemsetAsync(pushCount, 0, 4, c->stream));
@@ -568,10 +647,10 @@ int runLCVE(Ctx* c) {
             for (int b = 0; b < MIS_BATCH; b++, round++) {
                 if (smallGroups)
                     LAUNCH(c, k_mis_round<8>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
-                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max, prof);
+                           c->otSize, c->occurs, vinfo, blocker, maxcsize, prof);
                 else
                     LAUNCH(c, k_mis_round<32>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
-                           c->otSize, c->occurs, vinfo, blocker, c->o.lcve_clause_max, prof);
+                           c->otSize, c->occurs, vinfo, blocker, maxcsize, prof);
             }
             profCollect(c, c->ktLastId);
             CUDA_TRY(cudaMemcpyAsync(c->hdc, c->dc, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
@@ -588,7 +667,17 @@ int runLCVE(Ctx* c) {
         scanExclusiveU32(c, c->flagA, c->flagB, rEnd, 0, &c->dc->numElected);
         LAUNCH(c, k_elect_scatter, gridFor(rEnd, 256), 256, 0, c->eligible, c->flagA, rEnd, c->flagB, c->elected);
     }
-    if (c->o.ve_fun_en) {
+    if (c->o.ve_fun_en && fast) {
+        unsigned char* frozen = c->cstat;   // read by k_rank only
+        CUDA_TRY(cudaMemsetAsync(frozen, 0, (size_t)V + 1, c->stream));
+        if (rEnd) {
+            if (smallGroups) LAUNCH(c, k_mark_frozen<8>, gridFor((u64)rEnd * 8, 256), 256, 0, c->elected, &c->dc->numElected, c->hdr[c->cur], c->pool[c->cur],
+                                    c->otStart, c->otSize, c->occurs, frozen);
+            else LAUNCH(c, k_mark_frozen<32>, gridFor((u64)rEnd * 32, 256), 256, 0, c->elected, &c->dc->numElected, c->hdr[c->cur], c->pool[c->cur],
+                        c->otStart, c->otSize, c->occurs, frozen);
+        }
+        LAUNCH(c, k_first12_fast, 1, 1024, 0, frozen, V, c->dc, c->varcore, c->dc->froz12);
+    } else if (c->o.ve_fun_en) {
         const u32* walk = c->elected; const u32* nWalk = &c->dc->numElected;
         if (rEnd && c->hdc->scratch[8]) {   // some variables froze only their positive side: the walk order includes them
             LAUNCH(c, k_elect_flags, gridFor(rEnd, 256), 256, 0, c->eligible, vinfo, rEnd, c->flagA, 1);

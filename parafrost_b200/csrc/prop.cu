@@ -27,6 +27,7 @@ __global__ void k_bcp_seed(u32* state, u32* __restrict__ front, DevCounters* dc,
         const u32 old = atomicCAS(&state[v], BCP_UNSET, desired);
         if (old == BCP_UNSET) {
             eliminated[v] |= FORCED_MASK;
+            atomicAdd(&dc->unassignedDec, 1u);   // variables newly assigned: a unit emitted twice counts once
             front[atomicAdd(&dc->bcpCurr, 1u)] = LFLIP(u);
         } else if (old != desired) dc->bcpConfl = 1;
     }
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) k_bcp_level(const uint4* __restrict__ hdr
                 const u32 old = atomicCAS(&state[v], BCP_UNSET, desired);
                 if (old == BCP_UNSET) {
                     eliminated[v] |= FORCED_MASK;
+                    atomicAdd(&dc->unassignedDec, 1u);
                     const u32 slot = atomicAdd(&dc->numUnits, 1u);
                     if (slot < unitsCap) units[slot] = unit; else dc->flags |= 2u;
                     frontNext[atomicAdd(&dc->bcpNext, 1u)] = LFLIP(unit);
@@ -115,8 +117,7 @@ __global__ void k_bcp_trail(const u32* __restrict__ units, DevCounters* dc, u32*
 __global__ void k_bcp_finish(DevCounters* dc, u32 trailCap) {
     const u32 n = dc->numUnits;
     dc->trailSize = min(dc->trailSize + n, trailCap);
-    dc->unassignedDec += n;
-    dc->numUnits = 0;
+    dc->numUnits = 0;   // (unassignedDec: counted where the variables are assigned, k_bcp_seed / k_bcp_level)
 }
 __global__ void k_bcp_reset(DevCounters* dc) { dc->bcpCurr = dc->bcpNext = dc->bcpConfl = dc->bcpLevel = 0; }
 

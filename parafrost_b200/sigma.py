@@ -29,7 +29,7 @@ class SigmaOpts(C.Structure):
         ("xor_max_arity", C.c_uint32), ("ere_clause_max", C.c_int32), ("ere_max_occurs", C.c_uint32),
         ("sub_max_occurs", C.c_uint32), ("bce_max_occurs", C.c_uint32), ("sh_max_bve_out1", C.c_uint32),
         ("sigma_calls", C.c_int32), ("final_gc", C.c_int32), ("profile", C.c_int32), ("aggr_cnf_sort", C.c_int32),
-        ("proof_en", C.c_int32),
+        ("proof_en", C.c_int32), ("lcve_fast", C.c_int32),
     ]
 
 
@@ -38,11 +38,11 @@ class RoundReport(C.Structure):
         ("round", C.c_uint32), ("kind", C.c_uint32), ("elected", C.c_uint32), ("eliminated", C.c_uint32),
         ("resolvents", C.c_uint32), ("units", C.c_uint32), ("propagated", C.c_uint32), ("gc", C.c_uint32),
         ("clauses", C.c_uint64), ("literals", C.c_uint64), ("literals_in", C.c_uint64),
-        ("ms", C.c_float), ("pad", C.c_float),
+        ("ms", C.c_float), ("trail_added", C.c_uint32),
     ]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class Report(C.Structure):
@@ -61,6 +61,17 @@ class Report(C.Structure):
         return d
 
 
+class DeviceCnf(C.Structure):
+    """sigma_device_cnf: device pointers into the context's arena (Solver::getDeviceCNF / getVars, solver.hpp:694-705)."""
+    _fields_ = [
+        ("device", C.c_int32), ("stream", C.c_void_p), ("max_var", C.c_uint32), ("clause_slots", C.c_uint32), ("pool_words", C.c_uint64),
+        ("live_clauses", C.c_uint64), ("live_literals", C.c_uint64), ("headers", C.c_void_p), ("literals", C.c_void_p),
+        ("ot_start", C.c_void_p), ("ot_size", C.c_void_p), ("ot_entries", C.c_void_p), ("eliminated", C.c_void_p), ("vstate", C.c_void_p),
+        ("vorg", C.c_void_p), ("elected", C.c_void_p), ("num_elected", C.c_uint32), ("units", C.c_void_p), ("resolved", C.c_void_p),
+        ("resolved_words", C.c_uint64), ("trail", C.c_void_p), ("trail_units", C.c_uint64),
+    ]
+
+
 class SigmaError(RuntimeError):
     pass
 
@@ -76,7 +87,8 @@ SYMBOLS = [
     "sigma_run", "sigma_begin", "sigma_round", "sigma_finish", "sigma_num_rounds", "sigma_round_reports",
     "sigma_result_sizes", "sigma_store", "sigma_store_compact", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
     "sigma_set_proof_sink", "sigma_proof_chunks", "sigma_proof_chunk_size", "sigma_proof_chunk_copy",
-    "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_kernel_stats", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
+    "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_kernel_stats", "sigma_trail_info", "sigma_copy_trail", "sigma_pinned_alloc", "sigma_pinned_free",
+    "sigma_device_view", "sigma_continue", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
 ]
 
 
@@ -116,6 +128,12 @@ def lib():
         L.sigma_proof_chunk_copy.argtypes = [P, C.c_uint32, P]
         L.sigma_kernel_profile.argtypes = [P, C.c_int]
         L.sigma_kernel_times.argtypes = [P, P, P, P, C.POINTER(C.c_uint32)]
+        L.sigma_trail_info.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.sigma_copy_trail.argtypes = [P, C.c_uint64, C.c_uint64, P]
+        L.sigma_pinned_alloc.argtypes = [C.c_size_t]; L.sigma_pinned_alloc.restype = C.c_void_p
+        L.sigma_pinned_free.argtypes = [C.c_void_p]
+        L.sigma_device_view.argtypes = [P, C.POINTER(DeviceCnf)]
+        L.sigma_continue.argtypes = [P, C.c_uint64, P, P, P, P, P]
         L.sigma_kernel_stats.argtypes = [P, P, P, P, P, C.POINTER(C.c_uint32)]
         L.sigma_memory.argtypes = [P] + [C.POINTER(C.c_uint64)] * 3
         L.sigma_last_error.argtypes = [P]; L.sigma_last_error.restype = C.c_char_p
@@ -129,7 +147,7 @@ def lib():
 FLAG_MAP = {  # the reference's CLI flags (src/gpu/options.cpp:24-43, options.cu:36-60)
     "-no-ere": {"ere_en": 0}, "-ere": {"ere_en": 1}, "-no-vefunction": {"ve_fun_en": 0}, "-bce": {"bce_en": 1},
     "-all": {"all_en": 1}, "-no-sub": {"sub_en": 0}, "-no-veextend": {"ve_plus_en": 0}, "-no-ve": {"ve_en": 0},
-    "-velitsbound": {"ve_lbound_en": 1}, "-profilegpu": {"profile": 1}, "-aggresivesort": {"aggr_cnf_sort": 1}, "-no-lcvefast": {}, "-quiet": {},
+    "-velitsbound": {"ve_lbound_en": 1}, "-profilegpu": {"profile": 1}, "-aggresivesort": {"aggr_cnf_sort": 1}, "-no-lcvefast": {"lcve_fast": 0}, "-lcvefast": {"lcve_fast": 1}, "-quiet": {},
     "-proof": {"proof_en": 1},
 }
 VALUE_FLAGS = {
@@ -287,6 +305,25 @@ class Simplifier:
                 raise SigmaError(f"store_compact: buffer {k} holds {len(into[k])} < {n}")
         self._check(self._lib.sigma_store_compact(self._h, *[_ptr(into[k]) for k in ("bits", "sizes", "lits", "eliminated", "resolved", "trail")]))
         return {k: into[k][:n] for k, n in need.items()}
+
+    def device_view(self) -> DeviceCnf:
+        """Device pointers of the resident result (simplify(skip_transfer_to_host))."""
+        v = DeviceCnf()
+        self._check(self._lib.sigma_device_view(self._h, C.byref(v)))
+        return v
+
+    def continue_resident(self, new_lits=None, new_offs=None, new_meta=None, vstate=None, assumed=None):
+        """The next inprocessing call on the resident result (sigma_continue): only the clauses added since travel."""
+        k = [None if a is None else np.ascontiguousarray(a, dt) for a, dt in
+             ((new_lits, np.uint32), (new_offs, np.uint64), (new_meta, np.uint32), (vstate, np.uint8), (assumed, np.uint8))]
+        n = 0 if k[1] is None else len(k[1]) - 1
+        self._keep2 = k
+        self._check(self._lib.sigma_continue(self._h, n, _ptr(k[0]), _ptr(k[1]), _ptr(k[2]), _ptr(k[3]), _ptr(k[4])))
+
+    def trail_info(self):
+        tot, frm, cnt, seeds = C.c_uint64(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.sigma_trail_info(self._h, C.byref(tot), C.byref(frm), C.byref(cnt), C.byref(seeds)))
+        return {"total": tot.value, "last_from": frm.value, "last_count": cnt.value, "last_seeds": seeds.value}
 
     def store_sclauses(self):
         nc, nl, nr, nt = (C.c_uint64() for _ in range(4))

@@ -62,6 +62,14 @@ VARIANTS = {
     "aggr_p3": ["-aggresivesort", "--phases=3", "-no-ere"],
     "aggr_bce_p2": ["-aggresivesort", "-bce", "--phases=2", "-no-ere"],
 }
+# -lcvefast (the reference CLI's default election): the elected SET is deterministic, the order of elected[] and of the
+# frozen list comes from atomics (lcve.cu:204-217) - pinned as multisets, with -no-vefunction (function-table indices
+# follow the frozen-list order).  `--fast` runs only these.
+FAST_VARIANTS = {
+    "fast_nofun_p1": ["-lcvefast", "-no-vefunction", "--phases=1", "-no-ere"],
+    "fast_nofun_p3": ["-lcvefast", "-no-vefunction", "--phases=3", "-no-ere"],
+    "fast_nofun": ["-lcvefast", "-no-vefunction"],
+}
 MEDIUM_VARIANTS = ["p1", "p2", "def", "nofun"]
 # The reference's ERE launch is broken whenever numElected < 4 * 8 * #SMs (every small instance): ereAsync sizes the
 # dynamic shared memory for block.y = ereminthreads = 4 rows (elimination.cu:206), then LOOP_OVERSUB_Y raises block.y
@@ -96,6 +104,10 @@ def main():
         summary = json.load(open(os.path.join(ROOT, "tests", "golden", "summary.json")))
     log = open(os.path.join(OUT, "runs.log"), "w")
     groups = ((SMALL, only, True),) if only else ((SMALL, list(VARIANTS), True), (MEDIUM, MEDIUM_VARIANTS, False))
+    if "--fast" in sys.argv:
+        summary = json.load(open(os.path.join(ROOT, "tests", "golden", "summary.json")))
+        VARIANTS.update(FAST_VARIANTS)
+        groups = ((SMALL, list(FAST_VARIANTS), False), (MEDIUM, ["fast_nofun_p1", "fast_nofun"], False))
     if ere_only:
         summary = json.load(open(os.path.join(ROOT, "tests", "golden", "summary.json")))
         ere = [v for v, f in VARIANTS.items() if "-no-ere" not in f]
@@ -111,6 +123,8 @@ def main():
                 if os.path.exists(dump):
                     os.remove(dump)
                 flags = BASE + VARIANTS[var]
+                if "-lcvefast" in flags:
+                    flags = [f for f in flags if f != "-no-lcvefast"]
                 if "-no-ere" not in flags:
                     flags = flags + ERE_LAUNCH_FIX
                 t0 = time.time()

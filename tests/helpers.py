@@ -47,7 +47,7 @@ class OracleOpts(C.Structure):
         ("ve_fun_en", C.c_int32), ("ve_lbound_en", C.c_int32), ("ve_clause_max", C.c_uint32),
         ("xor_max_arity", C.c_uint32), ("ere_clause_max", C.c_int32), ("ere_max_occurs", C.c_uint32),
         ("sub_max_occurs", C.c_uint32), ("bce_max_occurs", C.c_uint32), ("sh_max_bve_out1", C.c_uint32),
-        ("sigma_calls", C.c_int32), ("final_gc", C.c_int32), ("aggr_cnf_sort", C.c_int32),
+        ("sigma_calls", C.c_int32), ("final_gc", C.c_int32), ("aggr_cnf_sort", C.c_int32), ("lcve_fast", C.c_int32),
     ]
 
 
@@ -99,7 +99,7 @@ def oracle_lib():
 FLAG_MAP = {  # reference CLI flag -> option override (src/gpu/options.cpp:24-43, options.cu:36-60)
     "-no-ere": {"ere_en": 0}, "-ere": {"ere_en": 1}, "-no-vefunction": {"ve_fun_en": 0}, "-bce": {"bce_en": 1}, "-all": {"all_en": 1},
     "-no-sub": {"sub_en": 0}, "-no-veextend": {"ve_plus_en": 0}, "-no-ve": {"ve_en": 0}, "-velitsbound": {"ve_lbound_en": 1}, "-aggresivesort": {"aggr_cnf_sort": 1},
-    "-no-lcvefast": {}, "-quiet": {},
+    "-no-lcvefast": {"lcve_fast": 0}, "-lcvefast": {"lcve_fast": 1}, "-quiet": {},
 }
 VALUE_FLAGS = {
     "--phases": "phases", "--mupos": "mu_pos", "--muneg": "mu_neg", "--electionsmin": "lcve_min_vars",

@@ -81,7 +81,8 @@ def test_default_and_normalised_options(lib):
     assert o.ere_clause_max == 250
     # the reference's CLI spelling
     d = sigma.opts_from_flags(["--phases=3", "-no-ere", "-bce", "--mupos=16", "-no-lcvefast"])
-    assert d == {"phases": 3, "ere_en": 0, "bce_en": 1, "mu_pos": 16}
+    assert d == {"phases": 3, "ere_en": 0, "bce_en": 1, "mu_pos": 16, "lcve_fast": 0}
+    assert sigma.opts_from_flags(["-lcvefast"]) == {"lcve_fast": 1} and sigma.make_opts().lcve_fast == 0
     with pytest.raises(KeyError):
         sigma.opts_from_flags(["-nonsense"])
 

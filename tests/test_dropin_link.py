@@ -44,7 +44,9 @@ def test_shim_defines_the_seven_symbols_and_imports_only_the_c_abi(dropin):
     hdr = open(os.path.join(ROOT, "include", "sigma.h")).read()
     for s in abi:
         assert re.search(r"\b" + s + r"\s*\(", hdr), f"{s} is not declared in include/sigma.h"
-    assert {"sigma_create", "sigma_load", "sigma_run", "sigma_store", "sigma_store_sclauses", "sigma_destroy"} <= set(abi)
+    # the reference's own host mirror in and out (pinned), the loop one round at a time, the per-prop trail ranges
+    assert {"sigma_create", "sigma_load_sclauses", "sigma_begin", "sigma_round", "sigma_finish", "sigma_store_compact", "sigma_store_sclauses",
+            "sigma_trail_info", "sigma_copy_trail", "sigma_pinned_alloc", "sigma_destroy"} <= set(abi)
 
 
 def test_cli_flags_of_the_simplifier_still_parse(dropin):

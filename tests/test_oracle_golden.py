@@ -20,7 +20,8 @@ KEYS = ["cnfstate", "clauses", "literals", "eliminated", "forced", "resolved_wor
 # All 156 runs pin.  The runs whose last round is ERE carry --ereminthreads=32: the unmodified reference sizes ere_k's dynamic
 # shared memory for 4 rows and then launches 32 whenever fewer than 4 * 8 * #SMs variables are elected, i.e. on every small
 # instance (tests/golden/make_golden.py, ERE_LAUNCH_FIX; compute-sanitizer log in profiles/r02_ref_ere_sanitizer_default.log).
-CASES = sorted(SUMMARY)
+CASES = sorted(k for k, e in SUMMARY.items() if "-lcvefast" not in e["flags"])
+FAST_CASES = sorted(k for k, e in SUMMARY.items() if "-lcvefast" in e["flags"] and "fingerprint" in e)
 BIG = {"cfg1_k3_100k", "miter_50k", "mult48", "k5_20k"}
 
 
@@ -41,3 +42,17 @@ def test_oracle_matches_reference(key):
         assert ref.resolved_groups() == d.resolved_groups()
         assert sorted(ref.trail.tolist()) == sorted(d.trail.tolist())
         assert (ref.bits == d.bits).all() and (ref.sig == d.sig).all()
+
+
+@pytest.mark.parametrize("key", FAST_CASES)
+def test_oracle_lcvefast_matches_reference_as_sets(key):
+    """-lcvefast runs of the unmodified reference: its elected[] and frozen-list ORDER comes from atomics (lcve.cu:204-217),
+    so clause order and ref tie-breaks may differ run to run; the elected set, and with it the eliminated variables and
+    the clause multiset, may not."""
+    e = SUMMARY[key]
+    V, lits, offs = helpers.gen_cnf(e["family"], e["seed"], e["args"])
+    d, _, _ = helpers.run_oracle(V, lits, offs, **helpers.opts_from_flags(e["flags"]))
+    fp, g = d.fingerprint(), e["fingerprint"]
+    keys = ["cnfstate", "clauses", "literals", "eliminated", "forced", "h_lits_multiset", "h_eliminated", "h_forced", "h_trail_multiset"]
+    diff = {k: (fp[k], g[k]) for k in keys if fp[k] != g[k]}
+    assert not diff, diff
