@@ -215,7 +215,9 @@ def reference_arm(a):
 # ----------------------------------------------------------------------------- reference GPU arm
 REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 # largest member of each family the UNMODIFIED reference GPU build gets through on a B200 (it aborts above: DESIGN.md 4)
-REF_GPU_SAMPLE = {"cfg1": 1.0, "cfg2": 2_000_000 / 21_000_000}
+# above 699 050 clauses its live-clause count halves (count.cu:131-141 sizes a 1024-thread reduction that reduce.cuh:88-102 cannot
+# finish, on GPUs with more than 128 SMs), the CNF is compacted to the wrong size and moderngpu's segmented sort reads out of bounds
+REF_GPU_SAMPLE = {"cfg1": 1.0, "cfg2": 650_000 / 21_000_000, "cfg3": 650_000 / 39_601_471, "cfg4": 650_000 / 8_400_000}
 
 
 def run_ref_gpu(cnf_path, flags, timeout=900, host_mode=True):
@@ -255,6 +257,48 @@ def ref_gpu_sample(workload):
     V, lits, offs = cnfgen.gen_cnf(fam, seed, args, dimacs_path=path)
     desc = f"{fam}{tuple(args)} seed {seed}: V={V} C={len(offs) - 1} L={len(lits)} ({scale:.4g} of {workload})"
     return path, V, lits, offs, desc
+
+
+def ref_gpu_block(workload, local, fixed=False):
+    """The reference's own GPU build beside the engine, end to end, on the largest member of the workload's family the
+    reference gets through correctly on this GPU (north_star: "the reference's own GPU build on the same B200 is also shown")."""
+    import numpy as _np
+    from parafrost_b200 import sigma
+    smp = ref_gpu_sample(workload)
+    if smp is None:
+        return {"unavailable": "no sample of this family"}
+    path, V, lits, offs, desc = smp
+    out = {"sample": desc, "why_not_full_size": "the reference GPU build halves its clause count above 699 050 clauses on GPUs with > 128 SMs and then "
+                                                "crashes (DESIGN.md 4, profiles/r02_ref_gpu_k5_4M_*.log)"}
+    try:
+        for name, flags in (("engine_lcvefast", ["-lcvefast"]), ("engine_fixed_order", [])):
+            s = sigma.Simplifier(local, flags=flags)
+            best = None
+            for _ in range(4):
+                t0 = time.perf_counter()
+                s.load(V, lits, offs)
+                rep = s.simplify()
+                st = s.store_compact()
+                dt = (time.perf_counter() - t0) * 1e3
+                best = dt if best is None else min(best, dt)
+            out[name] = {"ms_e2e": best, "ms_device": rep["ms_device"], "clauses_out": rep["clauses"], "eliminated_vars": rep["eliminated_vars"],
+                         "note": "sigma_load (pageable numpy arrays) + sigma_run + sigma_store_compact, best of 4"}
+            s.close()
+        r = run_ref_gpu(path, [], timeout=600, host_mode=True)
+        out["reference_default"] = {k: r.get(k) for k in ("simplify_ms", "clauses", "stage_ms", "rc", "tail") if r.get(k) is not None}
+        out["reference_default"]["note"] = "its default mode (-lcvefast), simplify(false): extract + H2D + rounds + write-back into the host clause database"
+        if "simplify_ms" in r:
+            out["speedup_e2e_vs_reference_default"] = r["simplify_ms"] / out["engine_lcvefast"]["ms_e2e"]
+        if fixed:
+            r2 = run_ref_gpu(path, ["-no-lcvefast"], timeout=900, host_mode=True)
+            out["reference_fixed_order"] = {k: r2.get(k) for k in ("simplify_ms", "clauses", "rc", "tail") if r2.get(k) is not None}
+            if "simplify_ms" in r2:
+                out["speedup_e2e_vs_reference_fixed_order"] = r2["simplify_ms"] / out["engine_fixed_order"]["ms_e2e"]
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)[:300]
+    finally:
+        os.remove(path)
+    return out
 
 
 def reference_gpu_arm(a):
@@ -319,11 +363,13 @@ def batch_main(a, torch, dist, barrier, rank, world, local):
         t = torch.empty(int(n), dtype={np.uint32: torch.int32, np.uint64: torch.int64}[dt], pin_memory=True)
         pin.append(t)
         return t.numpy().view(dt)
-    outbuf = {"bits": palloc(2 * maxC + 16, np.uint32), "sig": palloc(2 * maxC + 16, np.uint32), "offs": palloc(2 * maxC + 17, np.uint64),
-              "lits": palloc(2 * maxL + 16, np.uint32), "eliminated": np.zeros(maxV + 1, np.uint8), "resolved": palloc(maxC + maxL + 2, np.uint32),
-              "trail": palloc(3 * (maxV + 1), np.uint32)}
 
-    def one_pass(timed):
+    def outbuf():
+        return {"bits": palloc(2 * maxC + 16, np.uint32), "sizes": palloc(2 * maxC + 16, np.uint32), "lits": palloc(2 * maxL + 16, np.uint32),
+                "eliminated": np.zeros(maxV + 1, np.uint8), "resolved": palloc(maxC + maxL + 2, np.uint32), "trail": palloc(3 * (maxV + 1), np.uint32)}
+    out0 = outbuf()
+
+    def one_pass():
         """-> (ms of sigma_run summed over my instances, ms of the whole pass, launches, literals, h2d, d2h)"""
         run_ms, launches, lit, h2d, d2h = 0.0, 0, 0, 0, 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,49 +377,63 @@ def batch_main(a, torch, dist, barrier, rank, world, local):
         for V, lits, offs, _ in inst:
             s.load(V, lits, offs)
             rep = s.simplify()
-            outbuf["eliminated"] = np.zeros(V + 1, np.uint8)
-            st = s.store(into=outbuf)
+            st = s.store_compact(into=out0)
             run_ms += rep["ms_device"]; launches += rep["kernel_launches"]
-            lit += sum(r["literals_in"] for r in s.rounds())
+            lit += len(lits)
             h2d += int(lits.nbytes + offs.nbytes); d2h += sum(int(v.nbytes) for v in st.values())
         e1.record(stream)
         stream.synchronize()
         return run_ms, e0.elapsed_time(e1), launches, lit, h2d, d2h
 
     for _ in range(a.warmup):
-        one_pass(False)
+        one_pass()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    tot = [one_pass(True) for _ in range(a.steps)]
+    tot = [one_pass() for _ in range(a.steps)]
     barrier()
     clk = clocks.stop()
-    # ---- optional: the same passes through K contexts per GPU (replicas.Pipeline): copies of one instance overlap the
-    # kernels of another; every instance is still loaded from and stored to pinned host memory
+    # ---- the same passes through K contexts per GPU (replicas.Pipeline): copies of one instance overlap the kernels of
+    # another; every instance is still loaded from and stored to pinned host memory
     piped_ms = None
     if a.pipeline > 1:
-        bufs = [{"bits": palloc(2 * maxC + 16, np.uint32), "sig": palloc(2 * maxC + 16, np.uint32), "offs": palloc(2 * maxC + 17, np.uint64),
-                 "lits": palloc(2 * maxL + 16, np.uint32), "eliminated": np.zeros(maxV + 1, np.uint8),
-                 "resolved": palloc(maxC + maxL + 2, np.uint32), "trail": palloc(3 * (maxV + 1), np.uint32)} for _ in range(a.pipeline)]
+        bufs = [outbuf() for _ in range(a.pipeline)]
         jobs = [(V, lits, offs) for V, lits, offs, _ in inst]
-        with replicas.Pipeline(local, depth=a.pipeline) as pipe:
+        with replicas.Pipeline(local, depth=a.pipeline, compact=True) as pipe:
             pipe.run(jobs, lambda *_: None, bufs)          # warm-up
             torch.cuda.synchronize()
             barrier()
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
+            t0 = time.perf_counter()
             for _ in range(a.steps):
                 pipe.run(jobs, lambda *_: None, bufs)
             torch.cuda.synchronize()
-            p1.record()
-            p1.synchronize()
-            piped_ms = p0.elapsed_time(p1)
+            piped_ms = (time.perf_counter() - t0) * 1e3
         piped_ms, _ = replicas.reduce_timing(dist, piped_ms, 0.0, device="cuda")
+    # ---- profiled pass over this rank's instances (outside the timed regions): kernel table with the engine's byte counts
+    s.kernel_profile(1)
+    for V, lits, offs, _ in inst:
+        s.load(V, lits, offs)
+        s.simplify()
+    kstats = s.kernel_stats()
+    s.kernel_profile(0)
     run_ms = sum(t[0] for t in tot); all_ms = sum(t[1] for t in tot)
     n_mine = len(inst) * a.steps
     run_ms, n_all = replicas.reduce_timing(dist, run_ms, float(n_mine), device="cuda")
     all_ms, lit_all = replicas.reduce_timing(dist, all_ms, float(sum(t[3] for t in tot)), device="cuda")
     if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        e2e_serial = n_all / (all_ms * 1e-3)
+        e2e = {"value": e2e_serial, "unit": "CNFs/s", "ms_per_step": all_ms / a.steps, "mode": "one context per GPU", "h2d_bytes_per_step": tot[-1][4],
+               "d2h_bytes_per_step": tot[-1][5]}
+        if piped_ms:
+            e2e["serial"] = {"value": e2e_serial, "ms_per_step": all_ms / a.steps}
+            e2e["pipelined"] = {"value": n_all / (piped_ms * 1e-3), "ms_per_step": piped_ms / a.steps, "contexts_per_gpu": a.pipeline}
+            if e2e["pipelined"]["value"] > e2e_serial:
+                e2e.update({"value": e2e["pipelined"]["value"], "ms_per_step": piped_ms / a.steps, "mode": f"{a.pipeline} contexts per GPU (replicas.Pipeline)"})
         line = {
             "metric": "batch_cnfs_per_s", "value": n_all / (run_ms * 1e-3), "unit": "CNFs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": run_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -382,13 +442,30 @@ def batch_main(a, torch, dist, barrier, rank, world, local):
                        "schedule": "static longest-first over ranks (replicas.assign_longest_first)", "flags": "reference defaults",
                        "l2": "each instance is simplified once per step: cold caches", "parallelism": f"instance-parallel x{world}, no collective"},
             "literals_per_s": lit_all / (run_ms * 1e-3),
-            "e2e": {"value": n_all / (all_ms * 1e-3), "unit": "CNFs/s", "ms_per_step": all_ms / a.steps,
-                    "h2d_bytes_per_step": tot[-1][4], "d2h_bytes_per_step": tot[-1][5]},
-            **({"e2e_pipelined": {"value": n_all / (piped_ms * 1e-3), "unit": "CNFs/s", "contexts_per_gpu": a.pipeline,
-                                  "ms_per_step": piped_ms / a.steps}} if piped_ms else {}),
+            "e2e": e2e,
             "gpu_launches": int(sum(t[2] for t in tot)), "clocks": clk,
-            "roofline": None, "cpu_baseline": {"value": None, "unit": "CNFs/s", "cores": 0, "kind": "reference", "sample": "not run for the batch workload (see cfg2)"},
+            "roofline": roofline_block(kstats, peaks, "cfg5"),
         }
+        if world == 1 and not a.no_cpu_baseline and os.path.exists(REF_CPU):
+            # the reference CPU simplifier on one bounded member of each family; CNFs/s = 1 / mean seconds per instance scaled to the
+            # batch's mean instance size (literals), 1 core
+            fams = {"cfg1": "ksat3", "cfg2": "ksat5", "cfg3": "miter", "cfg4": "multpar"}
+            per = {}
+            for wl, nm in fams.items():
+                try:
+                    path, sV, sC, sL, desc = ref_sample(wl, budget_literals=5_000_000)
+                    try:
+                        r = run_ref_cpu(path, sL)
+                    finally:
+                        os.remove(path)
+                    per[nm] = {"literals_per_s": sL / (r["ms"] * 1e-3), "sample": desc}
+                except Exception as e:  # noqa: BLE001
+                    per[nm] = {"error": repr(e)[:120]}
+            rates = [v["literals_per_s"] for v in per.values() if "literals_per_s" in v]
+            mean_lits = lit_all / max(1.0, n_all)
+            line["cpu_baseline"] = {"value": (float(np.mean(rates)) / mean_lits) if rates else None, "unit": "CNFs/s", "cores": 1, "kind": "reference",
+                                    "sample": "one 5 M-literal member of each family; CNFs/s = mean literals/s over the families / mean literals per batch instance",
+                                    "families": per, "host_cores_available": os.cpu_count()}
         print(json.dumps(line))
     s.close()
     if dist is not None:
@@ -582,6 +659,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 block of the default (cfg2) line")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the ref_gpu block (the reference's own GPU build beside the engine)")
+    ap.add_argument("--ref-gpu-fixed", action="store_true", help="ref_gpu: also time the reference in its fixed-order mode (single-thread election: slow)")
     ap.add_argument("--flags", default="", help="reference CLI flags for the engine, space separated (e.g. '--phases=5 -no-ere')")
     a = ap.parse_args()
     if a.impl == "reference":
@@ -686,6 +765,9 @@ def main():
                 line["secondary"] = sec
             except Exception as e:  # noqa: BLE001 - the secondary block never costs the headline line
                 line["secondary"] = {"workload": "cfg3", "error": repr(e)[:300]}
+        if world == 1 and not a.no_ref_gpu and os.path.exists(REF_GPU) and a.scale == 1.0:
+            torch.cuda.empty_cache()
+            line["ref_gpu"] = ref_gpu_block(a.workload, local, a.ref_gpu_fixed)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier(device_ids=[local])

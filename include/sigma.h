@@ -73,6 +73,9 @@ typedef struct sigma_opts {
                                    filters, so more variables are elected).  sigma_default_opts leaves it 0 = -no-lcvefast, the
                                    deterministic mode every parity run uses; the shim forwards the CLI's value.  The elected SET
                                    equals the reference's; its order there comes from atomics, here it is the rank order. */
+    int32_t  log_reductions;    /* --verbose>=2 of the reference: LOGREDALL / LOGREDCL (logging.hpp:152-158, count.cu:185-208) - live
+                                   counts after BCP, SUB, BVE, BCE and ERE of every round (one counting pass + read-back per stage),
+                                   fetched with sigma_reduction_log */
 } sigma_opts;
 
 /* Per-round report; replaces the LOG2 lines + inf.* updates of simplify.cu:163-186. */
@@ -222,6 +225,18 @@ int  sigma_device_view(sigma_ctx* c, sigma_device_cnf* out);
  * Then sigma_run / sigma_begin as usual.  SIGMA_CNFALLOC_FAIL if the continued formula outgrew what sigma_load carved. */
 int  sigma_continue(sigma_ctx* c, uint64_t num_new, const uint32_t* new_lits, const uint64_t* new_offs, const uint32_t* new_meta,
                     const uint8_t* vstate, const uint8_t* assumed);
+
+/* Per-stage reduction tables (LOGREDALL "BCP / BVE Reductions", LOGREDCL "SUB / BCE / ERE Reductions"; elimbcp.cu:203,
+ * elimination.cu:245,276,289,304): with opts.log_reductions one entry per stage that ran, in execution order. */
+typedef struct sigma_stage_reduction {
+    uint32_t round;
+    uint32_t stage;             /* 0 BCP, 1 SUB, 2 BVE, 3 BCE, 4 ERE */
+    uint32_t vars_removed;      /* BCP: variables forced by prop(); BVE: variables eliminated; else 0 */
+    uint32_t pad;
+    uint64_t clauses_before, literals_before;   /* inf.numClauses / numLiterals when the round started */
+    uint64_t clauses, literals;                 /* survived after the stage */
+} sigma_stage_reduction;
+int  sigma_reduction_log(const sigma_ctx* c, sigma_stage_reduction* out, uint32_t* n);   /* *n: capacity in, entries out */
 
 /* Device DRAT proof stream; replaces cuPROOF (src/gpu/proof.cuh:30-71, proof.cu) and the proof hooks of
  * sub_k / ve_k_1 / ve_k_2 / bce_k / ere_k (proofutils.cuh).  With opts.proof_en the kernels append binary

@@ -102,6 +102,7 @@ namespace {
 		o.profile = g.profile_gpu;
 		o.aggr_cnf_sort = opts.aggr_cnf_sort;
 		o.proof_en = g.hostKOpts.proof_en;
+		o.log_reductions = verbose >= 2;              // LOGREDALL / LOGREDCL (logging.hpp:152-158)
 		o.lcve_fast = opts.lcve_fast;                 // -lcvefast, the CLI's default (options.cpp:32): filtered-candidate MIS
 		sigma_normalize_opts(&o);
 	}
@@ -300,9 +301,28 @@ void Solver::simplify(const bool& skip_transfer_to_host)
 		g_replay.solver = this, g_replay.seen = 0;
 		rc = sigma_begin(g_ctx);
 		int done = 0;
+		uint32_t redSeen = 0;
 		while (!rc && !done) {
 			rc = sigma_round(g_ctx, nullptr, &done);
 			if (!rc) cacheUnits(0);                                 // elimbcp.cu:185-200 (no-op when the proof sink did it already)
+			if (!rc && verbose >= 2) {                              // LOGREDALL / LOGREDCL tables of this round (count.cu:185-208)
+				static const char* names[5] = { "BCP Reductions", "SUB Reductions", "BVE Reductions", "BCE Reductions", "ERE Reductions" };
+				uint32_t n = 0;
+				sigma_reduction_log(g_ctx, nullptr, &n);
+				std::vector<sigma_stage_reduction> red(n ? n : 1);
+				uint32_t cap = n;
+				sigma_reduction_log(g_ctx, red.data(), &cap);
+				for (uint32_t i = redSeen; i < n; i++) {
+					const sigma_stage_reduction& e = red[i];
+					LOG1("\t\t %s%s%s", CLBLUE, names[e.stage < 5 ? e.stage : 0], CNORMAL);
+					LOG1("  %s%-10s  %-10s %-10s %-10s%s", CREPORT, " ", "Variables", "Clauses", "Literals", CNORMAL);
+					LOG1("  %s%-10s: %s-%-8u  -%-8lld  -%-8lld%s", CREPORT, "Removed", CREPORTVAL, e.vars_removed,
+						(long long)(e.clauses_before - e.clauses), (long long)(e.literals_before - e.literals), CNORMAL);
+					LOG1("  %s%-10s: %s%-10s  %-9llu  %-9llu%s", CREPORT, "Survived", CREPORTVAL, " ",
+						(unsigned long long)e.clauses, (unsigned long long)e.literals, CNORMAL);
+				}
+				redSeen = n;
+			}
 		}
 		sigma_report rep;
 		if (!rc) rc = sigma_finish(g_ctx, &rep);

@@ -181,7 +181,7 @@ extern "C" int sigma_destroy(sigma_ctx* c) {
     if (c->evRun1) cudaEventDestroy(c->evRun1);
     if (c->stream && c->ownStream) cudaStreamDestroy(c->stream);
     if (c->ktEv) { for (int i = 0; i < 2 * KT_POOL; i++) if (c->ktEv[i]) cudaEventDestroy(c->ktEv[i]); free(c->ktEv); free(c->ktId); }
-    free(c->rounds);
+    free(c->rounds); free(c->reds);
     delete c;
     return SIGMA_OK;
 }
@@ -217,7 +217,10 @@ static size_t carve(Ctx* c, char* base) {
     c->hist = a.take<u32>(ND + 2); c->otStart = a.take<u32>(ND + 2); c->otSize = a.take<u32>(ND + 2);
     c->occurs = a.take<u32>(capW + 4);
     c->otPairs = a.take<uint2>(capW + 4); c->otCur = a.take<u32>(8192 + 2);
-    c->otBig = a.take<u32>(8192 + capW / 32768 + 64);   // work units of oversized buckets (k_ot_place_big)
+    c->otBig = a.take<u32>(8192 + capW / 32768 + 64 + 8192 + 8);   // work units of oversized buckets (k_ot_place_big) + their bucket ids
+    c->rk8 = a.take<uint4>(capC + 1);
+    c->cntMat = a.take<u32>(((size_t)capC / (1024 * 3) + 2) * 8192);   // one row of <= 8192 bucket counts per tile of >= 3072 clauses
+    c->btot = a.take<u32>(8192 + 8); c->bstart = a.take<u32>(8192 + 8);
     c->scores = a.take<u32>(V1); c->eligible = a.take<u32>(V1); c->rank = a.take<u32>(V1);
     c->sortK = a.take<u32>(V1); c->sortV = a.take<u32>(V1); c->elected = a.take<u32>(V1);
     c->units = a.take<u32>(2 * V1); c->trail = a.take<u32>(3 * V1);
@@ -394,7 +397,7 @@ extern "C" int sigma_load_sclauses(sigma_ctx* c, uint32_t max_var, uint64_t num_
     CUDA_TRY(cudaMemcpyAsync(dData, data_words, num_words * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(dRefs, refs, num_clauses * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemsetAsync(bad, 0, 4, c->stream));
-    unsigned long long* orgCL = (unsigned long long*)&c->dc->scratch[10];
+    unsigned long long* orgCL = (unsigned long long*)c->dc->orgCL;
     CUDA_TRY(cudaMemsetAsync(orgCL, 0, 16, c->stream));
     if (num_clauses)
         LAUNCH(c, k_unpack_sclauses, gridFor(num_clauses, 256), 256, 0, dData, dRefs, num_clauses, num_words, c->inLits, c->inOffs, c->inMeta, bad, orgCL);
@@ -449,6 +452,7 @@ extern "C" int sigma_begin(sigma_ctx* c) {
     c->phase = c->multiplier = 0; c->simpstate = SIGMA_OK; c->cnfstate = SIGMA_UNSOLVED; c->compacted = false;
     c->nUnits = 0; c->numElected = 0; c->currMelted = 0; c->varcoreDead = false;
     c->lastPropSeeds = c->lastPropTrail0 = c->lastPropTotal = 0;
+    c->nReds = 0;
     c->nRounds = 0; c->loopDone = false; c->launches = 0; c->msTotal = 0; c->otValid = false; c->countsFresh = false; c->histFresh = false;
     memset(c->stageMs, 0, sizeof c->stageMs);
     c->unassigned = c->unassigned0;
@@ -517,6 +521,30 @@ static int flushProof(Ctx* c) {
     return SIGMA_OK;
 }
 
+// LOGREDALL / LOGREDCL (logging.hpp:152-158, count.cu:185-208): live counts after a stage, only with opts.log_reductions
+static int logReduction(Ctx* c, u32 stage, u32 varsRemoved) {
+    if (!c->o.log_reductions) return 0;
+    launchCount(c);
+    const int rc = syncCounters(c);
+    if (rc) return rc;
+    if (c->nReds == c->capReds) {
+        c->capReds = c->capReds ? c->capReds * 2 : 32;
+        c->reds = (sigma_stage_reduction*)realloc(c->reds, c->capReds * sizeof(sigma_stage_reduction));
+    }
+    sigma_stage_reduction& e = c->reds[c->nReds++];
+    e.round = (u32)c->phase; e.stage = stage; e.vars_removed = varsRemoved; e.pad = 0;
+    e.clauses_before = c->numClauses; e.literals_before = c->numLiterals;
+    e.clauses = c->hdc->liveCls; e.literals = c->hdc->liveLits;
+    return 0;
+}
+extern "C" int sigma_reduction_log(const sigma_ctx* c, sigma_stage_reduction* out, uint32_t* n) {
+    if (!c || !n) return SIGMA_BAD_ARGUMENT;
+    const u32 m = c->nReds < *n ? c->nReds : *n;
+    if (out && m) memcpy(out, c->reds, m * sizeof(sigma_stage_reduction));
+    *n = c->nReds;
+    return SIGMA_OK;
+}
+
 static void pushRound(Ctx* c, const sigma_round_report& r) {
     if (c->nRounds == c->capRounds) {
         c->capRounds = c->capRounds ? c->capRounds * 2 : 16;
@@ -544,7 +572,7 @@ static void buildOT(Ctx* c, bool withGC, bool* didGC) {
     }
     if (!c->histFresh || withGC) { StageTimer t(c, ST_VO); launchHistKey(c); }
     c->histFresh = false;
-    { StageTimer t(c, ST_VO); scanExclusiveU32(c, c->hist, c->otStart, c->ND, 0, c->otStart + c->ND); }
+    if (!otBuildV2()) { StageTimer t(c, ST_VO); scanExclusiveU32(c, c->hist, c->otStart, c->ND, 0, c->otStart + c->ND); }
     { StageTimer t(c, ST_COT); launchScatter(c); }
 }
 
@@ -599,6 +627,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
         }
         launchCount(c);
         if ((rc = syncCounters(c))) return rc;
+        if (c->o.log_reductions) { const u32 forced = c->hdc->unassignedDec; if ((rc = logReduction(c, 0, forced))) return rc; }   // "BCP Reductions", elimbcp.cu:203
         c->numClauses = c->hdc->liveCls; c->numLiterals = c->hdc->liveLits;
         c->unassigned -= (i64)c->hdc->unassignedDec;
         c->lastPropTotal = c->hdc->trailSize - c->lastPropTrail0;
@@ -638,6 +667,7 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
         r.kind = 1;
         const bool ereRan = c->o.ere_en && c->numElected;
         if (ereRan) { StageTimer t(c, ST_ERE); launchERE(c, k); }
+        if (ereRan && (rc = logReduction(c, 4, 0))) return rc;
         c->loopDone = true;
         launchCount(c);
         if ((rc = syncCounters(c))) return rc;
@@ -650,11 +680,17 @@ extern "C" int sigma_round(sigma_ctx* c, sigma_round_report* rep, int* done) {
     }
     r.kind = 0;
     if (c->o.sub_en || c->o.ve_plus_en) { StageTimer t(c, ST_SUB); launchSUB(c, k); }
+    if ((c->o.sub_en || c->o.ve_plus_en) && (rc = logReduction(c, 1, 0))) return rc;
     if (c->o.ve_en) { StageTimer t(c, ST_VE); launchVE(c, k); }
+    if (c->o.ve_en && c->o.log_reductions) {
+        if ((rc = syncCounters(c))) return rc;
+        if ((rc = logReduction(c, 2, c->lastElectedCount - c->hdc->numElected))) return rc;
+    }
     if (c->o.bce_en) {
         // BCE runs over the surviving elected variables (elimination.cu:280-291)
         if (c->o.ve_en) { if ((rc = syncCounters(c))) return rc; c->numElected = c->hdc->numElected; }
         if (c->numElected) { StageTimer t(c, ST_BCE); launchBCE(c, k); }
+        if (c->numElected && (rc = logReduction(c, 3, 0))) return rc;
     }
     { StageTimer t(c, ST_CNT); launchCount(c); }
     if ((rc = syncCounters(c))) return rc;
@@ -962,7 +998,7 @@ extern "C" int sigma_continue(sigma_ctx* c, uint64_t num_new, const uint32_t* ne
     const u32 n = c->hdc->numCls;
     const u64 newL = num_new ? new_offs[num_new] - new_offs[0] : 0;
     u32* tot = c->dc->scratch;
-    unsigned long long* orgCL = (unsigned long long*)&c->dc->scratch[10];   // scratch[10..13], 8-byte aligned
+    unsigned long long* orgCL = (unsigned long long*)c->dc->orgCL;
     CUDA_TRY(cudaMemsetAsync(orgCL, 0, 16, c->stream));
     CUDA_TRY(cudaMemsetAsync(tot, 0, 8, c->stream));
     u64 nc = 0, nl = 0;

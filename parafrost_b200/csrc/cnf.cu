@@ -75,8 +75,13 @@ __global__ void k_awaken(const u32* __restrict__ inLits, const u64* __restrict__
     }
 }
 
+static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 numClauses);
+static void launchScatter2(Ctx* c, u32 n);
+static bool otV2();
+
 void launchAwaken(Ctx* c) {
     if (!c->C0) return;
+    if (otV2()) { launchCountPass(c, true, (u32)c->C0, c->L0, c->C0); c->histFresh = true; return; }
     cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
     LAUNCH(c, k_awaken, gridFor(c->C0, 256), 256, 0, c->inLits, c->inOffs, c->inMeta, c->C0, c->hdr[c->cur], c->pool[c->cur], c->hist, c->key,
            &c->dc->flags, c->ND, c->L0);
@@ -106,6 +111,7 @@ __global__ void k_hist_key(const uint4* __restrict__ hdr, const u32* __restrict_
 }
 
 void launchHistKey(Ctx* c) {
+    if (otV2()) { if (c->hdc->numCls) launchCountPass(c, false, c->hdc->numCls, c->numLiterals, c->numClauses); return; }
     cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
     const u32 n = c->hdc->numCls;
     if (n) {
@@ -344,7 +350,12 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place_big(const uint2* __r
 void launchScatter(Ctx* c) {
     const u32 n = c->hdc->numCls;
     // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
-    if (!n || !c->numLiterals) { cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream); return; }
+    if (!n || !c->numLiterals) {
+        cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream);
+        if (otV2()) cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
+        return;
+    }
+    if (otV2()) { launchScatter2(c, n); return; }
     if (!c->attrOT) {
         cudaFuncSetAttribute(k_ot_part<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_part<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -378,6 +389,457 @@ void launchScatter(Ctx* c) {
     LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
     KB(c, 8.0 * c->numLiterals + 4.0 * c->numLiterals + 12.0 * c->ND);   // pairs in, list entries out, list bounds
     LAUNCH(c, k_ot_place_big, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs, c->otBig, nBig);
+}
+
+// ================================================================== occurrence-table build, version 2
+// Three passes over ~L items each used to pay one atomic per item: the per-literal histogram (global RED), the
+// partition's rank (shared-memory atomic) and the placement's cursor (shared-memory atomic); the RED pass and the
+// shared-memory atomics - not HBM - bounded all three (profiles/r02_bench_cfg2_v2.json: k_awaken 0.33, k_ot_part 0.25 of
+// the copy roofline).  Version 2 pays two:
+//   k_ot_count  (fused into awaken / the key pass, tile = 1024 x CPT clauses per CTA): one shared-memory atomic per literal on
+//               the tile's BUCKET counter; the value it returns is the literal's rank inside (tile, bucket) and is kept -
+//               8 x 16 bits per clause, one coalesced 16-byte store - together with the tile's row of bucket counts.
+//               No global histogram, no global reductions.
+//   k_ot_colsum / k_ot_bscan: bucket totals = column sums of the count matrix, exclusive scan -> segment starts.
+//   k_ot_part2  the same tile again: its row of counts gives run lengths (one global atomic per non-empty (tile, bucket)
+//               reserves the run - issued as independent atomics, one round trip), the stored ranks give every pair its
+//               slot: NO shared-memory atomics, no counter clearing; pairs are staged bucket by bucket and copied out
+//               with one table look-up per pair.  Literals of clauses longer than 8 take the tail of the run through
+//               a second counter (rare).
+//   k_ot_place2 one CTA per bucket as before; the per-literal histogram of the bucket (which IS hist[] / otSize[], and
+//               whose local scan is otStart[]) is counted here with the one shared-memory atomic the placement needs
+//               anyway: sweep 1 counts and keeps each pair's rank in registers, sweep 2 re-reads the pairs from L2 and
+//               stores entry = start[literal] + rank into the staged window.
+// Oversized buckets (structured formulas) keep the global-atomic work units: count, scan, place (k_ot_big_*).
+#define OT_T 1024
+#define OT_KEEP 5
+
+__device__ __forceinline__ void sort8(u32 (&r)[8]) {
+#pragma unroll
+    for (int pass = 0; pass < 8; pass++) {
+#pragma unroll
+        for (int k = (pass & 1); k + 1 < 8; k += 2) {
+            const u32 a = r[k], bb = r[k + 1];
+            r[k] = min(a, bb); r[k + 1] = max(a, bb);
+        }
+    }
+}
+
+template <int CPT, bool AWAKEN>
+__global__ void __launch_bounds__(OT_T) k_ot_count(const u32* __restrict__ inLits, const u64* __restrict__ inOffs, const u32* __restrict__ inMeta, u64 L0,
+                                                   uint4* __restrict__ hdr, u32* __restrict__ pool, u32 n, u32 ND, u32 shift, u32 NB, u32 NBp,
+                                                   uint4* __restrict__ rk8, u32* __restrict__ cntMat, uint4* __restrict__ key, u32* flags) {
+    extern __shared__ u32 sm[];
+    u32* cntS = sm;        // literals of clauses with <= 8 literals: their ranks are kept
+    u32* cntL = sm + NB;   // literals of longer clauses: counted only
+    for (u32 b = threadIdx.x; b < 2 * NB; b += OT_T) sm[b] = 0;
+    __syncthreads();
+    const u32 tile0 = blockIdx.x * (OT_T * CPT);
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const u32 i = tile0 + k * OT_T + threadIdx.x;
+        if (i >= n) continue;
+        u32 r[8];
+        int sz; u32 off, sig;
+        if (AWAKEN) {
+            const u64 b = inOffs[i];
+            u64 e = inOffs[i + 1];
+            // input validation (the C ABI takes raw buffers): a bad entry is neutralised and flagged, the call fails with
+            // SIGMA_BAD_ARGUMENT at its first read-back instead of indexing outside the tables
+            if (e < b || e > L0 || e - b >= (1ull << 31)) { atomicOr(flags, 128u); e = b; }
+            sz = (int)(e - b); off = (u32)b; sig = 0;
+            u32* dst = pool + b;
+            if (sz <= 8) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    r[q] = (q < sz) ? inLits[b + q] : 0xFFFFFFFFu;
+                    if (q < sz && (r[q] < 2u || r[q] >= ND)) { atomicOr(flags, 128u); r[q] = 2u; }
+                }
+                sort8(r);
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (q < sz) { dst[q] = r[q]; sig |= MAPHASH(r[q]); }
+            } else {
+                for (int q = 0; q < sz; q++) {
+                    u32 t = inLits[b + q];
+                    if (t < 2u || t >= ND) { atomicOr(flags, 128u); t = 2u; }
+                    int j = q;
+                    for (; j > 0 && t < dst[j - 1]; j--) dst[j] = dst[j - 1];
+                    dst[j] = t;
+                    sig |= MAPHASH(t);
+                }
+            }
+            if (sz <= 1) sig = 0;  // calcSig leaves the signature untouched for size <= 1 (primitives.cuh:177-185)
+            u32 bits = 0;
+            if (inMeta) { const u32 m = inMeta[i]; if (m & CB_LEARNT) bits = m & ~(CB_DELETED | CB_MOLTEN | CB_ADDED); }
+            hdr[i] = make_uint4(off, (u32)sz, sig, bits);
+        } else {
+            const uint4 h = hdr[i];
+            if (C_DELETED(h.w)) continue;
+            sz = (int)h.y; off = h.x; sig = h.z;
+            if (sz <= 8) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) r[q] = (q < sz) ? pool[off + q] : 0xFFFFFFFFu;
+            }
+        }
+        u32 rk[4] = {0, 0, 0, 0};
+        u32 first = 0, last = 0;
+        if (sz <= 8) {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (q < sz) {
+                    const u32 lit = r[q];
+                    if (q == 0) first = lit;
+                    last = lit;
+                    rk[q >> 1] |= atomicAdd(&cntS[lit >> shift], 1u) << ((q & 1) * 16);
+                }
+        } else {
+            const u32* l = pool + off;
+            first = l[0]; last = l[sz - 1];
+            for (int q = 0; q < sz; q++) atomicAdd(&cntL[l[q] >> shift], 1u);
+            if (sz >= (1 << 14)) atomicOr(flags, 8u);   // the list sort's folded key needs size < 2^14 (otsort.cu)
+        }
+        rk8[i] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+        key[i] = make_uint4((u32)sz, first, last, sig);
+    }
+    __syncthreads();
+    u32* row = cntMat + (size_t)blockIdx.x * NBp;
+    for (u32 b = threadIdx.x; b < NBp; b += OT_T) row[b] = b < NB ? cntS[b] + cntL[b] : 0u;
+}
+
+// bucket totals: column sums of the count matrix, a segment of rows per CTA row
+__global__ void __launch_bounds__(256) k_ot_colsum(const u32* __restrict__ cntMat, u32 tiles, u32 NB, u32 NBp, u32* __restrict__ btot) {
+    const u32 b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= NB) return;
+    const u32 per = (tiles + gridDim.y - 1) / gridDim.y;
+    const u32 r0 = blockIdx.y * per, r1 = min(tiles, r0 + per);
+    u32 s = 0;
+    for (u32 r = r0; r < r1; r++) s += cntMat[(size_t)r * NBp + b];
+    if (s) atomicAdd(&btot[b], s);
+}
+// exclusive scan of the bucket totals (NB <= 8192) -> segment starts; run cursors cleared; one CTA
+__global__ void __launch_bounds__(1024) k_ot_bscan(const u32* __restrict__ btot, u32 NB, u32* __restrict__ bstart, u32* __restrict__ gcur, u32* total) {
+    __shared__ u32 wt[32];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < NB; base += 1024) {
+        const u32 b = base + threadIdx.x;
+        const u32 v = b < NB ? btot[b] : 0u;
+        const u32 incl = warpIncl(v);
+        if ((threadIdx.x & 31u) == 31u) wt[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) { const u32 t = wt[threadIdx.x]; const u32 ti = warpIncl(t); wt[threadIdx.x] = ti - t; }
+        __syncthreads();
+        const u32 excl = carry + wt[threadIdx.x >> 5] + incl - v;
+        if (b < NB) { bstart[b] = excl; gcur[b] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { bstart[NB] = carry; *total = carry; }
+}
+
+template <int CPT, int KEEP>
+__global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ hdr, const u32* __restrict__ pool, const uint4* __restrict__ rk8, u32 n,
+                                                   u32 shift, u32 NB, u32 NBp, const u32* __restrict__ cntMat, const u32* __restrict__ bstart,
+                                                   u32 stageCap, u32* __restrict__ gcur, uint2* __restrict__ pairs) {
+    extern __shared__ u32 sm[];
+    u32* tileOff = sm;              // [NB + 1] start of the bucket inside the staged tile
+    u32* delta = sm + NB + 1;       // [NB] run start in pairs[] minus tileOff
+    u32* cntL2 = delta + NB;        // [NB] long-clause literals placed so far (tail of the run, downwards)
+    uint2* stage = (uint2*)(sm + ((3 * NB + 2) & ~1u));
+    __shared__ u32 warpTot[32];
+    __shared__ u32 tileTotal, nonEmpty;
+    const u32 tile0 = blockIdx.x * (OT_T * CPT);
+    if (threadIdx.x == 0) nonEmpty = 0;
+    u32 off[CPT], sz[CPT]; uint4 rk[CPT];
+    bool longHere = false;
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const u32 i = tile0 + k * OT_T + threadIdx.x;
+        sz[k] = 0; off[k] = 0; rk[k] = make_uint4(0, 0, 0, 0);
+        if (i < n) {
+            const uint4 h = hdr[i];
+            if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; rk[k] = rk8[i]; longHere |= h.y > 8u; }
+        }
+    }
+    const int anyLong = __syncthreads_or(longHere);
+    if (anyLong) for (u32 b = threadIdx.x; b < NB; b += OT_T) cntL2[b] = 0;
+    // the first literals of every short clause: loads in flight while the runs are reserved
+    u32 lk[CPT][KEEP];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const u32* l = pool + off[k];
+#pragma unroll
+        for (int q = 0; q < KEEP; q++) lk[k][q] = ((u32)q < sz[k] && sz[k] <= 8u) ? l[q] : 0u;
+    }
+    // this tile's row of bucket counts: run lengths; one global atomic per non-empty bucket, all independent
+    const u32 per = (NB + OT_T - 1) / OT_T;   // consecutive buckets per thread, <= 8
+    const u32 b0 = threadIdx.x * per;
+    const u32* row = cntMat + (size_t)blockIdx.x * NBp;
+    u32 cq[8], gq[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { const u32 b = b0 + q; cq[q] = ((u32)q < per && b < NB) ? row[b] : 0u; }
+    u32 mine = 0, used = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { gq[q] = cq[q] ? bstart[b0 + q] + atomicAdd(&gcur[b0 + q], cq[q]) : 0u; mine += cq[q]; used += cq[q] != 0u; }
+    const u32 incl = warpIncl(mine);
+    used = warpSum(used);
+    if ((threadIdx.x & 31u) == 0 && used) atomicAdd(&nonEmpty, used);
+    if ((threadIdx.x & 31u) == 31u) warpTot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const u32 t = warpTot[threadIdx.x];
+        const u32 ti = warpIncl(t);
+        warpTot[threadIdx.x] = ti - t;
+        if (threadIdx.x == 31) { tileTotal = ti; tileOff[NB] = ti; }
+    }
+    __syncthreads();
+    u32 run = warpTot[threadIdx.x >> 5] + incl - mine;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const u32 b = b0 + q;
+        if ((u32)q < per && b < NB) { tileOff[b] = run; delta[b] = gq[q] - run; run += cq[q]; }
+    }
+    __syncthreads();
+    // staging pays when the tile's runs are short (uniform random formulas); clause-local formulas already write long runs
+    const bool staged = tileTotal <= stageCap && tileTotal < 12u * nonEmpty;
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const u32 i = tile0 + k * OT_T + threadIdx.x;
+        const u32* l = pool + off[k];
+        if (sz[k] <= 8u) {
+            const u32 rw[4] = {rk[k].x, rk[k].y, rk[k].z, rk[k].w};
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if ((u32)q < sz[k]) {
+                    const u32 lit = q < KEEP ? lk[k][q < KEEP ? q : 0] : l[q];
+                    const u32 b = lit >> shift;
+                    const u32 pos = tileOff[b] + ((rw[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu);
+                    if (staged) stage[pos] = make_uint2(lit, i);
+                    else pairs[pos + delta[b]] = make_uint2(lit, i);
+                }
+        } else
+            for (u32 q = 0; q < sz[k]; q++) {
+                const u32 lit = l[q];
+                const u32 b = lit >> shift;
+                const u32 pos = tileOff[b + 1] - 1u - atomicAdd(&cntL2[b], 1u);
+                if (staged) stage[pos] = make_uint2(lit, i);
+                else pairs[pos + delta[b]] = make_uint2(lit, i);
+            }
+    }
+    if (!staged) return;
+    __syncthreads();
+    const u32 total = tileTotal;
+    for (u32 t = threadIdx.x; t < total; t += OT_T) {
+        const uint2 pr = stage[t];
+        pairs[t + delta[pr.x >> shift]] = pr;
+    }
+}
+
+#define PLACE2_ITERS ((PLACE_WINDOW + PLACE_THREADS - 1) / PLACE_THREADS)
+__global__ void __launch_bounds__(PLACE_THREADS) k_ot_place2(const uint2* __restrict__ pairs, const u32* __restrict__ bstart, u32 ND, u32 shift, u32 window,
+                                                             u32* __restrict__ hist, u32* __restrict__ otStart, u32* __restrict__ otSize,
+                                                             u32* __restrict__ occurs, u32* __restrict__ big, u32* nBig, u32* __restrict__ bigB, u32* nBigB) {
+    extern __shared__ u32 smem[];
+    const u32 W = 1u << shift;
+    u32* cnt = smem;          // [W] per-literal counts, then list starts
+    u32* win = smem + W;      // [window] staged entries
+    __shared__ u32 wt[32];
+    const u32 lit0 = blockIdx.x << shift;
+    const u32 litEnd = min(lit0 + W, ND);
+    const u32 nl = litEnd - lit0;
+    const u32 p0 = bstart[blockIdx.x], p1 = bstart[blockIdx.x + 1];
+    const u32 len = p1 - p0;
+    if (len > window || shift > 12) {   // oversized bucket (or cursors that do not fit shared memory): work units with global cursors (k_ot_big_*)
+        if (!len) {
+            for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) { hist[lit0 + k] = 0; otSize[lit0 + k] = 0; otStart[lit0 + k] = p0; }
+            return;
+        }
+        if (threadIdx.x == 0) {
+            u32 S = (len + PLACE_UNIT - 1) / PLACE_UNIT;
+            S = S > PLACE_SPLIT ? PLACE_SPLIT : S;
+            const u32 base = atomicAdd(nBig, S);
+            for (u32 s = 0; s < S; s++) big[base + s] = blockIdx.x | (s << 13) | (S << 19);
+            bigB[atomicAdd(nBigB, 1u)] = blockIdx.x;
+        }
+        for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) hist[lit0 + k] = 0;
+        return;
+    }
+    for (u32 k = threadIdx.x; k < W; k += PLACE_THREADS) cnt[k] = 0;
+    __syncthreads();
+    // sweep 1: count per literal; the value the atomic returns is the pair's rank in its list
+    u32 rr[(PLACE2_ITERS + 1) / 2];
+#pragma unroll
+    for (int q = 0; q < (PLACE2_ITERS + 1) / 2; q++) rr[q] = 0;
+#pragma unroll
+    for (int it = 0; it < PLACE2_ITERS; it++) {
+        const u32 j = p0 + it * PLACE_THREADS + threadIdx.x;
+        if (j < p1) rr[it >> 1] |= atomicAdd(&cnt[pairs[j].x - lit0], 1u) << ((it & 1) * 16);
+    }
+    __syncthreads();
+    // exclusive scan of the W counts (W / 1024 consecutive literals per thread) -> list starts; hist / otStart / otSize leave coalesced
+    {
+        const u32 per = (W + PLACE_THREADS - 1) / PLACE_THREADS;   // <= 4 for W <= 4096
+        const u32 k0 = threadIdx.x * per;
+        u32 c4[4], mine = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const u32 k = k0 + q; c4[q] = ((u32)q < per && k < W) ? cnt[k] : 0u; mine += c4[q]; }
+        const u32 incl = warpIncl(mine);
+        if ((threadIdx.x & 31u) == 31u) wt[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) { const u32 t = wt[threadIdx.x]; const u32 ti = warpIncl(t); wt[threadIdx.x] = ti - t; }
+        __syncthreads();
+        u32 run = wt[threadIdx.x >> 5] + incl - mine;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const u32 k = k0 + q;
+            if ((u32)q < per && k < W) {
+                cnt[k] = run;
+                if (k < nl) { hist[lit0 + k] = c4[q]; otSize[lit0 + k] = c4[q]; otStart[lit0 + k] = p0 + run; }
+                run += c4[q];
+            }
+        }
+    }
+    __syncthreads();
+    // sweep 2: the pairs again (L2), entry = list start + rank
+#pragma unroll
+    for (int it = 0; it < PLACE2_ITERS; it++) {
+        const u32 j = p0 + it * PLACE_THREADS + threadIdx.x;
+        if (j < p1) { const uint2 p = pairs[j]; win[cnt[p.x - lit0] + ((rr[it >> 1] >> ((it & 1) * 16)) & 0xFFFFu)] = p.y; }
+    }
+    __syncthreads();
+    for (u32 k = threadIdx.x; k < len; k += PLACE_THREADS) occurs[p0 + k] = win[k];
+}
+// oversized buckets: per-literal counts with global atomics (hist[] of the bucket was cleared by k_ot_place2) ...
+__global__ void __launch_bounds__(PLACE_THREADS) k_ot_big_count(const uint2* __restrict__ pairs, const u32* __restrict__ bstart, u32 shift,
+                                                                u32* __restrict__ hist, const u32* __restrict__ big, const u32* nBig) {
+    const u32 nItems = *nBig;
+    for (u32 item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const u32 code = big[item];
+        const u32 b = code & 0x1FFFu, s = (code >> 13) & 0x3Fu, S = code >> 19;
+        const u32 p0 = bstart[b], len = bstart[b + 1] - p0;
+        const u32 q0 = p0 + (u32)((u64)len * s / S), q1 = p0 + (u32)((u64)len * (s + 1) / S);
+        for (u32 j = q0 + threadIdx.x; j < q1; j += PLACE_THREADS) atomicAdd(&hist[pairs[j].x], 1u);
+    }
+}
+// ... their exclusive scan -> otStart, cursors (otSize) cleared ...
+__global__ void __launch_bounds__(1024) k_ot_big_scan(const u32* __restrict__ bstart, u32 ND, u32 shift, const u32* __restrict__ hist,
+                                                      u32* __restrict__ otStart, u32* __restrict__ otSize, const u32* __restrict__ bigB, const u32* nBigB) {
+    __shared__ u32 wt[32];
+    __shared__ u32 carry;
+    const u32 W = 1u << shift;
+    for (u32 it = blockIdx.x; it < *nBigB; it += gridDim.x) {
+        const u32 b = bigB[it];
+        const u32 lit0 = b << shift, nl = min(lit0 + W, ND) - lit0;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = bstart[b];
+        __syncthreads();
+        for (u32 base = 0; base < nl; base += 1024) {
+            const u32 k = base + threadIdx.x;
+            const u32 v = k < nl ? hist[lit0 + k] : 0u;
+            const u32 incl = warpIncl(v);
+            if ((threadIdx.x & 31u) == 31u) wt[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            if (threadIdx.x < 32) { const u32 t = wt[threadIdx.x]; const u32 ti = warpIncl(t); wt[threadIdx.x] = ti - t; }
+            __syncthreads();
+            const u32 excl = carry + wt[threadIdx.x >> 5] + incl - v;
+            if (k < nl) { otStart[lit0 + k] = excl; otSize[lit0 + k] = 0; }
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = excl + v;
+            __syncthreads();
+        }
+    }
+}
+// ... and the placement itself is k_ot_place_big (bucket bounds from otStart / hist instead of the next bucket's start)
+__global__ void __launch_bounds__(PLACE_THREADS) k_ot_big_place(const uint2* __restrict__ pairs, const u32* __restrict__ bstart, const u32* __restrict__ otStart,
+                                                                u32* __restrict__ otSize, u32* __restrict__ occurs, const u32* __restrict__ big, const u32* nBig) {
+    const u32 nItems = *nBig;
+    for (u32 item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const u32 code = big[item];
+        const u32 b = code & 0x1FFFu, s = (code >> 13) & 0x3Fu, S = code >> 19;
+        const u32 p0 = bstart[b], len = bstart[b + 1] - p0;
+        const u32 q0 = p0 + (u32)((u64)len * s / S), q1 = p0 + (u32)((u64)len * (s + 1) / S);
+        for (u32 j = q0 + threadIdx.x; j < q1; j += PLACE_THREADS) {
+            const uint2 p = pairs[j];
+            occurs[otStart[p.x] + atomicAdd(&otSize[p.x], 1u)] = p.y;
+        }
+    }
+}
+
+// bucket = 2^shift consecutive literals, sized so that an average bucket fills at most ~70 % of a placement window; at most
+// 8192 buckets.  Fixed BEFORE the counting pass: pass A, the partition and the placement must agree on it.
+static void otChooseShape(Ctx* c, u64 numLiterals, u64 numClauses, u32 nSlots) {
+    u32 shift = 6;
+    while (shift < 12 && ((u64)numLiterals << (shift + 1)) / c->ND <= PLACE_WINDOW * 7 / 10) shift++;
+    while (shift < 15 && ((c->ND + (1u << shift) - 1) >> shift) > 8192) shift++;
+    c->otShift = shift; c->otNB = (c->ND + (1u << shift) - 1) >> shift;
+    c->otNBp = (c->otNB + 3u) & ~3u;
+    c->otCPT = numLiterals <= 3 * numClauses ? 5 : 3;   // short clauses: more of them per tile
+    c->otTiles = divup(nSlots, OT_T * c->otCPT);
+}
+bool otBuildV2();
+static bool otV2() { return otBuildV2(); }
+bool otBuildV2() { static const int v = getenv("SIGMA_OT_V2") ? atoi(getenv("SIGMA_OT_V2")) : 1; return v != 0; }
+
+static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 numClauses) {
+    otChooseShape(c, numLiterals, numClauses, n);
+    if (!c->attrOT2) {
+        cudaFuncSetAttribute(k_ot_count<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_count<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_count<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_count<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_part2<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part2<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_place2, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
+        c->attrOT2 = true;
+    }
+    const size_t smem = 8 * (size_t)c->otNB;
+    const u32 NB = c->otNB, NBp = c->otNBp, sh = c->otShift;
+#define OT_COUNT_ARGS c->inLits, c->inOffs, c->inMeta, c->L0, c->hdr[c->cur], c->pool[c->cur], n, c->ND, sh, NB, NBp, c->rk8, c->cntMat, c->key, &c->dc->flags
+    if (awaken) {
+        if (c->otCPT == 5) LAUNCH(c, (k_ot_count<5, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
+        else LAUNCH(c, (k_ot_count<3, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
+        KB(c, 8.0 * n + 4.0 * numLiterals + (c->inMeta ? 4.0 * n : 0.0) + 16.0 * n + 4.0 * numLiterals + 32.0 * n + 4.0 * (double)c->otTiles * NBp);
+    } else {
+        if (c->otCPT == 5) LAUNCH(c, (k_ot_count<5, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
+        else LAUNCH(c, (k_ot_count<3, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
+        KB(c, 16.0 * n + 4.0 * numLiterals + 32.0 * numClauses + 4.0 * (double)c->otTiles * NBp);   // headers + literals in, keys + ranks + count rows out
+    }
+#undef OT_COUNT_ARGS
+}
+
+static void launchScatter2(Ctx* c, u32 n) {
+    const u32 NB = c->otNB, NBp = c->otNBp, shift = c->otShift, tiles = c->otTiles;
+    cudaMemsetAsync(c->btot, 0, (size_t)NB * 4, c->stream);
+    const u32 seg = tiles < 64 ? (tiles ? tiles : 1) : 64;
+    LAUNCH(c, k_ot_colsum, dim3(divup(NB, 256), seg), 256, 0, c->cntMat, tiles, NB, NBp, c->btot);
+    KB(c, 4.0 * (double)tiles * NBp);
+    LAUNCH(c, k_ot_bscan, 1, 1024, 0, c->btot, NB, c->bstart, c->otCur, c->otStart + c->ND);
+    // shared memory of k_ot_part2: 3 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
+    const size_t partFixed = 4 * (((size_t)3 * NB + 2) & ~(size_t)1) + 16;
+    const u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
+    if (c->otCPT == 5)
+        LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->bstart,
+               stageCap, c->otCur, c->otPairs);
+    else
+        LAUNCH(c, (k_ot_part2<3, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->bstart,
+               stageCap, c->otCur, c->otPairs);
+    KB(c, 32.0 * n + 4.0 * c->numLiterals + 4.0 * (double)tiles * NBp + 8.0 * c->numLiterals);   // headers + ranks + literals + count row in, pairs out
+    u32 window = shift <= 12 ? PLACE_WINDOW : 0;
+    if (const char* w = getenv("SIGMA_OT_WINDOW")) { const u32 v = (u32)atoi(w); if (v < window) window = v; }   // tests: force the work-unit path
+    const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : 64;
+    u32* nBig = &c->dc->scratch[7];
+    u32* nBigB = &c->dc->scratch[15];
+    cudaMemsetAsync(nBig, 0, 4, c->stream);
+    cudaMemsetAsync(nBigB, 0, 4, c->stream);
+    u32* bigB = c->otBig + (8192 + c->capW / 32768 + 64);
+    LAUNCH(c, k_ot_place2, NB, PLACE_THREADS, placeSmem, c->otPairs, c->bstart, c->ND, shift, window, c->hist, c->otStart, c->otSize, c->occurs, c->otBig,
+           nBig, bigB, nBigB);
+    KB(c, 8.0 * c->numLiterals + 4.0 * c->numLiterals + 12.0 * c->ND);   // pairs in (their second read is an L2 hit), list entries + hist / start / size out
+    LAUNCH(c, k_ot_big_count, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->bstart, shift, c->hist, c->otBig, nBig);
+    LAUNCH(c, k_ot_big_scan, 148, 1024, 0, c->bstart, c->ND, shift, c->hist, c->otStart, c->otSize, bigB, nBigB);
+    LAUNCH(c, k_ot_big_place, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->bstart, c->otStart, c->otSize, c->occurs, c->otBig, nBig);
 }
 
 // ------------------------------------------------------------------ live counts

@@ -116,6 +116,7 @@ struct DevCounters {
     u32 proofSize, proofCap, proofUnits0, proofPad;
     u64 proofLitBytes; // proof bytes of every literal of the loaded formula (cuPROOF::count, proof.cu:101-121)
     u64 profBytes;     // kernel profile mode: bytes walked by the per-variable kernels (sigma_kernel_stats)
+    u64 orgCL[2];      // original clauses / their literals counted on the device (sigma_load_sclauses, sigma_continue)
 };
 
 struct KOpts {   // kernel-side options (replaces __constant__ kOpts, options.cuh:27-45)
@@ -156,7 +157,9 @@ struct Ctx {
     uint4* key;
     // OT
     u32 *hist, *otStart, *otSize, *occurs;
-    uint2* otPairs; u32* otCur; u32* otBig; u32 otShift, otNB;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
+    uint2* otPairs; u32* otCur; u32* otBig; u32 otShift, otNB;
+    // OT build v2 (cnf.cu): ranks of the counting pass (8 x 16 bits per clause), count matrix [tiles][NBp], bucket totals / starts
+    uint4* rk8; u32* cntMat; u32* btot; u32* bstart; u32 otNBp, otCPT, otTiles; bool attrOT2;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
     // vars
     u32 *scores, *eligible, *rank, *sortK, *sortV, *elected, *units, *resolved, *trail, *vorg, *varcore;
     unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *assumedBuf, *eliminated, *needSort;
@@ -175,6 +178,7 @@ struct Ctx {
     i64 cdiff, ldiff, clsbefore, litsbefore;
     bool loopDone;
     sigma_round_report* rounds; u32 nRounds, capRounds;
+    sigma_stage_reduction* reds; u32 nReds, capReds;   // opts.log_reductions (LOGREDALL / LOGREDCL)
     u64 launches;
     float stageMs[16];
     cudaEvent_t ev0, ev1, evRun0, evRun1; bool ownStream;
@@ -271,6 +275,7 @@ void scanExclusiveU64(Ctx* c, const u64* in, u64* out, u64 n, u64 init);
 void launchAwaken(Ctx* c);
 void launchHistKey(Ctx* c);
 void launchScatter(Ctx* c);
+bool otBuildV2();   // cnf.cu: SIGMA_OT_V2 (default on)
 void launchCount(Ctx* c);
 void launchGC(Ctx* c);
 int  launchStore(Ctx* c, u64* nCls, u64* nLits, int form, bool writeBackOrder);   // form: 0 arrays (bits, sig, offs), 1 SCLAUSE records, 2 compact (bits, sizes);   // writeBackOrder: apply -aggresivesort (cacheCNF only)

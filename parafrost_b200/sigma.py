@@ -29,7 +29,7 @@ class SigmaOpts(C.Structure):
         ("xor_max_arity", C.c_uint32), ("ere_clause_max", C.c_int32), ("ere_max_occurs", C.c_uint32),
         ("sub_max_occurs", C.c_uint32), ("bce_max_occurs", C.c_uint32), ("sh_max_bve_out1", C.c_uint32),
         ("sigma_calls", C.c_int32), ("final_gc", C.c_int32), ("profile", C.c_int32), ("aggr_cnf_sort", C.c_int32),
-        ("proof_en", C.c_int32), ("lcve_fast", C.c_int32),
+        ("proof_en", C.c_int32), ("lcve_fast", C.c_int32), ("log_reductions", C.c_int32),
     ]
 
 
@@ -61,6 +61,12 @@ class Report(C.Structure):
         return d
 
 
+class StageReduction(C.Structure):
+    _fields_ = [("round", C.c_uint32), ("stage", C.c_uint32), ("vars_removed", C.c_uint32), ("pad", C.c_uint32),
+                ("clauses_before", C.c_uint64), ("literals_before", C.c_uint64), ("clauses", C.c_uint64), ("literals", C.c_uint64)]
+    STAGES = ["BCP", "SUB", "BVE", "BCE", "ERE"]
+
+
 class DeviceCnf(C.Structure):
     """sigma_device_cnf: device pointers into the context's arena (Solver::getDeviceCNF / getVars, solver.hpp:694-705)."""
     _fields_ = [
@@ -88,7 +94,7 @@ SYMBOLS = [
     "sigma_result_sizes", "sigma_store", "sigma_store_compact", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
     "sigma_set_proof_sink", "sigma_proof_chunks", "sigma_proof_chunk_size", "sigma_proof_chunk_copy",
     "sigma_debug_hist", "sigma_kernel_profile", "sigma_kernel_times", "sigma_kernel_stats", "sigma_trail_info", "sigma_copy_trail", "sigma_pinned_alloc", "sigma_pinned_free",
-    "sigma_device_view", "sigma_continue", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
+    "sigma_device_view", "sigma_continue", "sigma_reduction_log", "sigma_memory", "sigma_last_error", "sigma_version", "sigma_stage_prep", "sigma_stage_histogram",
 ]
 
 
@@ -133,6 +139,7 @@ def lib():
         L.sigma_pinned_alloc.argtypes = [C.c_size_t]; L.sigma_pinned_alloc.restype = C.c_void_p
         L.sigma_pinned_free.argtypes = [C.c_void_p]
         L.sigma_device_view.argtypes = [P, C.POINTER(DeviceCnf)]
+        L.sigma_reduction_log.argtypes = [P, P, C.POINTER(C.c_uint32)]
         L.sigma_continue.argtypes = [P, C.c_uint64, P, P, P, P, P]
         L.sigma_kernel_stats.argtypes = [P, P, P, P, P, C.POINTER(C.c_uint32)]
         L.sigma_memory.argtypes = [P] + [C.POINTER(C.c_uint64)] * 3
@@ -164,7 +171,10 @@ def opts_from_flags(flags) -> dict:
     for f in flags:
         if "=" in f:
             k, v = f.split("=", 1)
-            if k in VALUE_FLAGS:
+            if k == "--verbose":                       # LOGREDALL / LOGREDCL tables need --verbose >= 2 (logging.hpp:152-158)
+                if int(v) >= 2:
+                    o["log_reductions"] = 1
+            elif k in VALUE_FLAGS:
                 o[VALUE_FLAGS[k]] = float(v) if k == "--literalsmul" else int(v)
             elif k not in ("--mapperc", "--ereminthreads"):
                 raise ValueError(f"unknown flag {f}")
@@ -319,6 +329,16 @@ class Simplifier:
         n = 0 if k[1] is None else len(k[1]) - 1
         self._keep2 = k
         self._check(self._lib.sigma_continue(self._h, n, _ptr(k[0]), _ptr(k[1]), _ptr(k[2]), _ptr(k[3]), _ptr(k[4])))
+
+    def reduction_log(self):
+        """LOGREDALL / LOGREDCL tables of the last run (needs log_reductions=1): [{round, stage, vars_removed, clauses, literals, ...}]"""
+        n = C.c_uint32(0)
+        self._check(self._lib.sigma_reduction_log(self._h, None, C.byref(n)))
+        arr = (StageReduction * max(n.value, 1))()
+        m = C.c_uint32(n.value)
+        self._check(self._lib.sigma_reduction_log(self._h, arr, C.byref(m)))
+        return [{"round": e.round, "stage": StageReduction.STAGES[e.stage], "vars_removed": e.vars_removed, "clauses_before": e.clauses_before,
+                 "literals_before": e.literals_before, "clauses": e.clauses, "literals": e.literals} for e in arr[: n.value]]
 
     def trail_info(self):
         tot, frm, cnt, seeds = C.c_uint64(), C.c_uint32(), C.c_uint32(), C.c_uint32()

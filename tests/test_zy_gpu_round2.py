@@ -190,3 +190,31 @@ def test_bad_literal_is_rejected_not_dereferenced():
             s.simplify()
     finally:
         s.close()
+
+
+def test_reduction_log_tables_match_the_round_reports():
+    """LOGREDALL / LOGREDCL (logging.hpp:152-158): per-stage survivors; the last stage of a round equals the round report,
+    BVE's removed variables equal the round's eliminated count, and switching the log on changes nothing else."""
+    fam, seed, args = SMALL["miter_a"]
+    V, lits, offs = helpers.gen_cnf(fam, seed, args)
+    S = sigma()
+    s = S.Simplifier(0, flags=["-all", "--verbose=2"])
+    s0 = S.Simplifier(0, flags=["-all"])
+    try:
+        s.load(V, lits, offs); s0.load(V, lits, offs)
+        fin, fin0 = s.simplify(), s0.simplify()
+        assert (fin["clauses"], fin["literals"], fin["eliminated_vars"]) == (fin0["clauses"], fin0["literals"], fin0["eliminated_vars"])
+        assert s0.reduction_log() == []
+        log, rounds = s.reduction_log(), s.rounds()
+        assert {e["stage"] for e in log} >= {"SUB", "BVE", "BCE", "ERE"}
+        for r in rounds:
+            mine = [e for e in log if e["round"] == r["round"] and e["stage"] != "BCP"]
+            if r["kind"] == 0:
+                assert [e["stage"] for e in mine] == ["SUB", "BVE", "BCE"][: len(mine)]
+                assert mine[-1]["clauses"] == r["clauses"] and mine[-1]["literals"] == r["literals"]
+                assert [e for e in mine if e["stage"] == "BVE"][0]["vars_removed"] == r["eliminated"]
+                assert all(a["clauses"] >= b["clauses"] or b["stage"] == "BVE" for a, b in zip(mine, mine[1:]))
+            elif r["kind"] == 1 and mine:
+                assert mine[-1]["stage"] == "ERE" and mine[-1]["clauses"] == r["clauses"]
+    finally:
+        s.close(); s0.close()
