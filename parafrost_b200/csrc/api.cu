@@ -220,7 +220,8 @@ static size_t carve(Ctx* c, char* base) {
     c->otBig = a.take<u32>(8192 + capW / 32768 + 64 + 8192 + 8);   // work units of oversized buckets (k_ot_place_big) + their bucket ids
     c->rk8 = a.take<uint4>(capC + 1);
     c->cntMat = a.take<u32>(((size_t)capC / (1024 * 3) + 2) * 8192);   // one row of <= 8192 bucket counts per tile of >= 3072 clauses
-    c->btot = a.take<u32>(8192 + 8); c->bstart = a.take<u32>(8192 + 8);
+    c->runMat = a.take<u32>(((size_t)capC / (1024 * 3) + 2) * 8192);   // ... and of run starts (column scan of the counts)
+    c->otSeg = a.take<u32>((size_t)64 * 8192 + 8); c->bstart = a.take<u32>(8192 + 8);
     c->scores = a.take<u32>(V1); c->eligible = a.take<u32>(V1); c->rank = a.take<u32>(V1);
     c->sortK = a.take<u32>(V1); c->sortV = a.take<u32>(V1); c->elected = a.take<u32>(V1);
     c->units = a.take<u32>(2 * V1); c->trail = a.take<u32>(3 * V1);
@@ -291,7 +292,8 @@ static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u
     // that fits the logical capacities but not the arena fails the round loudly (flags bit 6), never silently.
     u64 numCls = c->logC;
     if (c->o.phases && c->o.ve_en && 2 * num_clauses > numCls) numCls = 2 * num_clauses;
-    const u64 numWords = c->logW + (numCls - c->logC) * NBUCKETS;
+    numCls += numCls / 8 + 1024;                // slack: the clauses a sigma_continue appends, capacities that grow a little after a GC
+    const u64 numWords = c->logW + (numCls - c->logC) * NBUCKETS + c->logW / 8;
     if (numCls >= 0xFFFFFFF0ull || numWords >= 0xFFFFFFF0ull) return SIGMA_CNFALLOC_FAIL;
     c->capC = (u32)numCls;
     c->capW = numWords;                         // data cap in words: a pool this big can never overflow below the logical caps

@@ -506,43 +506,60 @@ __global__ void __launch_bounds__(OT_T) k_ot_count(const u32* __restrict__ inLit
     for (u32 b = threadIdx.x; b < NBp; b += OT_T) row[b] = b < NB ? cntS[b] + cntL[b] : 0u;
 }
 
-// bucket totals: column sums of the count matrix, a segment of rows per CTA row
-__global__ void __launch_bounds__(256) k_ot_colsum(const u32* __restrict__ cntMat, u32 tiles, u32 NB, u32 NBp, u32* __restrict__ btot) {
+// Run starts without atomics: the start of tile t's run in bucket b is bstart[b] + sum of the counts of the tiles before t.
+// Column scan of the count matrix in three small steps: per-segment column sums, one CTA that turns them into bucket starts
+// and segment bases, per-segment running sums written to a second matrix (the counts themselves stay: the partition needs both).
+#define OT_SEG 64
+__global__ void __launch_bounds__(256) k_ot_colsum(const u32* __restrict__ cntMat, u32 tiles, u32 NB, u32 NBp, u32* __restrict__ segSum) {
     const u32 b = blockIdx.x * 256 + threadIdx.x;
     if (b >= NB) return;
-    const u32 per = (tiles + gridDim.y - 1) / gridDim.y;
+    const u32 per = (tiles + OT_SEG - 1) / OT_SEG;
     const u32 r0 = blockIdx.y * per, r1 = min(tiles, r0 + per);
     u32 s = 0;
     for (u32 r = r0; r < r1; r++) s += cntMat[(size_t)r * NBp + b];
-    if (s) atomicAdd(&btot[b], s);
+    segSum[(size_t)blockIdx.y * NBp + b] = s;
 }
-// exclusive scan of the bucket totals (NB <= 8192) -> segment starts; run cursors cleared; one CTA
-__global__ void __launch_bounds__(1024) k_ot_bscan(const u32* __restrict__ btot, u32 NB, u32* __restrict__ bstart, u32* __restrict__ gcur, u32* total) {
+// bucket totals -> exclusive scan (NB <= 8192) -> segment starts; segSum becomes the start of every segment's first run; one CTA
+__global__ void __launch_bounds__(1024) k_ot_bscan(u32* __restrict__ segSum, u32 NB, u32 NBp, u32* __restrict__ bstart, u32* total) {
     __shared__ u32 wt[32];
     __shared__ u32 carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (u32 base = 0; base < NB; base += 1024) {
         const u32 b = base + threadIdx.x;
-        const u32 v = b < NB ? btot[b] : 0u;
+        u32 v = 0;
+        if (b < NB) for (u32 sgm = 0; sgm < OT_SEG; sgm++) v += segSum[(size_t)sgm * NBp + b];
         const u32 incl = warpIncl(v);
         if ((threadIdx.x & 31u) == 31u) wt[threadIdx.x >> 5] = incl;
         __syncthreads();
         if (threadIdx.x < 32) { const u32 t = wt[threadIdx.x]; const u32 ti = warpIncl(t); wt[threadIdx.x] = ti - t; }
         __syncthreads();
         const u32 excl = carry + wt[threadIdx.x >> 5] + incl - v;
-        if (b < NB) { bstart[b] = excl; gcur[b] = 0; }
+        if (b < NB) {
+            bstart[b] = excl;
+            u32 run = excl;
+            for (u32 sgm = 0; sgm < OT_SEG; sgm++) { const u32 t = segSum[(size_t)sgm * NBp + b]; segSum[(size_t)sgm * NBp + b] = run; run += t; }
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
     if (threadIdx.x == 0) { bstart[NB] = carry; *total = carry; }
 }
+__global__ void __launch_bounds__(256) k_ot_colfix(const u32* __restrict__ cntMat, u32 tiles, u32 NB, u32 NBp, const u32* __restrict__ segBase,
+                                                   u32* __restrict__ runMat) {
+    const u32 b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= NB) return;
+    const u32 per = (tiles + OT_SEG - 1) / OT_SEG;
+    const u32 r0 = blockIdx.y * per, r1 = min(tiles, r0 + per);
+    u32 run = segBase[(size_t)blockIdx.y * NBp + b];
+    for (u32 r = r0; r < r1; r++) { runMat[(size_t)r * NBp + b] = run; run += cntMat[(size_t)r * NBp + b]; }
+}
 
 template <int CPT, int KEEP>
 __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ hdr, const u32* __restrict__ pool, const uint4* __restrict__ rk8, u32 n,
-                                                   u32 shift, u32 NB, u32 NBp, const u32* __restrict__ cntMat, const u32* __restrict__ bstart,
-                                                   u32 stageCap, u32* __restrict__ gcur, uint2* __restrict__ pairs) {
+                                                   u32 shift, u32 NB, u32 NBp, const u32* __restrict__ cntMat, const u32* __restrict__ runMat,
+                                                   u32 stageCap, uint2* __restrict__ pairs) {
     extern __shared__ u32 sm[];
     u32* tileOff = sm;              // [NB + 1] start of the bucket inside the staged tile
     u32* delta = sm + NB + 1;       // [NB] run start in pairs[] minus tileOff
@@ -573,16 +590,17 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
 #pragma unroll
         for (int q = 0; q < KEEP; q++) lk[k][q] = ((u32)q < sz[k] && sz[k] <= 8u) ? l[q] : 0u;
     }
-    // this tile's row of bucket counts: run lengths; one global atomic per non-empty bucket, all independent
+    // this tile's rows: run lengths (counting pass) and run starts (column scan) - no reservation, no atomic
     const u32 per = (NB + OT_T - 1) / OT_T;   // consecutive buckets per thread, <= 8
     const u32 b0 = threadIdx.x * per;
     const u32* row = cntMat + (size_t)blockIdx.x * NBp;
+    const u32* grow = runMat + (size_t)blockIdx.x * NBp;
     u32 cq[8], gq[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) { const u32 b = b0 + q; cq[q] = ((u32)q < per && b < NB) ? row[b] : 0u; }
+    for (int q = 0; q < 8; q++) { const u32 b = b0 + q; const bool in = (u32)q < per && b < NB; cq[q] = in ? row[b] : 0u; gq[q] = in ? grow[b] : 0u; }
     u32 mine = 0, used = 0;
 #pragma unroll
-    for (int q = 0; q < 8; q++) { gq[q] = cq[q] ? bstart[b0 + q] + atomicAdd(&gcur[b0 + q], cq[q]) : 0u; mine += cq[q]; used += cq[q] != 0u; }
+    for (int q = 0; q < 8; q++) { mine += cq[q]; used += cq[q] != 0u; }
     const u32 incl = warpIncl(mine);
     used = warpSum(used);
     if ((threadIdx.x & 31u) == 0 && used) atomicAdd(&nonEmpty, used);
@@ -637,133 +655,45 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
     }
 }
 
-#define PLACE2_ITERS ((PLACE_WINDOW + PLACE_THREADS - 1) / PLACE_THREADS)
-__global__ void __launch_bounds__(PLACE_THREADS) k_ot_place2(const uint2* __restrict__ pairs, const u32* __restrict__ bstart, u32 ND, u32 shift, u32 window,
-                                                             u32* __restrict__ hist, u32* __restrict__ otStart, u32* __restrict__ otSize,
-                                                             u32* __restrict__ occurs, u32* __restrict__ big, u32* nBig, u32* __restrict__ bigB, u32* nBigB) {
-    extern __shared__ u32 smem[];
-    const u32 W = 1u << shift;
-    u32* cnt = smem;          // [W] per-literal counts, then list starts
-    u32* win = smem + W;      // [window] staged entries
-    __shared__ u32 wt[32];
-    const u32 lit0 = blockIdx.x << shift;
-    const u32 litEnd = min(lit0 + W, ND);
-    const u32 nl = litEnd - lit0;
-    const u32 p0 = bstart[blockIdx.x], p1 = bstart[blockIdx.x + 1];
-    const u32 len = p1 - p0;
-    if (len > window || shift > 12) {   // oversized bucket (or cursors that do not fit shared memory): work units with global cursors (k_ot_big_*)
-        if (!len) {
-            for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) { hist[lit0 + k] = 0; otSize[lit0 + k] = 0; otStart[lit0 + k] = p0; }
-            return;
-        }
-        if (threadIdx.x == 0) {
-            u32 S = (len + PLACE_UNIT - 1) / PLACE_UNIT;
-            S = S > PLACE_SPLIT ? PLACE_SPLIT : S;
-            const u32 base = atomicAdd(nBig, S);
-            for (u32 s = 0; s < S; s++) big[base + s] = blockIdx.x | (s << 13) | (S << 19);
-            bigB[atomicAdd(nBigB, 1u)] = blockIdx.x;
-        }
-        for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) hist[lit0 + k] = 0;
-        return;
-    }
-    for (u32 k = threadIdx.x; k < W; k += PLACE_THREADS) cnt[k] = 0;
-    __syncthreads();
-    // sweep 1: count per literal; the value the atomic returns is the pair's rank in its list
-    u32 rr[(PLACE2_ITERS + 1) / 2];
-#pragma unroll
-    for (int q = 0; q < (PLACE2_ITERS + 1) / 2; q++) rr[q] = 0;
-#pragma unroll
-    for (int it = 0; it < PLACE2_ITERS; it++) {
-        const u32 j = p0 + it * PLACE_THREADS + threadIdx.x;
-        if (j < p1) rr[it >> 1] |= atomicAdd(&cnt[pairs[j].x - lit0], 1u) << ((it & 1) * 16);
-    }
-    __syncthreads();
-    // exclusive scan of the W counts (W / 1024 consecutive literals per thread) -> list starts; hist / otStart / otSize leave coalesced
-    {
-        const u32 per = (W + PLACE_THREADS - 1) / PLACE_THREADS;   // <= 4 for W <= 4096
-        const u32 k0 = threadIdx.x * per;
-        u32 c4[4], mine = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) { const u32 k = k0 + q; c4[q] = ((u32)q < per && k < W) ? cnt[k] : 0u; mine += c4[q]; }
-        const u32 incl = warpIncl(mine);
-        if ((threadIdx.x & 31u) == 31u) wt[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) { const u32 t = wt[threadIdx.x]; const u32 ti = warpIncl(t); wt[threadIdx.x] = ti - t; }
-        __syncthreads();
-        u32 run = wt[threadIdx.x >> 5] + incl - mine;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const u32 k = k0 + q;
-            if ((u32)q < per && k < W) {
-                cnt[k] = run;
-                if (k < nl) { hist[lit0 + k] = c4[q]; otSize[lit0 + k] = c4[q]; otStart[lit0 + k] = p0 + run; }
-                run += c4[q];
-            }
-        }
-    }
-    __syncthreads();
-    // sweep 2: the pairs again (L2), entry = list start + rank
-#pragma unroll
-    for (int it = 0; it < PLACE2_ITERS; it++) {
-        const u32 j = p0 + it * PLACE_THREADS + threadIdx.x;
-        if (j < p1) { const uint2 p = pairs[j]; win[cnt[p.x - lit0] + ((rr[it >> 1] >> ((it & 1) * 16)) & 0xFFFFu)] = p.y; }
-    }
-    __syncthreads();
-    for (u32 k = threadIdx.x; k < len; k += PLACE_THREADS) occurs[p0 + k] = win[k];
-}
-// oversized buckets: per-literal counts with global atomics (hist[] of the bucket was cleared by k_ot_place2) ...
-__global__ void __launch_bounds__(PLACE_THREADS) k_ot_big_count(const uint2* __restrict__ pairs, const u32* __restrict__ bstart, u32 shift,
-                                                                u32* __restrict__ hist, const u32* __restrict__ big, const u32* nBig) {
-    const u32 nItems = *nBig;
-    for (u32 item = blockIdx.x; item < nItems; item += gridDim.x) {
-        const u32 code = big[item];
-        const u32 b = code & 0x1FFFu, s = (code >> 13) & 0x3Fu, S = code >> 19;
-        const u32 p0 = bstart[b], len = bstart[b + 1] - p0;
-        const u32 q0 = p0 + (u32)((u64)len * s / S), q1 = p0 + (u32)((u64)len * (s + 1) / S);
-        for (u32 j = q0 + threadIdx.x; j < q1; j += PLACE_THREADS) atomicAdd(&hist[pairs[j].x], 1u);
-    }
-}
-// ... their exclusive scan -> otStart, cursors (otSize) cleared ...
-__global__ void __launch_bounds__(1024) k_ot_big_scan(const u32* __restrict__ bstart, u32 ND, u32 shift, const u32* __restrict__ hist,
-                                                      u32* __restrict__ otStart, u32* __restrict__ otSize, const u32* __restrict__ bigB, const u32* nBigB) {
+// per-literal histogram of one bucket = hist[] (and, scanned, otStart[]) of its literal range: counted from the bucket's
+// pairs with shared-memory atomics - the global reductions of the version-1 histogram pass are gone.  Light (W counters),
+// several CTAs per SM; oversized buckets just loop longer.  k_ot_place / k_ot_place_big then run unchanged.
+#define LITHIST_T 512
+__global__ void __launch_bounds__(LITHIST_T) k_ot_lithist(const uint2* __restrict__ pairs, const u32* __restrict__ bstart, u32 ND, u32 shift,
+                                                          u32* __restrict__ hist, u32* __restrict__ otStart) {
+    extern __shared__ u32 cnt[];   // [W]
     __shared__ u32 wt[32];
     __shared__ u32 carry;
     const u32 W = 1u << shift;
-    for (u32 it = blockIdx.x; it < *nBigB; it += gridDim.x) {
-        const u32 b = bigB[it];
-        const u32 lit0 = b << shift, nl = min(lit0 + W, ND) - lit0;
-        __syncthreads();
-        if (threadIdx.x == 0) carry = bstart[b];
-        __syncthreads();
-        for (u32 base = 0; base < nl; base += 1024) {
-            const u32 k = base + threadIdx.x;
-            const u32 v = k < nl ? hist[lit0 + k] : 0u;
-            const u32 incl = warpIncl(v);
-            if ((threadIdx.x & 31u) == 31u) wt[threadIdx.x >> 5] = incl;
-            __syncthreads();
-            if (threadIdx.x < 32) { const u32 t = wt[threadIdx.x]; const u32 ti = warpIncl(t); wt[threadIdx.x] = ti - t; }
-            __syncthreads();
-            const u32 excl = carry + wt[threadIdx.x >> 5] + incl - v;
-            if (k < nl) { otStart[lit0 + k] = excl; otSize[lit0 + k] = 0; }
-            __syncthreads();
-            if (threadIdx.x == 1023) carry = excl + v;
-            __syncthreads();
-        }
+    const u32 lit0 = blockIdx.x << shift;
+    const u32 nl = min(lit0 + W, ND) - lit0;
+    const u32 p0 = bstart[blockIdx.x], p1 = bstart[blockIdx.x + 1];
+    for (u32 k = threadIdx.x; k < W; k += LITHIST_T) cnt[k] = 0;
+    if (threadIdx.x == 0) carry = p0;
+    __syncthreads();
+    u32 j = p0 + threadIdx.x;
+    for (; j + 3 * LITHIST_T < p1; j += 4 * LITHIST_T) {
+        u32 l4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) l4[k] = pairs[j + k * LITHIST_T].x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(&cnt[l4[k] - lit0], 1u);
     }
-}
-// ... and the placement itself is k_ot_place_big (bucket bounds from otStart / hist instead of the next bucket's start)
-__global__ void __launch_bounds__(PLACE_THREADS) k_ot_big_place(const uint2* __restrict__ pairs, const u32* __restrict__ bstart, const u32* __restrict__ otStart,
-                                                                u32* __restrict__ otSize, u32* __restrict__ occurs, const u32* __restrict__ big, const u32* nBig) {
-    const u32 nItems = *nBig;
-    for (u32 item = blockIdx.x; item < nItems; item += gridDim.x) {
-        const u32 code = big[item];
-        const u32 b = code & 0x1FFFu, s = (code >> 13) & 0x3Fu, S = code >> 19;
-        const u32 p0 = bstart[b], len = bstart[b + 1] - p0;
-        const u32 q0 = p0 + (u32)((u64)len * s / S), q1 = p0 + (u32)((u64)len * (s + 1) / S);
-        for (u32 j = q0 + threadIdx.x; j < q1; j += PLACE_THREADS) {
-            const uint2 p = pairs[j];
-            occurs[otStart[p.x] + atomicAdd(&otSize[p.x], 1u)] = p.y;
-        }
+    for (; j < p1; j += LITHIST_T) atomicAdd(&cnt[pairs[j].x - lit0], 1u);
+    __syncthreads();
+    for (u32 base = 0; base < nl; base += LITHIST_T) {
+        const u32 k = base + threadIdx.x;
+        const u32 v = k < nl ? cnt[k] : 0u;
+        const u32 incl = warpIncl(v);
+        if ((threadIdx.x & 31u) == 31u) wt[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) { const u32 t = threadIdx.x < LITHIST_T / 32 ? wt[threadIdx.x] : 0u; const u32 ti = warpIncl(t); if (threadIdx.x < LITHIST_T / 32) wt[threadIdx.x] = ti - t; }
+        __syncthreads();
+        const u32 excl = carry + wt[threadIdx.x >> 5] + incl - v;
+        if (k < nl) { hist[lit0 + k] = v; otStart[lit0 + k] = excl; }
+        __syncthreads();
+        if (threadIdx.x == LITHIST_T - 1) carry = excl + v;
+        __syncthreads();
     }
 }
 
@@ -791,7 +721,8 @@ static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 num
         cudaFuncSetAttribute(k_ot_count<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_part2<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_part2<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_place2, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
+        cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
+        cudaFuncSetAttribute(k_ot_lithist, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
         c->attrOT2 = true;
     }
     const size_t smem = 8 * (size_t)c->otNB;
@@ -811,35 +742,33 @@ static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 num
 
 static void launchScatter2(Ctx* c, u32 n) {
     const u32 NB = c->otNB, NBp = c->otNBp, shift = c->otShift, tiles = c->otTiles;
-    cudaMemsetAsync(c->btot, 0, (size_t)NB * 4, c->stream);
-    const u32 seg = tiles < 64 ? (tiles ? tiles : 1) : 64;
-    LAUNCH(c, k_ot_colsum, dim3(divup(NB, 256), seg), 256, 0, c->cntMat, tiles, NB, NBp, c->btot);
+    u32* segSum = c->otSeg;
+    LAUNCH(c, k_ot_colsum, dim3(divup(NB, 256), OT_SEG), 256, 0, c->cntMat, tiles, NB, NBp, segSum);
     KB(c, 4.0 * (double)tiles * NBp);
-    LAUNCH(c, k_ot_bscan, 1, 1024, 0, c->btot, NB, c->bstart, c->otCur, c->otStart + c->ND);
+    LAUNCH(c, k_ot_bscan, 1, 1024, 0, segSum, NB, NBp, c->bstart, c->otStart + c->ND);
+    LAUNCH(c, k_ot_colfix, dim3(divup(NB, 256), OT_SEG), 256, 0, c->cntMat, tiles, NB, NBp, segSum, c->runMat);
+    KB(c, 8.0 * (double)tiles * NBp);
     // shared memory of k_ot_part2: 3 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
     const size_t partFixed = 4 * (((size_t)3 * NB + 2) & ~(size_t)1) + 16;
     const u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
     if (c->otCPT == 5)
-        LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->bstart,
-               stageCap, c->otCur, c->otPairs);
+        LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
+               stageCap, c->otPairs);
     else
-        LAUNCH(c, (k_ot_part2<3, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->bstart,
-               stageCap, c->otCur, c->otPairs);
-    KB(c, 32.0 * n + 4.0 * c->numLiterals + 4.0 * (double)tiles * NBp + 8.0 * c->numLiterals);   // headers + ranks + literals + count row in, pairs out
+        LAUNCH(c, (k_ot_part2<3, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
+               stageCap, c->otPairs);
+    KB(c, 32.0 * n + 4.0 * c->numLiterals + 8.0 * (double)tiles * NBp + 8.0 * c->numLiterals);   // headers + ranks + literals + the tile's two rows in, pairs out
+    LAUNCH(c, k_ot_lithist, NB, LITHIST_T, (size_t)4 << shift, c->otPairs, c->bstart, c->ND, shift, c->hist, c->otStart);
+    KB(c, 8.0 * c->numLiterals + 8.0 * c->ND);   // pairs in, hist + list starts out
+    // placement: the version-1 kernels (list cursors + the bucket's occurs[] window in shared memory; work units for oversized buckets)
     u32 window = shift <= 12 ? PLACE_WINDOW : 0;
     if (const char* w = getenv("SIGMA_OT_WINDOW")) { const u32 v = (u32)atoi(w); if (v < window) window = v; }   // tests: force the work-unit path
-    const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : 64;
+    const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
     u32* nBig = &c->dc->scratch[7];
-    u32* nBigB = &c->dc->scratch[15];
     cudaMemsetAsync(nBig, 0, 4, c->stream);
-    cudaMemsetAsync(nBigB, 0, 4, c->stream);
-    u32* bigB = c->otBig + (8192 + c->capW / 32768 + 64);
-    LAUNCH(c, k_ot_place2, NB, PLACE_THREADS, placeSmem, c->otPairs, c->bstart, c->ND, shift, window, c->hist, c->otStart, c->otSize, c->occurs, c->otBig,
-           nBig, bigB, nBigB);
-    KB(c, 8.0 * c->numLiterals + 4.0 * c->numLiterals + 12.0 * c->ND);   // pairs in (their second read is an L2 hit), list entries + hist / start / size out
-    LAUNCH(c, k_ot_big_count, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->bstart, shift, c->hist, c->otBig, nBig);
-    LAUNCH(c, k_ot_big_scan, 148, 1024, 0, c->bstart, c->ND, shift, c->hist, c->otStart, c->otSize, bigB, nBigB);
-    LAUNCH(c, k_ot_big_place, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->bstart, c->otStart, c->otSize, c->occurs, c->otBig, nBig);
+    LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
+    KB(c, 8.0 * c->numLiterals + 4.0 * c->numLiterals + 8.0 * c->ND);   // pairs in, list entries out, list bounds
+    LAUNCH(c, k_ot_place_big, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs, c->otBig, nBig);
 }
 
 // ------------------------------------------------------------------ live counts

@@ -112,7 +112,8 @@ def test_rounds_match_oracle_medium(name, var):
     assert not sgd.compare(ed, od)
 
 
-GOLD = sorted(k for k, e in SUMMARY.items() if "fingerprint" in e and "-no-ere" in e["flags"])
+GOLD = sorted(k for k, e in SUMMARY.items() if "fingerprint" in e and "-lcvefast" not in e["flags"])
+GOLD_FAST = sorted(k for k, e in SUMMARY.items() if "fingerprint" in e and "-lcvefast" in e["flags"])
 FP_KEYS = ["cnfstate", "clauses", "literals", "eliminated", "forced", "resolved_words", "resolved_groups", "trail",
            "h_lits_multiset", "h_full_multiset", "h_lits_ordered", "h_full_ordered", "h_eliminated", "h_forced",
            "h_resolved_groups", "h_trail_multiset"]
@@ -138,6 +139,20 @@ def test_engine_matches_reference_golden(key):
 
 
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", GOLD_FAST)
+def test_engine_lcvefast_matches_reference_as_sets(key):
+    """-lcvefast (the reference CLI's default election) against runs of the unmodified reference: the elected set - hence the
+    eliminated variables and the clause MULTISET - is deterministic there, the order of elected[] is not (lcve.cu:204)."""
+    e = SUMMARY[key]
+    V, lits, offs = helpers.gen_cnf(e["family"], e["seed"], e["args"])
+    flags = [f for f in e["flags"] if f not in ("-no-lcvefast", "-quiet")]
+    ed, fin, _, _ = run_engine_rounds(V, lits, offs, flags)
+    fp, g = ed.fingerprint(), e["fingerprint"]
+    keys = ["cnfstate", "clauses", "literals", "eliminated", "forced", "h_lits_multiset", "h_eliminated", "h_forced", "h_trail_multiset"]
+    diff = {k: (fp[k], g[k]) for k in keys if fp[k] != g[k]}
+    assert not diff, diff
+
+
 def test_stage_prep_and_histogram():
     rng = np.random.default_rng(5)
     sizes = np.concatenate([rng.integers(1, 9, 5000), rng.integers(9, 60, 300), [1, 2, 8, 9, 250]]).astype(np.uint64)
