@@ -289,6 +289,10 @@ def ref_gpu_block(workload, local, fixed=False):
         out["reference_default"]["note"] = "its default mode (-lcvefast), simplify(false): extract + H2D + rounds + write-back into the host clause database"
         if "simplify_ms" in r:
             out["speedup_e2e_vs_reference_default"] = r["simplify_ms"] / out["engine_lcvefast"]["ms_e2e"]
+            if r.get("stage_ms"):   # its own -profilegpu stage timers only (no arena creation, no host loops) against the engine's device time
+                ssum = sum(r["stage_ms"].values())
+                out["reference_default"]["stage_ms_sum"] = ssum
+                out["speedup_device_vs_reference_stage_sum"] = ssum / out["engine_lcvefast"]["ms_device"]
         if fixed:
             r2 = run_ref_gpu(path, ["-no-lcvefast"], timeout=900, host_mode=True)
             out["reference_fixed_order"] = {k: r2.get(k) for k in ("simplify_ms", "clauses", "rc", "tail") if r2.get(k) is not None}

@@ -225,7 +225,7 @@ static size_t carve(Ctx* c, char* base) {
     c->scores = a.take<u32>(V1); c->eligible = a.take<u32>(V1); c->rank = a.take<u32>(V1);
     c->sortK = a.take<u32>(V1); c->sortV = a.take<u32>(V1); c->elected = a.take<u32>(V1);
     c->units = a.take<u32>(2 * V1); c->trail = a.take<u32>(3 * V1);
-    c->resolved = a.take<u32>((size_t)c->resolvedCap + 2);
+    c->resolved = a.take<u32>((size_t)c->resolvedCapPhys + 2);
     c->vorg = a.take<u32>(V1); c->varcore = a.take<u32>(V1);
     c->mis = a.take<unsigned char>(V1); c->cstat = a.take<unsigned char>(V1);
     c->vstate = a.take<unsigned char>(V1); c->vstate0 = a.take<unsigned char>(V1);
@@ -299,7 +299,7 @@ static int prepareLoad(Ctx* c, uint32_t max_var, uint64_t num_clauses, u64 L0, u
     c->capW = numWords;                         // data cap in words: a pool this big can never overflow below the logical caps
     const u64 rc = num_clauses + L0;            // savedLits (simplify.cu:85)
     c->resolvedCap = (u32)(rc > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : rc);
-    c->resolvedCapPhys = c->resolvedCap;
+    { const u64 rp = rc + rc / 8 + 4096; c->resolvedCapPhys = rp > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : rp; }   // slack for sigma_continue
     const size_t need = carve(c, nullptr);
     if (need > c->arenaBytes) {
         if (c->arena) { CUDA_TRY(cudaFree(c->arena)); c->arena = nullptr; c->arenaBytes = 0; }

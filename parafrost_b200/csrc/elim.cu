@@ -1825,7 +1825,7 @@ void launchSUB(Ctx* c, const KOpts& k) {
     // the local-copy kernels win on short clauses (3-SAT, Tseitin gates: cfg1 -15 %, cfg3 -13 %) and lose on the 4-literal
     // adder clauses of cfg4 (+50 % on the 8-lane class: fixed 8-word slots, fewer resident CTAs) - profiles/r02_ab_local_c3.jsonl
     static const int subEnv = getenv("SIGMA_SUB_LOCAL") ? atoi(getenv("SIGMA_SUB_LOCAL")) : -1;   // 0 / 1: force (A/B measurements)
-    const bool subLocal = subEnv >= 0 ? subEnv != 0 : c->numLiterals * 10 <= c->numClauses * 31;
+    const bool subLocal = subEnv >= 0 ? subEnv != 0 : c->L0 * 10 <= c->C0 * 31;   // decided once per call, from the loaded formula
     if (subLocal) {
         const u32 E = c->numElected;
         u32* redo = c->rank;       // rank[] is dead after the election
@@ -1857,7 +1857,7 @@ void launchVE(Ctx* c, const KOpts& k) {
     u32* redoCount = &c->dc->bin[3];
     const ClassBytes cb1 = classBytes(c);   // + 20 bytes per variable: type, ucnt, rpos, rref (SURVEY 8d "BVE count")
     static const int veEnv = getenv("SIGMA_VE_LOCAL") ? atoi(getenv("SIGMA_VE_LOCAL")) : -1;   // 0 / 1: force (A/B measurements)
-    const bool veLocal = veEnv >= 0 ? veEnv != 0 : c->numLiterals * 10 <= c->numClauses * 31;   // see launchSUB
+    const bool veLocal = veEnv >= 0 ? veEnv != 0 : c->L0 * 10 <= c->C0 * 31;   // see launchSUB
     if (veLocal) {
         LAUNCH(c, k_ve_phase1_local<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
         KB(c, cb1.b[0]);
