@@ -553,7 +553,7 @@ def measure(a, torch, workload, rank, world, local, barrier, steps, warmup, pipe
     pinned = []
 
     def alloc(n, dt):
-        t = torch.empty(int(n), dtype={np.uint32: torch.int32, np.uint64: torch.int64}[dt], pin_memory=True)
+        t = torch.empty(int(n), dtype={np.uint32: torch.int32, np.uint64: torch.int64, np.uint8: torch.uint8}[dt], pin_memory=True)
         pinned.append(t)
         return t.numpy().view(dt)
 
@@ -569,7 +569,7 @@ def measure(a, torch, workload, rank, world, local, barrier, steps, warmup, pipe
 
     def outbuf():
         return {"bits": alloc(capC, np.uint32), "sizes": alloc(capC, np.uint32), "lits": alloc(capL, np.uint32),
-                "eliminated": np.zeros(V + 1, np.uint8), "resolved": alloc(C0 + L0 + 2, np.uint32), "trail": alloc(3 * (V + 1), np.uint32)}
+                "eliminated": alloc(V + 1, np.uint8), "resolved": alloc(C0 + L0 + 2, np.uint32), "trail": alloc(3 * (V + 1), np.uint32)}
     out0 = outbuf()
 
     def step_e2e():
