@@ -513,6 +513,36 @@ def bind_numa(local):
     return info
 
 
+def probe_pcie(torch, local, barrier, mb=256):
+    """Pinned host <-> device copy bandwidth of THIS rank while every rank does the same (barrier on both sides): names the
+    limiter of the e2e legs - at N = 8 the ranks share the box's host-memory / PCIe root bandwidth."""
+    try:
+        n = mb << 20
+        h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        d_a = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local}")
+        d_b = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local}")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        out = {}
+        for name, both in (("h2d", (True, False)), ("d2h", (False, True)), ("duplex", (True, True))):
+            for rep in range(2):           # first repetition warms up
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(4):
+                    if both[0]:
+                        with torch.cuda.stream(s1):
+                            d_a.copy_(h_in, non_blocking=True)
+                    if both[1]:
+                        with torch.cuda.stream(s2):
+                            h_out.copy_(d_b, non_blocking=True)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            out[name + "_gbs"] = round(4 * n * (both[0] + both[1]) / dt / 1e9, 1)
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:120]}
+
+
 def kernel_table(kstats, peak, traffic, top=10):
     """[{kernel, ms, launches, share, bytes_per_launch, gbs, frac, traffic}] sorted by time.  bytes = the engine's own
     algorithmic-byte count per kernel name (sigma_kernel_stats; formulas in DESIGN.md 3)."""
@@ -698,6 +728,10 @@ def main():
         return batch_main(a, torch, dist, barrier, rank, world, local)
 
     from parafrost_b200 import replicas
+    pcie = probe_pcie(torch, local, barrier)
+    pcie_sum = None
+    if "duplex_gbs" in pcie:
+        _, pcie_sum = replicas.reduce_timing(dist, 0.0, float(pcie["duplex_gbs"]), device="cuda")
     m = measure(a, torch, a.workload, rank, world, local, barrier, a.steps, a.warmup, a.pipeline)
     # units: literals of the input formula simplified (one simplify() call = one pass over the formula, however many rounds)
     ms, lit_all = replicas.reduce_timing(dist, m["ms"], float(m["L0"]), device="cuda")      # max over ranks, units summed
@@ -718,7 +752,9 @@ def main():
         e2e_serial = lit_all * steps / (ms_e2e * 1e-3)
         e2e = {"value": e2e_serial, "unit": UNIT, "ms_per_step": ms_e2e / steps, "mode": "one context: load -> run -> store, nothing overlapped",
                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
-               "api": "sigma_load (pinned host CSR) -> sigma_run -> sigma_store_compact (bits, sizes, literals, eliminated, witness stack, trail to pinned host)"}
+               "api": "sigma_load (pinned host CSR) -> sigma_run -> sigma_store_compact (bits, sizes, literals, eliminated, witness stack, trail to pinned host)",
+               "pcie_probe": {**pcie, "all_ranks_duplex_gbs": pcie_sum,
+                              "note": "pinned host <-> device copies of rank 0 while all ranks copy; a step moves h2d + d2h bytes per rank"}}
         if ms_pipe:
             e2e_pipe = lit_all / (ms_pipe * 1e-3)
             e2e["serial"] = {"value": e2e_serial, "ms_per_step": ms_e2e / steps}

@@ -64,7 +64,8 @@ typedef struct sigma_opts {
     uint32_t bce_max_occurs;    /* --bcemaxoccurs = 3000 */
     uint32_t sh_max_bve_out1;   /* SH_MAX_BVE_OUT1 of the replaced build: 250 (EXTSHMEM) / 190 */
     int32_t  sigma_calls;       /* stats.sigma.calls of this call: 1 = preprocessing */
-    int32_t  final_gc;          /* compact before store (simplify(skip_transfer_to_host)) */
+    int32_t  final_gc;          /* reserved, not read: every store entry point and sigma_continue compact on the way out, so the
+                                   reallocCNF(true) of simplify(skip_transfer_to_host) (simplify.cu:224-226) has no counterpart to switch */
     int32_t  profile;           /* -profilegpu: per-stage CUDA-event times */
     int32_t  aggr_cnf_sort;     /* -aggresivesort (off): clauses leave in OLIST_CMP order (cnf.cu:232-233, key.cuh:67-83) */
     int32_t  proof_en;          /* -proof (off): device DRAT stream (proof.cu, proofutils.cuh); set before sigma_load */

@@ -649,9 +649,14 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
     if (!staged) return;
     __syncthreads();
     const u32 total = tileTotal;
-    for (u32 t = threadIdx.x; t < total; t += OT_T) {
-        const uint2 pr = stage[t];
-        pairs[t + delta[pr.x >> shift]] = pr;
+    for (u32 t0 = threadIdx.x; t0 < total; t0 += 4 * OT_T) {   // four pairs in flight per thread: the look-ups are shared-memory latency
+        uint2 pr[4]; u32 d[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const u32 t = t0 + k * OT_T; pr[k] = t < total ? stage[t] : make_uint2(0, 0); }
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = delta[min(pr[k].x >> shift, NB - 1)];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const u32 t = t0 + k * OT_T; if (t < total) pairs[t + d[k]] = pr[k]; }
     }
 }
 
