@@ -347,6 +347,111 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place_big(const uint2* __r
     }
 }
 
+// ------------------------------------------------------------------ placement with the bulk-copy engine (sm_90+ / sm_100a)
+// k_ot_place is bound by the latency of its pair loads (ncu: 22 of 40 stall cycles per issue are long-scoreboard) and ends
+// with 1024 threads copying a contiguous window out of shared memory.  Both are what the TMA unit is for:
+//   * the bucket's pairs - one contiguous, 16-byte-alignable range of otPairs[] - arrive through `cp.async.bulk` into a
+//     two-stage shared-memory ring (16 KB per stage), completion signalled on an mbarrier; the 1024 threads only ever
+//     read shared memory, the next chunk is in flight while the current one is placed;
+//   * the finished window leaves as ONE `cp.async.bulk` shared -> global store (the window is laid out with the same
+//     16-byte phase as its destination; the unaligned head and tail - at most 3 entries each - are stored by threads).
+// Same result as k_ot_place (list order inside a bucket is arbitrary in both: shared-memory atomics hand out the slots).
+#define PLACE_CH 2048u   // pairs per ring stage
+__device__ __forceinline__ u32 smemU32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbarExpectTx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smemU32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gsrc, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemU32(smemDst)), "l"(gsrc), "r"(bytes), "r"(smemU32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulkStore(void* gdst, const void* smemSrc, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smemU32(smemSrc)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(PLACE_THREADS) k_ot_place_tma(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
+                                                                u32 shift, u32 window, u32* __restrict__ otSize, u32* __restrict__ occurs,
+                                                                u32* __restrict__ big, u32* nBig) {
+    extern __shared__ __align__(128) u32 smem[];
+    const u32 W = 1u << shift;
+    u32* cur = smem;                                      // [W] list cursors
+    u32* win = smem + W;                                  // [window + 8] staged entries, same 16-byte phase as occurs + p0
+    uint2* ring = (uint2*)(smem + W + window + 8);        // [2][PLACE_CH]
+    u64* bar = (u64*)(ring + 2 * PLACE_CH);               // [2]
+    const u32 lit0 = blockIdx.x << shift;
+    const u32 litEnd = min(lit0 + W, ND);
+    const u32 p0 = otStart[lit0], p1 = otStart[litEnd];
+    const u32 len = p1 - p0;
+    if (len > window) {
+        if (threadIdx.x == 0) {
+            u32 S = (len + PLACE_UNIT - 1) / PLACE_UNIT;
+            S = S > PLACE_SPLIT ? PLACE_SPLIT : S;
+            const u32 base = atomicAdd(nBig, S);
+            for (u32 s = 0; s < S; s++) big[base + s] = blockIdx.x | (s << 13) | (S << 19);
+        }
+        for (u32 k = threadIdx.x; lit0 + k < litEnd; k += PLACE_THREADS) otSize[lit0 + k] = 0;
+        return;
+    }
+    const u32 nl = litEnd - lit0;
+    const u32 a = p0 & 3u;                                // entry k of the window sits at win[a + k]
+    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) cur[k] = otStart[lit0 + k] - p0 + a;
+    // the pair range, widened to 16-byte alignment (a pair is 8 bytes): [q0, q1) contains [p0, p1)
+    const u32 q0 = p0 & ~1u, q1 = (p1 + 1u) & ~1u;
+    const u32 nCh = (q1 - q0 + PLACE_CH - 1) / PLACE_CH;
+    if (threadIdx.x == 0) {
+        mbarInit(&bar[0], 1); mbarInit(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (u32 c = 0; c < 2 && c < nCh; c++) {
+            const u32 n = min(PLACE_CH, q1 - (q0 + c * PLACE_CH));
+            mbarExpectTx(&bar[c], n * 8u);
+            bulkLoad(ring + c * PLACE_CH, pairs + q0 + c * PLACE_CH, n * 8u, &bar[c]);
+        }
+    for (u32 c = 0; c < nCh; c++) {
+        const u32 st = c & 1u;
+        mbarWait(&bar[st], (c >> 1) & 1u);
+        const u32 base = q0 + c * PLACE_CH;
+        const u32 n = min(PLACE_CH, q1 - base);
+        const uint2* src = ring + st * PLACE_CH;
+        for (u32 j = threadIdx.x; j < n; j += PLACE_THREADS) {
+            const u32 gidx = base + j;
+            if (gidx >= p0 && gidx < p1) { const uint2 p = src[j]; win[atomicAdd(&cur[p.x - lit0], 1u)] = p.y; }
+        }
+        __syncthreads();   // every reader of this stage is done: it may be refilled
+        if (threadIdx.x == 0 && c + 2 < nCh) {
+            const u32 n2 = min(PLACE_CH, q1 - (base + 2 * PLACE_CH));
+            mbarExpectTx(&bar[st], n2 * 8u);
+            bulkLoad(ring + st * PLACE_CH, pairs + base + 2 * PLACE_CH, n2 * 8u, &bar[st]);
+        }
+    }
+    // window -> occurs[p0 .. p1): the 16-byte-aligned middle as one bulk store, head and tail by threads
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of win[] -> visible to the bulk engine
+    __syncthreads();
+    const u32 k0 = (4u - a) & 3u;                          // first entry whose global index is a multiple of 4
+    const u32 mid = len > k0 ? ((len - k0) & ~3u) : 0u;
+    if (threadIdx.x == 0 && mid) {
+        for (u32 o = 0; o < mid; o += 8192u) bulkStore(occurs + p0 + k0 + o, win + a + k0 + o, min(8192u, mid - o) * 4u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (threadIdx.x < k0 && threadIdx.x < len) occurs[p0 + threadIdx.x] = win[a + threadIdx.x];            // head: < 4 entries
+    for (u32 k = k0 + mid + threadIdx.x; k < len; k += PLACE_THREADS) occurs[p0 + k] = win[a + k];       // tail: < 4 entries (or everything when mid == 0)
+    for (u32 k = threadIdx.x; k < nl; k += PLACE_THREADS) otSize[lit0 + k] = cur[k] - (otStart[lit0 + k] - p0 + a);
+    if (threadIdx.x == 0 && mid) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 void launchScatter(Ctx* c) {
     const u32 n = c->hdc->numCls;
     // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
@@ -649,14 +754,9 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
     if (!staged) return;
     __syncthreads();
     const u32 total = tileTotal;
-    for (u32 t0 = threadIdx.x; t0 < total; t0 += 4 * OT_T) {   // four pairs in flight per thread: the look-ups are shared-memory latency
-        uint2 pr[4]; u32 d[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const u32 t = t0 + k * OT_T; pr[k] = t < total ? stage[t] : make_uint2(0, 0); }
-#pragma unroll
-        for (int k = 0; k < 4; k++) d[k] = delta[min(pr[k].x >> shift, NB - 1)];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const u32 t = t0 + k * OT_T; if (t < total) pairs[t + d[k]] = pr[k]; }
+    for (u32 t = threadIdx.x; t < total; t += OT_T) {   // (four-way unrolling measured no faster: profiles/r02_ab_c10.jsonl)
+        const uint2 pr = stage[t];
+        pairs[t + delta[pr.x >> shift]] = pr;
     }
 }
 
@@ -771,7 +871,16 @@ static void launchScatter2(Ctx* c, u32 n) {
     const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
     u32* nBig = &c->dc->scratch[7];
     cudaMemsetAsync(nBig, 0, 4, c->stream);
-    LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
+    static const int placeTma = getenv("SIGMA_OT_TMA") ? atoi(getenv("SIGMA_OT_TMA")) : 1;   // 0: the LDG / STG placement (A/B measurements)
+    if (placeTma && shift <= 12) {
+        if (!c->attrTma) {
+            cudaFuncSetAttribute(k_ot_place_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + 8 + (1 << 12)) + 16 * PLACE_CH + 64);
+            c->attrTma = true;
+        }
+        const size_t tmaSmem = 4 * ((size_t)PLACE_WINDOW + 8 + (1u << shift)) + 16 * (size_t)PLACE_CH + 64;
+        LAUNCH(c, k_ot_place_tma, NB, PLACE_THREADS, tmaSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
+    } else
+        LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
     KB(c, 8.0 * c->numLiterals + 4.0 * c->numLiterals + 8.0 * c->ND);   // pairs in, list entries out, list bounds
     LAUNCH(c, k_ot_place_big, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs, c->otBig, nBig);
 }
