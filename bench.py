@@ -687,7 +687,7 @@ def main():
     ap.add_argument("--impl", default="sigma-b200", choices=["sigma-b200", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--batch", type=int, default=64, help="cfg5: number of instances in the batch")
-    ap.add_argument("--pipeline", type=int, default=3,
+    ap.add_argument("--pipeline", type=int, default=4,
                     help="K >= 2: e2e steps are also dealt to K engine contexts on the GPU (parafrost_b200.replicas.Pipeline), so that "
                          "copies and kernels of neighbouring steps overlap; 0/1: one context only")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; the line says so)")

@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place_big(const uint2* __r
 //   * the finished window leaves as ONE `cp.async.bulk` shared -> global store (the window is laid out with the same
 //     16-byte phase as its destination; the unaligned head and tail - at most 3 entries each - are stored by threads).
 // Same result as k_ot_place (list order inside a bucket is arbitrary in both: shared-memory atomics hand out the slots).
+// Built and measured in round 2, NOT the default: 15 % slower than k_ot_place (see launchScatter2); SIGMA_OT_TMA=1 selects it.
 #define PLACE_CH 2048u   // pairs per ring stage
 __device__ __forceinline__ u32 smemU32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(bar)), "r"(count)); }
@@ -871,7 +872,9 @@ static void launchScatter2(Ctx* c, u32 n) {
     const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
     u32* nBig = &c->dc->scratch[7];
     cudaMemsetAsync(nBig, 0, 4, c->stream);
-    static const int placeTma = getenv("SIGMA_OT_TMA") ? atoi(getenv("SIGMA_OT_TMA")) : 1;   // 0: the LDG / STG placement (A/B measurements)
+    // measured (profiles/r02_ab_tma_c11.jsonl, identical results): 0.373 vs 0.324 ms on cfg2, 1.45 vs 1.29 ms on cfg3 - the plain kernel
+    // already keeps 4 x 1024 pair loads in flight per SM, the ring adds a CTA barrier per 16 KB chunk.  Opt-in.
+    static const int placeTma = getenv("SIGMA_OT_TMA") ? atoi(getenv("SIGMA_OT_TMA")) : 0;
     if (placeTma && shift <= 12) {
         if (!c->attrTma) {
             cudaFuncSetAttribute(k_ot_place_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + 8 + (1 << 12)) + 16 * PLACE_CH + 64);
