@@ -1424,62 +1424,45 @@ __global__ void __launch_bounds__(256) k_ere_pairs(GT<GS> g, EreQueue Q, const u
 #pragma unroll
         for (int o = GS / 2; o; o >>= 1) { minP = min(minP, __shfl_xor_sync(FULL, minP, o, GS)); minN = min(minN, __shfl_xor_sync(FULL, minN, o, GS)); }
         if ((int)minP > clause_max || (int)minN > clause_max) continue;
-        // pairs (i, j): i walks the positive list uniformly over the group (header and literals of the positive clause are
-        // broadcast loads, the hash-bit positions of its literals are packed once per i), the lanes stride over the negative
-        // list.  When the negative list fits two entries per lane and nothing is deleted during this pass (queued mode), its
-        // headers stay in registers across all i: the signature filter below - where most pairs of a uniform k-SAT formula
-        // end - then runs without a single load.
-        const bool cacheN = Q.items != nullptr && fs <= 2u * GS;
-        u32 cN0 = 0, cN1 = 0;
-        uint4 hN0 = make_uint4(0, 0, 0, CB_DELETED), hN1 = hN0;
-        if (cacheN) {
-            if (lane < fs) { cN0 = N[lane]; hN0 = g.hdr[cN0]; }
-            if (lane + GS < fs) { cN1 = N[lane + GS]; hN1 = g.hdr[cN1]; }
-        }
-        for (u32 i = 0; i < ds; i++) {
-            const u32 ciP = P[i];
+        // pairs (i, j) in pos-major order, lane-strided; the indices advance without a division.  (A variant with the positive
+        // clause uniform over the group and the negative headers cached in registers measured 15 % SLOWER on cfg2 -
+        // profiles/r02_ab_c12.jsonl: lanes idle on the second pass of a 52-entry list, no parallelism over i.)
+        u32 i = lane / fs, j = lane - i * fs;
+        for (; i < ds; ereAdvance(i, j, (u32)GS, fs)) {
+            const u32 ciP = P[i], ciN = N[j];
             const uint4 hp = g.hdr[ciP];
             if (C_DELETED(hp.w)) continue;
+            const uint4 hn = g.hdr[ciN];
+            if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
             const u32* a = g.pool + hp.x; const int n1 = (int)hp.y;
-            unsigned long long packA = 0; u32 nA = 0;
-            const bool longA = n1 > 13;
-            if (!longA)
-                for (int q = 0; q < n1; q++) { const u32 l = a[q]; if (LABS(l) != v) { packA |= (unsigned long long)(l & 31u) << (5u * nA); nA++; } }
-            for (u32 j = lane, t = 0; j < fs; j += GS, t++) {
-                u32 ciN; uint4 hn;
-                if (cacheN) { ciN = t ? cN1 : cN0; hn = t ? hN1 : hN0; }
-                else { ciN = N[j]; hn = g.hdr[ciN]; }
-                if (C_DELETED(hn.w) || (int)(hp.y + hn.y - 2) > clause_max) continue;
-                const u32* b = g.pool + hn.x; const int n2 = (int)hn.y;
-                {   // cheapest filter first: bounds of the resolvent length from the two signatures alone.  A literal
-                    // of a can only be shared with b if its hash bit is set in b's signature, so at most U
-                    // literals merge and the length lies in [n1+n2-2-U, n1+n2-2]; no live clause of such a
-                    // size -> nothing can equal this resolvent (most pairs of a uniform k-SAT formula stop here)
-                    u32 U = 0;
-                    if (!longA) { unsigned long long pk = packA; for (u32 q = 0; q < nA; q++) { U += (hn.z >> (u32)(pk & 31u)) & 1u; pk >>= 5; } }
-                    else for (int q = 0; q < n1; q++) { const u32 l = a[q]; if (LABS(l) != v) U += (hn.z >> (l & 31u)) & 1u; }
-                    const u32 lenMax = (u32)(n1 + n2 - 2);
-                    if (U > (u32)(n2 - 1)) U = (u32)(n2 - 1);
-                    bool any = false;
-                    for (u32 sN = lenMax - U; sN <= lenMax; sN++) { const u32 sb = sN < 255u ? sN : 255u; any |= (sizeMask[sb >> 5] >> (sb & 31u)) & 1u; }
-                    if (!any) continue;
-                }
-                u32 len, first, last, sig;
-                if (!ereKey(a, n1, b, n2, v, len, first, last, sig) || len <= 1) continue;
-                // filters: is there a live clause of this size at all / with this key at all?
-                { const u32 sb = len < 255u ? len : 255u; if (!((sizeMask[sb >> 5] >> (sb & 31u)) & 1u)) continue; }
-                { const u32 hb = keyHash(len, first, last, sig) & g.bloomMask; if (!((g.bloom[hb >> 5] >> (hb & 31u)) & 1u)) continue; }
-                u32 minsize;
-                const u32 best = ereBest(g.otSize, a, n1, b, n2, v, minsize);
-                if (!minsize) continue;
-                if (Q.items) {
-                    const u32 slot = atomicAdd(Q.count, 1u);
-                    if (slot < Q.cap) { Q.items[3 * slot] = ciP; Q.items[3 * slot + 1] = ciN; Q.items[3 * slot + 2] = v; Q.need[best] = 1; }
-                    else *Q.overflow = 1u;
-                } else {
-                    const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
-                    ereSearchDelete(g, a, n1, b, n2, v, len, first, last, sig, type, best, minsize);
-                }
+            const u32* b = g.pool + hn.x; const int n2 = (int)hn.y;
+            {   // cheapest filter first: bounds of the resolvent length from the two signatures alone.  A literal
+                // of a can only be shared with b if its hash bit is set in b's signature, so at most U
+                // literals merge and the length lies in [n1+n2-2-U, n1+n2-2]; no live clause of such a
+                // size -> nothing can equal this resolvent (most pairs of a uniform k-SAT formula stop here)
+                u32 U = 0;
+                for (int q = 0; q < n1; q++) { const u32 l = a[q]; if (LABS(l) != v) U += (hn.z >> (l & 31u)) & 1u; }
+                const u32 lenMax = (u32)(n1 + n2 - 2);
+                if (U > (u32)(n2 - 1)) U = (u32)(n2 - 1);
+                bool any = false;
+                for (u32 sN = lenMax - U; sN <= lenMax; sN++) { const u32 sb = sN < 255u ? sN : 255u; any |= (sizeMask[sb >> 5] >> (sb & 31u)) & 1u; }
+                if (!any) continue;
+            }
+            u32 len, first, last, sig;
+            if (!ereKey(a, n1, b, n2, v, len, first, last, sig) || len <= 1) continue;
+            // filters: is there a live clause of this size at all / with this key at all?
+            { const u32 sb = len < 255u ? len : 255u; if (!((sizeMask[sb >> 5] >> (sb & 31u)) & 1u)) continue; }
+            { const u32 hb = keyHash(len, first, last, sig) & g.bloomMask; if (!((g.bloom[hb >> 5] >> (hb & 31u)) & 1u)) continue; }
+            u32 minsize;
+            const u32 best = ereBest(g.otSize, a, n1, b, n2, v, minsize);
+            if (!minsize) continue;
+            if (Q.items) {
+                const u32 slot = atomicAdd(Q.count, 1u);
+                if (slot < Q.cap) { Q.items[3 * slot] = ciP; Q.items[3 * slot + 1] = ciN; Q.items[3 * slot + 2] = v; Q.need[best] = 1; }
+                else *Q.overflow = 1u;
+            } else {
+                const u32 type = (C_LEARNT(hp.w) || C_LEARNT(hn.w)) ? CB_LEARNT : 0u;
+                ereSearchDelete(g, a, n1, b, n2, v, len, first, last, sig, type, best, minsize);
             }
         }
     }
