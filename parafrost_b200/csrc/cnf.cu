@@ -761,6 +761,136 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
     }
 }
 
+// Version 3 of the partition: the same tile algorithm on PERSISTENT CTAs (one per SM) with the tiles software-pipelined.
+// k_ot_part2 holds ~220 KB of shared memory, so one CTA lives on an SM and its phases run one after the other: header
+// load -> literal load (dependent) -> row scan -> staging -> copy-out, and the next CTA cannot start before the last
+// store has drained (ncu: long-scoreboard + barrier + drain = half of the stall cycles, LSU pipe 48 % busy).  Here the
+// loads of tile i+1 are in flight while tile i is copied out: its two matrix rows come in through cp.async
+// (global -> shared memory, no registers), headers and ranks are issued before the first half of the copy-out and the
+// literals - which need the headers - before the second half; the registers of tile i are dead by then.
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gsrc) {
+    const u32 d = (u32)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int CPT, int KEEP>
+__global__ void __launch_bounds__(OT_T, 1) k_ot_part3(const uint4* __restrict__ hdr, const u32* __restrict__ pool, const uint4* __restrict__ rk8, u32 n,
+                                                   u32 shift, u32 NB, u32 NBp, const u32* __restrict__ cntMat, const u32* __restrict__ runMat,
+                                                   u32 stageCap, u32 tiles, uint2* __restrict__ pairs) {
+    extern __shared__ __align__(16) u32 sm3[];
+    u32* rowC = sm3;                 // [NBp] this tile's run lengths   (cp.async target, 16-byte aligned)
+    u32* rowG = sm3 + NBp;           // [NBp] this tile's run starts
+    u32* tileOff = sm3 + 2 * NBp;    // [NB + 1]
+    u32* delta = tileOff + NB + 1;  // [NB]
+    u32* cntL2 = delta + NB;        // [NB]
+    uint2* stage = (uint2*)(sm3 + ((2 * NBp + 3 * NB + 2) & ~1u));
+    __shared__ u32 warpTot[32];
+    __shared__ u32 tileTotal, nonEmpty;
+    const u32 per = (NB + OT_T - 1) / OT_T;   // consecutive buckets per thread, <= 8
+    const u32 b0 = threadIdx.x * per;
+    u32 tile = blockIdx.x;
+    if (tile >= tiles) return;
+    u32 off[CPT], sz[CPT]; uint4 rk[CPT]; u32 lk[CPT][KEEP];
+#define PART3_LOAD_HDR(T_)                                                                                        \
+    _Pragma("unroll") for (int k = 0; k < CPT; k++) {                                                             \
+        const u32 i = (T_) * (OT_T * CPT) + k * OT_T + threadIdx.x;                                               \
+        sz[k] = 0; off[k] = 0; rk[k] = make_uint4(0, 0, 0, 0);                                                    \
+        if (i < n) { const uint4 h = hdr[i]; if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; rk[k] = rk8[i]; } } \
+    }
+#define PART3_LOAD_ROWS(T_)                                                                                       \
+    do {                                                                                                          \
+        const u32* rc = cntMat + (size_t)(T_) * NBp; const u32* rg = runMat + (size_t)(T_) * NBp;                 \
+        for (u32 w = threadIdx.x * 4; w < NBp; w += OT_T * 4) { cpAsync16(rowC + w, rc + w); cpAsync16(rowG + w, rg + w); } \
+        cpAsyncCommit();                                                                                          \
+    } while (0)
+#define PART3_LOAD_LITS()                                                                                         \
+    _Pragma("unroll") for (int k = 0; k < CPT; k++) {                                                             \
+        const u32* l = pool + off[k];                                                                             \
+        _Pragma("unroll") for (int q = 0; q < KEEP; q++) lk[k][q] = ((u32)q < sz[k] && sz[k] <= 8u) ? l[q] : 0u;  \
+    }
+    PART3_LOAD_HDR(tile);
+    PART3_LOAD_ROWS(tile);
+    PART3_LOAD_LITS();
+    for (;;) {
+        if (threadIdx.x == 0) nonEmpty = 0;
+        bool longHere = false;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) longHere |= sz[k] > 8u;
+        cpAsyncWaitAll();
+        const int anyLong = __syncthreads_or(longHere);   // rows of this tile visible to every thread
+        if (anyLong) for (u32 b = threadIdx.x; b < NB; b += OT_T) cntL2[b] = 0;
+        u32 cq[8];
+        u32 mine = 0, used = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { const u32 b = b0 + q; cq[q] = ((u32)q < per && b < NB) ? rowC[b] : 0u; mine += cq[q]; used += cq[q] != 0u; }
+        const u32 incl = warpIncl(mine);
+        used = warpSum(used);
+        if ((threadIdx.x & 31u) == 0 && used) atomicAdd(&nonEmpty, used);
+        if ((threadIdx.x & 31u) == 31u) warpTot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const u32 t = warpTot[threadIdx.x];
+            const u32 ti = warpIncl(t);
+            warpTot[threadIdx.x] = ti - t;
+            if (threadIdx.x == 31) { tileTotal = ti; tileOff[NB] = ti; }
+        }
+        __syncthreads();
+        u32 run = warpTot[threadIdx.x >> 5] + incl - mine;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const u32 b = b0 + q;
+            if ((u32)q < per && b < NB) { tileOff[b] = run; delta[b] = rowG[b] - run; run += cq[q]; }
+        }
+        __syncthreads();
+        const u32 total = tileTotal;
+        const bool staged = total <= stageCap && total < 12u * nonEmpty;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const u32 i = tile * (OT_T * CPT) + k * OT_T + threadIdx.x;
+            const u32* l = pool + off[k];
+            if (sz[k] <= 8u) {
+                const u32 rw[4] = {rk[k].x, rk[k].y, rk[k].z, rk[k].w};
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if ((u32)q < sz[k]) {
+                        const u32 lit = q < KEEP ? lk[k][q < KEEP ? q : 0] : l[q];
+                        const u32 b = lit >> shift;
+                        const u32 pos = tileOff[b] + ((rw[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu);
+                        if (staged) stage[pos] = make_uint2(lit, i);
+                        else pairs[pos + delta[b]] = make_uint2(lit, i);
+                    }
+            } else
+                for (u32 q = 0; q < sz[k]; q++) {
+                    const u32 lit = l[q];
+                    const u32 b = lit >> shift;
+                    const u32 pos = tileOff[b + 1] - 1u - atomicAdd(&cntL2[b], 1u);
+                    if (staged) stage[pos] = make_uint2(lit, i);
+                    else pairs[pos + delta[b]] = make_uint2(lit, i);
+                }
+        }
+        __syncthreads();   // the stage is complete; rowC / rowG and this tile's registers are free
+        const u32 next = tile + gridDim.x;
+        const bool more = next < tiles;
+        if (more) { PART3_LOAD_ROWS(next); PART3_LOAD_HDR(next); }
+        asm volatile("" ::: "memory");
+        const u32 half = staged ? ((total >> 1) & ~(u32)(OT_T - 1)) : 0u;
+        u32 t = threadIdx.x;
+        for (; t < half; t += OT_T) { const uint2 pr = stage[t]; pairs[t + delta[pr.x >> shift]] = pr; }
+        asm volatile("" ::: "memory");
+        if (more) { PART3_LOAD_LITS(); }
+        asm volatile("" ::: "memory");
+        if (staged) for (; t < total; t += OT_T) { const uint2 pr = stage[t]; pairs[t + delta[pr.x >> shift]] = pr; }
+        if (!more) break;
+        tile = next;
+        __syncthreads();   // every reader of stage / delta is done before the next tile rewrites them
+    }
+#undef PART3_LOAD_HDR
+#undef PART3_LOAD_ROWS
+#undef PART3_LOAD_LITS
+}
+
 // per-literal histogram of one bucket = hist[] (and, scanned, otStart[]) of its literal range: counted from the bucket's
 // pairs with shared-memory atomics - the global reductions of the version-1 histogram pass are gone.  Light (W counters),
 // several CTAs per SM; oversized buckets just loop longer.  k_ot_place / k_ot_place_big then run unchanged.
@@ -827,6 +957,8 @@ static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 num
         cudaFuncSetAttribute(k_ot_count<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_part2<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_part2<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part3<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part3<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
         cudaFuncSetAttribute(k_ot_lithist, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
         c->attrOT2 = true;
@@ -857,7 +989,20 @@ static void launchScatter2(Ctx* c, u32 n) {
     // shared memory of k_ot_part2: 3 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
     const size_t partFixed = 4 * (((size_t)3 * NB + 2) & ~(size_t)1) + 16;
     const u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
-    if (c->otCPT == 5)
+    // version 3 (persistent, software-pipelined tiles) needs two more rows of shared memory; it is used when its stage still
+    // holds a whole tile of the loaded formula, otherwise version 2 (SIGMA_OT_PART3=0 forces version 2 for A/B runs)
+    static const int part3 = getenv("SIGMA_OT_PART3") ? atoi(getenv("SIGMA_OT_PART3")) : 1;
+    const size_t p3Fixed = 4 * (((size_t)2 * NBp + 3 * NB + 2) & ~(size_t)1) + 16;
+    const u32 p3Cap = p3Fixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (p3Fixed < 220 * 1024 ? (u32)((220 * 1024 - p3Fixed) / 8) : 0u);
+    const u64 tileLits = c->numClauses ? (u64)OT_T * c->otCPT * c->numLiterals / c->numClauses : 0;
+    if (part3 && tiles > 148 && (p3Cap >= stageCap || tileLits + tileLits / 8 <= p3Cap)) {
+        if (c->otCPT == 5)
+            LAUNCH(c, (k_ot_part3<5, 3>), 148, OT_T, p3Fixed + 8 * (size_t)p3Cap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
+                   p3Cap, tiles, c->otPairs);
+        else
+            LAUNCH(c, (k_ot_part3<3, 5>), 148, OT_T, p3Fixed + 8 * (size_t)p3Cap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
+                   p3Cap, tiles, c->otPairs);
+    } else if (c->otCPT == 5)
         LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
                stageCap, c->otPairs);
     else
