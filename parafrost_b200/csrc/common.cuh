@@ -186,7 +186,6 @@ struct Ctx {
     u32 lastElectedCount;
     u32 lastPropSeeds, lastPropTrail0, lastPropTotal;   // the last prop(): BVE-origin units, trail size before it, entries it appended
     bool varcoreDead, attrSort, attrElim, attrOT;
-    bool veFused;      // launchSUB ran BVE phase 1 of the small classes together with SUB (elim.cu: k_subve_local)
     bool histFresh;    // hist[] / key[] were produced by k_awaken and the store is untouched since
     bool countsFresh;  // hdc->liveCls / liveLits describe the clause store as it is now
     bool otValid;      // the occurrence table built last round still describes the clause store (api.cu)

@@ -1218,193 +1218,7 @@ __global__ void __launch_bounds__(128) k_sub_local(GT<GS> g, const u32* __restri
         updateOL(g, n);
     }
 }
-// ------------------------------------------------------------------ SUB + BVE phase 1 fused on ONE local copy (4- and 8-lane classes)
-// sub_k and ve_k_1 visit the same elected variables back to back (elimination.cu:131-154 after subsume.cuh:402-484) and both
-// start with the same gather: list entries -> headers -> literals of the variable's <= MAXC clauses.  The elected variables
-// share no clause, so "SUB of every variable, then phase 1 of every variable" and "SUB then phase 1, variable by variable"
-// read and write the same clauses in the same order.  Here the clauses are gathered once; SUB runs on the copy, its
-// outcome goes back (strengthened / subsumed clauses, units) and updateOL is done from what the group already knows -
-// the kept slots are written straight over the global lists, no second walk list -> header -> mark -; the decision tree
-// of phase 1 then runs on the same copy over the compacted slot lists.  Not used with the DRAT stream or the LOGREDALL
-// tables (both observe the state between the two stages).
-// `redoBig`: variables with a clause longer than VE_LOCAL_K literals - k_sub<32> and k_ve_phase1<32> take them;
-// `redo`: function-table candidates of phase 1 (SUB already done) - k_ve_phase1<32> only.
-template <int GS>
-__global__ void __launch_bounds__(128) k_subve_local(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount,
-                                                     u32* __restrict__ redo, u32* redoCount, u32* __restrict__ redoBig, u32* redoBigCount) {
-    constexpr int MAXC = GS == 4 ? (int)BIN_T4 : (int)BIN_T8;
-    constexpr int NG = 128 / GS;
-    constexpr int CNT = MAXC / GS;
-    __shared__ uint4 s_h[NG][MAXC];
-    __shared__ u32 s_l[NG][MAXC * VE_LOCAL_K];
-    __shared__ u32 s_w0[GS == 4 ? NG : 1][MAXC];   // marks before phase 1 (the 8-lane class keeps them in registers: 48 KB of static shared memory)
-    __shared__ u32 s_out[NG][VE_SLICE_SMALL];
-    __shared__ u32 s_lp[NG][MAXC], s_ln[NG][MAXC];   // slot lists after SUB (positive / negative side)
-    __shared__ u32 s_iota[MAXC];
-    if (threadIdx.x < MAXC) s_iota[threadIdx.x] = threadIdx.x;
-    __syncthreads();
-    const u32 gidx = threadIdx.x / GS;
-    uint4* lh = s_h[gidx]; u32* ll = s_l[gidx]; u32* w0 = s_w0[GS == 4 ? gidx : 0]; u32* out_c = s_out[gidx];
-    u32* lp = s_lp[gidx]; u32* ln = s_ln[gidx];
-    GT<GS> lg = g;
-    lg.hdr = lh; lg.pool = ll;
-    const u32 groupsPerGrid = (gridDim.x * blockDim.x) / GS;
-    const u32 count = *wlCount;
-    for (u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) / GS; wi < count; wi += groupsPerGrid) {
-        const u32 tid = wl[wi];
-        const u32 x = g.elected[tid], p = V2L(x), n = p | 1u;
-        u32 np = g.otSize[p], nn = g.otSize[n];
-        const u32 tot = np + nn;
-        u32* Pg = g.occurs + g.otStart[p];
-        u32* Ng = g.occurs + g.otStart[n];
-        // ---- gather (as k_ve_phase1_local)
-        u32 ci[CNT]; uint4 h[CNT];
-        bool big = tot > (u32)MAXC;
-#pragma unroll
-        for (int q = 0; q < CNT; q++) { const u32 j = LANE + q * GS; ci[q] = j < tot && !big ? (j < np ? Pg[j] : Ng[j - np]) : NOVAR; }
-#pragma unroll
-        for (int q = 0; q < CNT; q++) { h[q] = ci[q] != NOVAR ? g.hdr[ci[q]] : make_uint4(0, 0, 0, 0); big |= h[q].y > VE_LOCAL_K; }
-        if (__any_sync(FULL, big)) {
-            if (LANE == 0) redoBig[atomicAdd(redoBigCount, 1u)] = tid;
-            GSYNC();
-            continue;
-        }
-        GSYNC();   // the previous variable's readers of this slice are done
-#pragma unroll
-        for (int q = 0; q < CNT; q++) {
-            const u32 j = LANE + q * GS;
-            if (ci[q] != NOVAR) {
-                const u32* src = g.pool + h[q].x;
-                u32 lv[VE_LOCAL_K];
-#pragma unroll
-                for (int k = 0; k < VE_LOCAL_K; k++) lv[k] = (u32)k < h[q].y ? src[k] : 0u;
-#pragma unroll
-                for (int k = 0; k < VE_LOCAL_K; k++) ll[j * VE_LOCAL_K + k] = lv[k];
-                lh[j] = make_uint4(j * VE_LOCAL_K, h[q].y, h[q].z, h[q].w);
-            }
-        }
-        GSYNC();
-        const u32* P = s_iota; const u32* N = s_iota + np;
-        // ---- SUB on the copy (k_sub_local), its outcome, and updateOL from the group's own knowledge
-        if (!(np > g.k.sub_max_occurs || nn > g.k.sub_max_occurs)) {
-            const u32 nPosUnits = subSide(lg, P, np, N, nn, p, n);
-            const u32 nNegUnits = subSide(lg, N, nn, P, np, n, p);
-            GSYNC();
-            if (nPosUnits || nNegUnits) {   // list order, positive side first: the copy still holds every clause of both lists
-                u32 cursor = reserveUnits(g, nPosUnits + nNegUnits);
-                if (nPosUnits) appendUnits(lg, P, np, cursor);
-                if (nNegUnits) appendUnits(lg, N, nn, cursor);
-            }
-            u32 outP = 0, outN = 0;
-            bool any = false;
-#pragma unroll
-            for (int q = 0; q < CNT; q++) {
-                const u32 j = LANE + q * GS;
-                bool keepP = false, keepN = false;
-                if (ci[q] != NOVAR) {
-                    const uint4 nh = lh[j];
-                    // a molten clause was strengthened: it lost x and leaves the list, un-melted (updateOL, subsume.cuh:293-303)
-                    const u32 wOut = nh.w & ~CB_MOLTEN;
-                    if (nh.y != h[q].y) { u32* dst = g.pool + h[q].x; for (u32 k = 0; k < nh.y; k++) dst[k] = ll[j * VE_LOCAL_K + k]; }
-                    if (nh.y != h[q].y || nh.z != h[q].z || wOut != h[q].w) g.hdr[ci[q]] = make_uint4(h[q].x, nh.y, nh.z, wOut);
-                    const bool keep = !C_MOLTEN(nh.w) && !C_DELETED(nh.w);
-                    any |= !keep;
-                    lh[j].w = wOut;
-                    keepP = keep && j < np; keepN = keep && j >= np;
-                }
-                const u32 mP = BALLOT(keepP), mN = BALLOT(keepN);
-                if (keepP) { const u32 pos = outP + __popc(mP & LTMASK); lp[pos] = j; if (pos != j) Pg[pos] = ci[q]; }
-                if (keepN) { const u32 pos = outN + __popc(mN & LTMASK); ln[pos] = j; if (pos != j - np) Ng[pos] = ci[q]; }
-                outP += __popc(mP); outN += __popc(mN);
-            }
-            if (__any_sync(FULL, any)) {
-                if (LANE == 0) { g.otSize[p] = outP; g.otSize[n] = outN; }
-                np = outP; nn = outN;
-                P = lp; N = ln;
-            }
-            GSYNC();
-        }
-#pragma unroll
-        u32 w0r[GS == 4 ? 1 : CNT];
-#pragma unroll
-        for (int q = 0; q < CNT; q++) {
-            const u32 j = LANE + q * GS;
-            if (ci[q] != NOVAR) { if constexpr (GS == 4) w0[j] = lh[j].w; else w0r[q] = lh[j].w; }
-        }
-        GSYNC();
-        // ---- BVE phase 1 on the copy (k_ve_phase1_local)
-        u32 pOrgs, nOrgs;
-        if (g.k.in_mode) { u32 d; countOrgsLits(lg, P, np, pOrgs, d); countOrgsLits(lg, N, nn, nOrgs, d); }
-        else { pOrgs = np; nOrgs = nn; }
-        u32 elimType = 0, nElements = 0, nAddedCls = 0, nAddedLits = 0, def = 0;
-        bool oblivion = false, record = false, handOver = false;
-        if (!pOrgs || !nOrgs) oblivion = true;
-        else {
-            def = findEquGate(lg, p, n, P, np, N, nn);
-            if (def) {}
-            else if ((pOrgs == 1 || nOrgs == 1) && !countPairs(lg, 0, x, P, np, N, nn, 0, nElements, nAddedCls, nAddedLits)) {
-                if (nAddedCls) { elimType = RES_MASK; record = true; }
-                else oblivion = true;
-            }
-            else {
-                const u32 nClsBefore = pOrgs + nOrgs;
-                elimType = 0; nElements = 0; nAddedCls = 0; nAddedLits = 0;
-                if (nClsBefore > 2) {
-                    if (nOrgs < g.k.sh_max_bve_out1 && findAOGate(lg, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits))
-                        elimType = AOIX_MASK;
-                    else if (!nAddedCls && pOrgs < g.k.sh_max_bve_out1 && findAOGate(lg, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits))
-                        elimType = AOIX_MASK;
-                }
-                if (!elimType && nClsBefore > 3) {
-                    if (findITEGate<GS, true>(lg, p, P, np, n, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
-                    else if (!nAddedCls && findITEGate<GS, true>(lg, n, N, nn, p, P, np, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
-                    else if (findXORGate<GS, true>(lg, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
-                    else if (!nAddedCls && findXORGate<GS, true>(lg, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
-                }
-                if (g.k.ve_fun_en && !elimType && nClsBefore > 2 && funPossible(lg, p, P, np) && funPossible(lg, n, N, nn)) handOver = true;
-                if (!handOver) {
-                    if (!elimType && !nAddedCls && !countPairs(lg, 1, x, P, np, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits))
-                        elimType = RES_MASK;
-                    if (!nAddedCls) oblivion = true;
-                    else if (elimType) record = true;
-                }
-            }
-        }
-        if (handOver) {   // phase 1 left nothing outside the copy: failed gate attempts restored their marks; SUB is done and written
-            if (LANE == 0) redo[atomicAdd(redoCount, 1u)] = tid;
-            GSYNC();
-            continue;
-        }
-        GSYNC();
-#pragma unroll
-        for (int q = 0; q < CNT; q++) {
-            const u32 j = LANE + q * GS;
-            if (ci[q] != NOVAR) {
-                const u32 w = lh[j].w;
-                u32 wb;
-                if constexpr (GS == 4) wb = w0[j]; else wb = w0r[q];
-                if (w != wb) g.hdr[ci[q]].w = w;
-            }
-        }
-        GSYNC();
-        bool eliminatedNow = false;
-        if (oblivion) { toblivionSave(g, p, n, pOrgs, nOrgs, Pg, np, Ng, nn); eliminatedNow = true; }
-        else if (def) {
-            if (pOrgs > nOrgs) saveSide(g, Ng, nn, n, p, nOrgs); else saveSide(g, Pg, np, p, n, pOrgs);
-            substituteSingle(g, p, n, def, Pg, np, Ng, nn);
-            eliminatedNow = true;
-        }
-        if (LANE == 0) {
-            if (record) {
-                g.veType[tid] = ENCODEVARINFO(elimType, nAddedCls, nAddedLits);
-                g.veUcnt[tid] = nElements; g.veRpos[tid] = nAddedCls; g.veRref[tid] = (u64)nAddedLits + (u64)NBUCKETS * nAddedCls;
-            } else { g.veType[tid] = 0; g.veUcnt[tid] = 0; g.veRpos[tid] = 0; g.veRref[tid] = 0; }
-            if (eliminatedNow) g.eliminated[x] |= MELTING_MASK;
-        }
-        GSYNC();
-    }
-}
-
+// the variables handed over by k_sub_local
 // ------------------------------------------------------------------ BCE (blocked.cuh:26-97)
 template <int GS>
 __global__ void __launch_bounds__(128) k_bce(GT<GS> g, const u32* __restrict__ wl, const u32* __restrict__ wlCount) {
@@ -2014,30 +1828,6 @@ void launchSUB(Ctx* c, const KOpts& k) {
     // adder clauses of cfg4 (+50 % on the 8-lane class: fixed 8-word slots, fewer resident CTAs) - profiles/r02_ab_local_c3.jsonl
     static const int subEnv = getenv("SIGMA_SUB_LOCAL") ? atoi(getenv("SIGMA_SUB_LOCAL")) : -1;   // 0 / 1: force (A/B measurements)
     const bool subLocal = subEnv >= 0 ? subEnv != 0 : c->L0 * 10 <= c->C0 * 31;   // decided once per call, from the loaded formula
-    // SUB and BVE phase 1 of the small classes in one kernel, on one gather (k_subve_local); the DRAT stream and the LOGREDALL
-    // tables observe the state between the two stages and keep them apart.  SIGMA_FUSE_SUBVE=0: A/B measurements.
-    static const int fuseEnv = getenv("SIGMA_FUSE_SUBVE") ? atoi(getenv("SIGMA_FUSE_SUBVE")) : 1;
-    c->veFused = false;
-    if (subLocal && fuseEnv && c->o.ve_en && !k.proof_en && !c->o.log_reductions) {
-        static const int veEnv = getenv("SIGMA_VE_LOCAL") ? atoi(getenv("SIGMA_VE_LOCAL")) : -1;
-        if (veEnv != 0) {
-            const u32 E = c->numElected;
-            u32* redo = c->rank;            // rank[] is dead after the election
-            u32* redoCount = &c->dc->bin[3];
-            u32* redoBig = c->sortV;        // the election's blocker array, free until postVE compacts elected[] through it
-            u32* redoBigCount = &c->dc->scratch[10];
-            cudaMemsetAsync(redoBigCount, 0, 4, c->stream);
-            LAUNCH(c, k_subve_local<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount, redoBig, redoBigCount);
-            KB(c, cb.b[0]);
-            LAUNCH(c, k_subve_local<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount, redoBig, redoBigCount);
-            KB(c, cb.b[1]);
-            LAUNCH(c, k_sub<32>, groupGrid(E, 32, 128), 128, 0, asGroup<32>(g), c->sortK, &c->dc->bin[2]);
-            KB(c, cb.b[2]);
-            LAUNCH(c, k_sub<32>, 148, 128, 0, asGroup<32>(g), redoBig, redoBigCount);
-            c->veFused = true;
-            return;
-        }
-    }
     if (subLocal) {
         const u32 E = c->numElected;
         u32* redo = c->rank;       // rank[] is dead after the election
@@ -2064,17 +1854,13 @@ void launchVE(Ctx* c, const KOpts& k) {
     G g = makeG(c, k);
     const u32 E = c->numElected;
     LAUNCH(c, k_ve_reset, 1, 1, 0, c->dc);
-    const bool fused = c->veFused;   // launchSUB ran phase 1 of the small classes with SUB (k_subve_local): its worklists stand
-    c->veFused = false;
-    if (!fused) binElected(c, k, false, true);   // SUB shrank the lists: classes by the current sizes
+    binElected(c, k, false, true);   // SUB shrank the lists: classes by the current sizes
     u32* redo = c->rank;       // rank[] is dead after the election
     u32* redoCount = &c->dc->bin[3];
     const ClassBytes cb1 = classBytes(c);   // + 20 bytes per variable: type, ucnt, rpos, rref (SURVEY 8d "BVE count")
     static const int veEnv = getenv("SIGMA_VE_LOCAL") ? atoi(getenv("SIGMA_VE_LOCAL")) : -1;   // 0 / 1: force (A/B measurements)
     const bool veLocal = veEnv >= 0 ? veEnv != 0 : c->L0 * 10 <= c->C0 * 31;   // see launchSUB
-    if (fused) {
-        LAUNCH(c, k_ve_phase1<32>, 148, 128, 0, asGroup<32>(g), c->sortV, &c->dc->scratch[10], redo, redoCount);   // long clauses in a small class
-    } else if (veLocal) {
+    if (veLocal) {
         LAUNCH(c, k_ve_phase1_local<4>, groupGrid(E, 4, 128), 128, 0, asGroup<4>(g), c->wlA, &c->dc->bin[0], redo, redoCount);
         KB(c, cb1.b[0]);
         LAUNCH(c, k_ve_phase1_local<8>, groupGrid(E, 8, 128), 128, 0, asGroup<8>(g), c->wlB, &c->dc->bin[1], redo, redoCount);
