@@ -574,7 +574,6 @@ static void buildOT(Ctx* c, bool withGC, bool* didGC) {
     }
     if (!c->histFresh || withGC) { StageTimer t(c, ST_VO); launchHistKey(c); }
     c->histFresh = false;
-    if (!otBuildV2()) { StageTimer t(c, ST_VO); scanExclusiveU32(c, c->hist, c->otStart, c->ND, 0, c->otStart + c->ND); }
     { StageTimer t(c, ST_COT); launchScatter(c); }
 }
 

@@ -15,261 +15,37 @@
 
 #include "common.cuh"
 
-// ------------------------------------------------------------------ awaken + prep
-// algorithmic bytes: read 8(C+1) offsets + 4L literals [+4C meta], write 16C headers + 4L literals
-// With hist != NULL the first round's histogram + sort-key pass (k_hist_key) is fused in: the sorted
-// literals are in registers anyway, so the clause store is not read again before the partition.
-__global__ void k_awaken(const u32* __restrict__ inLits, const u64* __restrict__ inOffs, const u32* __restrict__ inMeta,
-                         u64 C, uint4* __restrict__ hdr, u32* __restrict__ pool, u32* __restrict__ hist, uint4* __restrict__ key, u32* flags,
-                         u32 ND, u64 L0) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (u64)gridDim.x * blockDim.x) {
-        const u64 b = inOffs[i];
-        u64 e = inOffs[i + 1];
-        // input validation (the C ABI takes raw buffers): offsets must be monotone and inside the literal array, literals
-        // inside [2, 2V+2).  A bad entry is neutralised (empty clause / literal 2) and flagged: the call fails with
-        // SIGMA_BAD_ARGUMENT at its first read-back instead of indexing outside the tables.
-        if (e < b || e > L0 || e - b >= (1ull << 31)) { atomicOr(flags, 128u); e = b; }
-        const int sz = (int)(e - b);
-        u32* dst = pool + b;
-        u32 sig = 0;
-        if (sz <= 8) {
-            u32 r[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                r[k] = (k < sz) ? inLits[b + k] : 0xFFFFFFFFu;
-                if (k < sz && (r[k] < 2u || r[k] >= ND)) { atomicOr(flags, 128u); r[k] = 2u; }
-            }
-            // odd-even transposition network on 8 registers (padding sorts to the end)
-#pragma unroll
-            for (int pass = 0; pass < 8; pass++) {
-#pragma unroll
-                for (int k = (pass & 1); k + 1 < 8; k += 2) {
-                    const u32 a = r[k], bb = r[k + 1];
-                    r[k] = min(a, bb); r[k + 1] = max(a, bb);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) if (k < sz) { dst[k] = r[k]; sig |= MAPHASH(r[k]); }
-        } else {
-            for (int k = 0; k < sz; k++) {
-                u32 t = inLits[b + k];
-                if (t < 2u || t >= ND) { atomicOr(flags, 128u); t = 2u; }
-                int j = k;
-                for (; j > 0 && t < dst[j - 1]; j--) dst[j] = dst[j - 1];
-                dst[j] = t;
-                sig |= MAPHASH(t);
-            }
-        }
-        if (sz <= 1) sig = 0;  // calcSig leaves the signature untouched for size <= 1 (primitives.cuh:177-185)
-        u32 bits = 0;
-        if (inMeta) {
-            const u32 m = inMeta[i];
-            if (m & CB_LEARNT) bits = m & ~(CB_DELETED | CB_MOLTEN | CB_ADDED);
-        }
-        hdr[i] = make_uint4((u32)b, (u32)sz, sig, bits);
-        if (hist) {
-            for (int k = 0; k < sz; k++) atomicAdd(&hist[dst[k]], 1u);
-            key[i] = make_uint4((u32)sz, sz ? dst[0] : 0u, sz ? dst[sz - 1] : 0u, sig);
-            if (sz >= (1 << 14)) atomicOr(flags, 8u);
-        }
-    }
-}
+// ------------------------------------------------------------------ bucket shape of the occurrence-table build
+// A bucket is a range of W consecutive literals, W = 2^sh or 3 * 2^sh: the 1.5x steps let an average bucket fill the
+// placement window to 55-80 % instead of 35-70 % (uniform 5-SAT at 52 occurrences per literal: 768 literals per bucket
+// instead of 512 - a third fewer buckets, a third longer runs in the partition).  `shape` = sh | three << 8.
+__device__ __host__ __forceinline__ u32 bkW(u32 shape) { return ((shape >> 8) ? 3u : 1u) << (shape & 0xFFu); }
+__device__ __forceinline__ u32 bkOf(u32 lit, u32 shape) { const u32 t = lit >> (shape & 0xFFu); return (shape >> 8) ? t / 3u : t; }
+__device__ __forceinline__ u32 bkLit0(u32 b, u32 shape) { return ((shape >> 8) ? 3u * b : b) << (shape & 0xFFu); }
 
 static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 numClauses);
 static void launchScatter2(Ctx* c, u32 n);
-static bool otV2();
 
+// awaken + prep (prep_cnf_k, cnf.cu:45-53) fused with the first round's counting pass: k_ot_count<CPT, true>
 void launchAwaken(Ctx* c) {
     if (!c->C0) return;
-    if (otV2()) { launchCountPass(c, true, (u32)c->C0, c->L0, c->C0); c->histFresh = true; return; }
-    cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
-    LAUNCH(c, k_awaken, gridFor(c->C0, 256), 256, 0, c->inLits, c->inOffs, c->inMeta, c->C0, c->hdr[c->cur], c->pool[c->cur], c->hist, c->key,
-           &c->dc->flags, c->ND, c->L0);
-    KB(c, 8.0 * c->C0 + 4.0 * c->L0 + (c->inMeta ? 4.0 * c->C0 : 0.0) + 16.0 * c->C0 + 4.0 * c->L0 + 16.0 * c->C0 + 4.0 * c->ND);   // offsets + literals in, headers + literals + keys + histogram out
-    c->histFresh = true;   // hist[] and key[] describe the store until a kernel changes it (api.cu: buildOT)
+    launchCountPass(c, true, (u32)c->C0, c->L0, c->C0);
+    c->histFresh = true;   // key[] and the count matrix describe the store until a kernel changes it (api.cu: buildOT)
 }
-
-// ------------------------------------------------------------------ histogram + sort keys
-// algorithmic bytes: read 16C + 4L, 4 per literal of atomic traffic on hist (L2 resident), write 16C keys
-__global__ void k_hist_key(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
-                           u32* __restrict__ hist, uint4* __restrict__ key, u32* flags) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint4 h = hdr[i];
-        if (C_DELETED(h.w)) continue;
-        const u32* l = pool + h.x;
-        const int sz = (int)h.y;
-        u32 first = 0, last = 0;
-        for (int k = 0; k < sz; k++) {
-            const u32 lit = l[k];
-            if (k == 0) first = lit;
-            last = lit;
-            atomicAdd(&hist[lit], 1u);
-        }
-        key[i] = make_uint4(h.y, first, last, h.z);
-        if (sz >= (1 << 14)) atomicOr(flags, 8u);   // the list sort's folded key needs size < 2^14 (otsort.cu)
-    }
-}
-
+// sort keys + bucket counts + ranks of the later rounds (copy_if_k + histSimp, histogram.cu:54-72): k_ot_count<CPT, false>
 void launchHistKey(Ctx* c) {
-    if (otV2()) { if (c->hdc->numCls) launchCountPass(c, false, c->hdc->numCls, c->numLiterals, c->numClauses); return; }
-    cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
-    const u32 n = c->hdc->numCls;
-    if (n) {
-        LAUNCH(c, k_hist_key, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], n, c->hist, c->key, &c->dc->flags);
-        KB(c, 16.0 * n + 4.0 * c->numLiterals + 16.0 * c->numClauses + 4.0 * c->ND);
-    }
+    if (c->hdc->numCls) launchCountPass(c, false, c->hdc->numCls, c->numLiterals, c->numClauses);
 }
 
-// ------------------------------------------------------------------ occurrence lists: partition + place
-// create_ot_k (occurrence.cu:50-62) appends every clause reference to the lists of its literals
-// with one global atomic and one random 8-byte store per literal.  Random 4-byte stores over an
-// occurs[] array far larger than L2 cost a DRAM sector each, so the lists are built in two
-// streaming passes instead (an MSD radix partition by literal, the histogram being known):
-//   k_ot_part   streams the clause store once; every CTA bins the (literal, clause) pairs of its
-//               tile by literal range ("bucket" = 2^shift consecutive literals, <= 1024 buckets for
-//               V <= 2^24), reserves one run per bucket with a single global atomic and writes the
-//               pairs into the bucket's segment of pairs[] (the segment bounds are otStart[] at the
-//               bucket borders: no extra histogram).  Runs of neighbouring CTAs complete each
-//               other's sectors in L2.
-//   k_ot_place  one CTA per bucket: list cursors of the bucket's literals in shared memory, pairs
-//               streamed once (coalesced), clause indices stored into occurs[] inside the bucket's
-//               window (<= a few hundred KB: the sectors are completed in L2 before they reach HBM).
-// The order inside a list is arbitrary (as in the reference); k_sort_* fixes it afterwards.
-// Measured (profiles/r01_ncu_full_cfg2_v3.txt): both kernels are bound by the LSU/MIO path - one
-// shared-memory atomic (~2 cycles per lane) and one 4/8-byte store to its own sector per pair - not
-// by HBM.  A warp-match ranking variant (ballots + warp-private counters, no atomics) was measured
-// 10-100 % slower on cfg2-cfg4 and dropped; clause-local formulas (Tseitin, multiplier) already
-// write long runs per bucket and partition at ~3x the speed of uniform random k-SAT.
-// Algorithmic bytes: part 16C + 4L read + 8L written; place 8L read + 4L written + 12 ND.
-#define PART_THREADS 1024
-#define PART_SHORT 8       // clauses up to this size keep the ranks of their literals in registers
-#define PART_STAGE 16384u  // pairs of a tile staged in shared memory (128 KB)
-
-// One shared-memory atomic per pair: the rank the counting sweep hands out IS the pair's slot in the
-// tile's run of its bucket, so it is kept (16 bits per literal, four registers per clause) and the
-// writing sweep needs no second atomic.  Literals of longer clauses are counted separately and take
-// the tail of the run with a second atomic.
-// The writing sweep goes through shared memory: the tile's pairs are laid out bucket by bucket
-// (tileOff = exclusive scan of the tile's bucket counts) and copied out in that order, so that
-// neighbouring lanes store to neighbouring addresses of a run.  Per-lane scattered 8-byte stores cost
-// one L2 write transaction each, and that transaction rate - not HBM - bounded the unstaged kernel.
-// A tile with more pairs than the stage holds (long clauses) writes directly.
-// PART_CPT clauses per thread: 3 (tiles of 3072 clauses) or 5 for short clauses, so that a tile fills the stage;
-// the first PART_KEEP literals of a clause stay in registers between the two sweeps (the 220 KB of shared
-// memory leave almost no L1, a second read would come from L2)
-template <int PART_CPT, int PART_KEEP>
-__global__ void __launch_bounds__(PART_THREADS) k_ot_part(const uint4* __restrict__ hdr, const u32* __restrict__ pool, u32 n,
-                                                          const u32* __restrict__ otStart, u32 ND, u32 shift, u32 NB, u32 stageCap,
-                                                          u32* __restrict__ gcur, uint2* __restrict__ pairs) {
-    extern __shared__ u32 sm[];
-    u32* cntS = sm;             // literals of short clauses per bucket
-    u32* cntL = sm + NB;        // literals of long clauses per bucket, then their running slot
-    u32* gbase = sm + 2 * NB;   // start of this tile's run in the bucket's segment
-    u32* tileOff = sm + 3 * NB; // start of the bucket inside the staged tile
-    uint2* stage = (uint2*)(sm + 4 * NB);   // 16 NB bytes: 8-byte aligned
-    __shared__ u32 warpTot[32];
-    __shared__ u32 tileTotal, nonEmpty;
-    const u32 tile0 = blockIdx.x * (PART_THREADS * PART_CPT);
-    for (u32 b = threadIdx.x; b < 2 * NB; b += PART_THREADS) sm[b] = 0;
-    if (threadIdx.x == 0) nonEmpty = 0;
-    u32 off[PART_CPT], sz[PART_CPT], rk[PART_CPT][PART_SHORT / 2], lk[PART_CPT][PART_KEEP];
-#pragma unroll
-    for (int k = 0; k < PART_CPT; k++) {
-        const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
-        sz[k] = 0; off[k] = 0;
-        if (i < n) {
-            const uint4 h = hdr[i];
-            if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PART_CPT; k++) {
-        const u32* l = pool + off[k];
-#pragma unroll
-        for (int q = 0; q < PART_SHORT / 2; q++) rk[k][q] = 0;
-        if (sz[k] <= PART_SHORT) {
-#pragma unroll
-            for (int q = 0; q < PART_SHORT; q++)
-                if ((u32)q < sz[k]) {
-                    const u32 lit = l[q];
-                    if (q < PART_KEEP) lk[k][q < PART_KEEP ? q : 0] = lit;
-                    rk[k][q >> 1] |= atomicAdd(&cntS[lit >> shift], 1u) << ((q & 1) * 16);
-                }
-        } else
-            for (u32 q = 0; q < sz[k]; q++) atomicAdd(&cntL[l[q] >> shift], 1u);
-    }
-    __syncthreads();
-    // per bucket: reserve the run (one global atomic), exclusive scan of the tile's bucket counts
-    const u32 per = (NB + PART_THREADS - 1) / PART_THREADS;   // consecutive buckets per thread
-    const u32 b0 = threadIdx.x * per;
-    u32 mine = 0, used = 0;
-    for (u32 q = 0; q < per; q++) {
-        const u32 b = b0 + q;
-        if (b < NB) {
-            const u32 tS = cntS[b], tL = cntL[b];
-            if (tS + tL) { gbase[b] = otStart[min(b << shift, ND)] + atomicAdd(&gcur[b], tS + tL); used++; }
-            cntL[b] = tS;   // long-clause literals follow the short ones
-            tileOff[b] = mine;
-            mine += tS + tL;
-        }
-    }
-    const u32 incl = warpIncl(mine);
-    used = warpSum(used);
-    if ((threadIdx.x & 31u) == 0 && used) atomicAdd(&nonEmpty, used);
-    if ((threadIdx.x & 31u) == 31u) warpTot[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const u32 t = warpTot[threadIdx.x];
-        const u32 ti = warpIncl(t);
-        warpTot[threadIdx.x] = ti - t;
-        if (threadIdx.x == 31) tileTotal = ti;
-    }
-    __syncthreads();
-    const u32 base = warpTot[threadIdx.x >> 5] + incl - mine;
-    for (u32 q = 0; q < per; q++) { const u32 b = b0 + q; if (b < NB) tileOff[b] += base; }
-    __syncthreads();
-    // Staging pays when the tile's runs are short (uniform random formulas: ~4 pairs per bucket).  In
-    // clause-local formulas (Tseitin, arithmetic) neighbouring clauses fall into the same bucket with
-    // consecutive ranks, so the direct stores of a warp already coalesce and staging only adds a pass.
-    const bool staged = tileTotal <= stageCap && tileTotal < 12u * nonEmpty;
-#pragma unroll
-    for (int k = 0; k < PART_CPT; k++) {
-        const u32 i = tile0 + k * PART_THREADS + threadIdx.x;
-        const u32* l = pool + off[k];
-        if (sz[k] <= PART_SHORT) {
-#pragma unroll
-            for (int q = 0; q < PART_SHORT; q++)
-                if ((u32)q < sz[k]) {
-                    const u32 lit = q < PART_KEEP ? lk[k][q < PART_KEEP ? q : 0] : l[q];
-                    const u32 b = lit >> shift;
-                    const u32 r = (rk[k][q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
-                    if (staged) stage[tileOff[b] + r] = make_uint2(lit, i);
-                    else pairs[gbase[b] + r] = make_uint2(lit, i);
-                }
-        } else
-            for (u32 q = 0; q < sz[k]; q++) {
-                const u32 lit = l[q];
-                const u32 b = lit >> shift;
-                const u32 r = atomicAdd(&cntL[b], 1u);
-                if (staged) stage[tileOff[b] + r] = make_uint2(lit, i);
-                else pairs[gbase[b] + r] = make_uint2(lit, i);
-            }
-    }
-    if (!staged) return;
-    __syncthreads();
-    const u32 total = tileTotal;
-    for (u32 t = threadIdx.x; t < total; t += PART_THREADS) {
-        const uint2 pr = stage[t];
-        const u32 b = pr.x >> shift;
-        pairs[gbase[b] + (t - tileOff[b])] = pr;
-    }
-}
-
+// ------------------------------------------------------------------ occurrence lists: placement
+// create_ot_k (occurrence.cu:50-62) appends every clause reference to the lists of its literals with one global atomic
+// and one random 8-byte store per literal; random 4-byte stores over an occurs[] array far larger than L2 cost a DRAM
+// sector each.  The lists are built MSD-radix style instead: (literal, clause) pairs partitioned by literal range
+// (k_ot_count / k_ot_part2 below), then one CTA per bucket places the clause indices (k_ot_place).
 #define PLACE_THREADS 1024
 #define PLACE_SPLIT 64           // a bucket too large for the window is shared by up to 64 work units ...
 #define PLACE_UNIT (32u << 10)   // ... of about this many pairs each
-#define PLACE_WINDOW (40u << 10) // entries of a bucket's occurs[] window that can be staged in shared memory
+#define PLACE_WINDOW (50u << 10) // entries of a bucket's occurs[] window that can be staged in shared memory (200 KB)
 // Staged mode (the normal case, buckets are sized for it): the whole occurs[] window of the bucket is
 // assembled in shared memory - one shared-memory atomic and one shared-memory store per pair - and
 // written out with coalesced full-sector stores.  Scattering the 4-byte entries straight into global
@@ -282,10 +58,10 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restr
                                                             u32 shift, u32 window, u32* __restrict__ otSize, u32* __restrict__ occurs,
                                                             u32* __restrict__ big, u32* nBig) {
     extern __shared__ u32 smem[];
-    const u32 W = 1u << shift;
+    const u32 W = bkW(shift);
     u32* cur = smem;          // [W] list cursors
     u32* win = smem + W;      // [window] staged entries
-    const u32 lit0 = blockIdx.x << shift;
+    const u32 lit0 = bkLit0(blockIdx.x, shift);
     const u32 litEnd = min(lit0 + W, ND);
     const u32 p0 = otStart[lit0], p1 = otStart[litEnd];
     const u32 len = p1 - p0;
@@ -321,12 +97,12 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place(const uint2* __restr
 __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place_big(const uint2* __restrict__ pairs, const u32* __restrict__ otStart, u32 ND,
                                                                 u32 shift, u32* __restrict__ otSize, u32* __restrict__ occurs,
                                                                 const u32* __restrict__ big, const u32* nBig) {
-    const u32 W = 1u << shift;
+    const u32 W = bkW(shift);
     const u32 nItems = *nBig;
     for (u32 item = blockIdx.x; item < nItems; item += gridDim.x) {
         const u32 code = big[item];
         const u32 b = code & 0x1FFFu, s = (code >> 13) & 0x3Fu, S = code >> 19;
-        const u32 lit0 = b << shift;
+        const u32 lit0 = bkLit0(b, shift);
         const u32 p0 = otStart[lit0], p1 = otStart[min(lit0 + W, ND)];
         const u32 len = p1 - p0;
         const u32 q0 = p0 + (u32)((u64)len * s / S), q1 = p0 + (u32)((u64)len * (s + 1) / S);
@@ -385,12 +161,12 @@ __global__ void __launch_bounds__(PLACE_THREADS) k_ot_place_tma(const uint2* __r
                                                                 u32 shift, u32 window, u32* __restrict__ otSize, u32* __restrict__ occurs,
                                                                 u32* __restrict__ big, u32* nBig) {
     extern __shared__ __align__(128) u32 smem[];
-    const u32 W = 1u << shift;
+    const u32 W = bkW(shift);
     u32* cur = smem;                                      // [W] list cursors
     u32* win = smem + W;                                  // [window + 8] staged entries, same 16-byte phase as occurs + p0
     uint2* ring = (uint2*)(smem + W + window + 8);        // [2][PLACE_CH]
     u64* bar = (u64*)(ring + 2 * PLACE_CH);               // [2]
-    const u32 lit0 = blockIdx.x << shift;
+    const u32 lit0 = bkLit0(blockIdx.x, shift);
     const u32 litEnd = min(lit0 + W, ND);
     const u32 p0 = otStart[lit0], p1 = otStart[litEnd];
     const u32 len = p1 - p0;
@@ -458,43 +234,10 @@ void launchScatter(Ctx* c) {
     // nothing live (e.g. prop() satisfied every clause): empty lists; hist/otStart may be stale here
     if (!n || !c->numLiterals) {
         cudaMemsetAsync(c->otSize, 0, (size_t)c->ND * 4, c->stream);
-        if (otV2()) cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
+        cudaMemsetAsync(c->hist, 0, (size_t)c->ND * 4, c->stream);
         return;
     }
-    if (otV2()) { launchScatter2(c, n); return; }
-    if (!c->attrOT) {
-        cudaFuncSetAttribute(k_ot_part<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
-        c->attrOT = true;
-    }
-    // bucket = 2^shift consecutive literals, sized so that an average bucket fills at most ~70 % of a
-    // staging window; at most 8192 buckets (shared-memory counters of k_ot_part)
-    u32 shift = 6;
-    while (shift < 12 && ((u64)c->numLiterals << (shift + 1)) / c->ND <= PLACE_WINDOW * 7 / 10) shift++;
-    while (shift < 15 && ((c->ND + (1u << shift) - 1) >> shift) > 8192) shift++;
-    const u32 NB = (c->ND + (1u << shift) - 1) >> shift;
-    c->otShift = shift; c->otNB = NB;
-    // beyond 2^12 literals per bucket (more than 2^25 literals in all) the cursors alone fill the shared memory: direct mode only
-    u32 window = shift <= 12 ? PLACE_WINDOW : 0;
-    if (const char* w = getenv("SIGMA_OT_WINDOW")) { const u32 v = (u32)atoi(w); if (v < window) window = v; }   // tests: force the work-unit path
-    const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
-    cudaMemsetAsync(c->otCur, 0, (size_t)NB * 4, c->stream);
-    // shared memory of k_ot_part: 4 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
-    const size_t partFixed = 16 * (size_t)NB + 8;
-    u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
-    if (c->numLiterals <= 3 * c->numClauses)   // short clauses: more of them per tile
-        LAUNCH(c, (k_ot_part<5, 3>), divup(n, PART_THREADS * 5), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
-               c->otStart, c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
-    else
-        LAUNCH(c, (k_ot_part<3, 5>), divup(n, PART_THREADS * 3), PART_THREADS, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], n,
-               c->otStart, c->ND, shift, NB, stageCap, c->otCur, c->otPairs);
-    KB(c, 16.0 * n + 4.0 * c->numLiterals + 8.0 * c->numLiterals);   // headers + literals in, (literal, clause) pairs out
-    u32* nBig = &c->dc->scratch[7];
-    cudaMemsetAsync(nBig, 0, 4, c->stream);
-    LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
-    KB(c, 8.0 * c->numLiterals + 4.0 * c->numLiterals + 12.0 * c->ND);   // pairs in, list entries out, list bounds
-    LAUNCH(c, k_ot_place_big, 148 * 2, PLACE_THREADS, 0, c->otPairs, c->otStart, c->ND, shift, c->otSize, c->occurs, c->otBig, nBig);
+    launchScatter2(c, n);
 }
 
 // ================================================================== occurrence-table build, version 2
@@ -596,12 +339,12 @@ __global__ void __launch_bounds__(OT_T) k_ot_count(const u32* __restrict__ inLit
                     const u32 lit = r[q];
                     if (q == 0) first = lit;
                     last = lit;
-                    rk[q >> 1] |= atomicAdd(&cntS[lit >> shift], 1u) << ((q & 1) * 16);
+                    rk[q >> 1] |= atomicAdd(&cntS[bkOf(lit, shift)], 1u) << ((q & 1) * 16);
                 }
         } else {
             const u32* l = pool + off;
             first = l[0]; last = l[sz - 1];
-            for (int q = 0; q < sz; q++) atomicAdd(&cntL[l[q] >> shift], 1u);
+            for (int q = 0; q < sz; q++) atomicAdd(&cntL[bkOf(l[q], shift)], 1u);
             if (sz >= (1 << 14)) atomicOr(flags, 8u);   // the list sort's folded key needs size < 2^14 (otsort.cu)
         }
         rk8[i] = make_uint4(rk[0], rk[1], rk[2], rk[3]);
@@ -738,7 +481,7 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
             for (int q = 0; q < 8; q++)
                 if ((u32)q < sz[k]) {
                     const u32 lit = q < KEEP ? lk[k][q < KEEP ? q : 0] : l[q];
-                    const u32 b = lit >> shift;
+                    const u32 b = bkOf(lit, shift);
                     const u32 pos = tileOff[b] + ((rw[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu);
                     if (staged) stage[pos] = make_uint2(lit, i);
                     else pairs[pos + delta[b]] = make_uint2(lit, i);
@@ -746,7 +489,7 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
         } else
             for (u32 q = 0; q < sz[k]; q++) {
                 const u32 lit = l[q];
-                const u32 b = lit >> shift;
+                const u32 b = bkOf(lit, shift);
                 const u32 pos = tileOff[b + 1] - 1u - atomicAdd(&cntL2[b], 1u);
                 if (staged) stage[pos] = make_uint2(lit, i);
                 else pairs[pos + delta[b]] = make_uint2(lit, i);
@@ -757,138 +500,8 @@ __global__ void __launch_bounds__(OT_T, 1) k_ot_part2(const uint4* __restrict__ 
     const u32 total = tileTotal;
     for (u32 t = threadIdx.x; t < total; t += OT_T) {   // (four-way unrolling measured no faster: profiles/r02_ab_c10.jsonl)
         const uint2 pr = stage[t];
-        pairs[t + delta[pr.x >> shift]] = pr;
+        pairs[t + delta[bkOf(pr.x, shift)]] = pr;
     }
-}
-
-// Version 3 of the partition: the same tile algorithm on PERSISTENT CTAs (one per SM) with the tiles software-pipelined.
-// k_ot_part2 holds ~220 KB of shared memory, so one CTA lives on an SM and its phases run one after the other: header
-// load -> literal load (dependent) -> row scan -> staging -> copy-out, and the next CTA cannot start before the last
-// store has drained (ncu: long-scoreboard + barrier + drain = half of the stall cycles, LSU pipe 48 % busy).  Here the
-// loads of tile i+1 are in flight while tile i is copied out: its two matrix rows come in through cp.async
-// (global -> shared memory, no registers), headers and ranks are issued before the first half of the copy-out and the
-// literals - which need the headers - before the second half; the registers of tile i are dead by then.
-__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gsrc) {
-    const u32 d = (u32)__cvta_generic_to_shared(smemDst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int CPT, int KEEP>
-__global__ void __launch_bounds__(OT_T, 1) k_ot_part3(const uint4* __restrict__ hdr, const u32* __restrict__ pool, const uint4* __restrict__ rk8, u32 n,
-                                                   u32 shift, u32 NB, u32 NBp, const u32* __restrict__ cntMat, const u32* __restrict__ runMat,
-                                                   u32 stageCap, u32 tiles, uint2* __restrict__ pairs) {
-    extern __shared__ __align__(16) u32 sm3[];
-    u32* rowC = sm3;                 // [NBp] this tile's run lengths   (cp.async target, 16-byte aligned)
-    u32* rowG = sm3 + NBp;           // [NBp] this tile's run starts
-    u32* tileOff = sm3 + 2 * NBp;    // [NB + 1]
-    u32* delta = tileOff + NB + 1;  // [NB]
-    u32* cntL2 = delta + NB;        // [NB]
-    uint2* stage = (uint2*)(sm3 + ((2 * NBp + 3 * NB + 2) & ~1u));
-    __shared__ u32 warpTot[32];
-    __shared__ u32 tileTotal, nonEmpty;
-    const u32 per = (NB + OT_T - 1) / OT_T;   // consecutive buckets per thread, <= 8
-    const u32 b0 = threadIdx.x * per;
-    u32 tile = blockIdx.x;
-    if (tile >= tiles) return;
-    u32 off[CPT], sz[CPT]; uint4 rk[CPT]; u32 lk[CPT][KEEP];
-#define PART3_LOAD_HDR(T_)                                                                                        \
-    _Pragma("unroll") for (int k = 0; k < CPT; k++) {                                                             \
-        const u32 i = (T_) * (OT_T * CPT) + k * OT_T + threadIdx.x;                                               \
-        sz[k] = 0; off[k] = 0; rk[k] = make_uint4(0, 0, 0, 0);                                                    \
-        if (i < n) { const uint4 h = hdr[i]; if (!C_DELETED(h.w)) { off[k] = h.x; sz[k] = h.y; rk[k] = rk8[i]; } } \
-    }
-#define PART3_LOAD_ROWS(T_)                                                                                       \
-    do {                                                                                                          \
-        const u32* rc = cntMat + (size_t)(T_) * NBp; const u32* rg = runMat + (size_t)(T_) * NBp;                 \
-        for (u32 w = threadIdx.x * 4; w < NBp; w += OT_T * 4) { cpAsync16(rowC + w, rc + w); cpAsync16(rowG + w, rg + w); } \
-        cpAsyncCommit();                                                                                          \
-    } while (0)
-#define PART3_LOAD_LITS()                                                                                         \
-    _Pragma("unroll") for (int k = 0; k < CPT; k++) {                                                             \
-        const u32* l = pool + off[k];                                                                             \
-        _Pragma("unroll") for (int q = 0; q < KEEP; q++) lk[k][q] = ((u32)q < sz[k] && sz[k] <= 8u) ? l[q] : 0u;  \
-    }
-    PART3_LOAD_HDR(tile);
-    PART3_LOAD_ROWS(tile);
-    PART3_LOAD_LITS();
-    for (;;) {
-        if (threadIdx.x == 0) nonEmpty = 0;
-        bool longHere = false;
-#pragma unroll
-        for (int k = 0; k < CPT; k++) longHere |= sz[k] > 8u;
-        cpAsyncWaitAll();
-        const int anyLong = __syncthreads_or(longHere);   // rows of this tile visible to every thread
-        if (anyLong) for (u32 b = threadIdx.x; b < NB; b += OT_T) cntL2[b] = 0;
-        u32 cq[8];
-        u32 mine = 0, used = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) { const u32 b = b0 + q; cq[q] = ((u32)q < per && b < NB) ? rowC[b] : 0u; mine += cq[q]; used += cq[q] != 0u; }
-        const u32 incl = warpIncl(mine);
-        used = warpSum(used);
-        if ((threadIdx.x & 31u) == 0 && used) atomicAdd(&nonEmpty, used);
-        if ((threadIdx.x & 31u) == 31u) warpTot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const u32 t = warpTot[threadIdx.x];
-            const u32 ti = warpIncl(t);
-            warpTot[threadIdx.x] = ti - t;
-            if (threadIdx.x == 31) { tileTotal = ti; tileOff[NB] = ti; }
-        }
-        __syncthreads();
-        u32 run = warpTot[threadIdx.x >> 5] + incl - mine;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const u32 b = b0 + q;
-            if ((u32)q < per && b < NB) { tileOff[b] = run; delta[b] = rowG[b] - run; run += cq[q]; }
-        }
-        __syncthreads();
-        const u32 total = tileTotal;
-        const bool staged = total <= stageCap && total < 12u * nonEmpty;
-#pragma unroll
-        for (int k = 0; k < CPT; k++) {
-            const u32 i = tile * (OT_T * CPT) + k * OT_T + threadIdx.x;
-            const u32* l = pool + off[k];
-            if (sz[k] <= 8u) {
-                const u32 rw[4] = {rk[k].x, rk[k].y, rk[k].z, rk[k].w};
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if ((u32)q < sz[k]) {
-                        const u32 lit = q < KEEP ? lk[k][q < KEEP ? q : 0] : l[q];
-                        const u32 b = lit >> shift;
-                        const u32 pos = tileOff[b] + ((rw[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu);
-                        if (staged) stage[pos] = make_uint2(lit, i);
-                        else pairs[pos + delta[b]] = make_uint2(lit, i);
-                    }
-            } else
-                for (u32 q = 0; q < sz[k]; q++) {
-                    const u32 lit = l[q];
-                    const u32 b = lit >> shift;
-                    const u32 pos = tileOff[b + 1] - 1u - atomicAdd(&cntL2[b], 1u);
-                    if (staged) stage[pos] = make_uint2(lit, i);
-                    else pairs[pos + delta[b]] = make_uint2(lit, i);
-                }
-        }
-        __syncthreads();   // the stage is complete; rowC / rowG and this tile's registers are free
-        const u32 next = tile + gridDim.x;
-        const bool more = next < tiles;
-        if (more) { PART3_LOAD_ROWS(next); PART3_LOAD_HDR(next); }
-        asm volatile("" ::: "memory");
-        const u32 half = staged ? ((total >> 1) & ~(u32)(OT_T - 1)) : 0u;
-        u32 t = threadIdx.x;
-        for (; t < half; t += OT_T) { const uint2 pr = stage[t]; pairs[t + delta[pr.x >> shift]] = pr; }
-        asm volatile("" ::: "memory");
-        if (more) { PART3_LOAD_LITS(); }
-        asm volatile("" ::: "memory");
-        if (staged) for (; t < total; t += OT_T) { const uint2 pr = stage[t]; pairs[t + delta[pr.x >> shift]] = pr; }
-        if (!more) break;
-        tile = next;
-        __syncthreads();   // every reader of stage / delta is done before the next tile rewrites them
-    }
-#undef PART3_LOAD_HDR
-#undef PART3_LOAD_ROWS
-#undef PART3_LOAD_LITS
 }
 
 // per-literal histogram of one bucket = hist[] (and, scanned, otStart[]) of its literal range: counted from the bucket's
@@ -900,8 +513,8 @@ __global__ void __launch_bounds__(LITHIST_T) k_ot_lithist(const uint2* __restric
     extern __shared__ u32 cnt[];   // [W]
     __shared__ u32 wt[32];
     __shared__ u32 carry;
-    const u32 W = 1u << shift;
-    const u32 lit0 = blockIdx.x << shift;
+    const u32 W = bkW(shift);
+    const u32 lit0 = bkLit0(blockIdx.x, shift);
     const u32 nl = min(lit0 + W, ND) - lit0;
     const u32 p0 = bstart[blockIdx.x], p1 = bstart[blockIdx.x + 1];
     for (u32 k = threadIdx.x; k < W; k += LITHIST_T) cnt[k] = 0;
@@ -933,33 +546,58 @@ __global__ void __launch_bounds__(LITHIST_T) k_ot_lithist(const uint2* __restric
     }
 }
 
-// bucket = 2^shift consecutive literals, sized so that an average bucket fills at most ~70 % of a placement window; at most
-// 8192 buckets.  Fixed BEFORE the counting pass: pass A, the partition and the placement must agree on it.
+// Shape of the build, fixed BEFORE the counting pass (counting pass, partition and placement must agree on it):
+//   bucket width W = 2^sh or 3 * 2^sh literals - the largest with an average bucket at most SIGMA_OT_FILL % (default 80) of the
+//   placement window; at most 8192 buckets (bucket index < 2^13 in the work-unit codes, counters in shared memory);
+//   tile = 1024 x CPT clauses, the largest of 3 / 4 / 5 whose pairs still fit the partition's stage.
+#define PART2_STAGE 26624u   // pairs of a tile staged in shared memory, at most (what 220 KB leave after the bucket tables decides)
+static bool placeTmaOn() { static const int v = getenv("SIGMA_OT_TMA") ? atoi(getenv("SIGMA_OT_TMA")) : 0; return v != 0; }
+// entries of a bucket's occurs[] window staged by the placement; the bulk-copy variant also holds a 32 KB ring
+static u32 placeWindow() { return placeTmaOn() ? (40u << 10) : PLACE_WINDOW; }
+#define PLACE_WMAX 6144u     // widest bucket whose list cursors fit beside the window
+static size_t partFixedBytes(u32 NB) { return 4 * (((size_t)3 * NB + 2) & ~(size_t)1) + 16; }
+static u32 partStageCap(u32 NB) {
+    const size_t fixed = partFixedBytes(NB);
+    return fixed + 8 * (size_t)PART2_STAGE <= 220 * 1024 ? PART2_STAGE : (u32)((220 * 1024 - fixed) / 8);
+}
 static void otChooseShape(Ctx* c, u64 numLiterals, u64 numClauses, u32 nSlots) {
-    u32 shift = 6;
-    while (shift < 12 && ((u64)numLiterals << (shift + 1)) / c->ND <= PLACE_WINDOW * 7 / 10) shift++;
-    while (shift < 15 && ((c->ND + (1u << shift) - 1) >> shift) > 8192) shift++;
-    c->otShift = shift; c->otNB = (c->ND + (1u << shift) - 1) >> shift;
+    static const u32 fillPct = getenv("SIGMA_OT_FILL") ? (u32)atoi(getenv("SIGMA_OT_FILL")) : 80u;
+    const u64 limit = (u64)placeWindow() * fillPct / 100;
+    u32 shape = 6;   // W = 64
+    for (;;) {       // next wider candidate: 2^sh -> 3 * 2^(sh-1) -> 2^(sh+1)
+        const u32 sh = shape & 0xFFu, three = shape >> 8;
+        const u32 next = three ? (sh + 2) : ((sh - 1) | 0x100u);
+        const u32 Wn = bkW(next);
+        if (Wn > PLACE_WMAX || numLiterals * Wn / c->ND > limit) break;
+        shape = next;
+    }
+    while (bkW(shape) < (1u << 15) && (c->ND + bkW(shape) - 1) / bkW(shape) > 8192) shape = (shape >> 8) ? (shape & 0xFFu) + 2 : shape + 1;
+    const u32 W = bkW(shape);
+    c->otShift = shape; c->otNB = (c->ND + W - 1) / W;
     c->otNBp = (c->otNB + 3u) & ~3u;
-    c->otCPT = numLiterals <= 3 * numClauses ? 5 : 3;   // short clauses: more of them per tile
+    const u64 cap = partStageCap(c->otNB);
+    const u64 perClause100 = numClauses ? 105 * numLiterals / numClauses : 0;   // literals per clause, + 5 %
+    c->otCPT = numLiterals <= 3 * numClauses ? 5 : ((u64)OT_T * 4 * perClause100 <= 100 * cap ? 4 : 3);
+    static const int cptEnv = getenv("SIGMA_OT_CPT") ? atoi(getenv("SIGMA_OT_CPT")) : 0;   // A/B measurements: force 3 clauses per thread
+    if (cptEnv == 3 && c->otCPT == 4) c->otCPT = 3;
     c->otTiles = divup(nSlots, OT_T * c->otCPT);
 }
-bool otBuildV2();
-static bool otV2() { return otBuildV2(); }
-bool otBuildV2() { static const int v = getenv("SIGMA_OT_V2") ? atoi(getenv("SIGMA_OT_V2")) : 1; return v != 0; }
 
 static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 numClauses) {
     otChooseShape(c, numLiterals, numClauses, n);
     if (!c->attrOT2) {
         cudaFuncSetAttribute(k_ot_count<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_count<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        cudaFuncSetAttribute(k_ot_count<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_part2<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part2<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part2<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part2<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_part2<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part3<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part3<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + (1 << 12)));
+        cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + PLACE_WMAX));
         cudaFuncSetAttribute(k_ot_lithist, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
         c->attrOT2 = true;
     }
@@ -968,10 +606,12 @@ static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 num
 #define OT_COUNT_ARGS c->inLits, c->inOffs, c->inMeta, c->L0, c->hdr[c->cur], c->pool[c->cur], n, c->ND, sh, NB, NBp, c->rk8, c->cntMat, c->key, &c->dc->flags
     if (awaken) {
         if (c->otCPT == 5) LAUNCH(c, (k_ot_count<5, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
+        else if (c->otCPT == 4) LAUNCH(c, (k_ot_count<4, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         else LAUNCH(c, (k_ot_count<3, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         KB(c, 8.0 * n + 4.0 * numLiterals + (c->inMeta ? 4.0 * n : 0.0) + 16.0 * n + 4.0 * numLiterals + 32.0 * n + 4.0 * (double)c->otTiles * NBp);
     } else {
         if (c->otCPT == 5) LAUNCH(c, (k_ot_count<5, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
+        else if (c->otCPT == 4) LAUNCH(c, (k_ot_count<4, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         else LAUNCH(c, (k_ot_count<3, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         KB(c, 16.0 * n + 4.0 * numLiterals + 32.0 * numClauses + 4.0 * (double)c->otTiles * NBp);   // headers + literals in, keys + ranks + count rows out
     }
@@ -980,52 +620,43 @@ static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 num
 
 static void launchScatter2(Ctx* c, u32 n) {
     const u32 NB = c->otNB, NBp = c->otNBp, shift = c->otShift, tiles = c->otTiles;
+    const u32 W = bkW(shift);
     u32* segSum = c->otSeg;
     LAUNCH(c, k_ot_colsum, dim3(divup(NB, 256), OT_SEG), 256, 0, c->cntMat, tiles, NB, NBp, segSum);
     KB(c, 4.0 * (double)tiles * NBp);
     LAUNCH(c, k_ot_bscan, 1, 1024, 0, segSum, NB, NBp, c->bstart, c->otStart + c->ND);
     LAUNCH(c, k_ot_colfix, dim3(divup(NB, 256), OT_SEG), 256, 0, c->cntMat, tiles, NB, NBp, segSum, c->runMat);
     KB(c, 8.0 * (double)tiles * NBp);
-    // shared memory of k_ot_part2: 3 words per bucket + the stage (whatever is left of ~220 KB, at most PART_STAGE pairs)
-    const size_t partFixed = 4 * (((size_t)3 * NB + 2) & ~(size_t)1) + 16;
-    const u32 stageCap = partFixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (u32)((220 * 1024 - partFixed) / 8);
-    // version 3 (persistent, software-pipelined tiles) needs two more rows of shared memory; it is used when its stage still
-    // holds a whole tile of the loaded formula, otherwise version 2 (SIGMA_OT_PART3=0 forces version 2 for A/B runs)
-    static const int part3 = getenv("SIGMA_OT_PART3") ? atoi(getenv("SIGMA_OT_PART3")) : 1;
-    const size_t p3Fixed = 4 * (((size_t)2 * NBp + 3 * NB + 2) & ~(size_t)1) + 16;
-    const u32 p3Cap = p3Fixed + 8 * (size_t)PART_STAGE <= 220 * 1024 ? PART_STAGE : (p3Fixed < 220 * 1024 ? (u32)((220 * 1024 - p3Fixed) / 8) : 0u);
-    const u64 tileLits = c->numClauses ? (u64)OT_T * c->otCPT * c->numLiterals / c->numClauses : 0;
-    if (part3 && tiles > 148 && (p3Cap >= stageCap || tileLits + tileLits / 8 <= p3Cap)) {
-        if (c->otCPT == 5)
-            LAUNCH(c, (k_ot_part3<5, 3>), 148, OT_T, p3Fixed + 8 * (size_t)p3Cap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
-                   p3Cap, tiles, c->otPairs);
-        else
-            LAUNCH(c, (k_ot_part3<3, 5>), 148, OT_T, p3Fixed + 8 * (size_t)p3Cap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
-                   p3Cap, tiles, c->otPairs);
-    } else if (c->otCPT == 5)
-        LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
-               stageCap, c->otPairs);
-    else
-        LAUNCH(c, (k_ot_part2<3, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat,
-               stageCap, c->otPairs);
+    // shared memory of k_ot_part2: 3 words per bucket + the stage (whatever is left of ~220 KB, at most PART2_STAGE pairs)
+    const size_t partFixed = partFixedBytes(NB);
+    const u32 stageCap = partStageCap(NB);
+#define OT_PART_ARGS c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat, stageCap, c->otPairs
+    if (c->otCPT == 5) LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
+    else if (c->otCPT == 4) {
+        static const int keep4 = getenv("SIGMA_OT_KEEP") ? atoi(getenv("SIGMA_OT_KEEP")) : 5;   // literals per clause kept in registers between the sweeps (A/B)
+        if (keep4 == 3) LAUNCH(c, (k_ot_part2<4, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
+        else if (keep4 == 4) LAUNCH(c, (k_ot_part2<4, 4>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
+        else LAUNCH(c, (k_ot_part2<4, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
+    }
+    else LAUNCH(c, (k_ot_part2<3, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
+#undef OT_PART_ARGS
     KB(c, 32.0 * n + 4.0 * c->numLiterals + 8.0 * (double)tiles * NBp + 8.0 * c->numLiterals);   // headers + ranks + literals + the tile's two rows in, pairs out
-    LAUNCH(c, k_ot_lithist, NB, LITHIST_T, (size_t)4 << shift, c->otPairs, c->bstart, c->ND, shift, c->hist, c->otStart);
+    LAUNCH(c, k_ot_lithist, NB, LITHIST_T, (size_t)4 * W, c->otPairs, c->bstart, c->ND, shift, c->hist, c->otStart);
     KB(c, 8.0 * c->numLiterals + 8.0 * c->ND);   // pairs in, hist + list starts out
-    // placement: the version-1 kernels (list cursors + the bucket's occurs[] window in shared memory; work units for oversized buckets)
-    u32 window = shift <= 12 ? PLACE_WINDOW : 0;
+    // placement: list cursors + the bucket's occurs[] window in shared memory; work units for oversized buckets
+    u32 window = W <= PLACE_WMAX ? placeWindow() : 0;
     if (const char* w = getenv("SIGMA_OT_WINDOW")) { const u32 v = (u32)atoi(w); if (v < window) window = v; }   // tests: force the work-unit path
-    const size_t placeSmem = shift <= 12 ? 4 * ((size_t)PLACE_WINDOW + (1u << shift)) : (size_t)4 << shift;
+    const size_t placeSmem = W <= PLACE_WMAX ? 4 * ((size_t)PLACE_WINDOW + W) : (size_t)4 * W;
     u32* nBig = &c->dc->scratch[7];
     cudaMemsetAsync(nBig, 0, 4, c->stream);
     // measured (profiles/r02_ab_tma_c11.jsonl, identical results): 0.373 vs 0.324 ms on cfg2, 1.45 vs 1.29 ms on cfg3 - the plain kernel
     // already keeps 4 x 1024 pair loads in flight per SM, the ring adds a CTA barrier per 16 KB chunk.  Opt-in.
-    static const int placeTma = getenv("SIGMA_OT_TMA") ? atoi(getenv("SIGMA_OT_TMA")) : 0;
-    if (placeTma && shift <= 12) {
+    if (placeTmaOn() && W <= PLACE_WMAX) {
         if (!c->attrTma) {
-            cudaFuncSetAttribute(k_ot_place_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + 8 + (1 << 12)) + 16 * PLACE_CH + 64);
+            cudaFuncSetAttribute(k_ot_place_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * ((40 << 10) + 8 + PLACE_WMAX) + 16 * PLACE_CH + 64);
             c->attrTma = true;
         }
-        const size_t tmaSmem = 4 * ((size_t)PLACE_WINDOW + 8 + (1u << shift)) + 16 * (size_t)PLACE_CH + 64;
+        const size_t tmaSmem = 4 * ((size_t)placeWindow() + 8 + W) + 16 * (size_t)PLACE_CH + 64;
         LAUNCH(c, k_ot_place_tma, NB, PLACE_THREADS, tmaSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);
     } else
         LAUNCH(c, k_ot_place, NB, PLACE_THREADS, placeSmem, c->otPairs, c->otStart, c->ND, shift, window, c->otSize, c->occurs, c->otBig, nBig);

@@ -275,7 +275,6 @@ void scanExclusiveU64(Ctx* c, const u64* in, u64* out, u64 n, u64 init);
 void launchAwaken(Ctx* c);
 void launchHistKey(Ctx* c);
 void launchScatter(Ctx* c);
-bool otBuildV2();   // cnf.cu: SIGMA_OT_V2 (default on)
 void launchCount(Ctx* c);
 void launchGC(Ctx* c);
 int  launchStore(Ctx* c, u64* nCls, u64* nLits, int form, bool writeBackOrder);   // form: 0 arrays (bits, sig, offs), 1 SCLAUSE records, 2 compact (bits, sizes);   // writeBackOrder: apply -aggresivesort (cacheCNF only)
