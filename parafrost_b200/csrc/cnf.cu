@@ -580,6 +580,7 @@ static void otChooseShape(Ctx* c, u64 numLiterals, u64 numClauses, u32 nSlots) {
     c->otCPT = numLiterals <= 3 * numClauses ? 5 : ((u64)OT_T * 4 * perClause100 <= 100 * cap ? 4 : 3);
     static const int cptEnv = getenv("SIGMA_OT_CPT") ? atoi(getenv("SIGMA_OT_CPT")) : 0;   // A/B measurements: force 3 clauses per thread
     if (cptEnv == 3 && c->otCPT == 4) c->otCPT = 3;
+    if (cptEnv == 4 && c->otCPT == 5 && (u64)OT_T * 4 * perClause100 <= 100 * cap) c->otCPT = 4;
     c->otTiles = divup(nSlots, OT_T * c->otCPT);
 }
 
@@ -592,11 +593,9 @@ static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 num
         cudaFuncSetAttribute(k_ot_count<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-        cudaFuncSetAttribute(k_ot_part2<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part2<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part2<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part2<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_ot_part2<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+#define OT_PART_ATTR(C_, K_) cudaFuncSetAttribute(k_ot_part2<C_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
+        OT_PART_ATTR(3, 5); OT_PART_ATTR(3, 3); OT_PART_ATTR(3, 2); OT_PART_ATTR(4, 3); OT_PART_ATTR(4, 2); OT_PART_ATTR(5, 3); OT_PART_ATTR(5, 2);
+#undef OT_PART_ATTR
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + PLACE_WMAX));
         cudaFuncSetAttribute(k_ot_lithist, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
         c->attrOT2 = true;
@@ -631,14 +630,12 @@ static void launchScatter2(Ctx* c, u32 n) {
     const size_t partFixed = partFixedBytes(NB);
     const u32 stageCap = partStageCap(NB);
 #define OT_PART_ARGS c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat, stageCap, c->otPairs
-    if (c->otCPT == 5) LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
-    else if (c->otCPT == 4) {
-        static const int keep4 = getenv("SIGMA_OT_KEEP") ? atoi(getenv("SIGMA_OT_KEEP")) : 5;   // literals per clause kept in registers between the sweeps (A/B)
-        if (keep4 == 3) LAUNCH(c, (k_ot_part2<4, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
-        else if (keep4 == 4) LAUNCH(c, (k_ot_part2<4, 4>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
-        else LAUNCH(c, (k_ot_part2<4, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
-    }
-    else LAUNCH(c, (k_ot_part2<3, 5>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
+    static const int keep = getenv("SIGMA_OT_KEEP") ? atoi(getenv("SIGMA_OT_KEEP")) : 3;   // literals per clause kept in registers between the sweeps (A/B)
+#define OT_PART(C_, K_) LAUNCH(c, (k_ot_part2<C_, K_>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS)
+    if (c->otCPT == 5) { if (keep == 2) OT_PART(5, 2); else OT_PART(5, 3); }
+    else if (c->otCPT == 4) { if (keep == 2) OT_PART(4, 2); else OT_PART(4, 3); }
+    else { if (keep == 2) OT_PART(3, 2); else if (keep == 3) OT_PART(3, 3); else OT_PART(3, 5); }
+#undef OT_PART
 #undef OT_PART_ARGS
     KB(c, 32.0 * n + 4.0 * c->numLiterals + 8.0 * (double)tiles * NBp + 8.0 * c->numLiterals);   // headers + ranks + literals + the tile's two rows in, pairs out
     LAUNCH(c, k_ot_lithist, NB, LITHIST_T, (size_t)4 * W, c->otPairs, c->bstart, c->ND, shift, c->hist, c->otStart);

@@ -18,7 +18,7 @@ import helpers  # noqa: E402
 OUT = os.path.join(HERE, "fullsize_fingerprints.json")
 KEYS = ["cnfstate", "clauses", "literals", "eliminated", "forced", "resolved_words", "resolved_groups", "trail",
         "h_lits_multiset", "h_full_multiset", "h_lits_ordered", "h_full_ordered", "h_eliminated", "h_forced",
-        "h_resolved_groups", "h_trail_multiset"]
+        "h_resolved_groups", "h_resolved_records", "h_trail_multiset"]
 
 
 def main():

@@ -172,6 +172,9 @@ class Dump:
         forced_vars = np.nonzero(self.eliminated & 4)[0].astype(U64)
         groups = self.resolved_groups()
         gh = np.array([int(_mix64(np.array([hash_words(g)], U64))[0]) for g in groups], U64) if groups else np.empty(0, U64)
+        # the same stack record by record: with BCE the blocked-clause records (no closing unit) sit in front of whichever
+        # group the atomic append put behind them, so runs with BCE compare this multiset instead of the groups
+        rh = self.record_hashes()
         return {
             "max_var": self.max_var,
             "cnfstate": self.cnfstate,
@@ -191,6 +194,7 @@ class Dump:
             "h_eliminated": ms(_mix64(elim_vars)),
             "h_forced": ms(_mix64(forced_vars)),
             "h_resolved_groups": ms(gh),
+            "h_resolved_records": ms(rh),
             "h_trail_multiset": ms(_mix64(self.trail.astype(U64))),
         }
 
@@ -207,6 +211,28 @@ class Dump:
 
     def eliminated_vars(self) -> list[int]:
         return np.nonzero(self.eliminated & 1)[0].tolist()
+
+    def record_hashes(self) -> np.ndarray:
+        """One 64-bit hash per record `[lits..., size]` of the witness stack (position inside the record matters: the
+        witness literal comes first).  The sizes sit at the END of the records, so the boundaries are found by a
+        sequential walk from the top; the hashing is vectorised."""
+        n = len(self.resolved)
+        if not n:
+            return np.empty(0, U64)
+        rl = self.resolved.tolist()
+        ends = []
+        p = n
+        while p > 0:
+            sz = rl[p - 1]
+            assert 0 < sz < p + 1, "corrupt resolved stack"
+            ends.append(p)
+            p -= 1 + sz
+        ends = np.array(ends[::-1], np.int64)
+        starts = np.concatenate((np.zeros(1, np.int64), ends[:-1]))
+        pos = np.arange(n, dtype=np.int64) - np.repeat(starts, ends - starts)
+        with np.errstate(over="ignore"):
+            w = _mix64(self.resolved.astype(U64) + (pos.astype(U64) << U64(32)))
+            return _mix64(np.add.reduceat(w, starts))
 
     def resolved_groups(self) -> list[tuple[int, ...]]:
         """Split the witness stack into per-variable groups.

@@ -414,6 +414,8 @@ def test_full_size_matches_oracle_fingerprint(name):
     assert got == g["rounds"]
     fp = to_dump(V, st, fin["cnfstate"]).fingerprint()
     diff = {k: (fp[k], v) for k, v in g["fingerprint"].items() if fp[k] != v}
+    if any(f in ("-all", "-bce") for f in g["flags"]) and "h_resolved_records" in g["fingerprint"]:
+        diff.pop("h_resolved_groups", None)   # blocked-clause records attach to arbitrary neighbours (sgd.py: canonical_witness); the records are compared
     assert not diff, diff
 
 
