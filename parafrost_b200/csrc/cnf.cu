@@ -547,55 +547,58 @@ __global__ void __launch_bounds__(LITHIST_T) k_ot_lithist(const uint2* __restric
 }
 
 // Shape of the build, fixed BEFORE the counting pass (counting pass, partition and placement must agree on it):
-//   bucket width W = 2^sh or 3 * 2^sh literals - the largest with an average bucket at most SIGMA_OT_FILL % (default 80) of the
-//   placement window; at most 8192 buckets (bucket index < 2^13 in the work-unit codes, counters in shared memory);
-//   tile = 1024 x CPT clauses, the largest of 3 / 4 / 5 whose pairs still fit the partition's stage.
+//   bucket width W = 2^sh or 3 * 2^sh literals - the largest with an average bucket at most 80 % of the placement window
+//   (SIGMA_OT_FILL); at most 8192 buckets (bucket index < 2^13 in the work-unit codes, counters in shared memory).
+//   Formulas with hot literal ranges (multiplier inputs: one bucket with 28x the mean) overflow the window whatever the
+//   width, and a wider bucket only sends more pairs through the work-unit path: once a build of the loaded formula has
+//   queued work units, the later ones go back to powers of two at <= 70 % of a 40 K-entry window (measured on cfg3 / cfg4,
+//   profiles/r02_ab_c15.jsonl);
+//   tile = 1024 x CPT clauses: 5 per thread for short clauses, else 3.
 #define PART2_STAGE 26624u   // pairs of a tile staged in shared memory, at most (what 220 KB leave after the bucket tables decides)
 static bool placeTmaOn() { static const int v = getenv("SIGMA_OT_TMA") ? atoi(getenv("SIGMA_OT_TMA")) : 0; return v != 0; }
 // entries of a bucket's occurs[] window staged by the placement; the bulk-copy variant also holds a 32 KB ring
 static u32 placeWindow() { return placeTmaOn() ? (40u << 10) : PLACE_WINDOW; }
 #define PLACE_WMAX 6144u     // widest bucket whose list cursors fit beside the window
 static size_t partFixedBytes(u32 NB) { return 4 * (((size_t)3 * NB + 2) & ~(size_t)1) + 16; }
-static u32 partStageCap(u32 NB) {
+// the stage holds the pairs of an average tile + 1/8 (a tile with more writes directly); no larger than needed: what the
+// kernel does not take as shared memory stays L1 for its header / rank / literal loads (0.87 -> 0.80 ms on cfg2)
+static u32 partStageCap(u32 NB, u64 tilePairs) {
     const size_t fixed = partFixedBytes(NB);
-    return fixed + 8 * (size_t)PART2_STAGE <= 220 * 1024 ? PART2_STAGE : (u32)((220 * 1024 - fixed) / 8);
+    const u64 room = fixed + 8 * (size_t)PART2_STAGE <= 220 * 1024 ? PART2_STAGE : (220 * 1024 - fixed) / 8;
+    const u64 want = (tilePairs + tilePairs / 8 + 1023) & ~(u64)1023;
+    return (u32)(want < room ? (want < 4096 ? 4096 : want) : room);
 }
 static void otChooseShape(Ctx* c, u64 numLiterals, u64 numClauses, u32 nSlots) {
     static const u32 fillPct = getenv("SIGMA_OT_FILL") ? (u32)atoi(getenv("SIGMA_OT_FILL")) : 80u;
-    const u64 limit = (u64)placeWindow() * fillPct / 100;
+    if (c->hdc->scratch[7]) c->otHot = true;   // the last build queued work units for oversized buckets
+    const bool hot = c->otHot;
+    const u64 limit = hot ? (u64)(40u << 10) * 7 / 10 : (u64)placeWindow() * fillPct / 100;
     u32 shape = 6;   // W = 64
     for (;;) {       // next wider candidate: 2^sh -> 3 * 2^(sh-1) -> 2^(sh+1)
         const u32 sh = shape & 0xFFu, three = shape >> 8;
-        const u32 next = three ? (sh + 2) : ((sh - 1) | 0x100u);
+        const u32 next = hot ? sh + 1 : (three ? (sh + 2) : ((sh - 1) | 0x100u));
         const u32 Wn = bkW(next);
-        if (Wn > PLACE_WMAX || numLiterals * Wn / c->ND > limit) break;
+        if (Wn > (hot ? 4096u : PLACE_WMAX) || numLiterals * Wn / c->ND > limit) break;
         shape = next;
     }
     while (bkW(shape) < (1u << 15) && (c->ND + bkW(shape) - 1) / bkW(shape) > 8192) shape = (shape >> 8) ? (shape & 0xFFu) + 2 : shape + 1;
     const u32 W = bkW(shape);
     c->otShift = shape; c->otNB = (c->ND + W - 1) / W;
     c->otNBp = (c->otNB + 3u) & ~3u;
-    const u64 cap = partStageCap(c->otNB);
-    const u64 perClause100 = numClauses ? 105 * numLiterals / numClauses : 0;   // literals per clause, + 5 %
-    c->otCPT = numLiterals <= 3 * numClauses ? 5 : ((u64)OT_T * 4 * perClause100 <= 100 * cap ? 4 : 3);
-    static const int cptEnv = getenv("SIGMA_OT_CPT") ? atoi(getenv("SIGMA_OT_CPT")) : 0;   // A/B measurements: force 3 clauses per thread
-    if (cptEnv == 3 && c->otCPT == 4) c->otCPT = 3;
-    if (cptEnv == 4 && c->otCPT == 5 && (u64)OT_T * 4 * perClause100 <= 100 * cap) c->otCPT = 4;
+    c->otCPT = numLiterals <= 3 * numClauses ? 5 : 3;   // short clauses: more of them per tile
     c->otTiles = divup(nSlots, OT_T * c->otCPT);
+    c->otTilePairs = numClauses ? (u64)OT_T * c->otCPT * numLiterals / numClauses : 0;
 }
 
 static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 numClauses) {
     otChooseShape(c, numLiterals, numClauses, n);
     if (!c->attrOT2) {
         cudaFuncSetAttribute(k_ot_count<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-        cudaFuncSetAttribute(k_ot_count<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-        cudaFuncSetAttribute(k_ot_count<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
         cudaFuncSetAttribute(k_ot_count<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
-#define OT_PART_ATTR(C_, K_) cudaFuncSetAttribute(k_ot_part2<C_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
-        OT_PART_ATTR(3, 5); OT_PART_ATTR(3, 3); OT_PART_ATTR(3, 2); OT_PART_ATTR(4, 3); OT_PART_ATTR(4, 2); OT_PART_ATTR(5, 3); OT_PART_ATTR(5, 2);
-#undef OT_PART_ATTR
+        cudaFuncSetAttribute(k_ot_part2<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_ot_part2<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(k_ot_place, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (PLACE_WINDOW + PLACE_WMAX));
         cudaFuncSetAttribute(k_ot_lithist, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15);
         c->attrOT2 = true;
@@ -605,12 +608,10 @@ static void launchCountPass(Ctx* c, bool awaken, u32 n, u64 numLiterals, u64 num
 #define OT_COUNT_ARGS c->inLits, c->inOffs, c->inMeta, c->L0, c->hdr[c->cur], c->pool[c->cur], n, c->ND, sh, NB, NBp, c->rk8, c->cntMat, c->key, &c->dc->flags
     if (awaken) {
         if (c->otCPT == 5) LAUNCH(c, (k_ot_count<5, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
-        else if (c->otCPT == 4) LAUNCH(c, (k_ot_count<4, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         else LAUNCH(c, (k_ot_count<3, true>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         KB(c, 8.0 * n + 4.0 * numLiterals + (c->inMeta ? 4.0 * n : 0.0) + 16.0 * n + 4.0 * numLiterals + 32.0 * n + 4.0 * (double)c->otTiles * NBp);
     } else {
         if (c->otCPT == 5) LAUNCH(c, (k_ot_count<5, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
-        else if (c->otCPT == 4) LAUNCH(c, (k_ot_count<4, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         else LAUNCH(c, (k_ot_count<3, false>), c->otTiles, OT_T, smem, OT_COUNT_ARGS);
         KB(c, 16.0 * n + 4.0 * numLiterals + 32.0 * numClauses + 4.0 * (double)c->otTiles * NBp);   // headers + literals in, keys + ranks + count rows out
     }
@@ -628,22 +629,22 @@ static void launchScatter2(Ctx* c, u32 n) {
     KB(c, 8.0 * (double)tiles * NBp);
     // shared memory of k_ot_part2: 3 words per bucket + the stage (whatever is left of ~220 KB, at most PART2_STAGE pairs)
     const size_t partFixed = partFixedBytes(NB);
-    const u32 stageCap = partStageCap(NB);
+    const u32 stageCap = partStageCap(NB, c->otTilePairs);
 #define OT_PART_ARGS c->hdr[c->cur], c->pool[c->cur], c->rk8, n, shift, NB, NBp, c->cntMat, c->runMat, stageCap, c->otPairs
-    static const int keep = getenv("SIGMA_OT_KEEP") ? atoi(getenv("SIGMA_OT_KEEP")) : 3;   // literals per clause kept in registers between the sweeps (A/B)
-#define OT_PART(C_, K_) LAUNCH(c, (k_ot_part2<C_, K_>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS)
-    if (c->otCPT == 5) { if (keep == 2) OT_PART(5, 2); else OT_PART(5, 3); }
-    else if (c->otCPT == 4) { if (keep == 2) OT_PART(4, 2); else OT_PART(4, 3); }
-    else { if (keep == 2) OT_PART(3, 2); else if (keep == 3) OT_PART(3, 3); else OT_PART(3, 5); }
-#undef OT_PART
+    // 3 literals per clause stay in registers between the sweeps, the others are re-read (L1): 5 of them cost spills under the
+    // 64-register cap of a 1024-thread CTA (0.78 -> 0.73 ms on cfg2, profiles/r02_ab_c15.jsonl)
+    if (c->otCPT == 5) LAUNCH(c, (k_ot_part2<5, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
+    else LAUNCH(c, (k_ot_part2<3, 3>), tiles, OT_T, partFixed + 8 * (size_t)stageCap, OT_PART_ARGS);
 #undef OT_PART_ARGS
     KB(c, 32.0 * n + 4.0 * c->numLiterals + 8.0 * (double)tiles * NBp + 8.0 * c->numLiterals);   // headers + ranks + literals + the tile's two rows in, pairs out
     LAUNCH(c, k_ot_lithist, NB, LITHIST_T, (size_t)4 * W, c->otPairs, c->bstart, c->ND, shift, c->hist, c->otStart);
     KB(c, 8.0 * c->numLiterals + 8.0 * c->ND);   // pairs in, hist + list starts out
     // placement: list cursors + the bucket's occurs[] window in shared memory; work units for oversized buckets
-    u32 window = W <= PLACE_WMAX ? placeWindow() : 0;
+    // (hot formulas keep the 40 K window their buckets were sized for: shared memory the kernel does not take stays L1)
+    const u32 winCap = c->otHot ? (40u << 10) : placeWindow();
+    u32 window = W <= PLACE_WMAX ? winCap : 0;
     if (const char* w = getenv("SIGMA_OT_WINDOW")) { const u32 v = (u32)atoi(w); if (v < window) window = v; }   // tests: force the work-unit path
-    const size_t placeSmem = W <= PLACE_WMAX ? 4 * ((size_t)PLACE_WINDOW + W) : (size_t)4 * W;
+    const size_t placeSmem = W <= PLACE_WMAX ? 4 * ((size_t)winCap + W) : (size_t)4 * W;
     u32* nBig = &c->dc->scratch[7];
     cudaMemsetAsync(nBig, 0, 4, c->stream);
     // measured (profiles/r02_ab_tma_c11.jsonl, identical results): 0.373 vs 0.324 ms on cfg2, 1.45 vs 1.29 ms on cfg3 - the plain kernel

@@ -159,7 +159,7 @@ struct Ctx {
     u32 *hist, *otStart, *otSize, *occurs;
     uint2* otPairs; u32* otCur; u32* otBig; u32 otShift, otNB;
     // OT build v2 (cnf.cu): ranks of the counting pass (8 x 16 bits per clause), count matrix [tiles][NBp], bucket totals / starts
-    uint4* rk8; u32* cntMat; u32* runMat; u32* otSeg; u32* bstart; u32 otNBp, otCPT, otTiles; bool attrOT2, attrTma;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
+    uint4* rk8; u32* cntMat; u32* runMat; u32* otSeg; u32* bstart; u32 otNBp, otCPT, otTiles; u64 otTilePairs; bool otHot; bool attrOT2, attrTma;   // partition buffer of the OT build (cnf.cu): (literal, clause) pairs, bucket cursors
     // vars
     u32 *scores, *eligible, *rank, *sortK, *sortV, *elected, *units, *resolved, *trail, *vorg, *varcore;
     unsigned char *mis, *cstat, *vstate, *vstate0, *assumed, *assumedBuf, *eliminated, *needSort;

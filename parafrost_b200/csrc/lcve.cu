@@ -645,11 +645,14 @@ int runLCVE(Ctx* c) {
             u64 blocks = ((u64)n * gs + 255) / 256;
             if (blocks > 148ull * 32) blocks = 148ull * 32;
             for (int b = 0; b < MIS_BATCH; b++, round++) {
+                // the worklist shrinks fast and the later rounds of a batch are often empty: they stride over it with at most
+                // eight CTAs per SM instead of paying for the first round's grid
+                const u32 grid = b == 0 ? (u32)blocks : (u32)(blocks < 148ull * 8 ? blocks : 148ull * 8);
                 if (smallGroups)
-                    LAUNCH(c, k_mis_round<8>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
+                    LAUNCH(c, k_mis_round<8>, grid, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
                            c->otSize, c->occurs, vinfo, blocker, maxcsize, prof);
                 else
-                    LAUNCH(c, k_mis_round<32>, (u32)blocks, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
+                    LAUNCH(c, k_mis_round<32>, grid, 256, 0, c->wlA, c->wlB, round, c->dc, c->hdr[c->cur], c->pool[c->cur], c->otStart,
                            c->otSize, c->occurs, vinfo, blocker, maxcsize, prof);
             }
             profCollect(c, c->ktLastId);
