@@ -1280,14 +1280,15 @@ __device__ __forceinline__ u32 keyHash(u32 sz, u32 first, u32 last, u32 sig) {
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
     return h;
 }
-__global__ void __launch_bounds__(256) k_ere_bloom(const uint4* __restrict__ hdr, const uint4* __restrict__ key, u32 n, u32* __restrict__ bloom, u32 mask) {
+// Streams key[] only: the counting pass of this round (k_ot_count) wrote a zero key for every deleted slot.
+__global__ void __launch_bounds__(256) k_ere_bloom(const uint4* __restrict__ key, u32 n, u32* __restrict__ bloom, u32 mask) {
     __shared__ u32 sizes[8];   // 256-bit mask of the clause sizes seen by this CTA; stored after the filter words
     if (threadIdx.x < 8) sizes[threadIdx.x] = 0;
     __syncthreads();
     u32 seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (C_DELETED(hdr[i].w)) continue;
         const uint4 k = key[i];
+        if (!k.x) continue;
         const u32 h = keyHash(k.x, k.y, k.z, k.w) & mask;
         atomicOr(&bloom[h >> 5], 1u << (h & 31u));
         const u32 sb = k.x < 255u ? k.x : 255u;
@@ -1937,8 +1938,8 @@ void launchERE(Ctx* c, const KOpts& k) {
     while (bits > 32 && bits / 8 + 32 > bufBytes / 2) bits >>= 1;
     u32* bloom = (u32*)c->otPairs;
     cudaMemsetAsync(bloom, 0, bits / 8 + 32, c->stream);   // + the 256-bit clause-size mask
-    LAUNCH(c, k_ere_bloom, gridFor(n, 256), 256, 0, c->hdr[c->cur], c->key, n, bloom, (u32)(bits - 1));
-    KB(c, 32.0 * n);   // header word + key per clause (the filter bits stay in L2)
+    LAUNCH(c, k_ere_bloom, gridFor(n, 256), 256, 0, c->key, n, bloom, (u32)(bits - 1));
+    KB(c, 16.0 * n);   // one key per clause slot (the filter bits stay in L2)
     g.bloom = bloom; g.bloomMask = (u32)(bits - 1);
     binElected(c, k, false);
     // Phase A records the resolvents that pass the filters; only the lists they will be searched in
