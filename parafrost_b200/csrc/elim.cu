@@ -66,7 +66,7 @@ template <int GS> __device__ __forceinline__ void markDeleted(GT<GS>& g, u32 ci)
 // Pull the clauses of a small variable into L1 up front: the gate searches below chase
 // list entry -> header -> literals serially, so without this every step is an L2/HBM round trip.
 template <int GS> __device__ __forceinline__ void prefetchLists(GT<GS>& g, const u32* P, u32 np, const u32* N, u32 nn) {
-    if (np + nn > 96u) return;
+    if (np + nn > 512u) return;   // up to 16 clauses per lane of a full warp (uniform k-SAT: ~50 occurrences per literal)
     for (u32 j = LANE; j < np + nn; j += GS) {
         const u32 ci = j < np ? P[j] : N[j - np];
         const uint4 h = g.hdr[ci];

@@ -193,17 +193,22 @@ __global__ void k_mis_fill(const u32* __restrict__ eligible, const u32* __restri
 // chain list entry -> header -> literals -> election words is four dependent loads deep; with small
 // worklists a MIS round is pure latency, so each lane keeps four clauses in flight (entries and
 // headers loaded as a batch) and loads the literals and the election words of a clause as batches of 8.
+// Both lists are walked as ONE index range (positive list first): the clauses of the two sides are in flight together
+// instead of one side's chain after the other's - half the latency of a walk when the worklist is small.
 #define MIS_WALK(GS_, V_, LANE_, NSIDES_, APPLY_)                                                      \
-    for (u32 side_ = 0; side_ < (NSIDES_); side_++) {                                                          \
-        const u32 lit_ = V2L(V_) | side_;                                                              \
-        const u32 n_ = otSize[lit_];                                                                   \
-        const u32* list_ = occurs + otStart[lit_];                                                     \
+    {                                                                                                  \
+        const u32 litP_ = V2L(V_);                                                                     \
+        const u32 nP_ = otSize[litP_], nN_ = (NSIDES_) > 1u ? otSize[litP_ | 1u] : 0u;                 \
+        const u32* listP_ = occurs + otStart[litP_];                                                   \
+        const u32* listN_ = occurs + otStart[litP_ | 1u];                                              \
+        const u32 n_ = nP_ + nN_;                                                                      \
         for (u32 j0_ = (LANE_); j0_ < n_; j0_ += 4 * (GS_)) {                                          \
             u32 ci_[4]; uint4 h_[4];                                                                   \
-            _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) { const u32 j_ = j0_ + u_ * (GS_); ci_[u_] = j_ < n_ ? list_[j_] : NOVAR; } \
+            _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) { const u32 j_ = j0_ + u_ * (GS_); ci_[u_] = j_ < n_ ? (j_ < nP_ ? listP_[j_] : listN_[j_ - nP_]) : NOVAR; } \
             _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) h_[u_] = ci_[u_] != NOVAR ? hdr[ci_[u_]] : make_uint4(0, 0, 0, CB_DELETED);  \
             _Pragma("unroll") for (int u_ = 0; u_ < 4; u_++) {                                         \
                 if (C_DELETED(h_[u_].w)) continue;                                                     \
+                const u32 side_ = (j0_ + u_ * (GS_)) >= nP_ ? 1u : 0u; (void)side_;                    \
                 const u32 csize = h_[u_].y; (void)csize;                                               \
                 pb_ += 20u + 8u * csize;                                                               \
                 const u32* l_ = pool + h_[u_].x;                                                       \
@@ -575,10 +580,15 @@ int runLCVE(Ctx* c) {
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
            c->scores, c->eligible, c->cstat, c->dc, fast, ovsFast);
     KB(c, 18.0 * V);
-    int rc = syncCounters(c);   // the largest score decides how many radix passes the sort needs (usually 2 of 4)
-    if (rc) return rc;
-    u32 bits = 0;
-    while (bits < 32 && (c->hdc->scratch[6] >> bits)) bits++;
+    // the largest score decides how many radix passes the sort needs (usually 2 of 4): worth a round trip (~25 us) only
+    // when two passes over V keys cost more than that
+    int rc = 0;
+    u32 bits = 32;
+    if (V > (1u << 18)) {
+        if ((rc = syncCounters(c))) return rc;
+        bits = 0;
+        while (bits < 32 && (c->hdc->scratch[6] >> bits)) bits++;
+    }
     radixSortPairs(c, c->scores, c->eligible, c->sortK, c->sortV, V, bits);
     // the per-variable MIS scratch is cleared with coalesced memsets; k_rank only scatters the election words
     CUDA_TRY(cudaMemsetAsync(blocker, 0, (size_t)(V + 1) * 4, c->stream));
@@ -611,13 +621,12 @@ int runLCVE(Ctx* c) {
         // first round of the chunk: one streaming pass over the clauses when many candidates are
         // undecided, otherwise the candidates walk their own lists
         bool clausePass = (u64)n * avgOcc * 2 > nCls;
-        if (dense && hPrev) {   // most of the chunk is frozen already: count what is left before choosing
+        if (dense && hPrev) {
+            // the elected variables of the earlier chunks have frozen most of this one (hundreds of neighbours each): what is
+            // left walks its own lists - no read-back to count it first, the rounds stride over the device-side count
             LAUNCH(c, k_mis_fill, gridFor(H - hPrev, 256), 256, 0, c->eligible, vinfo, hPrev, H, wlIn, c->dc, round % 3u);
             KB(c, 12.0 * (H - hPrev));
-            if ((rc = syncCounters(c))) return rc;
-            n = c->hdc->wlCnt[round % 3u];
-            clausePass = (u64)n * avgOcc * 2 > nCls;
-            if (clausePass) CUDA_TRY(cudaMemsetAsync(&c->dc->wlCnt[round % 3u], 0, 4, c->stream));   // k_mis_first refills the slot
+            clausePass = false;
         }
         if (clausePass) {
             LAUNCH(c, k_mis_clauses, gridFor(nCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], nCls, vinfo, nbr, ovs, H, maxcsize);
