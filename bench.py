@@ -357,6 +357,7 @@ def batch_main(a, torch, dist, barrier, rank, world, local):
             keep.append(t)
             return t.numpy().view(dt)
         V, lits, offs = cnfgen.gen_cnf(fam, seed, args, alloc=alloc)
+        offs = offs32_of(offs, alloc)
         inst.append((V, lits, offs, keep))
     maxC = max((len(x[2]) - 1 for x in inst), default=1)
     maxL = max((len(x[1]) for x in inst), default=1)
@@ -543,6 +544,16 @@ def probe_pcie(torch, local, barrier, mb=256):
         return {"error": repr(e)[:120]}
 
 
+def offs32_of(offs, alloc):
+    """Clause offsets as 32-bit words in pinned memory (sigma_load32: 4 instead of 8 bytes per clause over PCIe) when the
+    formula has fewer than 2^32 literals."""
+    if int(offs[-1]) >= 1 << 32:
+        return offs
+    o = alloc(len(offs), np.uint32)
+    o[:] = offs
+    return o
+
+
 def kernel_table(kstats, peak, traffic, top=10):
     """[{kernel, ms, launches, share, bytes_per_launch, gbs, frac, traffic}] sorted by time.  bytes = the engine's own
     algorithmic-byte count per kernel name (sigma_kernel_stats; formulas in DESIGN.md 3)."""
@@ -588,6 +599,7 @@ def measure(a, torch, workload, rank, world, local, barrier, steps, warmup, pipe
         return t.numpy().view(dt)
 
     V, lits, offs = cnfgen.gen_cnf(fam, seed, args, alloc=alloc)
+    offs = offs32_of(offs, alloc)
     C0, L0 = len(offs) - 1, len(lits)
     flags = a.flags.split()
     stream = torch.cuda.Stream()
@@ -752,7 +764,7 @@ def main():
         e2e_serial = lit_all * steps / (ms_e2e * 1e-3)
         e2e = {"value": e2e_serial, "unit": UNIT, "ms_per_step": ms_e2e / steps, "mode": "one context: load -> run -> store, nothing overlapped",
                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
-               "api": "sigma_load (pinned host CSR) -> sigma_run -> sigma_store_compact (bits, sizes, literals, eliminated, witness stack, trail to pinned host)",
+               "api": "sigma_load32 (pinned host CSR, 32-bit offsets) -> sigma_run -> sigma_store_compact (bits, sizes, literals, eliminated, witness stack, trail to pinned host)",
                "pcie_probe": {**pcie, "all_ranks_duplex_gbs": pcie_sum,
                               "note": "pinned host <-> device copies of rank 0 while all ranks copy; a step moves h2d + d2h bytes per rank"}}
         if ms_pipe:

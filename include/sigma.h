@@ -141,6 +141,12 @@ int  sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses,
                 const uint32_t* lits, const uint64_t* offs, const uint32_t* meta,
                 const uint32_t* vorg, const uint8_t* vstate, const uint8_t* assumed);
 
+/* sigma_load with 32-bit clause offsets (offs32[num_clauses] < 2^32 literals): 4 instead of 8 bytes per clause over PCIe;
+ * the offsets are widened on the device.  Same result as sigma_load. */
+int  sigma_load32(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses,
+                  const uint32_t* lits, const uint32_t* offs32, const uint32_t* meta,
+                  const uint32_t* vorg, const uint8_t* vstate, const uint8_t* assumed);
+
 /* The same from the reference's own host mirror `hcnf` (CNF::newClause, cnf.cuh:82-97): the SCLAUSE
  * record stream {word 0 = st:2 f:1 a:1 u:2 lbd:26, sig, size, literals...} of num_words words and the
  * uint64 word offsets `refs[num_clauses]`, gap-free in ref order - exactly the two buffers

@@ -360,6 +360,32 @@ extern "C" int sigma_load(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, 
     return finishLoad(c, vorg, vstate, assumed);
 }
 
+// 32-bit offsets over PCIe, widened on the device (staged in rk8[], free until the first counting pass)
+__global__ void k_widen_offs(const u32* __restrict__ in, u64 n, u64* __restrict__ out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = in[i];
+}
+extern "C" int sigma_load32(sigma_ctx* c, uint32_t max_var, uint64_t num_clauses, const uint32_t* lits,
+                            const uint32_t* offs32, const uint32_t* meta, const uint32_t* vorg, const uint8_t* vstate,
+                            const uint8_t* assumed) {
+    if (!c || !lits || !offs32 || !max_var) return SIGMA_BAD_ARGUMENT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const u64 L0 = offs32[num_clauses];
+    u64 orgC = num_clauses, orgL = L0;
+    if (meta) {
+        orgC = 0; orgL = 0;
+        for (u64 i = 0; i < num_clauses; i++) if (!(meta[i] & CB_LEARNT)) { orgC++; orgL += offs32[i + 1] - offs32[i]; }
+    }
+    int rc = prepareLoad(c, max_var, num_clauses, L0, orgC, orgL, vorg);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->inLits, lits, L0 * 4, cudaMemcpyHostToDevice, c->stream));
+    u32* stage = (u32*)c->rk8;   // 16 bytes per clause slot
+    CUDA_TRY(cudaMemcpyAsync(stage, offs32, (num_clauses + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_widen_offs, gridFor(num_clauses + 1, 256, 4), 256, 0, stage, num_clauses + 1, c->inOffs);
+    if (meta) CUDA_TRY(cudaMemcpyAsync(c->inMeta, meta, num_clauses * 4, cudaMemcpyHostToDevice, c->stream));
+    else c->inMeta = nullptr;
+    return finishLoad(c, vorg, vstate, assumed);
+}
+
 // SCLAUSE records {word 0, sig, size, literals...} at refs[i] -> the engine's input arrays
 __global__ void k_unpack_sclauses(const u32* __restrict__ data, const u64* __restrict__ refs, u64 C, u64 numWords,
                                   u32* __restrict__ inLits, u64* __restrict__ inOffs, u32* __restrict__ inMeta, u32* bad,

@@ -580,15 +580,12 @@ int runLCVE(Ctx* c) {
     LAUNCH(c, k_scores, gridFor(V, 256), 256, 0, c->hist, c->vstate, c->assumed, V, pmax, nmax, c->o.lcve_max_occurs,
            c->scores, c->eligible, c->cstat, c->dc, fast, ovsFast);
     KB(c, 18.0 * V);
-    // the largest score decides how many radix passes the sort needs (usually 2 of 4): worth a round trip (~25 us) only
-    // when two passes over V keys cost more than that
-    int rc = 0;
-    u32 bits = 32;
-    if (V > (1u << 18)) {
-        if ((rc = syncCounters(c))) return rc;
-        bits = 0;
-        while (bits < 32 && (c->hdc->scratch[6] >> bits)) bits++;
-    }
+    // the largest score decides how many radix passes the sort needs (usually 2 of 4); the round trip is cheaper than the two
+    // spare passes even at V = 100 k (six more launches: cfg1 3.48 -> 3.62 ms without it, profiles/r02_ab_c19.jsonl)
+    int rc = syncCounters(c);
+    if (rc) return rc;
+    u32 bits = 0;
+    while (bits < 32 && (c->hdc->scratch[6] >> bits)) bits++;
     radixSortPairs(c, c->scores, c->eligible, c->sortK, c->sortV, V, bits);
     // the per-variable MIS scratch is cleared with coalesced memsets; k_rank only scatters the election words
     CUDA_TRY(cudaMemsetAsync(blocker, 0, (size_t)(V + 1) * 4, c->stream));

@@ -89,7 +89,7 @@ _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 # every symbol include/sigma.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "sigma_default_opts", "sigma_normalize_opts", "sigma_create", "sigma_destroy", "sigma_set_opts", "sigma_set_stream", "sigma_load", "sigma_load_sclauses",
+    "sigma_default_opts", "sigma_normalize_opts", "sigma_create", "sigma_destroy", "sigma_set_opts", "sigma_set_stream", "sigma_load", "sigma_load32", "sigma_load_sclauses",
     "sigma_run", "sigma_begin", "sigma_round", "sigma_finish", "sigma_num_rounds", "sigma_round_reports",
     "sigma_result_sizes", "sigma_store", "sigma_store_compact", "sigma_store_sclauses", "sigma_snapshot", "sigma_debug_elected",
     "sigma_set_proof_sink", "sigma_proof_chunks", "sigma_proof_chunk_size", "sigma_proof_chunk_copy",
@@ -114,6 +114,7 @@ def lib():
         L.sigma_set_opts.argtypes = [P, C.POINTER(SigmaOpts)]
         L.sigma_set_stream.argtypes = [P, P]
         L.sigma_load.argtypes = [P, C.c_uint32, C.c_uint64, P, P, P, P, P, P]
+        L.sigma_load32.argtypes = [P, C.c_uint32, C.c_uint64, P, P, P, P, P, P]
         L.sigma_load_sclauses.argtypes = [P, C.c_uint32, C.c_uint64, P, C.c_uint64, P, P, P, P]
         L.sigma_run.argtypes = [P, C.POINTER(Report)]
         L.sigma_begin.argtypes = [P]
@@ -227,14 +228,16 @@ class Simplifier:
 
     # Solver::awaken (host half)
     def load(self, max_var, lits, offs, meta=None, vorg=None, vstate=None, assumed=None):
-        self._keep = [np.ascontiguousarray(lits, np.uint32), np.ascontiguousarray(offs, np.uint64),
+        """CSR clause list; `offs` of dtype uint32 goes through sigma_load32 (half the offset bytes over PCIe)."""
+        o32 = isinstance(offs, np.ndarray) and offs.dtype == np.uint32
+        self._keep = [np.ascontiguousarray(lits, np.uint32), np.ascontiguousarray(offs, np.uint32 if o32 else np.uint64),
                       None if meta is None else np.ascontiguousarray(meta, np.uint32),
                       None if vorg is None else np.ascontiguousarray(vorg, np.uint32),
                       None if vstate is None else np.ascontiguousarray(vstate, np.uint8),
                       None if assumed is None else np.ascontiguousarray(assumed, np.uint8)]
         k = self._keep
         self.max_var = int(max_var)
-        self._check(self._lib.sigma_load(self._h, self.max_var, len(k[1]) - 1, *[_ptr(a) for a in k]))
+        self._check((self._lib.sigma_load32 if o32 else self._lib.sigma_load)(self._h, self.max_var, len(k[1]) - 1, *[_ptr(a) for a in k]))
 
     def load_sclauses(self, max_var, data_words, refs, vorg=None, vstate=None, assumed=None):
         """The reference's host mirror (SCLAUSE record stream + uint64 refs, cnf.cuh:82-97), as produced
@@ -248,10 +251,11 @@ class Simplifier:
         self._check(self._lib.sigma_load_sclauses(self._h, self.max_var, len(k[1]), _ptr(k[0]), len(k[0]), _ptr(k[1]),
                                                   _ptr(k[2]), _ptr(k[3]), _ptr(k[4])))
 
-    def load_pointers(self, max_var, num_clauses, lits_ptr, offs_ptr):
+    def load_pointers(self, max_var, num_clauses, lits_ptr, offs_ptr, offs32=False):
         """Raw host pointers (e.g. pinned torch tensors) - used by bench.py's e2e leg."""
         self.max_var = int(max_var)
-        self._check(self._lib.sigma_load(self._h, self.max_var, num_clauses, lits_ptr, offs_ptr, None, None, None, None))
+        fn = self._lib.sigma_load32 if offs32 else self._lib.sigma_load
+        self._check(fn(self._h, self.max_var, num_clauses, lits_ptr, offs_ptr, None, None, None, None))
 
     # Solver::simplify
     def simplify(self) -> dict:

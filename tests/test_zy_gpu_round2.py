@@ -127,6 +127,27 @@ def test_compact_store_equals_full_store():
         s.close()
 
 
+def test_load_with_32_bit_offsets_equals_load():
+    """sigma_load32 (4-byte clause offsets over PCIe, widened on the device) gives the result of sigma_load, learnt marks included."""
+    for name in ("miter_x", "k3_r30"):
+        fam, seed, args = SMALL[name]
+        V, lits, offs = helpers.gen_cnf(fam, seed, args)
+        meta = np.zeros(len(offs) - 1, np.uint32)
+        meta[::7] = 1 | (3 << 6)   # some learnt clauses (word 0: CB_LEARNT, lbd 3 as the later-call tests build them)
+        res = []
+        for o in (np.asarray(offs, np.uint64), np.asarray(offs, np.uint64).astype(np.uint32)):
+            s = sigma().Simplifier(0)
+            try:
+                s.load(V, lits, o, meta=meta if name == "k3_r30" else None)
+                s.simplify()
+                res.append(s.store())
+            finally:
+                s.close()
+        for k in ("bits", "sig", "offs", "lits", "eliminated"):
+            assert (res[0][k] == res[1][k]).all(), (name, k)
+        assert sorted(res[0]["resolved"].tolist()) == sorted(res[1]["resolved"].tolist())
+
+
 def test_trail_ranges_split_seed_units_from_derived_ones():
     """sigma_trail_info: per prop() the units SUB/BVE produced come first (enqueueDevUnit), the derived ones after
     (enqueueUnit), elimbcp.cu:185-200."""
