@@ -13,11 +13,11 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_o
 echo "full cfg2 rc=$?"
 ncu -i /tmp/c20_full_cfg2.ncu-rep --page raw --csv > $O/full_cfg2_v20_raw.csv 2>/dev/null
 python tools/ncu_digest.py $O/full_cfg2_v20_raw.csv > $O/full_cfg2_v20_digest.txt 2>&1; head -50 $O/full_cfg2_v20_digest.txt
-python tools/ncu_digest.py $O/full_cfg2_v20_raw.csv --json > $O/ncu_traffic_cfg2_v20.json 2>/dev/null
+python tools/ncu_digest.py $O/full_cfg2_v20_raw.csv --json $O/ncu_traffic_cfg2_v20.json
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_ve_phase1|k_sub|k_ve_phase3|k_mis_round|k_mis_push|k_mis_clauses|k_ot_part2|k_ot_place" -c 30 -f -o /tmp/c20_full_cfg3 \
     python tools/profile_run.py cfg3 > $O/full_cfg3_v20.log 2>&1
 echo "full cfg3 rc=$?"
 ncu -i /tmp/c20_full_cfg3.ncu-rep --page raw --csv > $O/full_cfg3_v20_raw.csv 2>/dev/null
 python tools/ncu_digest.py $O/full_cfg3_v20_raw.csv > $O/full_cfg3_v20_digest.txt 2>&1; head -34 $O/full_cfg3_v20_digest.txt
-python tools/ncu_digest.py $O/full_cfg3_v20_raw.csv --json > $O/ncu_traffic_cfg3_v20.json 2>/dev/null
+python tools/ncu_digest.py $O/full_cfg3_v20_raw.csv --json $O/ncu_traffic_cfg3_v20.json
 ls -la $O/*v20* | awk '{print $5, $9}'
