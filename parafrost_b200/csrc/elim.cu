@@ -701,10 +701,21 @@ __global__ void __launch_bounds__(128) k_ve_phase1(GT<GS> g, const u32* __restri
                         elimType = AOIX_MASK;
                 }
                 if (!elimType && nClsBefore > 3) {
-                    if (findITEGate(g, p, P, np, n, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
-                    else if (!nAddedCls && findITEGate(g, n, N, nn, p, P, np, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
-                    else if (findXORGate(g, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
-                    else if (!nAddedCls && findXORGate(g, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    // The ITE / XOR searches look for clauses that contain x or its negation, so they can walk x's OWN lists
+                    // (in L1 after prefetchLists) instead of the shortest foreign list (cold: two L2 / DRAM round trips per
+                    // probe) and find the same clause - the argument of k_ve_phase1_local.  Long lists keep the foreign walk.
+                    const bool own = GS < 32 || np + nn <= 512u;
+                    if (own) {
+                        if (findITEGate<GS, true>(g, p, P, np, n, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                        else if (!nAddedCls && findITEGate<GS, true>(g, n, N, nn, p, P, np, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                        else if (findXORGate<GS, true>(g, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                        else if (!nAddedCls && findXORGate<GS, true>(g, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    } else if constexpr (GS == 32) {
+                        if (findITEGate(g, p, P, np, n, N, nn, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                        else if (!nAddedCls && findITEGate(g, n, N, nn, p, P, np, nClsBefore, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                        else if (findXORGate(g, p, P, np, n, N, nn, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                        else if (!nAddedCls && findXORGate(g, n, N, nn, p, P, np, nClsBefore, out_c, nElements, nAddedCls, nAddedLits)) elimType = AOIX_MASK;
+                    }
                 }
                 bool funHit = false;
                 if (g.k.ve_fun_en && !elimType && nClsBefore > 2) {
