@@ -109,9 +109,11 @@ def ncu_traffic(workload):
     written by tools/ncu_digest.py --json)."""
     import glob
     best = {}
-    def version(f):   # ..._vNN.json, natural order
-        m = re.search(r"_v(\d+)[a-z]*\.json$", f)
-        return int(m.group(1)) if m else -1
+    def version(f):   # rNN_..._vMM.json: by round, then by capture number (later captures override earlier ones)
+        b = os.path.basename(f)
+        r = re.match(r"r(\d+)_", b)
+        m = re.search(r"_v(\d+)[a-z]*\.json$", b)
+        return (int(r.group(1)) if r else -1, int(m.group(1)) if m else -1)
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_ncu_traffic_{workload}*.json")), key=version):
         try:
             best.update(json.load(open(f)).get("kernels", {}))
