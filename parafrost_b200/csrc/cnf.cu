@@ -1,11 +1,11 @@
-// parafrost_b200/csrc/cnf.cu -- clause store kernels: awaken/prep (+ the first round's histogram), literal
-// histogram + sort keys, occurrence-table construction (radix partition + staged placement), live counts,
+// parafrost_b200/csrc/cnf.cu -- clause store kernels: awaken/prep fused with the counting pass of the occurrence-table
+// build (bucket counts, ranks, sort keys), the table's radix partition + staged placement, live counts,
 // garbage-collecting compaction, result store (+ the -aggresivesort write-back order).
 //
 // Reference behaviour being replaced (results must be identical):
-//   prep_cnf_k            src/gpu/cnf.cu:45-53        sort literals, 32-bit signature
-//   copy_if_k + histSimp  src/gpu/cnf.cu:33-43, histogram.cu:54-72  (thrust sort only to count!)
-//   create_ot_k           src/gpu/occurrence.cu:50-62   (k_ot_part + k_ot_place)
+//   prep_cnf_k            src/gpu/cnf.cu:45-53        sort literals, 32-bit signature        (k_ot_count<CPT, true>)
+//   copy_if_k + histSimp  src/gpu/cnf.cu:33-43, histogram.cu:54-72  (thrust sort only to count!)  (k_ot_count, k_ot_lithist)
+//   create_ot_k           src/gpu/occurrence.cu:50-62   (k_ot_part2 + k_ot_place / k_ot_place_big)
 //   cnt_cls_lits          src/gpu/count.cu:83-106
 //   scatter_k/compact_k   src/gpu/recycle.cu:34-105
 //   cacheCNF              src/gpu/cnf.cu:200-237
@@ -240,28 +240,22 @@ void launchScatter(Ctx* c) {
     launchScatter2(c, n);
 }
 
-// ================================================================== occurrence-table build, version 2
-// Three passes over ~L items each used to pay one atomic per item: the per-literal histogram (global RED), the
-// partition's rank (shared-memory atomic) and the placement's cursor (shared-memory atomic); the RED pass and the
-// shared-memory atomics - not HBM - bounded all three (profiles/r02_bench_cfg2_v2.json: k_awaken 0.33, k_ot_part 0.25 of
-// the copy roofline).  Version 2 pays two:
+// ================================================================== occurrence-table build: count, scan, partition, histogram
+// One atomic per literal twice, both in shared memory (round 1 paid three, one of them a global reduction: k_awaken at 0.33
+// and k_ot_part at 0.25 of the copy roofline, profiles/r02_bench_cfg2_v2.json):
 //   k_ot_count  (fused into awaken / the key pass, tile = 1024 x CPT clauses per CTA): one shared-memory atomic per literal on
 //               the tile's BUCKET counter; the value it returns is the literal's rank inside (tile, bucket) and is kept -
 //               8 x 16 bits per clause, one coalesced 16-byte store - together with the tile's row of bucket counts.
 //               No global histogram, no global reductions.
-//   k_ot_colsum / k_ot_bscan: bucket totals = column sums of the count matrix, exclusive scan -> segment starts.
-//   k_ot_part2  the same tile again: its row of counts gives run lengths (one global atomic per non-empty (tile, bucket)
-//               reserves the run - issued as independent atomics, one round trip), the stored ranks give every pair its
-//               slot: NO shared-memory atomics, no counter clearing; pairs are staged bucket by bucket and copied out
-//               with one table look-up per pair.  Literals of clauses longer than 8 take the tail of the run through
-//               a second counter (rare).
-//   k_ot_place2 one CTA per bucket as before; the per-literal histogram of the bucket (which IS hist[] / otSize[], and
-//               whose local scan is otStart[]) is counted here with the one shared-memory atomic the placement needs
-//               anyway: sweep 1 counts and keeps each pair's rank in registers, sweep 2 re-reads the pairs from L2 and
-//               stores entry = start[literal] + rank into the staged window.
-// Oversized buckets (structured formulas) keep the global-atomic work units: count, scan, place (k_ot_big_*).
+//   k_ot_colsum / k_ot_bscan / k_ot_colfix: bucket totals = column sums of the count matrix, exclusive scan -> segment
+//               starts, running column sums -> the start of every (tile, bucket) run.  No reservation atomics.
+//   k_ot_part2  the same tile again: its two rows give run lengths and run starts, the stored ranks give every pair its
+//               slot: NO atomics, no counter clearing; pairs are staged bucket by bucket and copied out with one table
+//               look-up per pair.  Literals of clauses longer than 8 take the tail of the run through a second counter (rare).
+//   k_ot_lithist one CTA per bucket: the per-literal histogram of the bucket's pairs (= hist[]; its local scan = otStart[])
+//               with shared-memory atomics.
+//   k_ot_place / k_ot_place_big (above): list cursors + the bucket's window in shared memory; work units for oversized buckets.
 #define OT_T 1024
-#define OT_KEEP 5
 
 __device__ __forceinline__ void sort8(u32 (&r)[8]) {
 #pragma unroll
