@@ -1669,6 +1669,24 @@ uint64_t oracle_check_model(const uint8_t* value, uint64_t num_clauses, const ui
     return bad;
 }
 
+// ---- helpers of tests/sgd.py (fingerprints of 100 M-word witness stacks in seconds instead of minutes of Python loops)
+// Records of the witness stack are `[lits..., size]` (model.cuh:29-53): the sizes sit at the END, so the boundaries are found
+// walking back from the top.  ends[k] = one past record k, ascending; returns the number of records, ~0 if the stack is corrupt.
+uint64_t oracle_record_ends(const uint32_t* r, uint64_t n, uint64_t* ends) {
+    uint64_t cnt = 0;
+    for (uint64_t p = n; p > 0;) { const uint64_t sz = r[p - 1]; if (!sz || sz + 1 > p) return ~0ull; p -= sz + 1; cnt++; }
+    if (ends) { uint64_t k = cnt; for (uint64_t p = n; p > 0;) { ends[--k] = p; p -= (uint64_t)r[p - 1] + 1; } }
+    return cnt;
+}
+// FNV-1a over the words of every segment [starts[k], ends[k]) (sgd.hash_words)
+void oracle_hash_segments(const uint32_t* r, const uint64_t* starts, const uint64_t* ends, uint64_t m, uint64_t* out) {
+    for (uint64_t k = 0; k < m; k++) {
+        uint64_t h = 0xCBF29CE484222325ull;
+        for (uint64_t p = starts[k]; p < ends[k]; p++) { h ^= r[p]; h *= 0x100000001B3ull; }
+        out[k] = h;
+    }
+}
+
 } // extern "C"
 
 #ifdef ORACLE_MAIN

@@ -111,6 +111,11 @@ uint64_t oracle_extend_model(uint8_t* value, uint32_t max_var, const uint32_t* r
 /* returns the number of falsified clauses of a CNF under value[] */
 uint64_t oracle_check_model(const uint8_t* value, uint64_t num_clauses, const uint32_t* lits, const uint64_t* offs);
 
+/* helpers of tests/sgd.py: boundaries of the witness-stack records `[lits..., size]` (ends[k] = one past record k; returns the
+ * record count, ~0 if corrupt; ends may be NULL to count only) and FNV-1a hashes of word segments */
+uint64_t oracle_record_ends(const uint32_t* resolved, uint64_t n, uint64_t* ends);
+void oracle_hash_segments(const uint32_t* words, const uint64_t* starts, const uint64_t* ends, uint64_t m, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

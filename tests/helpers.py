@@ -71,6 +71,8 @@ def oracle_lib():
         lib.oracle_run.argtypes = [P]; lib.oracle_run.restype = C.c_int
         lib.oracle_rounds.argtypes = [P]; lib.oracle_rounds.restype = C.c_int
         lib.oracle_round_stats.argtypes = [P, _u64p]
+        lib.oracle_record_ends.argtypes = [P, C.c_uint64, P]; lib.oracle_record_ends.restype = C.c_uint64
+        lib.oracle_hash_segments.argtypes = [P, P, P, C.c_uint64, P]; lib.oracle_hash_segments.restype = None
         for f in ("oracle_num_clauses", "oracle_num_literals", "oracle_num_resolved", "oracle_num_trail"):
             getattr(lib, f).argtypes = [P]; getattr(lib, f).restype = C.c_uint64
         lib.oracle_copy_result.argtypes = [P, _u32p, _u32p, _u64p, _u32p, _u8p, _u32p, _u32p]

@@ -170,8 +170,7 @@ class Dump:
         hf = self.clause_hashes(True)
         elim_vars = np.nonzero(self.eliminated & 1)[0].astype(U64)
         forced_vars = np.nonzero(self.eliminated & 4)[0].astype(U64)
-        groups = self.resolved_groups()
-        gh = np.array([int(_mix64(np.array([hash_words(g)], U64))[0]) for g in groups], U64) if groups else np.empty(0, U64)
+        gh = self.group_hashes()   # == _mix64(hash_words(g)) for g in resolved_groups(), without the Python loops
         # the same stack record by record: with BCE the blocked-clause records (no closing unit) sit in front of whichever
         # group the atomic append put behind them, so runs with BCE compare this multiset instead of the groups
         rh = self.record_hashes()
@@ -185,7 +184,7 @@ class Dump:
             "eliminated": int(len(elim_vars)),
             "forced": int(len(forced_vars)),
             "resolved_words": int(len(self.resolved)),
-            "resolved_groups": len(groups),
+            "resolved_groups": int(len(gh)),
             "trail": int(len(self.trail)),
             "h_lits_multiset": ms(hl),
             "h_full_multiset": ms(hf),
@@ -212,14 +211,25 @@ class Dump:
     def eliminated_vars(self) -> list[int]:
         return np.nonzero(self.eliminated & 1)[0].tolist()
 
-    def record_hashes(self) -> np.ndarray:
-        """One 64-bit hash per record `[lits..., size]` of the witness stack (position inside the record matters: the
-        witness literal comes first).  The sizes sit at the END of the records, so the boundaries are found by a
-        sequential walk from the top; the hashing is vectorised."""
+    def record_ends(self) -> np.ndarray:
+        """ends[k] = one past record k of the witness stack.  Records are `[lits..., size]`: the sizes sit at the END, so
+        the boundaries are found walking back from the top - in C when the oracle library is there (a 100 M-word stack takes
+        a minute of Python otherwise)."""
         n = len(self.resolved)
         if not n:
-            return np.empty(0, U64)
-        rl = self.resolved.tolist()
+            return np.empty(0, np.int64)
+        r = np.ascontiguousarray(self.resolved, np.uint32)
+        try:
+            import helpers
+            lib = helpers.oracle_lib()
+            cnt = lib.oracle_record_ends(r.ctypes.data, n, None)
+            assert cnt != 0xFFFFFFFFFFFFFFFF, "corrupt resolved stack"
+            ends = np.empty(cnt, np.uint64)
+            lib.oracle_record_ends(r.ctypes.data, n, ends.ctypes.data)
+            return ends.astype(np.int64)
+        except (ImportError, OSError, AttributeError):
+            pass
+        rl = r.tolist()
         ends = []
         p = n
         while p > 0:
@@ -227,12 +237,46 @@ class Dump:
             assert 0 < sz < p + 1, "corrupt resolved stack"
             ends.append(p)
             p -= 1 + sz
-        ends = np.array(ends[::-1], np.int64)
+        return np.array(ends[::-1], np.int64)
+
+    def record_hashes(self) -> np.ndarray:
+        """One 64-bit hash per record `[lits..., size]` of the witness stack (position inside the record matters: the
+        witness literal comes first)."""
+        n = len(self.resolved)
+        if not n:
+            return np.empty(0, U64)
+        ends = self.record_ends()
         starts = np.concatenate((np.zeros(1, np.int64), ends[:-1]))
         pos = np.arange(n, dtype=np.int64) - np.repeat(starts, ends - starts)
         with np.errstate(over="ignore"):
             w = _mix64(self.resolved.astype(U64) + (pos.astype(U64) << U64(32)))
             return _mix64(np.add.reduceat(w, starts))
+
+    def group_hashes(self) -> np.ndarray:
+        """_mix64(hash_words(g)) for every group g of resolved_groups(): a group is the run of records up to and including a
+        unit record - a contiguous slice of the stack -, records after the last unit are groups of their own."""
+        n = len(self.resolved)
+        if not n:
+            return np.empty(0, U64)
+        r = np.ascontiguousarray(self.resolved, np.uint32)
+        ends = self.record_ends()
+        rstarts = np.concatenate((np.zeros(1, np.int64), ends[:-1]))
+        unit = r[ends - 1] == 1
+        gends = ends[unit]
+        gstarts = np.concatenate((np.zeros(1, np.int64), gends[:-1])) if len(gends) else np.empty(0, np.int64)
+        last = int(gends[-1]) if len(gends) else 0
+        loose = rstarts >= last            # records behind the last unit (blocked clauses of the last round)
+        gstarts = np.concatenate((gstarts, rstarts[loose])).astype(np.uint64)
+        gends = np.concatenate((gends, ends[loose])).astype(np.uint64)
+        out = np.empty(len(gends), U64)
+        try:
+            import helpers
+            helpers.oracle_lib().oracle_hash_segments(r.ctypes.data, gstarts.ctypes.data, gends.ctypes.data, len(gends), out.ctypes.data)
+        except (ImportError, OSError, AttributeError):
+            rl = r.tolist()
+            for k in range(len(gends)):
+                out[k] = hash_words(rl[int(gstarts[k]):int(gends[k])])
+        return _mix64(out)
 
     def resolved_groups(self) -> list[tuple[int, ...]]:
         """Split the witness stack into per-variable groups.
