@@ -67,12 +67,15 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.p, self.lines = index, None, []
+    def __init__(self, indices):
+        """indices: the GPUs of the job.  ONE sampler (rank 0) watches all of them: a poller per rank means 8 nvidia-smi
+        processes taking the driver's locks every 100 ms inside a 20 ms timed region."""
+        self.index = ",".join(str(i) for i in (indices if isinstance(indices, (list, tuple, range)) else [indices]))
+        self.p, self.lines = None, []
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", self.index],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.p.stdout), daemon=True)
             self.t.start()
@@ -394,12 +397,13 @@ def batch_main(a, torch, dist, barrier, rank, world, local):
 
     for _ in range(a.warmup):
         one_pass()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(range(world)) if rank == 0 else None   # one sampler for the job's GPUs
     barrier()
-    clocks.start()
+    if clocks:
+        clocks.start()
     tot = [one_pass() for _ in range(a.steps)]
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     # ---- the same passes through K contexts per GPU (replicas.Pipeline): copies of one instance overlap the kernels of
     # another; every instance is still loaded from and stored to pinned host memory
     piped_ms = None
@@ -624,7 +628,7 @@ def measure(a, torch, workload, rank, world, local, barrier, steps, warmup, pipe
     for _ in range(warmup):
         s.simplify()
     # ---- value: inputs resident in HBM, no per-kernel events in the timed region
-    clocks = ClockSampler(local) if with_clocks else None
+    clocks = ClockSampler(range(world)) if with_clocks and rank == 0 else None   # one sampler for the job's GPUs
     barrier()
     if clocks:
         clocks.start()
