@@ -57,3 +57,35 @@ def test_batch_specs_cover_the_config5_range():
     w = [replicas.spec_weight(s) for s in specs]
     assert len(specs) == 64 and 0.9e6 <= min(w) <= 1.1e6 and 4.0e7 <= max(w) <= 6.0e7
     assert {s[0] for s in specs} == {"ksat", "miter", "multpar"}
+
+
+def test_traffic_files_are_ordered_by_round_then_capture(tmp_path, monkeypatch):
+    """profiles/rNN_ncu_traffic_<cfg>_vMM.json: a later round overrides an earlier one whatever its capture number."""
+    b = load_bench()
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "r01_ncu_traffic_cfg2_v41.json").write_text(json.dumps({"kernels": {"k_a": 1.0, "k_b": 10.0}}))
+    (prof / "r02_ncu_traffic_cfg2_v7.json").write_text(json.dumps({"kernels": {"k_a": 2.0}}))
+    (prof / "r02_ncu_traffic_cfg2_v20.json").write_text(json.dumps({"kernels": {"k_a": 3.0}}))
+    monkeypatch.setattr(b, "ROOT", str(tmp_path))
+    assert b.ncu_traffic("cfg2") == {"k_a": 3.0, "k_b": 10.0}
+
+
+def test_one_clock_sampler_watches_every_gpu_of_the_job():
+    b = load_bench()
+    assert b.ClockSampler(range(4)).index == "0,1,2,3" and b.ClockSampler(0).index == "0"
+    s = b.ClockSampler(range(2))
+    s.p, s.t = type("P", (), {"terminate": lambda self: None})(), type("T", (), {"join": lambda self, timeout=None: None})()
+    s.lines = ["0, 1965, 1965, 400.0, Not Active, Not Active, Not Active, Not Active\n", "1, 1950, 1965, 900.0, Not Active, Not Active, Not Active, Active\n"]
+    c = s.stop()
+    assert c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"] and c["samples"] == 2
+
+
+def test_offsets_go_over_pcie_as_32_bit_words_when_they_fit():
+    import numpy as np
+    b = load_bench()
+    alloc = lambda n, dt: np.empty(int(n), dt)
+    o = b.offs32_of(np.array([0, 3, 8], np.uint64), alloc)
+    assert o.dtype == np.uint32 and o.tolist() == [0, 3, 8]
+    big = np.array([0, 1 << 32], np.uint64)
+    assert b.offs32_of(big, alloc) is big
