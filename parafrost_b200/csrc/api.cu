@@ -23,7 +23,7 @@ static std::mutex gKtMutex;
 static char gKtNames[KT_MAX_KERNELS][64];
 static int gKtN = 0;
 int ktRegister(const char* rawName) {
-    // the LAUNCH macro stringifies its argument: "(k_ot_part<3, 5>)" -> "k_ot_part<3, 5>"
+    // the LAUNCH macro stringifies its argument: "(k_ot_part2<3, 3>)" -> "k_ot_part2<3, 3>"
     char name[64];
     const size_t len = strlen(rawName);
     const bool paren = len >= 2 && rawName[0] == '(' && rawName[len - 1] == ')';

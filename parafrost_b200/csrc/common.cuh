@@ -186,7 +186,7 @@ struct Ctx {
     u32 lastElectedCount;
     u32 lastPropSeeds, lastPropTrail0, lastPropTotal;   // the last prop(): BVE-origin units, trail size before it, entries it appended
     bool varcoreDead, attrSort, attrElim, attrOT;
-    bool histFresh;    // hist[] / key[] were produced by k_awaken and the store is untouched since
+    bool histFresh;    // key[] and the count matrix were produced by the awaken pass (k_ot_count) and the store is untouched since
     bool countsFresh;  // hdc->liveCls / liveLits describe the clause store as it is now
     bool otValid;      // the occurrence table built last round still describes the clause store (api.cu)
     i64 unassigned0;   // unassigned variables of the loaded formula (inf.unassigned)

@@ -23,7 +23,7 @@
 struct G {
     uint4* hdr; u32* pool;
     const u32* otStart; u32* otSize; u32* occurs;
-    const uint4* key;   // OLIST_CMP keys of this round (k_hist_key); lists are sorted by (key, index)
+    const uint4* key;   // OLIST_CMP keys of this round (k_ot_count); lists are sorted by (key, index)
     const u32* bloom; u32 bloomMask;   // ERE: one bit per hashed key of a live clause (k_ere_bloom)
     const u32* elected; unsigned char* eliminated; const u32* vorg; const u32* varcore;
     u32* units; u32 unitsCap; u32* resolved; u32 resolvedCap;

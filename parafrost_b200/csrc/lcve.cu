@@ -572,7 +572,7 @@ int runLCVE(Ctx* c) {
     if (fast) { const int rc0 = syncCounters(c); if (rc0) return rc0; }   // flags bit 3 (a clause with >= 2^14 literals) must be current
     const int maxcsize = fast ? 0x7FFFFFFF : c->o.lcve_clause_max;   // -lcvefast: oversized clauses are filtered up front, never seen by the rounds
     const unsigned char* ovsFast = nullptr;
-    if (fast && (c->o.lcve_clause_max < (1 << 14) || (c->hdc->flags & 8u))) {   // flags bit 3: some clause has >= 2^14 literals (k_hist_key)
+    if (fast && (c->o.lcve_clause_max < (1 << 14) || (c->hdc->flags & 8u))) {   // flags bit 3: some clause has >= 2^14 literals (k_ot_count)
         CUDA_TRY(cudaMemsetAsync(c->needSort, 0, (size_t)V + 1, c->stream));
         LAUNCH(c, k_mark_oversize, gridFor(c->hdc->numCls, 256), 256, 0, c->hdr[c->cur], c->pool[c->cur], c->hdc->numCls, c->o.lcve_clause_max, c->needSort);
         ovsFast = c->needSort;

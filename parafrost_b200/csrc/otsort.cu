@@ -3,7 +3,7 @@
 // mgpu::segmented_sort + OLIST_CMP (src/gpu/segsort.cu:37-48, src/gpu/key.cuh:67-83).
 //
 // The reference's comparator dereferences two clauses per comparison.  Here the 16-byte key
-// of a clause is precomputed once per round (k_hist_key), gathered once per list entry, and
+// of a clause is precomputed once per round (k_ot_count), gathered once per list entry, and
 // the whole list is sorted on chip: in registers (<= 16 entries, one thread per list), in a
 // warp's shared-memory slice (<= 512), in a CTA's shared memory (<= 8192), or - for the rare
 // longer list - in place in global memory by one CTA.
@@ -298,7 +298,7 @@ void launchSortOT(Ctx* c, int mode) {
     LAUNCH(c, k_sort_reset, 1, 1, 0, c->dc);
     LAUNCH(c, k_sort_count, gridFor(c->ND, 256, 4), 256, 0, c->otSize, c->ND, c->dc, vinfo, need);
     LAUNCH(c, k_sort_fill, gridFor(c->ND, 256, FILL_TILE / 256), 256, 0, c->otSize, c->ND, q, c->dc, vinfo, need);
-    // the folded 128-bit key is exact while literals < 2^25 and clauses are shorter than 2^14 (flag 8: k_hist_key)
+    // the folded 128-bit key is exact while literals < 2^25 and clauses are shorter than 2^14 (flag 8: k_ot_count)
     const bool fold = c->ND <= (1u << 25) && !(c->hdc->flags & 8u);
     // grids: enough groups for every list of a class if all of them fell into it, capped
     const u32 nLists = c->ND;
